@@ -1,0 +1,92 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (needs /root/reference; build
+container only).  Usage: python -m oracle.make_goldens
+
+The reference has no tests or golden vectors of its own; these files pin the oracle
+restatement and the CUDA path to the reference's behaviour with numpy 2.3.5 / scipy 1.18.1 /
+scikit-learn 1.9.0 / torchvision 0.26 (versions recorded inside each file).
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import refshim, ssg_oracle as O, resnet_oracle as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def versions():
+    import scipy, sklearn, torch, torchvision
+    return np.array("numpy %s scipy %s sklearn %s torch %s torchvision %s" % (
+        np.__version__, scipy.__version__, sklearn.__version__, torch.__version__,
+        torchvision.__version__))
+
+
+def rerank_case(name, n, ns, d, seed, lam, rhos, per_cluster=20, noise=0.5):
+    from sklearn.cluster import DBSCAN
+    tgt, _ = O.synth_features(n, d, seed, per_cluster, noise)
+    src, _ = O.synth_features(ns, d, seed + 100, per_cluster, noise * 1.2)
+    e32, f32 = refshim.ref_re_ranking(src, tgt, mode="f32", lambda_value=lam)
+    e16, f16 = refshim.ref_re_ranking(src, tgt, mode="ref", lambda_value=lam)
+    st = {}
+    O.re_ranking(src, tgt, lambda_value=lam, mode="f32", stages=st)
+    out = dict(tgt=tgt, src=src, lam=lam, euclid_f32=e32, final_f32=f32, euclid_ref=e16, final_ref=f16,
+               vec_f32=st["vec"], rank21_f32=st["rank"][:, :21], rhos=np.array(rhos), versions=versions())
+    for bi, rho in enumerate(rhos):
+        # selftraining.py:289-296,306 verbatim on the reference's own output
+        tri = np.triu(f32, 1)
+        tri = tri[np.nonzero(tri)]
+        tri = np.sort(tri, axis=None)
+        top = np.round(rho * tri.size).astype(int)
+        eps = tri[:top].mean()
+        lab = DBSCAN(eps=eps, min_samples=4, metric="precomputed", n_jobs=8).fit_predict(f32)
+        out["eps_%d" % bi] = eps
+        out["labels_%d" % bi] = lab
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, "clusters", [int(out["labels_%d" % b].max()) + 1 for b in range(len(rhos))])
+
+
+def rerank_init_case(name, q, g, d, seed):
+    f, _ = O.synth_features(q + g, d, seed, per_cluster=10)
+    qf, gf = f[:q], f[q:]
+    q_g, q_q, g_g = qf @ gf.T, qf @ qf.T, gf @ gf.T
+    out = refshim.ref_re_ranking_init(q_g, q_q, g_g, stable=True)
+    np.savez_compressed(os.path.join(OUT, name), qf=qf, gf=gf, final=out, versions=versions())
+    print(name, out.shape, out.dtype)
+
+
+def embed_case(name, n_img, seed_img):
+    import torch
+    ref = refshim.load_reference()
+    imgs = R.synth_images(n_img, seed_img)
+    names = ["im%03d" % i for i in range(n_img)]
+    batches = [(imgs, names, list(range(n_img)), [0] * n_img)]
+    out = dict(n_img=n_img, seed_img=seed_img, weight_seed=0, versions=versions())
+    for S in (1, 2, 3):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m = ref.models.create("resnet50", num_classes=0, num_split=S, pretrained=False)
+        m.base.load_state_dict(R.make_state_dict(0), strict=False)
+        m.eval()
+        fl, _ = ref.evaluators.extract_features(m, batches, for_eval=False)
+        fe, _ = ref.evaluators.extract_features(m, batches, for_eval=True)
+        if S == 1:
+            out["list_S1"] = torch.stack([fl[k] for k in names]).numpy()[None]
+        else:
+            out["list_S%d" % S] = torch.stack(
+                [torch.stack([fl[k][b] for k in names]) for b in range(S + 1)]).numpy()
+        out["eval_S%d" % S] = torch.stack([fe[k] for k in names]).numpy()
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    rerank_case("rerank_n160_d256.npz", 160, 150, 256, seed=3, lam=0.1, rhos=[1.6e-3, 1.6e-2, 5e-2])
+    rerank_case("rerank_n257_d2048.npz", 257, 200, 2048, seed=7, lam=0.1, rhos=[1.6e-2, 4e-2])
+    rerank_case("rerank_n96_d64_ties.npz", 96, 64, 64, seed=11, lam=0.3, rhos=[2e-2], per_cluster=8,
+                noise=0.0)   # noise 0 => duplicate features: exact ties everywhere
+    rerank_init_case("rerank_init_q40_g90.npz", 40, 90, 512, seed=5)
+    embed_case("embed_4img.npz", 4, 1234)

@@ -1,0 +1,50 @@
+"""CPU, build container only: the restatement against the UNMODIFIED reference, live, bit-for-bit."""
+import numpy as np
+import pytest
+
+from oracle import refshim, ssg_oracle as O
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("mode", ["f32", "ref"])
+@pytest.mark.parametrize("n,ns,d,seed", [(120, 90, 128, 0), (200, 200, 512, 1)])
+def test_re_ranking_bit_exact(mode, n, ns, d, seed):
+    tgt, _ = O.synth_features(n, d, seed)
+    src, _ = O.synth_features(ns, d, seed + 50)
+    e0, f0 = refshim.ref_re_ranking(src, tgt, mode=mode, lambda_value=0.1)
+    e1, f1 = O.re_ranking(src, tgt, lambda_value=0.1, mode=mode)
+    assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
+
+
+def test_no_rerank_returns_none():
+    tgt, _ = O.synth_features(40, 32, 0)
+    e0, f0 = refshim.ref_re_ranking(tgt, tgt, mode="f32", no_rerank=True)
+    e1, f1 = O.re_ranking(tgt, tgt, mode="f32", no_rerank=True)
+    assert f0 is None and f1 is None and np.array_equal(e0, e1)
+
+
+def test_re_ranking_init_bit_exact():
+    f, _ = O.synth_features(100, 128, 2, per_cluster=10)
+    q, g = f[:30], f[30:]
+    a = refshim.ref_re_ranking_init(q @ g.T, q @ q.T, g @ g.T, stable=True)
+    b = O.re_ranking_init(q @ g.T, q @ q.T, g @ g.T)
+    assert np.array_equal(a, b)
+
+
+def test_reference_model_matches_oracle_model():
+    import torch, warnings
+    from oracle import resnet_oracle as R
+    ref = refshim.load_reference()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = ref.models.create("resnet50", num_classes=0, num_split=2, pretrained=False)
+    m.base.load_state_dict(R.make_state_dict(0), strict=False)
+    m.eval()
+    o = R.build_model(2, 0)
+    x = R.synth_images(2, 99)
+    with torch.no_grad():
+        a = m(x, False)[0]
+        b = o(x, False)[0]
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
