@@ -1,0 +1,125 @@
+/* ssg_b200.h — C ABI of the B200-native pseudo-label hot path of Self-Similarity Grouping.
+ *
+ * The reference (SHI-Labs/Self-Similarity-Grouping) is pure Python and has no FFI of its own
+ * (SURVEY.md §8b); this header is the boundary a maintainer would bind with ctypes/cffi (see
+ * INTEGRATION.md).  Each group of entry points cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns SSG_OK (0) or a negative SSG_ERR_* code; ssg_last_error() returns a
+ *     thread-local message for the last failure.  No exception crosses this boundary.
+ *   - `d_*` pointers are DEVICE pointers on the plan's device, `h_*` pointers are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device entry
+ *     points are stream-ordered and asynchronous unless they return a host scalar.
+ *   - plans own their workspace (allocated once at creation); nothing is allocated per call.
+ *   - plans are bound to one device and are not thread-safe.
+ */
+#ifndef SSG_B200_H
+#define SSG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSG_OK 0
+#define SSG_ERR_INVALID (-1)     /* bad argument (shape, alignment, null pointer)           */
+#define SSG_ERR_CUDA (-2)        /* a CUDA runtime call failed; message has the CUDA string  */
+#define SSG_ERR_CAPACITY (-3)    /* a bounded workspace overflowed; re-create with more room */
+#define SSG_ERR_UNSUPPORTED (-4) /* feature not built / device is not sm_100                 */
+
+int ssg_version(void);
+const char* ssg_last_error(void);
+/* number of visible CUDA devices and compute capability (major*10+minor) of `device`. */
+int ssg_device_info(int device, int* n_devices, int* sm);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pairwise squared Euclidean distance  (scipy cdist as used by reid/rerank.py:37,61-62; and
+ * reid/evaluators.py:63-85 pairwise_distance).
+ *   out[i*ldo + j] = fl32( fl32( sqrt( sum_k (x_ik - y_jk)^2 ) )^2 ), the sum taken sequentially in
+ *   float64 exactly as cdist does.
+ * mode: SSG_DIST_EXACT (float64 direct difference, bit-identical to cdist) or
+ *       SSG_DIST_TENSOR (bf16x3 split on tcgen05 tensor cores, |err| <~ 2e-5; candidates are
+ *       re-scored exactly inside ssg_rerank_run).
+ * ------------------------------------------------------------------------------------------------ */
+#define SSG_DIST_EXACT 0
+#define SSG_DIST_TENSOR 1
+int ssg_sqdist(const float* d_x, int nx, const float* d_y, int ny, int d, int mode, float* d_out,
+               size_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Source-aware k-reciprocal / Jaccard re-ranking: reid/rerank.py:27-127 re_ranking(
+ *   input_feature_source, input_feature, k1=20, k2=6, lambda_value, ...), O-f32 arithmetic
+ *   (float16 -> float32, stable argsort).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ssg_rerank_plan ssg_rerank_plan;
+
+#define SSG_RANK_STRIDE 32   /* rank table row stride; k1+1 <= 32          */
+#define SSG_V_STRIDE 256     /* k-reciprocal row capacity (bound 21+21*11) */
+#define SSG_VQ_STRIDE 1536   /* expanded row capacity (bound 6*252)        */
+
+int ssg_rerank_plan_create(ssg_rerank_plan** plan, int device, int n_max, int ns_max, int d);
+int ssg_rerank_plan_destroy(ssg_rerank_plan* plan);
+size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* plan);
+
+/* Device in / device out.  d_final: [n,n] float64 (row-major) = final_dist of the reference;
+ * d_euclid: optional [n,n] float32 = euclidean_dist of the reference (pre-normalisation squared
+ * distances), may be NULL.  k1 <= 31, k2 <= 8. */
+int ssg_rerank_run(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                   int k1, int k2, double lambda_value, int dist_mode, double* d_final,
+                   float* d_euclid, void* stream);
+/* Host in / host out (the literal drop-in of re_ranking): copies features up, results down. */
+int ssg_rerank_host(ssg_rerank_plan* plan, const float* h_src, int ns, const float* h_tgt, int n, int d,
+                    int k1, int k2, double lambda_value, int dist_mode, int no_rerank, double* h_final,
+                    float* h_euclid);
+
+/* Intermediate results of the last ssg_rerank_run, copied to the host (stage-isolated parity tests). */
+#define SSG_STAGE_VEC 0       /* float  [n]        normalised source vector v (rerank.py:36-40)     */
+#define SSG_STAGE_ROWMAX 1    /* float  [n]        row maximum of the squared distance (rerank.py:68) */
+#define SSG_STAGE_RANK 2      /* int32  [n,32]     initial_rank[:, :k1+1] (rerank.py:70)            */
+#define SSG_STAGE_RANK_VAL 3  /* float  [n,32]     normalised distance of those entries             */
+#define SSG_STAGE_V_CNT 4     /* int32  [n]        nnz of V rows (rerank.py:74-92)                  */
+#define SSG_STAGE_V_IDX 5     /* int32  [n,256]                                                     */
+#define SSG_STAGE_V_VAL 6     /* float  [n,256]                                                     */
+#define SSG_STAGE_VQ_CNT 7    /* int32  [n]        nnz of expanded rows (rerank.py:94-98)           */
+#define SSG_STAGE_VQ_IDX 8    /* int32  [n,1536]                                                    */
+#define SSG_STAGE_VQ_VAL 9    /* float  [n,1536]                                                    */
+#define SSG_STAGE_FLAGGED 10  /* int32  [1]        rows that took the exact fallback (tensor mode)  */
+int ssg_rerank_get_stage(ssg_rerank_plan* plan, int stage, void* h_dst, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * eps estimate and DBSCAN: selftraining.py:289-306 (np.triu/nonzero/sort/mean; sklearn
+ * DBSCAN(eps, min_samples=4, metric='precomputed').fit_predict on the dense matrix).
+ * dtype: SSG_F64 or SSG_F32 matrix elements (comparisons are made in the matrix dtype, as numpy does).
+ * ------------------------------------------------------------------------------------------------ */
+#define SSG_F32 0
+#define SSG_F64 1
+typedef struct ssg_cluster_plan ssg_cluster_plan;
+
+/* max_neighbors bounds the total number of (i,j) pairs with dist<=eps the plan can hold. */
+int ssg_cluster_plan_create(ssg_cluster_plan** plan, int device, int n_max, long long max_neighbors);
+int ssg_cluster_plan_destroy(ssg_cluster_plan* plan);
+size_t ssg_cluster_plan_bytes(const ssg_cluster_plan* plan);
+
+/* eps = mean of the round-half-even(rho * M) smallest non-zero entries above the diagonal, M = their
+ * count.  Synchronises the stream (returns host scalars).  eps is NaN when the count rounds to 0. */
+int ssg_eps_estimate(ssg_cluster_plan* plan, const void* d_dist, int dtype, int n, double rho,
+                     double* h_eps, long long* h_top_num, void* stream);
+/* labels: int64 [n] on the device, -1 = noise, cluster ids as sklearn assigns them.
+ * h_n_clusters (optional) forces a stream synchronisation. */
+int ssg_dbscan(ssg_cluster_plan* plan, const void* d_dist, int dtype, int n, double eps, int min_samples,
+               int64_t* d_labels, int* h_n_clusters, void* stream);
+/* core-sample mask of the last ssg_dbscan (uint8 [n], host). */
+int ssg_dbscan_core_mask(ssg_cluster_plan* plan, uint8_t* h_core, int n);
+
+/* Host-matrix conveniences (sklearn drop-in: matrix is copied to the device first). */
+int ssg_eps_estimate_host(ssg_cluster_plan* plan, const void* h_dist, int dtype, int n, double rho,
+                          double* h_eps, long long* h_top_num);
+int ssg_dbscan_host(ssg_cluster_plan* plan, const void* h_dist, int dtype, int n, double eps,
+                    int min_samples, int64_t* h_labels, int* h_n_clusters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSG_B200_H */

@@ -1,0 +1,279 @@
+// C ABI of libssg_b200: error plumbing, device info, ssg_sqdist and the re-ranking plan
+// (reid/rerank.py:27-127).  The eps / DBSCAN entry points live in cluster.cu, the embedding ones in
+// embed.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace ssg;
+
+static thread_local char g_err[1024] = "";
+
+int ssg_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char* ssg_last_error(void) { return g_err; }
+extern "C" int ssg_version(void) { return 100; }
+
+extern "C" int ssg_device_info(int device, int* n_devices, int* sm) {
+    int n = 0;
+    SSG_CUDA_TRY(cudaGetDeviceCount(&n));
+    if (n_devices) *n_devices = n;
+    if (sm) {
+        cudaDeviceProp prop;
+        SSG_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        *sm = prop.major * 10 + prop.minor;
+    }
+    return SSG_OK;
+}
+
+extern "C" int ssg_sqdist(const float* d_x, int nx, const float* d_y, int ny, int d, int mode, float* d_out,
+                          size_t ldo, void* stream) {
+    if (!d_x || !d_y || !d_out || nx < 0 || ny < 0 || d <= 0 || ldo < (size_t)ny)
+        return ssg_set_error(SSG_ERR_INVALID, "sqdist: bad arguments");
+    if (mode == SSG_DIST_EXACT) return launch_sqdist_exact(d_x, nx, d_y, ny, d, d_out, ldo, (cudaStream_t)stream);
+    if (mode == SSG_DIST_TENSOR) return launch_sqdist_tensor(d_x, nx, d_y, ny, d, d_out, ldo, (cudaStream_t)stream);
+    return ssg_set_error(SSG_ERR_INVALID, "sqdist: unknown mode %d", mode);
+}
+
+// ------------------------------------------------------------------------------------- rerank plan
+struct ssg_rerank_plan {
+    int device, n_max, ns_max, d;
+    size_t bytes;
+    size_t dmat_elems;           // capacity of the distance block (floats)
+    float* dmat;
+    float *rowmin, *rowmax, *vec, *scratch;
+    int* rank; float* rank_val;
+    int* v_idx; float* v_val; int* v_cnt;
+    int* q_idx; float* q_val; int* q_cnt;
+    int *colcnt, *colptr, *cursor, *csc_row;
+    int* flagged;
+    // lazily grown device I/O buffers for the host entry point
+    float *io_src, *io_tgt; size_t io_src_bytes, io_tgt_bytes;
+    double* io_final; size_t io_final_bytes;
+    float* io_euclid; size_t io_euclid_bytes;
+    int last_n;
+};
+
+static int dalloc(void** p, size_t bytes, size_t* total) {
+    SSG_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    if (total) *total += bytes;
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_plan_create(ssg_rerank_plan** out, int device, int n_max, int ns_max, int d) {
+    if (!out || n_max <= 0 || ns_max <= 0 || d <= 0)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_plan_create: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(device));
+    ssg_rerank_plan* p = new ssg_rerank_plan();
+    memset(p, 0, sizeof(*p));
+    p->device = device; p->n_max = n_max; p->ns_max = ns_max; p->d = d;
+    const size_t n = (size_t)n_max;
+    const size_t cols = (size_t)(n_max > ns_max ? n_max : ns_max);
+    // distance block: whole matrix up to 4 GiB, else row blocks (at least 256 rows)
+    size_t elems = n * cols;
+    const size_t cap = (size_t)1 << 30;   // 2^30 floats = 4 GiB
+    if (elems > cap) {
+        size_t rows = cap / cols;
+        if (rows < 256) rows = 256;
+        elems = rows * cols;
+    }
+    p->dmat_elems = elems;
+    int rc = SSG_OK;
+#define A(ptr, nbytes) if (rc == SSG_OK) rc = dalloc((void**)&(ptr), (nbytes), &p->bytes)
+    A(p->dmat, sizeof(float) * elems);
+    A(p->rowmin, sizeof(float) * n);
+    A(p->rowmax, sizeof(float) * n);
+    A(p->vec, sizeof(float) * n);
+    A(p->scratch, sizeof(float) * 4);
+    A(p->rank, sizeof(int) * n * SSG_RANK_STRIDE);
+    A(p->rank_val, sizeof(float) * n * SSG_RANK_STRIDE);
+    A(p->v_idx, sizeof(int) * n * SSG_V_STRIDE);
+    A(p->v_val, sizeof(float) * n * SSG_V_STRIDE);
+    A(p->v_cnt, sizeof(int) * n);
+    A(p->q_idx, sizeof(int) * n * SSG_VQ_STRIDE);
+    A(p->q_val, sizeof(float) * n * SSG_VQ_STRIDE);
+    A(p->q_cnt, sizeof(int) * n);
+    A(p->colcnt, sizeof(int) * n);
+    A(p->colptr, sizeof(int) * (n + 1));
+    A(p->cursor, sizeof(int) * n);
+    A(p->csc_row, sizeof(int) * n * SSG_VQ_STRIDE);
+    A(p->flagged, sizeof(int) * 4);
+#undef A
+    if (rc != SSG_OK) { ssg_rerank_plan_destroy(p); return rc; }
+    *out = p;
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
+    if (!p) return SSG_OK;
+    cudaSetDevice(p->device);
+    void* ptrs[] = {p->dmat, p->rowmin, p->rowmax, p->vec, p->scratch, p->rank, p->rank_val, p->v_idx,
+                    p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, p->colcnt, p->colptr, p->cursor,
+                    p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete p;
+    return SSG_OK;
+}
+
+extern "C" size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* p) {
+    return p ? p->bytes + p->io_src_bytes + p->io_tgt_bytes + p->io_final_bytes + p->io_euclid_bytes : 0;
+}
+
+static int check_run_args(ssg_rerank_plan* p, const void* src, int ns, const void* tgt, int n, int d,
+                          int k1, int k2) {
+    if (!p || !src || !tgt) return ssg_set_error(SSG_ERR_INVALID, "rerank: null argument");
+    if (n <= 0 || ns <= 0 || n > p->n_max || ns > p->ns_max || d != p->d)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank: shape (n=%d, ns=%d, d=%d) exceeds plan (%d, %d, %d)",
+                             n, ns, d, p->n_max, p->ns_max, p->d);
+    if (k1 < 1 || k1 > 31 || k2 < 1 || k2 > 8)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank: k1=%d k2=%d out of range", k1, k2);
+    return SSG_OK;
+}
+
+// squared distances of a block of target rows against all of Y, then what the caller needs from it
+static int dist_block(ssg_rerank_plan* p, const float* X, int rows, const float* Y, int ny, int d,
+                      int dist_mode, cudaStream_t st) {
+    if (dist_mode == SSG_DIST_EXACT) return launch_sqdist_exact(X, rows, Y, ny, d, p->dmat, (size_t)ny, st);
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "rerank: dist_mode %d not available in this build", dist_mode);
+}
+
+// stages (i)-(iv): source vector, squared distance, row normaliser, leading k1+1 rank columns
+static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                           int k1, int dist_mode, float* d_euclid, bool want_rank, cudaStream_t st) {
+    const int k1p = k1 + 1;
+    // (i) rerank.py:36-40
+    {
+        const int rows_blk = (int)(p->dmat_elems / (size_t)ns < (size_t)n ? p->dmat_elems / (size_t)ns : (size_t)n);
+        for (int r0 = 0; r0 < n; r0 += rows_blk) {
+            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+            SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_src, ns, d, dist_mode, st));
+            SSG_TRY(launch_row_minmax(p->dmat, (size_t)ns, rows, ns, p->rowmin + r0, nullptr, st));
+        }
+        SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st));
+    }
+    // (ii)-(iv) rerank.py:61-70
+    {
+        const int rows_blk = (int)(p->dmat_elems / (size_t)n < (size_t)n ? p->dmat_elems / (size_t)n : (size_t)n);
+        for (int r0 = 0; r0 < n; r0 += rows_blk) {
+            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+            SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_tgt, n, d, dist_mode, st));
+            SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, rows, n, nullptr, p->rowmax + r0, st));
+            if (want_rank)
+                SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, p->rowmax + r0, k1p, false,
+                                          p->rank + (size_t)r0 * SSG_RANK_STRIDE,
+                                          p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, SSG_RANK_STRIDE, st));
+            if (d_euclid)
+                SSG_CUDA_TRY(cudaMemcpyAsync(d_euclid + (size_t)r0 * n, p->dmat, sizeof(float) * (size_t)rows * n,
+                                             cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                              int k1, int k2, double lambda_value, int dist_mode, double* d_final,
+                              float* d_euclid, void* stream) {
+    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
+    if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k1p = k1 + 1;
+    const int khp = (int)rint(k1 / 2.0) + 1;   // int(np.around(k1/2)) + 1, rerank.py:83
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
+    SSG_TRY(distance_stages(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, true, st));
+    // (v) rerank.py:74-92
+    SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st));
+    SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, p->v_idx, SSG_V_STRIDE, p->v_cnt, 0, p->v_val, SSG_V_STRIDE, st));
+    SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st));
+    // (vi) rerank.py:94-98  (k2 == 1: V is used as it is)
+    if (k2 != 1) {
+        SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st));
+    } else {
+        SSG_CUDA_TRY(cudaMemcpy2DAsync(p->q_idx, sizeof(int) * SSG_VQ_STRIDE, p->v_idx, sizeof(int) * SSG_V_STRIDE,
+                                       sizeof(int) * SSG_V_STRIDE, n, cudaMemcpyDeviceToDevice, st));
+        SSG_CUDA_TRY(cudaMemcpy2DAsync(p->q_val, sizeof(float) * SSG_VQ_STRIDE, p->v_val, sizeof(float) * SSG_V_STRIDE,
+                                       sizeof(float) * SSG_V_STRIDE, n, cudaMemcpyDeviceToDevice, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(p->q_cnt, p->v_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
+    // (vii)-(viii) rerank.py:101-122
+    SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st));
+    SSG_TRY(launch_jaccard_final(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
+                                 d_final, st));
+    p->last_n = n;
+    return SSG_OK;
+}
+
+static int grow(void** ptr, size_t* have, size_t need) {
+    if (need <= *have) return SSG_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *have = 0;
+    SSG_CUDA_TRY(cudaMalloc(ptr, need));
+    *have = need;
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_host(ssg_rerank_plan* p, const float* h_src, int ns, const float* h_tgt, int n, int d,
+                               int k1, int k2, double lambda_value, int dist_mode, int no_rerank,
+                               double* h_final, float* h_euclid) {
+    SSG_TRY(check_run_args(p, h_src, ns, h_tgt, n, d, k1, k2));
+    if (!no_rerank && !h_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_host: h_final is null");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    const size_t nn = (size_t)n * n;
+    SSG_TRY(grow((void**)&p->io_src, &p->io_src_bytes, sizeof(float) * (size_t)ns * d));
+    SSG_TRY(grow((void**)&p->io_tgt, &p->io_tgt_bytes, sizeof(float) * (size_t)n * d));
+    if (!no_rerank) SSG_TRY(grow((void**)&p->io_final, &p->io_final_bytes, sizeof(double) * nn));
+    if (h_euclid) SSG_TRY(grow((void**)&p->io_euclid, &p->io_euclid_bytes, sizeof(float) * nn));
+    cudaStream_t st = nullptr;
+    SSG_CUDA_TRY(cudaMemcpyAsync(p->io_src, h_src, sizeof(float) * (size_t)ns * d, cudaMemcpyHostToDevice, st));
+    SSG_CUDA_TRY(cudaMemcpyAsync(p->io_tgt, h_tgt, sizeof(float) * (size_t)n * d, cudaMemcpyHostToDevice, st));
+    if (no_rerank) {
+        // rerank.py:65-66: the source term is still computed before the early return; only
+        // euclidean_dist is handed back.
+        SSG_TRY(distance_stages(p, p->io_src, ns, p->io_tgt, n, d, k1, dist_mode, h_euclid ? p->io_euclid : nullptr,
+                                false, st));
+    } else {
+        SSG_TRY(ssg_rerank_run(p, p->io_src, ns, p->io_tgt, n, d, k1, k2, lambda_value, dist_mode, p->io_final,
+                               h_euclid ? p->io_euclid : nullptr, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(h_final, p->io_final, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_euclid)
+        SSG_CUDA_TRY(cudaMemcpyAsync(h_euclid, p->io_euclid, sizeof(float) * nn, cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_get_stage(ssg_rerank_plan* p, int stage, void* h_dst, size_t bytes) {
+    if (!p || !h_dst) return ssg_set_error(SSG_ERR_INVALID, "get_stage: null argument");
+    const size_t n = (size_t)p->last_n;
+    const void* src = nullptr;
+    size_t need = 0;
+    switch (stage) {
+        case SSG_STAGE_VEC: src = p->vec; need = 4 * n; break;
+        case SSG_STAGE_ROWMAX: src = p->rowmax; need = 4 * n; break;
+        case SSG_STAGE_RANK: src = p->rank; need = 4 * n * SSG_RANK_STRIDE; break;
+        case SSG_STAGE_RANK_VAL: src = p->rank_val; need = 4 * n * SSG_RANK_STRIDE; break;
+        case SSG_STAGE_V_CNT: src = p->v_cnt; need = 4 * n; break;
+        case SSG_STAGE_V_IDX: src = p->v_idx; need = 4 * n * SSG_V_STRIDE; break;
+        case SSG_STAGE_V_VAL: src = p->v_val; need = 4 * n * SSG_V_STRIDE; break;
+        case SSG_STAGE_VQ_CNT: src = p->q_cnt; need = 4 * n; break;
+        case SSG_STAGE_VQ_IDX: src = p->q_idx; need = 4 * n * SSG_VQ_STRIDE; break;
+        case SSG_STAGE_VQ_VAL: src = p->q_val; need = 4 * n * SSG_VQ_STRIDE; break;
+        case SSG_STAGE_FLAGGED: src = p->flagged; need = 4; break;
+        default: return ssg_set_error(SSG_ERR_INVALID, "get_stage: unknown stage %d", stage);
+    }
+    if (bytes < need) return ssg_set_error(SSG_ERR_INVALID, "get_stage: buffer too small (%zu < %zu)", bytes, need);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_CUDA_TRY(cudaDeviceSynchronize());
+    SSG_CUDA_TRY(cudaMemcpy(h_dst, src, need, cudaMemcpyDeviceToHost));
+    return SSG_OK;
+}

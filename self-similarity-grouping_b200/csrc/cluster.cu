@@ -1,0 +1,485 @@
+// eps estimate (selftraining.py:289-293) and DBSCAN on a dense precomputed matrix
+// (sklearn DBSCAN(eps, min_samples, metric='precomputed').fit_predict, selftraining.py:295-306).
+//
+// eps   : exact order statistic by 6-pass radix select over the 64-bit order-preserving keys of the
+//         non-zero strict-upper-triangle entries (HBM-bound row scans), then one masked-sum pass.
+// DBSCAN: order-free restatement validated against sklearn: region query = row scan
+//         (count, then neighbour lists), union-find over core-core edges hooked towards the smaller
+//         index (root = minimum core index of the component), cluster id = rank of the root, border
+//         point = minimum id over its core neighbours, noise = -1.
+#include <math.h>
+#include <limits.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+struct ssg_cluster_plan {
+    int device;
+    int n_max;
+    long long max_nbr;
+    size_t bytes;
+    // eps
+    unsigned long long* hist;      // [4096]
+    unsigned long long* state;     // [8]: 0 prefix key, 1 remaining, 2 top_num, 3 M, 4 done-flag
+    double* partial;               // [n_max]
+    double* eps_out;               // [2]: eps, (unused)
+    // dbscan
+    int* cnt;                      // [n_max]
+    int* rowptr;                   // [n_max+1]
+    int* nbr;                      // [max_nbr]
+    int* parent;                   // [n_max]
+    int* isroot;                   // [n_max]
+    int* cid;                      // [n_max+1]
+    unsigned char* core;           // [n_max]
+    int* flags;                    // [4]: 0 overflow
+    void* staging;                 // device copy of a host matrix (host entry points), grown lazily
+    size_t staging_bytes;
+    int last_n;
+};
+
+namespace ssg {
+
+template <typename T> __device__ __forceinline__ double ld_as_double(const T* p, size_t i);
+template <> __device__ __forceinline__ double ld_as_double<double>(const double* p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ double ld_as_double<float>(const float* p, size_t i) { return (double)p[i]; }
+
+// ----------------------------------------------------------------------------------------------- eps
+constexpr int EPS_NT = 256;
+constexpr int EPS_BINS = 4096;
+// pass p looks at key bits [shift, shift+width)
+__constant__ int c_eps_shift[6] = {52, 40, 28, 16, 4, 0};
+__constant__ int c_eps_width[6] = {12, 12, 12, 12, 12, 4};
+
+template <typename T>
+__global__ void __launch_bounds__(EPS_NT)
+eps_hist_kernel(const T* __restrict__ D, int n, int pass, const unsigned long long* __restrict__ state,
+                unsigned long long* __restrict__ ghist) {
+    __shared__ unsigned int hist[EPS_BINS];
+    for (int b = threadIdx.x; b < EPS_BINS; b += EPS_NT) hist[b] = 0u;
+    __syncthreads();
+    const int shift = c_eps_shift[pass], width = c_eps_width[pass];
+    const unsigned long long prefix = state[0];
+    const unsigned mask = (1u << width) - 1u;
+    const int hs = shift + width;                     // bits above are the established prefix
+    // rows are paired (i, n-1-i) so that every CTA sees ~n elements of the upper triangle
+    for (int half = 0; half < 2; ++half) {
+        const int i = half == 0 ? (int)blockIdx.x : n - 1 - (int)blockIdx.x;
+        if (half == 1 && i <= (int)blockIdx.x) break;
+        const T* row = D + (size_t)i * n;
+        for (int j0 = i + 1; j0 < n; j0 += EPS_NT) {
+            const int j = j0 + threadIdx.x;
+            bool in = false;
+            unsigned bin = 0;
+            if (j < n) {
+                const double v = ld_as_double<T>(row, j);
+                if (v != 0.0) {
+                    const unsigned long long k = f64_key(v);
+                    in = (pass == 0) || ((k >> hs) == (prefix >> hs));
+                    bin = (unsigned)(k >> shift) & mask;
+                }
+            }
+            // warp-aggregated shared-memory histogram (the values are heavily clustered)
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(act, bin);
+                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < EPS_BINS; b += EPS_NT) {
+        const unsigned c = hist[b];
+        if (c) atomicAdd(&ghist[b], (unsigned long long)c);
+    }
+}
+
+// single CTA: pick the bin holding the `remaining`-th smallest key, extend the prefix.
+__global__ void __launch_bounds__(1024)
+eps_pick_kernel(unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ state, int pass,
+                double rho) {
+    __shared__ unsigned long long cum[EPS_BINS];
+    const int tid = threadIdx.x;
+    // serial-ish scan: 4096 bins, 1024 threads x 4 bins, then thread 0 stitches 1024 partials
+    unsigned long long loc[4], s = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { loc[q] = ghist[tid * 4 + q]; s += loc[q]; }
+    cum[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const unsigned long long v = cum[t]; cum[t] = run; run += v; }
+        cum[1024] = run;
+    }
+    __syncthreads();
+    const unsigned long long total = cum[1024];
+    if (pass == 0 && tid == 0) {
+        // M = number of non-zero upper-triangle entries; top_num = np.round(rho*M) (half to even)
+        double t = rint(rho * (double)total);
+        if (t < 0.0) t = 0.0;
+        unsigned long long top = (unsigned long long)t;
+        if (top > total) top = total;
+        state[3] = total;
+        state[2] = top;
+        state[1] = top;      // remaining
+        state[0] = 0ull;     // prefix
+    }
+    __syncthreads();
+    const unsigned long long rem = state[1];
+    __syncthreads();
+    if (rem > 0) {
+        unsigned long long c = cum[tid];
+        const int shift = c_eps_shift[pass];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (c < rem && rem <= c + loc[q]) {
+                state[0] = state[0] | ((unsigned long long)(tid * 4 + q) << shift);
+                state[1] = rem - c;
+            }
+            c += loc[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ghist[tid * 4 + q] = 0ull;   // ready for the next pass
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EPS_NT)
+eps_sum_kernel(const T* __restrict__ D, int n, const unsigned long long* __restrict__ state,
+               double* __restrict__ partial) {
+    const unsigned long long thr = state[0];
+    double acc = 0.0;
+    if (state[2] > 0) {
+        for (int half = 0; half < 2; ++half) {
+            const int i = half == 0 ? (int)blockIdx.x : n - 1 - (int)blockIdx.x;
+            if (half == 1 && i <= (int)blockIdx.x) break;
+            const T* row = D + (size_t)i * n;
+            for (int j = i + 1 + threadIdx.x; j < n; j += EPS_NT) {
+                const double v = ld_as_double<T>(row, j);
+                if (v != 0.0 && f64_key(v) < thr) acc += v;
+            }
+        }
+    }
+    // deterministic tree: fixed thread->element map and fixed combine order
+    __shared__ double sh[EPS_NT];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = EPS_NT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void __launch_bounds__(1024)
+eps_final_kernel(const double* __restrict__ partial, int nparts, const unsigned long long* __restrict__ state,
+                 double* __restrict__ eps_out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += 1024) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const unsigned long long top = state[2];
+        if (top == 0) {
+            eps_out[0] = __longlong_as_double(0x7ff8000000000000ll);   // mean of an empty slice
+        } else {
+            const double thr = f64_from_key(state[0]);
+            eps_out[0] = (sh[0] + (double)state[1] * thr) / (double)top;
+        }
+    }
+}
+
+template <typename T>
+static int eps_run(ssg_cluster_plan* p, const T* D, int n, double rho, cudaStream_t st) {
+    SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
+    const int grid = (n + 1) / 2;
+    for (int pass = 0; pass < 6; ++pass) {
+        eps_hist_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, pass, p->state, p->hist);
+        SSG_CHECK_LAUNCH();
+        eps_pick_kernel<<<1, 1024, 0, st>>>(p->hist, p->state, pass, rho);
+        SSG_CHECK_LAUNCH();
+    }
+    eps_sum_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, p->state, p->partial);
+    SSG_CHECK_LAUNCH();
+    eps_final_kernel<<<1, 1024, 0, st>>>(p->partial, grid, p->state, p->eps_out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// -------------------------------------------------------------------------------------------- DBSCAN
+constexpr int DB_NT = 256;
+
+// region query, pass 1: neighbour count per row (all j, the diagonal included: sklearn does not force
+// self-inclusion for a dense precomputed matrix).
+template <typename T>
+__global__ void __launch_bounds__(DB_NT)
+db_count_kernel(const T* __restrict__ D, int n, double eps, int* __restrict__ cnt) {
+    const T* row = D + (size_t)blockIdx.x * n;
+    int c = 0;
+    for (int j = threadIdx.x; j < n; j += DB_NT) c += (ld_as_double<T>(row, j) <= eps);
+    c = warp_sum_i(c);
+    __shared__ int sh[DB_NT / 32];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < DB_NT / 32; ++w) t += sh[w];
+        cnt[blockIdx.x] = t;
+    }
+}
+
+// pass 2: neighbour lists (CSR).  Order inside a row is irrelevant to the order-free formulation.
+template <typename T>
+__global__ void __launch_bounds__(DB_NT)
+db_fill_kernel(const T* __restrict__ D, int n, double eps, const int* __restrict__ rowptr,
+               long long max_nbr, int* __restrict__ nbr, int* __restrict__ flags) {
+    const int i = blockIdx.x;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    if (end == beg) return;
+    if ((long long)end > max_nbr) { if (threadIdx.x == 0) flags[0] = 1; return; }
+    __shared__ int cursor;
+    if (threadIdx.x == 0) cursor = 0;
+    __syncthreads();
+    const T* row = D + (size_t)i * n;
+    for (int j0 = 0; j0 < n; j0 += DB_NT) {
+        const int j = j0 + threadIdx.x;
+        const bool hit = j < n && ld_as_double<T>(row, j) <= eps;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+            int base = 0;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(&cursor, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) nbr[beg + base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = j;
+        }
+    }
+}
+
+__global__ void db_init_kernel(int n, const int* __restrict__ cnt, int min_samples, int* __restrict__ parent,
+                               unsigned char* __restrict__ core) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { parent[i] = i; core[i] = cnt[i] >= min_samples; }
+}
+
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = ((volatile int*)parent)[x];
+    while (p != x) { x = p; p = ((volatile int*)parent)[x]; }
+    return x;
+}
+
+// one warp per row: union every core-core edge (j < i) of a core row.
+__global__ void __launch_bounds__(DB_NT)
+db_union_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                const unsigned char* __restrict__ core, int* parent) {
+    const int i = blockIdx.x * (DB_NT / 32) + (threadIdx.x >> 5);
+    if (i >= n || !core[i]) return;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    for (int e = beg + (threadIdx.x & 31); e < end; e += 32) {
+        const int j = nbr[e];
+        if (j >= i || !core[j]) continue;
+        int a = i, b = j;
+        while (true) {
+            a = uf_find(parent, a);
+            b = uf_find(parent, b);
+            if (a == b) break;
+            if (a < b) { const int t = a; a = b; b = t; }     // hook the larger root under the smaller
+            const int old = atomicCAS(&parent[a], a, b);
+            if (old == a) break;
+        }
+    }
+}
+
+__global__ void db_flatten_kernel(int n, const unsigned char* __restrict__ core, int* parent,
+                                  int* __restrict__ isroot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = 0;
+    if (core[i]) r = (uf_find(parent, i) == i);
+    isroot[i] = r;
+}
+
+__global__ void __launch_bounds__(DB_NT)
+db_label_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                const unsigned char* __restrict__ core, int* parent, const int* __restrict__ cid,
+                int64_t* __restrict__ labels) {
+    const int i = blockIdx.x * (DB_NT / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    if (core[i]) {
+        if (lane == 0) labels[i] = (int64_t)cid[uf_find(parent, i)];
+        return;
+    }
+    int best = INT_MAX;
+    for (int e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+        const int j = nbr[e];
+        if (core[j]) best = min(best, cid[uf_find(parent, j)]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) labels[i] = best == INT_MAX ? (int64_t)-1 : (int64_t)best;
+}
+
+template <typename T>
+static int dbscan_run(ssg_cluster_plan* p, const T* D, int n, double eps, int min_samples,
+                      int64_t* labels, cudaStream_t st) {
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
+    db_count_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->cnt);
+    SSG_CHECK_LAUNCH();
+    SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
+    db_fill_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags);
+    SSG_CHECK_LAUNCH();
+    db_init_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(n, p->cnt, min_samples, p->parent, p->core);
+    SSG_CHECK_LAUNCH();
+    const int wgrid = ssg_cdiv(n, DB_NT / 32);
+    db_union_kernel<<<wgrid, DB_NT, 0, st>>>(n, p->rowptr, p->nbr, p->core, p->parent);
+    SSG_CHECK_LAUNCH();
+    db_flatten_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(n, p->core, p->parent, p->isroot);
+    SSG_CHECK_LAUNCH();
+    SSG_TRY(launch_exclusive_scan_i32(p->isroot, p->cid, n, st));
+    db_label_kernel<<<wgrid, DB_NT, 0, st>>>(n, p->rowptr, p->nbr, p->core, p->parent, p->cid, labels);
+    SSG_CHECK_LAUNCH();
+    p->last_n = n;
+    return SSG_OK;
+}
+
+}  // namespace ssg
+
+// ------------------------------------------------------------------------------------------ C ABI
+using namespace ssg;
+
+static int dev_alloc(void** p, size_t bytes, size_t* total) {
+    SSG_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    *total += bytes;
+    return SSG_OK;
+}
+
+extern "C" int ssg_cluster_plan_create(ssg_cluster_plan** out, int device, int n_max, long long max_neighbors) {
+    if (!out || n_max <= 0) return ssg_set_error(SSG_ERR_INVALID, "cluster_plan_create: bad arguments");
+    if (max_neighbors <= 0) max_neighbors = 64ll * n_max + (1 << 20);
+    if (max_neighbors > 0x7fffffffll) max_neighbors = 0x7fffffffll;
+    SSG_CUDA_TRY(cudaSetDevice(device));
+    ssg_cluster_plan* p = new ssg_cluster_plan();
+    p->device = device; p->n_max = n_max; p->max_nbr = max_neighbors; p->bytes = 0;
+    p->staging = nullptr; p->staging_bytes = 0; p->last_n = 0;
+    size_t n = (size_t)n_max;
+    int rc = SSG_OK;
+#define A(ptr, nbytes) if (rc == SSG_OK) rc = dev_alloc((void**)&(ptr), (nbytes), &p->bytes)
+    A(p->hist, sizeof(unsigned long long) * 4096);
+    A(p->state, sizeof(unsigned long long) * 8);
+    A(p->partial, sizeof(double) * n);
+    A(p->eps_out, sizeof(double) * 2);
+    A(p->cnt, sizeof(int) * n);
+    A(p->rowptr, sizeof(int) * (n + 1));
+    A(p->nbr, sizeof(int) * (size_t)max_neighbors);
+    A(p->parent, sizeof(int) * n);
+    A(p->isroot, sizeof(int) * n);
+    A(p->cid, sizeof(int) * (n + 1));
+    A(p->core, n);
+    A(p->flags, sizeof(int) * 4);
+#undef A
+    if (rc != SSG_OK) { ssg_cluster_plan_destroy(p); return rc; }
+    *out = p;
+    return SSG_OK;
+}
+
+extern "C" int ssg_cluster_plan_destroy(ssg_cluster_plan* p) {
+    if (!p) return SSG_OK;
+    cudaSetDevice(p->device);
+    void* ptrs[] = {p->hist, p->state, p->partial, p->eps_out, p->cnt, p->rowptr, p->nbr, p->parent,
+                    p->isroot, p->cid, p->core, p->flags, p->staging};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete p;
+    return SSG_OK;
+}
+
+extern "C" size_t ssg_cluster_plan_bytes(const ssg_cluster_plan* p) { return p ? p->bytes + p->staging_bytes : 0; }
+
+extern "C" int ssg_eps_estimate(ssg_cluster_plan* p, const void* d_dist, int dtype, int n, double rho,
+                                double* h_eps, long long* h_top_num, void* stream) {
+    if (!p || !d_dist || n <= 0 || n > p->n_max || !h_eps)
+        return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SSG_F64) SSG_TRY(eps_run<double>(p, (const double*)d_dist, n, rho, st));
+    else if (dtype == SSG_F32) SSG_TRY(eps_run<float>(p, (const float*)d_dist, n, rho, st));
+    else return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: dtype %d", dtype);
+    unsigned long long hs[8];
+    SSG_CUDA_TRY(cudaMemcpyAsync(h_eps, p->eps_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_top_num) *h_top_num = (long long)hs[2];
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan(ssg_cluster_plan* p, const void* d_dist, int dtype, int n, double eps,
+                          int min_samples, int64_t* d_labels, int* h_n_clusters, void* stream) {
+    if (!p || !d_dist || !d_labels || n <= 0 || n > p->n_max)
+        return ssg_set_error(SSG_ERR_INVALID, "dbscan: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SSG_F64) SSG_TRY(dbscan_run<double>(p, (const double*)d_dist, n, eps, min_samples, d_labels, st));
+    else if (dtype == SSG_F32) SSG_TRY(dbscan_run<float>(p, (const float*)d_dist, n, eps, min_samples, d_labels, st));
+    else return ssg_set_error(SSG_ERR_INVALID, "dbscan: dtype %d", dtype);
+    if (h_n_clusters) {
+        int flags[4], ncl = 0;
+        SSG_CUDA_TRY(cudaMemcpyAsync(flags, p->flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(&ncl, p->cid + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (flags[0])
+            return ssg_set_error(SSG_ERR_CAPACITY, "dbscan: more than %lld neighbour pairs within eps; "
+                                 "re-create the plan with a larger max_neighbors", p->max_nbr);
+        *h_n_clusters = ncl;
+    }
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan_core_mask(ssg_cluster_plan* p, uint8_t* h_core, int n) {
+    if (!p || !h_core || n <= 0 || n > p->n_max) return ssg_set_error(SSG_ERR_INVALID, "core_mask: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_CUDA_TRY(cudaMemcpy(h_core, p->core, (size_t)n, cudaMemcpyDeviceToHost));
+    return SSG_OK;
+}
+
+static int stage_host_matrix(ssg_cluster_plan* p, const void* h, int dtype, int n) {
+    const size_t bytes = (size_t)n * n * (dtype == SSG_F64 ? 8 : 4);
+    if (bytes > p->staging_bytes) {
+        if (p->staging) cudaFree(p->staging);
+        p->staging = nullptr; p->staging_bytes = 0;
+        SSG_CUDA_TRY(cudaMalloc(&p->staging, bytes));
+        p->staging_bytes = bytes;
+    }
+    SSG_CUDA_TRY(cudaMemcpy(p->staging, h, bytes, cudaMemcpyHostToDevice));
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_estimate_host(ssg_cluster_plan* p, const void* h_dist, int dtype, int n, double rho,
+                                     double* h_eps, long long* h_top_num) {
+    if (!p || !h_dist || n <= 0 || n > p->n_max || (dtype != SSG_F32 && dtype != SSG_F64))
+        return ssg_set_error(SSG_ERR_INVALID, "eps_estimate_host: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_TRY(stage_host_matrix(p, h_dist, dtype, n));
+    return ssg_eps_estimate(p, p->staging, dtype, n, rho, h_eps, h_top_num, nullptr);
+}
+
+extern "C" int ssg_dbscan_host(ssg_cluster_plan* p, const void* h_dist, int dtype, int n, double eps,
+                               int min_samples, int64_t* h_labels, int* h_n_clusters) {
+    if (!p || !h_dist || !h_labels || n <= 0 || n > p->n_max || (dtype != SSG_F32 && dtype != SSG_F64))
+        return ssg_set_error(SSG_ERR_INVALID, "dbscan_host: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_TRY(stage_host_matrix(p, h_dist, dtype, n));
+    int64_t* d_labels = nullptr;
+    SSG_CUDA_TRY(cudaMalloc(&d_labels, sizeof(int64_t) * (size_t)n));
+    int ncl = 0;
+    int rc = ssg_dbscan(p, p->staging, dtype, n, eps, min_samples, d_labels, &ncl, nullptr);
+    if (rc == SSG_OK) {
+        cudaError_t e = cudaMemcpy(h_labels, d_labels, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = ssg_set_error(SSG_ERR_CUDA, "dbscan_host: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_labels);
+    if (rc == SSG_OK && h_n_clusters) *h_n_clusters = ncl;
+    return rc;
+}

@@ -1,0 +1,450 @@
+// Distance-side kernels of the re-ranking path.
+//   * sqdist_exact      : bit-identical restatement of scipy cdist + fp32 squaring (rerank.py:37,61-62)
+//   * row_minmax        : row minimum / maximum of an fp32 matrix block       (rerank.py:39,68)
+//   * row_select        : K smallest entries of every row ordered by (value, index), i.e. the
+//                         leading columns of a stable argsort                 (rerank.py:70)
+//   * pair_exact        : exact distance for sparse (row, column) pairs      (rerank.py:91 gathers)
+#include <limits.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ssg {
+
+// out = fl32(fl32(sqrt(s))^2)
+__device__ __forceinline__ float finish_sqdist(double s) {
+    float r = (float)sqrt(s);
+    return __fmul_rn(r, r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// sqdist_exact: 64x64 output tile per CTA, 4x4 outputs per thread, float64 accumulation in the exact
+// order cdist uses (sequential over k, separate multiply and add: no FMA contraction).
+// FP64-pipe bound by design: this is the reference-exact path (fallback + verification); the fast path
+// is the tensor-core GEMM in gemm_tc.cu.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256)
+sqdist_exact_kernel(const float* __restrict__ X, int nx, const float* __restrict__ Y, int ny, int d,
+                    float* __restrict__ out, size_t ldo) {
+    __shared__ double sx[TK][TM];
+    __shared__ double sy[TK][TN];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    const bool vec_ok = (d & 3) == 0;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int k0 = 0; k0 < d; k0 += TK) {
+        float vx[4] = {0.f, 0.f, 0.f, 0.f}, vy[4] = {0.f, 0.f, 0.f, 0.f};
+        const int gx = row0 + lr, gy = col0 + lr, kk = k0 + lk;
+        if (gx < nx) {
+            const float* p = X + (size_t)gx * d + kk;
+            if (vec_ok && kk + 3 < d) {
+                float4 t = *reinterpret_cast<const float4*>(p);
+                vx[0] = t.x; vx[1] = t.y; vx[2] = t.z; vx[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (kk + q < d) vx[q] = p[q];
+            }
+        }
+        if (gy < ny) {
+            const float* p = Y + (size_t)gy * d + kk;
+            if (vec_ok && kk + 3 < d) {
+                float4 t = *reinterpret_cast<const float4*>(p);
+                vy[0] = t.x; vy[1] = t.y; vy[2] = t.z; vy[3] = t.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (kk + q < d) vy[q] = p[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            sx[lk + q][lr] = (double)vx[q];
+            sy[lk + q][lr] = (double)vy[q];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TK; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sx[k][ty + 16 * i]; b[i] = sy[k][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double df = __dsub_rn(a[i], b[j]);
+                    acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(df, df));
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = row0 + ty + 16 * i;
+        if (r >= nx) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = col0 + tx + 16 * j;
+            if (c < ny) out[(size_t)r * ldo + c] = finish_sqdist(acc[i][j]);
+        }
+    }
+}
+
+int launch_sqdist_exact(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
+                        cudaStream_t st) {
+    if (nx <= 0 || ny <= 0) return SSG_OK;
+    dim3 grid(ssg_cdiv(ny, TN), ssg_cdiv(nx, TM));
+    sqdist_exact_kernel<<<grid, 256, 0, st>>>(X, nx, Y, ny, d, out, ldo);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row_minmax: one CTA per row.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_minmax_kernel(const float* __restrict__ M, size_t ld, int cols, float* __restrict__ rmin,
+                  float* __restrict__ rmax) {
+    const float* row = M + (size_t)blockIdx.x * ld;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        const float v = row[j];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+    __shared__ float slo[8], shi[8];
+    lo = warp_min_f(lo);
+    hi = warp_max_f(hi);
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, slo[w]); hi = fmaxf(hi, shi[w]); }
+        if (rmin) rmin[blockIdx.x] = lo;
+        if (rmax) rmax[blockIdx.x] = hi;
+    }
+}
+
+int launch_row_minmax(const float* M, size_t ld, int rows, int cols, float* rmin, float* rmax,
+                      cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
+    row_minmax_kernel<<<rows, 256, 0, st>>>(M, ld, cols, rmin, rmax);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row_select: K smallest (value, index) pairs of each row, ascending — the first K columns of
+// np.argsort(row, kind='stable').  value = M[j] / scale[row] (IEEE division) when `scale` is given.
+// Three-pass radix select on the order-preserving 32-bit key in shared memory, then an
+// index-ordered collection of threshold ties, then a rank sort of the K survivors.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SEL_NT = 256;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_KMAX = 64;
+
+__device__ __forceinline__ float sel_value(const float* row, int j, bool scaled, float s) {
+    const float v = row[j];
+    return scaled ? __fdiv_rn(v, s) : v;
+}
+// `largest` selects by descending value (ties still by ascending index): complement the key.
+__device__ __forceinline__ uint32_t sel_key(float v, bool largest) {
+    const uint32_t k = f32_key(v);
+    return largest ? ~k : k;
+}
+
+__global__ void __launch_bounds__(SEL_NT)
+row_select_kernel(const float* __restrict__ M, size_t ld, int cols, const float* __restrict__ scale,
+                  int K, bool largest, int* __restrict__ out_idx, float* __restrict__ out_val, int out_stride) {
+    __shared__ int hist[SEL_BINS];
+    __shared__ int wsum[SEL_NT / 32];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_remaining;
+    __shared__ uint32_t c_key[SEL_KMAX];
+    __shared__ int c_idx[SEL_KMAX];
+    __shared__ int s_nless, s_ties_seen;
+
+    const int row_id = blockIdx.x;
+    const float* row = M + (size_t)row_id * ld;
+    const bool scaled = scale != nullptr;
+    const float s = scaled ? scale[row_id] : 1.0f;
+    const int Keff = min(K, cols);
+    const int tid = threadIdx.x;
+
+    if (tid == 0) { s_prefix = 0u; s_remaining = Keff; s_nless = 0; s_ties_seen = 0; }
+    // pass p examines bits [shift, shift+width)
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        for (int b = tid; b < SEL_BINS; b += SEL_NT) hist[b] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const int shift = shifts[p], width = widths[p];
+        const uint32_t mask = (1u << width) - 1u;
+        for (int j = tid; j < cols; j += SEL_NT) {
+            const uint32_t k = sel_key(sel_value(row, j, scaled, s), largest);
+            const bool in = (p == 0) || ((k >> (shift + width)) == (prefix >> (shift + width)));
+            if (in) atomicAdd(&hist[(k >> shift) & mask], 1);
+        }
+        __syncthreads();
+        // find the bin holding the `remaining`-th smallest element
+        constexpr int PER = SEL_BINS / SEL_NT;  // 8 bins per thread
+        int local[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { local[q] = hist[tid * PER + q]; sum += local[q]; }
+        int total;
+        int excl = block_exclusive_scan<SEL_NT>(sum, wsum, total);
+        const int rem = s_remaining;
+        __syncthreads();
+        if (excl < rem && rem <= excl + sum) {
+            int c = excl;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                if (c < rem && rem <= c + local[q]) {
+                    s_prefix = prefix | ((uint32_t)(tid * PER + q) << shift);
+                    s_remaining = rem - c;
+                }
+                c += local[q];
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t thr = s_prefix;     // exact key of the Keff-th smallest element
+    const int take_ties = s_remaining; // how many elements equal to thr belong to the result
+
+    // collect: everything below thr, plus the first `take_ties` ties in index order
+    for (int base = 0; base < cols; base += SEL_NT) {
+        const int j = base + tid;
+        uint32_t k = 0xffffffffu;
+        bool valid = j < cols;
+        if (valid) k = sel_key(sel_value(row, j, scaled, s), largest);
+        const bool less = valid && k < thr;
+        const bool tie = valid && k == thr;
+        if (less) {
+            const int pos = atomicAdd(&s_nless, 1);
+            c_key[pos] = k;
+            c_idx[pos] = j;
+        }
+        if (__syncthreads_or(tie)) {
+            int total;
+            const int pos = block_exclusive_scan<SEL_NT>(tie ? 1 : 0, wsum, total);
+            const int seen = s_ties_seen;
+            __syncthreads();
+            if (tie && seen + pos < take_ties) {
+                const int slot = (Keff - take_ties) + seen + pos;
+                c_key[slot] = k;
+                c_idx[slot] = j;
+            }
+            if (tid == 0) s_ties_seen = seen + total;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    // rank sort of the Keff survivors by (key, idx)
+    if (tid < Keff) {
+        const uint32_t k = c_key[tid];
+        const int ix = c_idx[tid];
+        int r = 0;
+        for (int q = 0; q < Keff; ++q) {
+            const uint32_t kq = c_key[q];
+            r += (kq < k) || (kq == k && c_idx[q] < ix);
+        }
+        out_idx[(size_t)row_id * out_stride + r] = ix;
+        out_val[(size_t)row_id * out_stride + r] = sel_value(row, ix, scaled, s);
+    }
+    for (int q = Keff + tid; q < K; q += SEL_NT) {   // short rows: pad
+        out_idx[(size_t)row_id * out_stride + q] = -1;
+        out_val[(size_t)row_id * out_stride + q] = INFINITY;
+    }
+}
+
+int launch_row_select(const float* M, size_t ld, int rows, int cols, const float* scale, int K, bool largest,
+                      int* out_idx, float* out_val, int out_stride, cudaStream_t st) {
+    if (K < 1 || K > SEL_KMAX || K > out_stride)
+        return ssg_set_error(SSG_ERR_INVALID, "row_select: K=%d out of range", K);
+    if (rows <= 0) return SSG_OK;
+    row_select_kernel<<<rows, SEL_NT, 0, st>>>(M, ld, cols, scale, K, largest, out_idx, out_val, out_stride);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pair_exact: out[i, s] = exact squared distance between A[row0+i] and B[idx[i, s]] for s < cnt[i]
+// (cnt == nullptr -> fixed_cnt).  One CTA per row, the row staged in shared memory as float64, one
+// thread per pair walking its partner row sequentially (cdist order, see sqdist_exact).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pair_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, int d,
+                  const int* __restrict__ idx, int idx_stride, const int* __restrict__ cnt,
+                  int fixed_cnt, float* __restrict__ out, int out_stride) {
+    extern __shared__ double sa[];
+    const int i = blockIdx.x;
+    const float* a = A + (size_t)i * d;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) sa[k] = (double)a[k];
+    __syncthreads();
+    const int c = cnt ? cnt[i] : fixed_cnt;
+    const bool vec_ok = (d & 3) == 0;
+    for (int sidx = threadIdx.x; sidx < c; sidx += blockDim.x) {
+        const int m = idx[(size_t)i * idx_stride + sidx];
+        if (m < 0) { out[(size_t)i * out_stride + sidx] = INFINITY; continue; }
+        const float* b = B + (size_t)m * d;
+        double acc = 0.0;
+        if (vec_ok) {
+            for (int k = 0; k < d; k += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(b + k);
+                double df;
+                df = __dsub_rn(sa[k], (double)t.x);     acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = __dsub_rn(sa[k + 1], (double)t.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = __dsub_rn(sa[k + 2], (double)t.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                df = __dsub_rn(sa[k + 3], (double)t.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+        } else {
+            for (int k = 0; k < d; ++k) {
+                const double df = __dsub_rn(sa[k], (double)b[k]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+        }
+        out[(size_t)i * out_stride + sidx] = finish_sqdist(acc);
+    }
+}
+
+int launch_pair_exact(const float* A, int rows, const float* B, int d, const int* idx, int idx_stride,
+                      const int* cnt, int fixed_cnt, float* out, int out_stride, cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
+    const size_t smem = (size_t)d * sizeof(double);
+    if (smem > 200 * 1024) return ssg_set_error(SSG_ERR_INVALID, "pair_exact: d=%d too large", d);
+    if (smem > 48 * 1024)   // per-device attribute: set on every launch that needs it (cheap host call)
+        SSG_CUDA_TRY(cudaFuncSetAttribute(pair_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)smem));
+    pair_exact_kernel<<<rows, 256, smem, st>>>(A, B, d, idx, idx_stride, cnt, fixed_cnt, out, out_stride);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Tensor distance mode: candidates picked on the approximate matrix are re-scored exactly; each result
+// is accepted only if the approximation error bound E proves that no non-candidate could change it,
+// otherwise the row is flagged for the exact fallback.
+// ---------------------------------------------------------------------------------------------------
+// row extreme from K exact candidate values.  cand_approx is sorted by selection order, so its last
+// entry is the weakest candidate: every non-candidate is at least (min) / at most (max) that good.
+__global__ void cand_reduce_kernel(int rows, int cols, int K, bool is_max, const float* __restrict__ exact,
+                                   const float* __restrict__ cand_approx, int stride,
+                                   const float* __restrict__ norm_row, const float* __restrict__ norm_other_max,
+                                   float eps_rel, float* __restrict__ out, int* __restrict__ flag_cnt,
+                                   int* __restrict__ flag_rows, int row_offset) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const int kk = min(K, cols);
+    float best = is_max ? -INFINITY : INFINITY;
+    for (int q = 0; q < kk; ++q) {
+        const float v = exact[(size_t)r * stride + q];
+        best = is_max ? fmaxf(best, v) : fminf(best, v);
+    }
+    out[r] = best;
+    if (cols > K) {
+        const float E = eps_rel * (norm_row[r] + *norm_other_max);
+        const float weakest = cand_approx[(size_t)r * stride + kk - 1];
+        const bool ok = is_max ? (best >= weakest + E) : (best <= weakest - E);
+        if (!ok) flag_rows[atomicAdd(flag_cnt, 1)] = row_offset + r;
+    }
+}
+
+int launch_cand_reduce(int rows, int cols, int K, bool is_max, const float* exact, const float* cand_approx,
+                       int stride, const float* norm_row, const float* norm_other_max, float eps_rel, float* out,
+                       int* flag_cnt, int* flag_rows, int row_offset, cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
+    cand_reduce_kernel<<<ssg_cdiv(rows, 128), 128, 0, st>>>(rows, cols, K, is_max, exact, cand_approx, stride,
+                                                            norm_row, norm_other_max, eps_rel, out, flag_cnt,
+                                                            flag_rows, row_offset);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// leading k1p rank columns from K exactly re-scored candidates: order by (od/rowmax, index).
+__global__ void __launch_bounds__(64)
+rank_finalize_kernel(int cols, int K, int k1p, const int* __restrict__ cand_idx,
+                     const float* __restrict__ cand_approx, const float* __restrict__ exact, int stride,
+                     const float* __restrict__ rowmax, const float* __restrict__ norm_row,
+                     const float* __restrict__ norm_other_max, float eps_rel, int* __restrict__ rank,
+                     float* __restrict__ rank_val, int* __restrict__ flag_cnt, int* __restrict__ flag_rows,
+                     int row_offset) {
+    __shared__ float s_v[64];
+    __shared__ int s_i[64];
+    const int r = blockIdx.x, t = threadIdx.x;
+    const float mx = rowmax[r];
+    float v = INFINITY;
+    int ix = INT_MAX;
+    if (t < K) {
+        const int ci = cand_idx[(size_t)r * stride + t];
+        if (ci >= 0) { ix = ci; v = __fdiv_rn(exact[(size_t)r * stride + t], mx); }
+    }
+    s_v[t] = v;
+    s_i[t] = ix;
+    __syncthreads();
+    const uint32_t kv = f32_key(v);
+    int pos = 0;
+    for (int q = 0; q < 64; ++q) {
+        const uint32_t kq = f32_key(s_v[q]);
+        pos += (kq < kv) || (kq == kv && s_i[q] < ix);
+    }
+    if (t < K && pos < k1p) {
+        rank[(size_t)r * SSG_RANK_STRIDE + pos] = ix == INT_MAX ? -1 : ix;
+        rank_val[(size_t)r * SSG_RANK_STRIDE + pos] = v;
+        if (pos == k1p - 1 && cols > K) {
+            // every non-candidate has approx >= weakest candidate, hence exact >= weakest - E
+            const float E = eps_rel * (norm_row[r] + *norm_other_max);
+            const float weakest = cand_approx[(size_t)r * stride + K - 1];
+            const float bound = __fdiv_rn(fmaxf(weakest - E, 0.f), mx);
+            if (!(v < bound)) flag_rows[atomicAdd(flag_cnt, 1)] = row_offset + r;
+        }
+    }
+}
+
+int launch_rank_finalize(int rows, int cols, int K, int k1p, const int* cand_idx, const float* cand_approx,
+                         const float* exact, int stride, const float* rowmax, const float* norm_row,
+                         const float* norm_other_max, float eps_rel, int* rank, float* rank_val, int* flag_cnt,
+                         int* flag_rows, int row_offset, cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
+    if (K > 64 || k1p > K) return ssg_set_error(SSG_ERR_INVALID, "rank_finalize: K=%d k1p=%d", K, k1p);
+    rank_finalize_kernel<<<rows, 64, 0, st>>>(cols, K, k1p, cand_idx, cand_approx, exact, stride, rowmax, norm_row,
+                                              norm_other_max, eps_rel, rank, rank_val, flag_cnt, flag_rows,
+                                              row_offset);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// fallback plumbing: gather the flagged feature rows, scatter the exact results back
+__global__ void gather_rows_kernel(const float* __restrict__ X, int d, const int* __restrict__ rows,
+                                   float* __restrict__ out) {
+    const float* src = X + (size_t)rows[blockIdx.x] * d;
+    float* dst = out + (size_t)blockIdx.x * d;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) dst[k] = src[k];
+}
+__global__ void scatter_f32_kernel(const float* __restrict__ in, int cnt, int width, int in_stride,
+                                   const int* __restrict__ rows, float* __restrict__ out, int out_stride) {
+    const int f = blockIdx.x;
+    for (int k = threadIdx.x; k < width; k += blockDim.x)
+        out[(size_t)rows[f] * out_stride + k] = in[(size_t)f * in_stride + k];
+}
+int launch_gather_rows(const float* X, int d, const int* rows, int cnt, float* out, cudaStream_t st) {
+    if (cnt <= 0) return SSG_OK;
+    gather_rows_kernel<<<cnt, 256, 0, st>>>(X, d, rows, out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int launch_scatter_f32(const float* in, int cnt, int width, int in_stride, const int* rows, float* out,
+                       int out_stride, cudaStream_t st) {
+    if (cnt <= 0) return SSG_OK;
+    scatter_f32_kernel<<<cnt, 32, 0, st>>>(in, cnt, width, in_stride, rows, out, out_stride);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // namespace ssg

@@ -1,0 +1,181 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a:   C[M,N] = A[M,K] * B[N,K]^T
+//   A, B : bf16, K-major (row-major with K contiguous), fed by TMA into 128B-swizzled shared memory
+//   acc  : fp32 in TMEM (two accumulator stages so that the epilogue of tile t overlaps the MMAs of t+1)
+//   roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..5 = epilogue
+// Epilogues (template): squared-distance (norms - 2*acc -> fp32) for the re-ranking path, and
+// bias(+residual)(+ReLU) -> bf16 NHWC for the convolution path (conv.cu instantiates those).
+//
+// The squared-distance path feeds it bf16x3 split operands (A' = [hi|hi|lo], B' = [hi|lo|hi], K = 3d) so that
+// the fp32 features are represented to ~2^-17 relative: the result is an approximation (|err| ~1e-5) that is
+// only used to pick candidates; api.cu re-scores candidates exactly (DESIGN.md "tensor distance mode").
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.cuh"
+
+namespace ssg {
+
+// ---------------------------------------------------------------------------------------------------
+// host: cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency,
+// so the library still loads on a machine without a GPU driver).
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode(PFN_encodeTiled* out) {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SSG_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p)
+            return ssg_set_error(SSG_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available in this driver");
+        fn = (PFN_encodeTiled)p;
+    }
+    *out = fn;
+    return SSG_OK;
+}
+
+// 2-D bf16 tensor [rows, cols] (cols contiguous, row pitch `ld` elements), box = box_rows x 64 cols, SW128.
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows) {
+    PFN_encodeTiled enc;
+    SSG_TRY(get_encode(&enc));
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16)
+        return ssg_set_error(SSG_ERR_INVALID, "tensor map: base/pitch must be 16-byte aligned");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ssg_set_error(SSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return SSG_OK;
+}
+
+// 4-D bf16 NHWC activation [B, H, W, C] seen as dims (C, W, H, B); box = (64, bw, bh, bb): one box is a
+// [bb*bh*bw, 64] K-major tile of an implicit-GEMM A operand; out-of-bounds (halo) elements are zero-filled.
+int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                        uint32_t bw, uint32_t bh, uint32_t bb) {
+    PFN_encodeTiled enc;
+    SSG_TRY(get_encode(&enc));
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (C * 2) % 16)
+        return ssg_set_error(SSG_ERR_INVALID, "tensor map: NHWC base/channel pitch must be 16-byte aligned");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {64, bw, bh, bb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ssg_set_error(SSG_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
+    return SSG_OK;
+}
+
+int tc_num_sms(int* out) {
+    static int cached[64] = {0};
+    int dev = 0;
+    SSG_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && cached[dev]) { *out = cached[dev]; return SSG_OK; }
+    int n = 0;
+    SSG_CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 64) cached[dev] = n;
+    *out = n;
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// squared-distance front end
+// ---------------------------------------------------------------------------------------------------
+// x (fp32 [n,d]) -> bf16 hi/lo split laid out as [n, 3d]: which = 0: [hi|hi|lo] (A side), 1: [hi|lo|hi] (B side);
+// also the squared norm (fp64 accumulate, rounded to fp32).
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ x, int n, int d, int which, __nv_bfloat16* __restrict__ out,
+                    float* __restrict__ norm2) {
+    const int i = blockIdx.x;
+    const float* row = x + (size_t)i * d;
+    __nv_bfloat16* o = out + (size_t)i * 3 * d;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < d; k += 256) {
+        const float v = row[k];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        o[k] = hi;
+        o[d + k] = which == 0 ? hi : lo;
+        o[2 * d + k] = which == 0 ? lo : hi;
+        acc += (double)v * (double)v;
+    }
+    __shared__ double sh[256];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && norm2) norm2[i] = (float)sh[0];
+}
+
+int launch_split_bf16x3(const float* x, int n, int d, int which, void* out_bf16, float* norm2, cudaStream_t st) {
+    if (n <= 0) return SSG_OK;
+    split_bf16x3_kernel<<<n, 256, 0, st>>>(x, n, d, which, (__nv_bfloat16*)out_bf16, norm2);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+struct EpiDist {
+    const float* na;   // [M]
+    const float* nb;   // [N]
+    float* out;        // [M, ldc]
+    size_t ldc;
+    __device__ __forceinline__ void operator()(int row, int col0, int ncols, const uint32_t (&acc)[32]) const {
+        const float a = na[row];
+        float* o = out + (size_t)row * ldc + col0;
+        if (ncols == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 b = *reinterpret_cast<const float4*>(nb + col0 + 4 * q);
+                float4 r;
+                r.x = fmaf(-2.0f, __uint_as_float(acc[4 * q + 0]), a + b.x);
+                r.y = fmaf(-2.0f, __uint_as_float(acc[4 * q + 1]), a + b.y);
+                r.z = fmaf(-2.0f, __uint_as_float(acc[4 * q + 2]), a + b.z);
+                r.w = fmaf(-2.0f, __uint_as_float(acc[4 * q + 3]), a + b.w);
+                *reinterpret_cast<float4*>(o + 4 * q) = r;
+            }
+        } else {
+            for (int q = 0; q < ncols; ++q) o[q] = fmaf(-2.0f, __uint_as_float(acc[q]), a + nb[col0 + q]);
+        }
+    }
+};
+
+// C = dist(A', B') with pre-split operands.  M x N output, K = 3d.
+int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_split, const float* nb, int n,
+                     int k, float* out, size_t ldc, cudaStream_t st) {
+    EpiDist epi{na, nb, out, ldc};
+    return tc::launch_gemm<128, EpiDist>(a_split, m, b_split, n, k, epi, st);
+}
+
+// Stand-alone ssg_sqdist(mode = TENSOR): split both operands into scratch memory, run the GEMM.
+int launch_sqdist_tensor(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
+                         cudaStream_t st) {
+    if (nx <= 0 || ny <= 0) return SSG_OK;
+    if (d % 8) return ssg_set_error(SSG_ERR_INVALID, "sqdist tensor mode: d must be a multiple of 8");
+    void *ax = nullptr, *by = nullptr;
+    float *na = nullptr, *nb = nullptr;
+    SSG_CUDA_TRY(cudaMallocAsync(&ax, (size_t)nx * 3 * d * 2, st));
+    SSG_CUDA_TRY(cudaMallocAsync(&by, (size_t)ny * 3 * d * 2, st));
+    SSG_CUDA_TRY(cudaMallocAsync((void**)&na, sizeof(float) * nx, st));
+    SSG_CUDA_TRY(cudaMallocAsync((void**)&nb, sizeof(float) * ny, st));
+    int rc = launch_split_bf16x3(X, nx, d, 0, ax, na, st);
+    if (rc == SSG_OK) rc = launch_split_bf16x3(Y, ny, d, 1, by, nb, st);
+    if (rc == SSG_OK) rc = launch_gemm_dist(ax, na, nx, by, nb, ny, 3 * d, out, ldo, st);
+    cudaFreeAsync(ax, st);
+    cudaFreeAsync(by, st);
+    cudaFreeAsync(na, st);
+    cudaFreeAsync(nb, st);
+    return rc;
+}
+
+}  // namespace ssg

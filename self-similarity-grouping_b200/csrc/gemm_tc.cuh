@@ -1,0 +1,213 @@
+// tcgen05 GEMM kernel template (see gemm_tc.cu for the overview).  Included by gemm_tc.cu and conv.cu.
+#pragma once
+#include <string.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace ssg {
+
+int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_rows);
+int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                        uint32_t bw, uint32_t bh, uint32_t bb);
+int tc_num_sms(int* out);
+
+namespace tc {
+
+constexpr int BM = 128;        // UMMA M (one TMEM lane per output row)
+constexpr int BK = 64;         // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int GROUP_M = 16;    // tile rasterisation: 16 m-blocks share each B tile while it is L2-hot
+
+// A operand: plain [M,K] matrix (mode 0) or implicit-GEMM view of NHWC activations (mode 1): the K axis runs over
+// (tap, channel block); each tap reads a shifted box of one of up to four (stride-parity) planes; halo
+// elements are zero-filled by TMA.
+struct AOperand {
+    CUtensorMap map[4];
+    int mode;
+    int cblks;             // channel blocks of 64 per tap
+    int taps;
+    int bh, bb;            // box rows / images per 128-pixel tile
+    int tiles_per_img;     // >= 1
+    signed char tap_plane[9], tap_dh[9], tap_dw[9];
+};
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
+    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N,
+            int num_k_blocks, Epi epi) {
+    using L = SmemLayout<BN>;
+    constexpr int STAGES = L::STAGES;
+    constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+    const int num_tiles = m_blocks * n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&A.map[0]);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // tile index -> (m_blk, n_blk), grouped along M so that concurrently resident CTAs share B tiles in L2
+    auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
+        const int per_group = GROUP_M * n_blocks;
+        const int g = t / per_group;
+        const int first_m = g * GROUP_M;
+        const int gsz = min(GROUP_M, m_blocks - first_m);
+        const int r = t - g * per_group;
+        m_blk = first_m + r % gsz;
+        n_blk = r / gsz;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                int b0 = 0, h0 = 0;
+                if (A.mode == 1) {
+                    if (A.bb > 1) { b0 = m_blk * A.bb; }
+                    else { b0 = m_blk / A.tiles_per_img; h0 = (m_blk % A.tiles_per_img) * A.bh; }
+                }
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * L::STAGE_BYTES;
+                    unsigned char* sb = sa + L::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (A.mode == 0) {
+                        tma_load_2d(sa, &A.map[0], &full_bar[stage], kb * BK, m_blk * BM);
+                    } else {
+                        const int tap = kb / A.cblks, cb = kb - tap * A.cblks;
+                        tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
+                                    h0 + A.tap_dh[tap], b0);
+                    }
+                    tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = make_idesc_bf16_f32(BM, BN);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+                    const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 32 bytes (16 bf16) inside the swizzle row: +2 in the (addr >> 4) field
+                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                 (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                        // smem slot free once the MMAs retire
+                    if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;               // TMEM lane quarter this warp may access
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            int m_blk, n_blk;
+            tile_coords(t, m_blk, n_blk);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BM + q * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + c * 32;
+                if (row < M && col0 < N) epi(row, col0, min(32, N - col0), v);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Launch with a fully prepared A operand.
+template <int BN, class Epi>
+int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
+    using L = SmemLayout<BN>;
+    if (k % BK) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of %d", k, BK);
+    CUtensorMap mapB;
+    SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
+    int sms = 0;
+    SSG_TRY(tc_num_sms(&sms));
+    const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
+    const int grid = tiles < sms ? tiles : sms;
+    auto kern = gemm_kernel<BN, Epi>;
+    SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, k / BK, epi);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// Plain C = A * B^T with A [m,k], B [n,k] bf16 row-major.
+template <int BN, class Epi>
+int launch_gemm(const void* a, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
+    AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 0;
+    A.cblks = k / BK;
+    A.taps = 1;
+    A.tiles_per_img = 1;
+    SSG_TRY(make_tmap_2d_bf16(&A.map[0], a, (uint64_t)m, (uint64_t)k, (uint64_t)k, BM));
+    return launch_gemm_op<BN, Epi>(A, m, b, n, k, epi, st);
+}
+
+}  // namespace tc
+}  // namespace ssg

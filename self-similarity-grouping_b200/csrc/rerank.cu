@@ -1,0 +1,466 @@
+// k-reciprocal encoding, query expansion, inverted index and Jaccard/final distance of
+// reid/rerank.py:74-122 (O-f32 arithmetic).  All rows are kept sparse (index-sorted) on the device;
+// only the final N x N float64 matrix the reference API returns is dense.
+#include <limits.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ssg {
+
+// ---------------------------------------------------------------------------------------------------
+// generic exclusive scan of int32 (single CTA; inputs here are at most a few 100k entries)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) exclusive_scan_i32_kernel(const int* __restrict__ in,
+                                                                   int* __restrict__ out, int n) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int j = base + threadIdx.x;
+        const int v = j < n ? in[j] : 0;
+        int total;
+        const int ex = block_exclusive_scan<1024>(v, wsum, total);
+        const int c = carry;
+        if (j < n) out[j] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+int launch_exclusive_scan_i32(const int* in, int* out, int n, cudaStream_t st) {
+    exclusive_scan_i32_kernel<<<1, 1024, 0, st>>>(in, out, n);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// source vector: v_i = 1 - exp(-min_j d2(t_i, s_j)); v /= max(v)        (rerank.py:38-40)
+// exp/subtract are monotone, so the row minimum is taken on the distances.
+// ---------------------------------------------------------------------------------------------------
+__global__ void source_vec_kernel(const float* __restrict__ rowmin, int n, float* __restrict__ vec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vec[i] = __fsub_rn(1.0f, expf(-rowmin[i]));
+}
+__global__ void __launch_bounds__(1024) vec_max_kernel(const float* __restrict__ vec, int n,
+                                                       float* __restrict__ out_max) {
+    float m = -INFINITY;
+    bool nan = false;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { m = fmaxf(m, vec[i]); nan |= isnan(vec[i]); }
+    __shared__ float sm[32];
+    __shared__ int snan;
+    if (threadIdx.x == 0) snan = 0;
+    __syncthreads();
+    if (nan) snan = 1;
+    m = warp_max_f(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 32; ++w) m = fmaxf(m, sm[w]);
+        *out_max = snan ? NAN : m;   // np.max propagates NaN
+    }
+}
+__global__ void vec_div_kernel(float* __restrict__ vec, int n, const float* __restrict__ mx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vec[i] = __fdiv_rn(vec[i], *mx);
+}
+
+int launch_vec_max(const float* vec, int n, float* out_max, cudaStream_t st) {
+    vec_max_kernel<<<1, 1024, 0, st>>>(vec, n, out_max);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int launch_source_vector(const float* rowmin, int n, float* vec, float* scratch, cudaStream_t st) {
+    source_vec_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(rowmin, n, vec);
+    SSG_CHECK_LAUNCH();
+    vec_max_kernel<<<1, 1024, 0, st>>>(vec, n, scratch);
+    SSG_CHECK_LAUNCH();
+    vec_div_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(vec, n, scratch);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k-reciprocal sets with half-k expansion (rerank.py:74-90): one CTA per row, output = sorted unique
+// index list R* (at most SSG_V_STRIDE entries).
+// ---------------------------------------------------------------------------------------------------
+constexpr int KR_NT = 256;
+
+__global__ void __launch_bounds__(KR_NT)
+krecip_build_kernel(const int* __restrict__ rank, int n, int k1p, int khp, int* __restrict__ v_idx,
+                    int* __restrict__ v_cnt) {
+    __shared__ int R[32];
+    __shared__ int list[SSG_V_STRIDE];
+    __shared__ int s_nR, s_nlist;
+    __shared__ int wsum[KR_NT / 32];
+    const int i = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int RS = SSG_RANK_STRIDE;
+
+    for (int t = tid; t < SSG_V_STRIDE; t += KR_NT) list[t] = INT_MAX;
+    if (wid == 0) {
+        // R(i,k1): forward neighbours whose own top-(k1+1) list contains i, in rank order
+        int c = -1;
+        bool found = false;
+        if (lane < k1p) {
+            c = rank[(size_t)i * RS + lane];
+            if (c >= 0)
+                for (int b = 0; b < k1p; ++b) found |= (rank[(size_t)c * RS + b] == i);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, found);
+        if (found) R[__popc(mask & ((1u << lane) - 1u))] = c;
+        if (lane == 0) { s_nR = __popc(mask); s_nlist = __popc(mask); }
+    }
+    __syncthreads();
+    const int nR = s_nR;
+    if (tid < nR) list[tid] = R[tid];
+    __syncthreads();
+    // expansion: candidates are distributed over the warps
+    for (int ci = wid; ci < nR; ci += KR_NT / 32) {
+        const int c = R[ci];
+        int e = -1;
+        bool found = false;
+        if (lane < khp) {
+            e = rank[(size_t)c * RS + lane];
+            if (e >= 0)
+                for (int b = 0; b < khp; ++b) found |= (rank[(size_t)e * RS + b] == c);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, found);
+        bool inR = false;
+        if (found)
+            for (int q = 0; q < nR; ++q) inR |= (R[q] == e);
+        const int ninter = __popc(__ballot_sync(0xffffffffu, inR));
+        const int nrc = __popc(mask);
+        // len(intersect1d(Rc, R)) > 2/3*len(Rc)   (rerank.py:86, double arithmetic)
+        if ((double)ninter > (2.0 / 3.0) * (double)nrc) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nlist, nrc);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (found) {
+                const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                if (pos < SSG_V_STRIDE) list[pos] = e;
+            }
+        }
+    }
+    __syncthreads();
+    // bitonic sort of the 256-entry list (INT_MAX padding), then unique (np.unique, rerank.py:90)
+    for (int k = 2; k <= SSG_V_STRIDE; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int t = tid, p = t ^ j;
+            if (p > t) {
+                const int a = list[t], b = list[p];
+                const bool up = (t & k) == 0;
+                if ((a > b) == up) { list[t] = b; list[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    const int val = list[tid];
+    const bool head = (val != INT_MAX) && (tid == 0 || list[tid - 1] != val);
+    int total;
+    const int pos = block_exclusive_scan<KR_NT>(head ? 1 : 0, wsum, total);
+    if (head) v_idx[(size_t)i * SSG_V_STRIDE + pos] = val;
+    if (tid == 0) v_cnt[i] = total;
+}
+
+int launch_krecip_build(const int* rank, int n, int k1p, int khp, int* v_idx, int* v_cnt,
+                        cudaStream_t st) {
+    static_assert(KR_NT == SSG_V_STRIDE, "one thread per list slot");
+    if (k1p > 32 || khp > 32 || k1p + k1p * khp > SSG_V_STRIDE)
+        return ssg_set_error(SSG_ERR_INVALID, "k1=%d exceeds the k-reciprocal row capacity", k1p - 1);
+    krecip_build_kernel<<<n, KR_NT, 0, st>>>(rank, n, k1p, khp, v_idx, v_cnt);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weights (rerank.py:91-92): v_val holds the exact squared distances d2(i, R*) on entry;
+// w = exp(-d2/rowmax_i); V = w / np.sum(w).  np.sum's pairwise summation is replicated exactly
+// (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum: 8 partial sums, blocks of 128).
+// ---------------------------------------------------------------------------------------------------
+__device__ float np_pairwise_sum_f32(const float* a, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = a[q];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = __fadd_rn(r[q], a[i + q]);
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
+}
+
+__global__ void __launch_bounds__(128)
+krecip_weights_kernel(const float* __restrict__ rowmax, int n, const int* __restrict__ v_cnt,
+                      float* __restrict__ v_val) {
+    __shared__ float w[4][SSG_V_STRIDE];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + wid;
+    if (i >= n) return;
+    const int c = v_cnt[i];
+    const float mx = rowmax[i];
+    float* row = v_val + (size_t)i * SSG_V_STRIDE;
+    for (int s = lane; s < c; s += 32) w[wid][s] = expf(-__fdiv_rn(row[s], mx));
+    __syncwarp();
+    float sum = 0.f;
+    if (lane == 0) sum = np_pairwise_sum_f32(w[wid], c);
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    for (int s = lane; s < c; s += 32) row[s] = __fdiv_rn(w[wid][s], sum);
+}
+
+int launch_krecip_weights(const float* rowmax, int n, const int* v_cnt, float* v_val, cudaStream_t st) {
+    krecip_weights_kernel<<<ssg_cdiv(n, 4), 128, 0, st>>>(rowmax, n, v_cnt, v_val);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// query expansion (rerank.py:94-98): V_qe[i] = mean(V[rank[i,:k2]], axis=0); np.mean reduces the k2
+// rows sequentially in float32 and divides by k2.  One CTA per row: gather the k2 sparse rows,
+// bitonic-sort by (column, j), sum each column's run in j order, compact.
+// ---------------------------------------------------------------------------------------------------
+constexpr int QE_NT = 256;
+constexpr int QE_CAP = 2048;
+
+__global__ void __launch_bounds__(QE_NT)
+query_expand_kernel(const int* __restrict__ rank, int n, int k2, const int* __restrict__ v_idx,
+                    const float* __restrict__ v_val, const int* __restrict__ v_cnt,
+                    int* __restrict__ q_idx, float* __restrict__ q_val, int* __restrict__ q_cnt) {
+    __shared__ uint32_t key[QE_CAP];
+    __shared__ float val[QE_CAP];
+    __shared__ int wsum[QE_NT / 32];
+    __shared__ int s_base;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    int off[9];
+    int rows[8];
+    off[0] = 0;
+    for (int j = 0; j < k2; ++j) {
+        rows[j] = rank[(size_t)i * SSG_RANK_STRIDE + j];
+        off[j + 1] = off[j] + (rows[j] >= 0 ? v_cnt[rows[j]] : 0);
+    }
+    const int total = off[k2];
+    int P = 32;
+    while (P < total) P <<= 1;
+    for (int t = tid; t < P; t += QE_NT) key[t] = 0xffffffffu;
+    __syncthreads();
+    for (int j = 0; j < k2; ++j) {
+        const int r = rows[j];
+        const int c = off[j + 1] - off[j];
+        for (int s = tid; s < c; s += QE_NT) {
+            key[off[j] + s] = ((uint32_t)v_idx[(size_t)r * SSG_V_STRIDE + s] << 3) | (uint32_t)j;
+            val[off[j] + s] = v_val[(size_t)r * SSG_V_STRIDE + s];
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < P; t += QE_NT) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const uint32_t a = key[t], b = key[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) {
+                        key[t] = b; key[p] = a;
+                        const float fa = val[t]; val[t] = val[p]; val[p] = fa;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    const float kf = (float)k2;
+    for (int base = 0; base < total; base += QE_NT) {
+        const int e = base + tid;
+        bool head = false;
+        uint32_t col = 0;
+        if (e < total) {
+            col = key[e] >> 3;
+            head = (e == 0) || ((key[e - 1] >> 3) != col);
+        }
+        int tot;
+        const int pos = block_exclusive_scan<QE_NT>(head ? 1 : 0, wsum, tot);
+        const int b0 = s_base;
+        if (head) {
+            float s = val[e];
+            for (int q = e + 1; q < total && (key[q] >> 3) == col; ++q) s = __fadd_rn(s, val[q]);
+            q_idx[(size_t)i * SSG_VQ_STRIDE + b0 + pos] = (int)col;
+            q_val[(size_t)i * SSG_VQ_STRIDE + b0 + pos] = __fdiv_rn(s, kf);
+        }
+        __syncthreads();
+        if (tid == 0) s_base = b0 + tot;
+        __syncthreads();
+    }
+    if (tid == 0) q_cnt[i] = s_base;
+}
+
+int launch_query_expand(const int* rank, int n, int k2, const int* v_idx, const float* v_val,
+                        const int* v_cnt, int* q_idx, float* q_val, int* q_cnt, cudaStream_t st) {
+    if (k2 < 1 || k2 > 8 || k2 * 252 > QE_CAP)
+        return ssg_set_error(SSG_ERR_INVALID, "k2=%d out of range (1..8)", k2);
+    query_expand_kernel<<<n, QE_NT, 0, st>>>(rank, n, k2, v_idx, v_val, v_cnt, q_idx, q_val, q_cnt);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inverted index (rerank.py:101-103): CSC row lists of the expanded matrix.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+csc_count_kernel(int n, const int* __restrict__ q_idx, const int* __restrict__ q_cnt,
+                 int* __restrict__ colcnt) {
+    const int i = blockIdx.x;
+    const int c = q_cnt[i];
+    for (int s = threadIdx.x; s < c; s += blockDim.x) atomicAdd(&colcnt[q_idx[(size_t)i * SSG_VQ_STRIDE + s]], 1);
+}
+__global__ void __launch_bounds__(128)
+csc_fill_kernel(int n, const int* __restrict__ q_idx, const int* __restrict__ q_cnt,
+                const int* __restrict__ colptr, int* __restrict__ cursor, int* __restrict__ csc_row) {
+    const int i = blockIdx.x;
+    const int c = q_cnt[i];
+    for (int s = threadIdx.x; s < c; s += blockDim.x) {
+        const int k = q_idx[(size_t)i * SSG_VQ_STRIDE + s];
+        csc_row[colptr[k] + atomicAdd(&cursor[k], 1)] = i;
+    }
+}
+
+int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int* colptr, int* cursor,
+                     int* csc_row, cudaStream_t st) {
+    SSG_CUDA_TRY(cudaMemsetAsync(colcnt, 0, sizeof(int) * (size_t)n, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)n, st));
+    csc_count_kernel<<<n, 128, 0, st>>>(n, q_idx, q_cnt, colcnt);
+    SSG_CHECK_LAUNCH();
+    SSG_TRY(launch_exclusive_scan_i32(colcnt, colptr, n, st));
+    csc_fill_kernel<<<n, 128, 0, st>>>(n, q_idx, q_cnt, colptr, cursor, csc_row);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Jaccard + final distance (rerank.py:105-122): one CTA per row i.
+//   final[i,m] = fl32(J*fl32(1-lambda)) + fl32(v_i+v_m)*lambda   (float64),  J = 1 - S/(2-S),
+//   S = sum over common columns k (ascending) of min(Vq[i,k], Vq[m,k]) in float32.
+// Every column m that shares no k with row i has S = 0 (J = 1): the row is first filled with that
+// base value; the touched columns (found through the inverted index, de-duplicated with a
+// shared-memory bitmap) are then overwritten by the thread that claimed them, which merges the two
+// index-sorted sparse rows.  Same terms in the same order for (i,m) and (m,i): exactly symmetric.
+// ---------------------------------------------------------------------------------------------------
+constexpr int JF_NT = 256;
+
+__global__ void __launch_bounds__(JF_NT)
+jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+                     const int* __restrict__ q_cnt, const int* __restrict__ colptr,
+                     const int* __restrict__ csc_row, const float* __restrict__ vec, double lambda_value,
+                     float one_minus_lambda, double* __restrict__ final_dist) {
+    extern __shared__ unsigned char jf_smem[];
+    int* si = reinterpret_cast<int*>(jf_smem);                       // [VQ_STRIDE]
+    float* sv = reinterpret_cast<float*>(si + SSG_VQ_STRIDE);        // [VQ_STRIDE]
+    int* pref = reinterpret_cast<int*>(sv + SSG_VQ_STRIDE);          // [VQ_STRIDE + 1]
+    unsigned* bitmap = reinterpret_cast<unsigned*>(pref + SSG_VQ_STRIDE + 1);  // [(n+31)/32]
+    __shared__ int wsum[JF_NT / 32];
+    __shared__ int s_carry;
+
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int ci = q_cnt[i];
+    const float vi = vec[i];
+    double* out = final_dist + (size_t)i * n;
+    const int nwords = (n + 31) >> 5;
+
+    for (int s = tid; s < ci; s += JF_NT) {
+        si[s] = q_idx[(size_t)i * SSG_VQ_STRIDE + s];
+        sv[s] = q_val[(size_t)i * SSG_VQ_STRIDE + s];
+    }
+    for (int w = tid; w < nwords; w += JF_NT) bitmap[w] = 0u;
+    // base fill (S = 0  ->  J = 1)
+    const double jbase = (double)__fmul_rn(1.0f, one_minus_lambda);
+    for (int m = tid; m < n; m += JF_NT)
+        out[m] = __dadd_rn(jbase, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    // prefix sums of the inverted-list lengths of this row's columns
+    for (int base = 0; base < ci; base += JF_NT) {
+        const int s = base + tid;
+        int len = 0;
+        if (s < ci) len = colptr[si[s] + 1] - colptr[si[s]];
+        int tot;
+        const int ex = block_exclusive_scan<JF_NT>(len, wsum, tot);
+        const int c = s_carry;
+        if (s < ci) pref[s] = c + ex;
+        __syncthreads();
+        if (tid == 0) s_carry = c + tot;
+        __syncthreads();
+    }
+    const int T = s_carry;
+    if (tid == 0) pref[ci] = T;
+    __syncthreads();
+
+    for (int f = tid; f < T; f += JF_NT) {
+        int lo = 0, hi = ci - 1;          // largest s with pref[s] <= f
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pref[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        const int m = csc_row[colptr[si[lo]] + (f - pref[lo])];
+        const unsigned bit = 1u << (m & 31);
+        const unsigned old = atomicOr(&bitmap[m >> 5], bit);
+        if (old & bit) continue;          // another thread owns column m
+        const int cm = q_cnt[m];
+        const int* mi = q_idx + (size_t)m * SSG_VQ_STRIDE;
+        const float* mv = q_val + (size_t)m * SSG_VQ_STRIDE;
+        float S = 0.f;
+        int a = 0, b = 0;
+        int ib = cm > 0 ? mi[0] : INT_MAX;
+        while (a < ci && b < cm) {
+            const int ia = si[a];
+            if (ia == ib) {
+                S = __fadd_rn(S, fminf(sv[a], mv[b]));
+                ++a; ++b;
+                ib = b < cm ? mi[b] : INT_MAX;
+            } else if (ia < ib) {
+                ++a;
+            } else {
+                ++b;
+                ib = b < cm ? mi[b] : INT_MAX;
+            }
+        }
+        float J = __fsub_rn(1.0f, __fdiv_rn(S, __fsub_rn(2.0f, S)));
+        if (J < 0.f) J = 0.f;
+        const float Jm = __fmul_rn(J, one_minus_lambda);
+        out[m] = __dadd_rn((double)Jm, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+    }
+}
+
+int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                         const int* csc_row, const float* vec, double lambda_value, double* final_dist,
+                         cudaStream_t st) {
+    const size_t smem = sizeof(int) * SSG_VQ_STRIDE + sizeof(float) * SSG_VQ_STRIDE +
+                        sizeof(int) * (SSG_VQ_STRIDE + 1) + sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
+    if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
+    SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    // (1 - lambda_value) is a Python float cast to float32 by numpy when it multiplies the fp32 array
+    const float oml = (float)(1.0 - lambda_value);
+    jaccard_final_kernel<<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value,
+                                                 oml, final_dist);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // namespace ssg

@@ -1,0 +1,10 @@
+"""ssg_b200 — B200-native pseudo-label hot path of Self-Similarity Grouping (host-side Python).
+
+Thin layer over libssg_b200.so (hand-written sm_100a CUDA behind the C ABI of include/ssg_b200.h).
+PyTorch is used for device memory, streams and torch.distributed only.
+"""
+from . import _lib  # noqa: F401
+from .rerank import RerankPlan, re_ranking, re_ranking_device, sqdist  # noqa: F401
+from .cluster import ClusterPlan, DBSCAN, eps_estimate, dbscan_labels  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,136 @@
+"""Re-ranking host API (reid/rerank.py:27-127 of the reference) on top of the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+_plans = {}
+
+
+class RerankPlan(object):
+    """Owns the device workspace for one (n_max, ns_max, d) problem size on one GPU."""
+
+    def __init__(self, n_max, ns_max, d, device=None):
+        dev = _lib.require_cuda(device)
+        self.device = dev
+        self.n_max, self.ns_max, self.d = int(n_max), int(ns_max), int(d)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.load().ssg_rerank_plan_create(ctypes.byref(self._h), dev.index, self.n_max,
+                                                      self.ns_max, self.d))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().ssg_rerank_plan_destroy(h)
+            except Exception:
+                pass
+
+    @property
+    def nbytes(self):
+        return int(_lib.load().ssg_rerank_plan_bytes(self._h))
+
+    def run(self, src, tgt, k1=20, k2=6, lambda_value=0.2, dist_mode=_lib.DIST_EXACT, want_euclid=False,
+            out=None):
+        """src [ns,d], tgt [n,d]: float32 CUDA tensors.  Returns (euclid or None, final) CUDA tensors
+        (float32 [n,n], float64 [n,n]); asynchronous on the current stream."""
+        import torch
+        assert src.is_cuda and tgt.is_cuda and src.dtype == torch.float32 and tgt.dtype == torch.float32
+        src, tgt = src.contiguous(), tgt.contiguous()
+        n, d = tgt.shape
+        ns = src.shape[0]
+        final = out if out is not None else torch.empty((n, n), dtype=torch.float64, device=tgt.device)
+        euclid = torch.empty((n, n), dtype=torch.float32, device=tgt.device) if want_euclid else None
+        _lib.check(_lib.load().ssg_rerank_run(
+            self._h, src.data_ptr(), ns, tgt.data_ptr(), n, d, int(k1), int(k2), float(lambda_value),
+            int(dist_mode), final.data_ptr(), euclid.data_ptr() if want_euclid else None, _lib.stream_ptr()))
+        return euclid, final
+
+    def run_host(self, src, tgt, k1=20, k2=6, lambda_value=0.2, dist_mode=_lib.DIST_EXACT, no_rerank=False,
+                 want_euclid=True):
+        """numpy in / numpy out through ssg_rerank_host (pinned result buffers)."""
+        src = np.ascontiguousarray(src, dtype=np.float32)
+        tgt = np.ascontiguousarray(tgt, dtype=np.float32)
+        n, d = tgt.shape
+        ns = src.shape[0]
+        final = None if no_rerank else _pinned((n, n), np.float64)
+        euclid = _pinned((n, n), np.float32) if want_euclid else None
+        _lib.check(_lib.load().ssg_rerank_host(
+            self._h, src.ctypes.data, ns, tgt.ctypes.data, n, d, int(k1), int(k2), float(lambda_value),
+            int(dist_mode), int(bool(no_rerank)), final.ctypes.data if final is not None else None,
+            euclid.ctypes.data if euclid is not None else None))
+        return euclid, final
+
+    def stage(self, which, n):
+        """Copy an intermediate of the last run to the host (stage-isolated parity tests)."""
+        shapes = {
+            _lib.STAGE_VEC: ((n,), np.float32), _lib.STAGE_ROWMAX: ((n,), np.float32),
+            _lib.STAGE_RANK: ((n, _lib.RANK_STRIDE), np.int32),
+            _lib.STAGE_RANK_VAL: ((n, _lib.RANK_STRIDE), np.float32),
+            _lib.STAGE_V_CNT: ((n,), np.int32), _lib.STAGE_V_IDX: ((n, _lib.V_STRIDE), np.int32),
+            _lib.STAGE_V_VAL: ((n, _lib.V_STRIDE), np.float32),
+            _lib.STAGE_VQ_CNT: ((n,), np.int32), _lib.STAGE_VQ_IDX: ((n, _lib.VQ_STRIDE), np.int32),
+            _lib.STAGE_VQ_VAL: ((n, _lib.VQ_STRIDE), np.float32),
+            _lib.STAGE_FLAGGED: ((1,), np.int32),
+        }
+        shape, dt = shapes[which]
+        out = np.empty(shape, dtype=dt)
+        _lib.check(_lib.load().ssg_rerank_get_stage(self._h, which, out.ctypes.data, out.nbytes))
+        return out
+
+
+def _pinned(shape, dtype):
+    """A numpy array backed by pinned host memory (fast D2H); the tensor is kept alive by the array."""
+    import torch
+    tdt = {np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64}[dtype]
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+
+
+def get_plan(n, ns, d, device=None):
+    dev = _lib.require_cuda(device)
+    key = (dev.index, d)
+    plan = _plans.get(key)
+    if plan is None or plan.n_max < n or plan.ns_max < ns:
+        _plans.pop(key, None)
+        plan = RerankPlan(max(n, plan.n_max if plan else 0), max(ns, plan.ns_max if plan else 0), d, dev.index)
+        _plans[key] = plan
+    return plan
+
+
+def re_ranking_device(src, tgt, k1=20, k2=6, lambda_value=0.2, dist_mode=_lib.DIST_EXACT, want_euclid=False):
+    """Device-resident variant: CUDA float32 tensors in, (euclid|None, final float64) CUDA tensors out."""
+    plan = get_plan(tgt.shape[0], src.shape[0], tgt.shape[1], tgt.device.index)
+    return plan.run(src, tgt, k1, k2, lambda_value, dist_mode, want_euclid)
+
+
+def re_ranking(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.2, MemorySave=False,
+               Minibatch=2000, no_rerank=False, dist_mode=None):
+    """Drop-in for reid/rerank.py:27 re_ranking (same positional order and defaults).
+
+    Returns (euclidean_dist, final_dist) as numpy arrays — float32 [N,N] and float64 [N,N]
+    (``final_dist`` is None when ``no_rerank``).  Arithmetic follows the reference with float16
+    replaced by float32 and a stable argsort (the O-f32 oracle); MemorySave/Minibatch
+    only chunk the reference's cdist and have no effect on results, so they are accepted and ignored.
+    """
+    import os
+    if dist_mode is None:
+        dist_mode = int(os.environ.get("SSG_DIST_MODE", _lib.DIST_EXACT))
+    src = np.ascontiguousarray(input_feature_source, dtype=np.float32)
+    tgt = np.ascontiguousarray(input_feature, dtype=np.float32)
+    plan = get_plan(tgt.shape[0], src.shape[0], tgt.shape[1])
+    print('computing source distance...')
+    print('computing original distance...')
+    if not no_rerank:
+        print('starting re_ranking...')
+    return plan.run_host(src, tgt, k1, k2, lambda_value, dist_mode, no_rerank, want_euclid=True)
+
+
+def sqdist(x, y, mode=_lib.DIST_EXACT):
+    """Squared Euclidean distance matrix of two float32 CUDA tensors (ssg_sqdist)."""
+    import torch
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ssg_sqdist(x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], x.shape[1], int(mode),
+                                      out.data_ptr(), y.shape[0], _lib.stream_ptr()))
+    return out

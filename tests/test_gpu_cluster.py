@@ -1,0 +1,120 @@
+"""GPU parity: eps estimate and DBSCAN (through the C ABI) against numpy / scikit-learn.
+
+Labels are compared bit-for-bit; eps to 1e-12 relative (the mean is taken in a different but
+deterministic summation order).
+"""
+import numpy as np
+import pytest
+
+from oracle import ssg_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ssg():
+    import ssg_b200
+    return ssg_b200
+
+
+def _sym(n, seed, diag_scale=0.5, dtype=np.float64):
+    rng = np.random.RandomState(seed)
+    A = rng.rand(n, n)
+    D = np.minimum(A, A.T)
+    np.fill_diagonal(D, rng.rand(n) * diag_scale)
+    return D.astype(dtype)
+
+
+@pytest.mark.parametrize("n,eps", [(1, 0.5), (5, 0.9), (50, 0.2), (200, 0.08), (333, 0.03), (1024, 0.01),
+                                   (2000, 0.004)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_dbscan_matches_sklearn_bit_exact(ssg, n, eps, dtype):
+    from sklearn.cluster import DBSCAN
+    D = _sym(n, n, dtype=dtype)
+    eps = np.float64(eps)
+    want = DBSCAN(eps=eps, min_samples=4, metric="precomputed").fit(D)
+    got = ssg.DBSCAN(eps=eps, min_samples=4, metric="precomputed", n_jobs=8).fit(D)
+    assert got.labels_.dtype == np.int64
+    assert np.array_equal(got.labels_, want.labels_)
+    assert np.array_equal(got.core_sample_indices_, want.core_sample_indices_)
+
+
+def test_dbscan_on_device_tensor_and_reuse(ssg):
+    import torch
+    from sklearn.cluster import DBSCAN
+    est = ssg.DBSCAN(eps=0.05, min_samples=4, metric="precomputed")
+    for seed in (1, 2):                      # the reference re-uses the estimator (selftraining.py:296-298)
+        D = _sym(600, seed)
+        want = DBSCAN(eps=0.05, min_samples=4, metric="precomputed").fit_predict(D)
+        assert np.array_equal(est.fit_predict(torch.from_numpy(D).cuda()), want)
+        assert np.array_equal(est.fit_predict(D), want)
+
+
+def test_dbscan_everything_is_a_neighbour(ssg):
+    """eps above the maximum: one cluster, neighbour list = n*n entries (capacity growth path)."""
+    D = _sym(300, 3)
+    lab = ssg.DBSCAN(eps=2.0, min_samples=4, metric="precomputed").fit_predict(D)
+    assert np.array_equal(lab, np.zeros(300, np.int64))
+    lab = ssg.DBSCAN(eps=-1.0, min_samples=4, metric="precomputed").fit_predict(D)
+    assert np.array_equal(lab, -np.ones(300, np.int64))
+
+
+def test_dbscan_on_rerank_output(ssg):
+    from sklearn.cluster import DBSCAN
+    tgt, _ = O.synth_features(1500, 256, 4)
+    src, _ = O.synth_features(900, 256, 5, noise=0.6)
+    _, f = ssg.re_ranking(src, tgt, lambda_value=0.1)
+    for rho in (1.6e-3, 1e-2):
+        eps = O.eps_estimate(f, rho)
+        want = DBSCAN(eps=eps, min_samples=4, metric="precomputed", n_jobs=8).fit_predict(f)
+        assert np.array_equal(ssg.DBSCAN(eps=eps, min_samples=4, metric="precomputed").fit_predict(f), want)
+        assert want.max() >= 1
+
+
+@pytest.mark.parametrize("n,rho", [(2, 0.5), (40, 0.05), (300, 1.6e-3), (300, 0.3), (1111, 1.6e-3), (64, 1.0)])
+def test_eps_matches_numpy(ssg, n, rho):
+    D = _sym(n, 100 + n)
+    D[D < 0.02] = 0.0                       # exact zeros are dropped by np.nonzero (selftraining.py:290)
+    D = np.minimum(D, D.T)
+    tri = np.triu(D, 1)
+    tri = np.sort(tri[np.nonzero(tri)], axis=None)
+    top = int(np.round(rho * tri.size))
+    got = ssg.eps_estimate(D, rho)
+    if top == 0:
+        assert np.isnan(got)
+    else:
+        want = tri[:top].mean()
+        assert abs(got - want) <= 1e-12 * abs(want)
+
+
+def test_eps_heavy_ties_and_float32(ssg):
+    import torch
+    rng = np.random.RandomState(0)
+    vals = np.array([0.25, 0.5, 0.75, 0.899999976158142, 1.0])
+    A = vals[rng.randint(0, 5, (500, 500))]
+    D = np.minimum(A, A.T)
+    for rho in (1e-3, 0.2, 0.41, 0.9):
+        assert abs(ssg.eps_estimate(D, rho) - O.eps_estimate(D, rho)) < 1e-12
+    D32 = D.astype(np.float32)
+    got = ssg.eps_estimate(torch.from_numpy(D32).cuda(), 0.3)
+    assert abs(got - O.eps_estimate(D32.astype(np.float64), 0.3)) < 1e-9
+
+
+def test_full_size_cycle_labels(ssg):
+    """N = 16 702: eps and labels from the device-resident matrix equal numpy / sklearn on its host copy."""
+    import torch
+    from sklearn.cluster import DBSCAN
+    n, d = 16702, 2048
+    tgt, _ = O.synth_features(n, d, 0)
+    src, _ = O.synth_features(n, d, 1, noise=0.6)
+    _, f = ssg.re_ranking_device(torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda(), lambda_value=0.1)
+    plan = ssg.ClusterPlan(n)
+    eps, top = plan.eps(f, 1.6e-3)
+    labels, ncl = plan.dbscan(f, eps, 4)
+    fh = f.cpu().numpy()
+    assert top == 223152                                   # round(rho*M)
+    want_eps = O.eps_estimate(fh, 1.6e-3)
+    assert abs(eps - want_eps) <= 1e-12 * want_eps
+    want = DBSCAN(eps=eps, min_samples=4, metric="precomputed", n_jobs=8).fit_predict(fh)
+    assert np.array_equal(labels.cpu().numpy(), want)
+    assert ncl == want.max() + 1 and ncl > 100
