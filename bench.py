@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — pseudo-label-cycle throughput on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (the reference's CPU path on this box's host cores)
+
+A step is one pass of the hot path over one batch of synthetic input: the pseudo-label cycle of
+selftraining.py:189-222 at Market-1501 shape (BASELINE.json configs[1]): N = 16 702 target images and as
+many source images, num_split = 2 -> 3 feature banks of 2048-d; per bank re-ranking (k1=20, k2=6,
+lambda=0.1), eps at rho=1.6e-3 and DBSCAN(min_samples=4).  `value` is Mpairs/s = banks*N^2 ordered pairs per
+second of re-rank + eps + DBSCAN with the features resident in HBM; `e2e` is the same metric through the
+host-buffer API (pinned host features in, host labels out, copies inside the timed region).
+The embedding half of the metric (images/s) is reported under "embed" once that stage is built.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "self-similarity-grouping_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "pseudo-label cycle: images/s embed + Mpairs/s re-rank+DBSCAN @ N=16702"
+UNIT = "Mpairs/s (banks*N^2 ordered pairs re-ranked + eps + DBSCAN-labelled per second)"
+D = 2048
+LAMBDA, RHO, K1, K2, MIN_SAMPLES = 0.1, 1.6e-3, 20, 6, 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=16702)
+    ap.add_argument("--banks", type=int, default=3)
+    ap.add_argument("--dist-mode", default="tensor", choices=["tensor", "exact"])
+    ap.add_argument("--cpu-sample", type=int, default=1280, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------- inputs
+def synth_bank(n, d, seed, noise, device, per_cluster=20):
+    """Feature-level generator of SURVEY.md §8d on the device: n/20 Gaussian centres + noise, L2-normalised."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    c = max(n // per_cluster, 1)
+    centres = torch.randn(c, d, generator=g, device=device)
+    lab = torch.randint(0, c, (n,), generator=g, device=device)
+    f = centres[lab] + noise * torch.randn(n, d, generator=g, device=device)
+    return (f / f.norm(dim=1, keepdim=True)).contiguous()
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_cycle_sample(n_sample, d=D, seed=0, mode="ref"):
+    """The reference's CPU path (oracle port; the unmodified reference when /root/reference exists) on a
+    bounded sample: one bank, n_sample target and source rows.  Returns (seconds, kind)."""
+    import numpy as np
+    from oracle import ssg_oracle as O, refshim
+    from sklearn.cluster import DBSCAN
+    tgt, _ = O.synth_features(n_sample, d, seed)
+    src, _ = O.synth_features(n_sample, d, seed + 1, noise=0.6)
+    kind = "reference" if refshim.available() else "port"
+    t0 = time.perf_counter()
+    if kind == "reference":
+        _, final = refshim.ref_re_ranking(src, tgt, mode=mode, lambda_value=LAMBDA)
+    else:
+        _, final = O.re_ranking(src, tgt, k1=K1, k2=K2, lambda_value=LAMBDA, mode=mode)
+    eps = O.eps_estimate(final, RHO * 10)     # a small sample needs a larger rho for a non-empty slice
+    DBSCAN(eps=eps, min_samples=MIN_SAMPLES, metric="precomputed", n_jobs=8).fit_predict(final)
+    return time.perf_counter() - t0, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s = args.cpu_sample
+    for _ in range(min(args.warmup, 1)):
+        cpu_cycle_sample(256)
+    times = []
+    kind = "port"
+    for _ in range(args.steps):
+        t, kind = cpu_cycle_sample(n_s)
+        times.append(t)
+    sec = sum(times) / len(times)
+    val = n_s * n_s / sec / 1e6
+    sample = "1 bank, N=Ns=%d rows of the %d-row workload, d=%d, fp16 reference arithmetic" % (n_s, args.n, D)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16/f64 (numpy/scipy/sklearn)", "data": "synthetic",
+        "config": {"workload": "pseudo-label cycle (re-rank+eps+DBSCAN), bounded sample: " + sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
+                         "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+ALGO = {   # per launch: (bound, algorithmic work as a function of (rows, cols, d))
+    "gemm_dist_tc": ("tensor", lambda r, c, d: 2.0 * d * r * c),        # flops: 2*d per ordered pair
+    "sqdist_exact": ("fp64", lambda r, c, d: 3.0 * d * r * c),
+    "jaccard_final": ("hbm", lambda r, c, d: 8.0 * r * c),              # float64 final_dist written once
+    "eps_hist": ("hbm", lambda r, c, d: 8.0 * r * c / 2),               # upper triangle read once per pass
+    "eps_sum": ("hbm", lambda r, c, d: 8.0 * r * c / 2),
+    "dbscan_count": ("hbm", lambda r, c, d: 8.0 * r * c),
+    "dbscan_fill": ("hbm", lambda r, c, d: 8.0 * r * c),
+    "row_select": ("hbm", lambda r, c, d: 4.0 * r * c),                 # fp32 distance block read once
+    "row_minmax": ("hbm", lambda r, c, d: 4.0 * r * c),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": p.get("hbm_gbs", 6650.0), "tensor": p.get("bf16_tflops_sustained", 1400.0),
+                "source": "measured (MEASURED_PEAKS.json; bf16 sustained)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import ssg_b200
+    from ssg_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mode = _lib.DIST_TENSOR if args.dist_mode == "tensor" else _lib.DIST_EXACT
+    n, banks = args.n, args.banks
+
+    # every rank owns an independent target set of the same shape (weak scaling, no data-path collective)
+    tgt = [synth_bank(n, D, 1000 * rank + 10 + b, 0.5, dev) for b in range(banks)]
+    src = [synth_bank(n, D, 1000 * rank + 20 + b, 0.6, dev) for b in range(banks)]
+    pairs_per_step = float(banks) * n * n
+
+    def step_device():
+        return ssg_b200.pseudo_label_cycle(src, tgt, LAMBDA, RHO, dist_mode=mode, device=local)
+
+    # host-resident copies for the end-to-end measurement (pinned)
+    tgt_h = [t.cpu().pin_memory() for t in tgt]
+    src_h = [s.cpu().pin_memory() for s in src]
+
+    def step_e2e():
+        return ssg_b200.pseudo_label_cycle(src_h, tgt_h, LAMBDA, RHO, dist_mode=mode, device=local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            _lib.profile(reset=True)
+            _lib.profile(on=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        prof = {}
+        if profile:
+            prof = _lib.profile()
+            _lib.profile(on=False)
+        return float(ms.item()), out, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(local)
+    ms_dev, out, prof = timed(step_device, args.steps, profile=True)
+    clk = clocks.stop()
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, out_e2e, _ = timed(step_e2e, args.steps)
+
+    labels, eps_list, keep = out
+    value = pairs_per_step * world * args.steps / (ms_dev / 1e3) / 1e6
+    e2e_value = pairs_per_step * world * args.steps / (ms_e2e / 1e3) / 1e6
+
+    line = None
+    if rank == 0:
+        peaks = load_peaks()
+        # dominant kernel of the step
+        launches = sum(v[1] for v in prof.values())
+        kern_ms = {k: v[0] for k, v in prof.items()}
+        top = max(kern_ms, key=kern_ms.get) if kern_ms else None
+        roof = None
+        if top in ALGO:
+            bound, fn = ALGO[top]
+            per_launch_ms = prof[top][0] / prof[top][1]
+            # all the big launches of this path cover the whole N x N (or N x Ns) problem of one bank
+            work = fn(n, n, D)
+            if bound == "tensor":
+                ach = work / (per_launch_ms / 1e3) / 1e12
+                roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tensor"], "traffic": None, "ms_per_launch": per_launch_ms,
+                        "peak_source": peaks["source"],
+                        "note": "algorithmic flops 2*d*N^2 per launch; the bf16x3 split issues 3x that on the tensor pipe"}
+            elif bound == "hbm":
+                ach = work / (per_launch_ms / 1e3) / 1e9
+                roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm"], "traffic": None, "ms_per_launch": per_launch_ms,
+                        "peak_source": peaks["source"]}
+            else:
+                roof = {"kernel": top, "bound": bound, "achieved": work / (per_launch_ms / 1e3) / 1e12, "peak": None,
+                        "unit": "Tflop64/s", "frac": None, "traffic": None, "ms_per_launch": per_launch_ms}
+        cpu = None
+        if not args.no_cpu_baseline:
+            sec, kind = cpu_cycle_sample(args.cpu_sample)
+            cpu = {"value": args.cpu_sample ** 2 / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
+                   "seconds": sec,
+                   "sample": "1 bank, N=Ns=%d rows of the %d-row workload (re_ranking fp16 reference arithmetic + eps + "
+                             "sklearn DBSCAN n_jobs=8); numpy/scipy parts are single-threaded" % (args.cpu_sample, n)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (bf16x3 tensor-core candidates, exact f64 re-score)"
+            if mode == _lib.DIST_TENSOR else "f32/f64 (exact f64 distances)",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: N=Ns=%d, %d banks x 2048-d (num_split=2), re-rank k1=20 k2=6 lambda=0.1 + "
+                                   "eps rho=1.6e-3 + DBSCAN min_samples=4; features device-resident; embed stage not "
+                                   "built yet" % (n, banks),
+                       "l2": "inputs (%.0f MB of features, %.1f GB distance block) exceed the 126 MB L2"
+                             % (2 * banks * n * D * 4 / 1e6, n * n * 4 / 1e9),
+                       "parallelism": "%d independent replicas (one target set per GPU)" % world,
+                       "dist_mode": args.dist_mode},
+            "embed": None,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * banks * n * D * 4, "d2h_bytes_per_step": banks * n * 8,
+                    "api": "ssg_b200.pseudo_label_cycle(host pinned features) -> host labels"},
+            "gpu_launches": int(launches),
+            "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "result": {"clusters": [int(l.max()) + 1 for l in labels], "eps": [round(e, 6) for e in eps_list],
+                       "kept_images": int(keep.sum())},
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

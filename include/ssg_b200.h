@@ -119,6 +119,62 @@ int ssg_eps_estimate_host(ssg_cluster_plan* plan, const void* h_dist, int dtype,
 int ssg_dbscan_host(ssg_cluster_plan* plan, const void* h_dist, int dtype, int n, double eps,
                     int min_samples, int64_t* h_labels, int* h_n_clusters);
 
+/* ------------------------------------------------------------------------------------------------
+ * Embedding: reid/evaluators.py:18-60 extract_features + reid/feature_extraction/cnn.py:10-23 +
+ * reid/models/resnet.py:86-134 (ResNet-50 trunk, num_classes=0, cluster=False) for 256x128 inputs.
+ *   forward: images fp32 NCHW [n,3,256,128] (already mean/std normalised, as the reference's loaders
+ *   deliver them) -> per image the (num_split>1 ? num_split+1 : 1) pooled 2048-d banks of
+ *   model(x) + model(fliplr(x)) (flip != 0), L2-normalised:
+ *     eval_mode == 0 : d_feat[bank * bank_stride + (row0+i) * 2048 + c]      (each bank normalised alone)
+ *     eval_mode != 0 : d_feat[((row0+i) * banks + bank) * 2048 + c]           (one norm over the concatenation)
+ *   Convolutions run in bf16 with fp32 accumulation on the tcgen05 tensor cores; eval-mode BatchNorm is
+ *   folded into the weights when a layer is loaded.
+ * Layers are indexed in a fixed order (stem, then conv1, conv2, conv3[, downsample] per bottleneck);
+ * ssg_embed_layer_info gives the torchvision state_dict key prefixes of each index.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ssg_embed_plan ssg_embed_plan;
+int ssg_embed_num_layers(void);
+int ssg_embed_layer_info(int idx, int* cin, int* cout, int* ksize, int* stride, char* conv_key, char* bn_key,
+                         size_t cap);
+int ssg_embed_plan_create(ssg_embed_plan** plan, int device, int batch_max, int height, int width);
+int ssg_embed_plan_destroy(ssg_embed_plan* plan);
+size_t ssg_embed_plan_bytes(const ssg_embed_plan* plan);
+/* d_w: conv weight fp32 [cout,cin,k,k]; BatchNorm weight/bias/running_mean/running_var fp32 [cout]. */
+int ssg_embed_load_layer(ssg_embed_plan* plan, int idx, const float* d_w, const float* d_gamma,
+                         const float* d_beta, const float* d_mean, const float* d_var, float eps, void* stream);
+int ssg_embed_forward(ssg_embed_plan* plan, const float* d_images, int n, int num_split, int eval_mode, int flip,
+                      float* d_feat, size_t bank_stride, int row0, void* stream);
+
+/* Building blocks of the trunk (NHWC bf16 activations, weights bf16 [cout][k][k][cin] with BatchNorm folded):
+ * exported for stage-isolated parity tests and for callers with their own graph.
+ *   ssg_op_conv   : k x k convolution (k in {1,3}, padding k/2, stride in {1,2}) + bias (+ residual, 1x1 only)
+ *                   (+ ReLU).  H, W are the INPUT map size; stride 2 needs a scratch buffer of the input's size.
+ *                   3x3 needs W (output) to divide 128 and H*W (output) to be a multiple or a divisor of 128.
+ *   ssg_op_fold_bn: fp32 [cout,cin,k,k] conv weight + BatchNorm statistics -> bf16 [cout,kpad] + fp32 bias.
+ *   ssg_op_stem   : 7x7/2 conv (K padded 147->192) + ReLU on fp32 NCHW images (and their mirror images when
+ *                   flip != 0), optionally followed by the 3x3/2 max-pool.
+ *   ssg_op_pooled_tail : global + stripe average pools, flip sum, L2 normalisation (see ssg_embed_forward). */
+int ssg_op_conv(const void* d_x, int B, int H, int W, int cin, int ksize, int stride, const void* d_w,
+                const float* d_bias, int cout, const void* d_res, int relu, void* d_y, void* d_scratch, void* stream);
+int ssg_op_fold_bn(const float* d_w, int cout, int cin, int ksize, const float* d_gamma, const float* d_beta,
+                   const float* d_mean, const float* d_var, float eps, int kpad, void* d_wout, float* d_bout,
+                   void* stream);
+int ssg_op_stem(const float* d_images, int n, int flip, const void* d_w, const float* d_bias, void* d_col,
+                void* d_conv_out, void* d_pool_out, void* stream);
+int ssg_op_pooled_tail(const void* d_x, int n, int num_split, int eval_mode, int flip, float* d_feat,
+                       size_t bank_stride, int row0, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-kernel CUDA-event timers (the reference only has wall-clock AverageMeters, reid/utils/meters.py:4-23,
+ * printed from reid/evaluators.py:48-57).  Disabled by default; when enabled every kernel group launched by
+ * this library is bracketed by events on its own stream.  collect() synchronises the device, accumulates
+ * and returns the number of distinct names; entry(i) reads one accumulated row.
+ * ------------------------------------------------------------------------------------------------ */
+int ssg_profile_enable(int on);
+int ssg_profile_reset(void);
+int ssg_profile_collect(void);
+int ssg_profile_entry(int i, char* name, size_t cap, double* ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

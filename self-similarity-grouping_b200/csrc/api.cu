@@ -56,7 +56,15 @@ struct ssg_rerank_plan {
     int* v_idx; float* v_val; int* v_cnt;
     int* q_idx; float* q_val; int* q_cnt;
     int *colcnt, *colptr, *cursor, *csc_row;
-    int* flagged;
+    int* flagged;                // [4]: 0 rows that took the exact fallback (total), 1 src flags, 2 tgt flags
+    // tensor distance mode (allocated on first use)
+    bool tensor_ready;
+    void *split_ta, *split_tb, *split_sb;        // bf16 [n,3d] / [ns,3d]
+    float *norm_t, *norm_s, *norm_max;           // [n], [ns], [2]
+    int* cand_idx; float *cand_val, *cand_exact; // [n,64]
+    int *flag_src, *flag_tgt;                    // [n], [2n]
+    float* fb_rows;                              // gathered feature rows for the fallback [FB_ROWS, d]
+    float* fb_f32; int* fb_i32;                  // [FB_ROWS, 32]
     // lazily grown device I/O buffers for the host entry point
     float *io_src, *io_tgt; size_t io_src_bytes, io_tgt_bytes;
     double* io_final; size_t io_final_bytes;
@@ -119,7 +127,9 @@ extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
     cudaSetDevice(p->device);
     void* ptrs[] = {p->dmat, p->rowmin, p->rowmax, p->vec, p->scratch, p->rank, p->rank_val, p->v_idx,
                     p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, p->colcnt, p->colptr, p->cursor,
-                    p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid};
+                    p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid, p->split_ta,
+                    p->split_tb, p->split_sb, p->norm_t, p->norm_s, p->norm_max, p->cand_idx, p->cand_val,
+                    p->cand_exact, p->flag_src, p->flag_tgt, p->fb_rows, p->fb_f32, p->fb_i32};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return SSG_OK;
@@ -147,8 +157,150 @@ static int dist_block(ssg_rerank_plan* p, const float* X, int rows, const float*
     return ssg_set_error(SSG_ERR_UNSUPPORTED, "rerank: dist_mode %d not available in this build", dist_mode);
 }
 
+constexpr int CAND_STRIDE = 64;   // candidate table row stride
+constexpr int CAND_K = 40;        // nearest-neighbour candidates re-scored per row (k1+1 <= 32 needed)
+constexpr int CAND_EXT = 8;       // candidates for the row minimum / maximum
+constexpr int FB_ROWS = 1024;     // rows per exact-fallback batch
+// Certified error of the tensor-core squared distance, relative to (|x|^2 + max|y|^2):
+//   * the bf16 hi/lo split drops products below 3 * 2^-18 |x||y|                      -> 1.15e-5 (x2 for -2*dot, /2 for
+//     |x||y| <= (|x|^2+|y|^2)/2);
+//   * the tensor core adds each 16-wide partial product to the fp32 accumulator with truncation: 3d/16 updates of at
+//     most 2^-23 |x||y| each                                                          -> 2.24e-8 * d.
+// Measured maximum at d = 2048, unit norms: 2.05e-5 of (|x|^2+|y|^2) (tests/test_gpu_tensor.py), bound 5.7e-5.
+static inline float tensor_eps_rel(int d) { return 1.15e-5f + 2.24e-8f * (float)d; }
+
+static int ensure_tensor_buffers(ssg_rerank_plan* p) {
+    if (p->tensor_ready) return SSG_OK;
+    const size_t n = (size_t)p->n_max, ns = (size_t)p->ns_max, d = (size_t)p->d;
+    int rc = SSG_OK;
+#define A(ptr, nbytes) if (rc == SSG_OK) rc = dalloc((void**)&(ptr), (nbytes), &p->bytes)
+    A(p->split_ta, n * 3 * d * 2);
+    A(p->split_tb, n * 3 * d * 2);
+    A(p->split_sb, ns * 3 * d * 2);
+    A(p->norm_t, sizeof(float) * n);
+    A(p->norm_s, sizeof(float) * ns);
+    A(p->norm_max, sizeof(float) * 2);
+    A(p->cand_idx, sizeof(int) * n * CAND_STRIDE);
+    A(p->cand_val, sizeof(float) * n * CAND_STRIDE);
+    A(p->cand_exact, sizeof(float) * n * CAND_STRIDE);
+    A(p->flag_src, sizeof(int) * n);
+    A(p->flag_tgt, sizeof(int) * 2 * n);
+    A(p->fb_rows, sizeof(float) * FB_ROWS * d);
+    A(p->fb_f32, sizeof(float) * FB_ROWS * SSG_RANK_STRIDE);
+    A(p->fb_i32, sizeof(int) * FB_ROWS * SSG_RANK_STRIDE);
+#undef A
+    if (rc == SSG_OK) p->tensor_ready = true;
+    return rc;
+}
+
+// Tensor distance mode: bf16x3 tcgen05 GEMM for the bulk, exact float64 re-scoring of the candidates, exact
+// fallback for the rows whose result the error bound cannot certify.  Synchronises the stream once (flag counts).
+static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                                  int k1, float* d_euclid, bool want_rank, cudaStream_t st) {
+    if (d % 8) return ssg_set_error(SSG_ERR_INVALID, "tensor distance mode needs d %% 8 == 0 (d=%d)", d);
+    SSG_TRY(ensure_tensor_buffers(p));
+    const int k1p = k1 + 1;
+    const int k3 = 3 * d;
+    const float TENSOR_EPS_REL = tensor_eps_rel(d);
+    int* cnt_src = p->flagged + 1;
+    int* cnt_tgt = p->flagged + 2;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
+    { SSG_PROF("split_bf16x3", st); SSG_TRY(launch_split_bf16x3(d_tgt, n, d, 0, p->split_ta, p->norm_t, st)); }
+    { SSG_PROF("split_bf16x3", st); SSG_TRY(launch_split_bf16x3(d_tgt, n, d, 1, p->split_tb, nullptr, st)); }
+    { SSG_PROF("split_bf16x3", st); SSG_TRY(launch_split_bf16x3(d_src, ns, d, 1, p->split_sb, p->norm_s, st)); }
+    SSG_TRY(launch_vec_max(p->norm_t, n, p->norm_max, st));
+    SSG_TRY(launch_vec_max(p->norm_s, ns, p->norm_max + 1, st));
+    const char* ta = (const char*)p->split_ta;
+    // (i) source term: row minimum over the sources
+    {
+        const int rows_blk = (int)(p->dmat_elems / (size_t)ns < (size_t)n ? p->dmat_elems / (size_t)ns : (size_t)n);
+        const int ke = ns < CAND_EXT ? ns : CAND_EXT;
+        for (int r0 = 0; r0 < n; r0 += rows_blk) {
+            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+            { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_sb, p->norm_s, ns, k3,
+                                     p->dmat, (size_t)ns, st)); }
+            { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)ns, rows, ns, nullptr, ke, false, p->cand_idx, p->cand_val,
+                                      CAND_STRIDE, st)); }
+            { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_src, d, p->cand_idx, CAND_STRIDE, nullptr, ke,
+                                      p->cand_exact, CAND_STRIDE, st)); }
+            { SSG_PROF("cand_reduce", st); SSG_TRY(launch_cand_reduce(rows, ns, ke, false, p->cand_exact, p->cand_val, CAND_STRIDE, p->norm_t + r0,
+                                       p->norm_max + 1, TENSOR_EPS_REL, p->rowmin + r0, cnt_src, p->flag_src, r0, st)); }
+        }
+    }
+    // (ii)-(iv) target-target distances: row maximum and the leading rank columns
+    {
+        const int rows_blk = (int)(p->dmat_elems / (size_t)n < (size_t)n ? p->dmat_elems / (size_t)n : (size_t)n);
+        const int ke = n < CAND_EXT ? n : CAND_EXT;
+        const int kc = n < CAND_K ? n : CAND_K;
+        for (int r0 = 0; r0 < n; r0 += rows_blk) {
+            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+            { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_tb, p->norm_t, n, k3,
+                                     p->dmat, (size_t)n, st)); }
+            { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, nullptr, ke, true, p->cand_idx, p->cand_val,
+                                      CAND_STRIDE, st)); }
+            { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_tgt, d, p->cand_idx, CAND_STRIDE, nullptr, ke,
+                                      p->cand_exact, CAND_STRIDE, st)); }
+            { SSG_PROF("cand_reduce", st); SSG_TRY(launch_cand_reduce(rows, n, ke, true, p->cand_exact, p->cand_val, CAND_STRIDE, p->norm_t + r0,
+                                       p->norm_max, TENSOR_EPS_REL, p->rowmax + r0, cnt_tgt, p->flag_tgt, r0, st)); }
+            if (want_rank) {
+                { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, nullptr, kc, false, p->cand_idx, p->cand_val,
+                                          CAND_STRIDE, st)); }
+                { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_tgt, d, p->cand_idx, CAND_STRIDE, nullptr,
+                                          kc, p->cand_exact, CAND_STRIDE, st)); }
+                { SSG_PROF("rank_finalize", st); SSG_TRY(launch_rank_finalize(rows, n, kc, k1p < kc ? k1p : kc, p->cand_idx, p->cand_val,
+                                             p->cand_exact, CAND_STRIDE, p->rowmax + r0, p->norm_t + r0, p->norm_max,
+                                             TENSOR_EPS_REL, p->rank + (size_t)r0 * SSG_RANK_STRIDE,
+                                             p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, cnt_tgt, p->flag_tgt, r0, st)); }
+            }
+            if (d_euclid)
+                SSG_CUDA_TRY(cudaMemcpyAsync(d_euclid + (size_t)r0 * n, p->dmat, sizeof(float) * (size_t)rows * n,
+                                             cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    // exact fallback for the flagged rows
+    int h_flags[4];
+    SSG_CUDA_TRY(cudaMemcpyAsync(h_flags, p->flagged, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    const int nsrc = h_flags[1], ntgt = h_flags[2];
+    for (int f0 = 0; f0 < nsrc; f0 += FB_ROWS) {
+        int cnt = nsrc - f0 < FB_ROWS ? nsrc - f0 : FB_ROWS;
+        const int cap = (int)(p->dmat_elems / (size_t)ns);
+        if (cnt > cap) cnt = cap;
+        SSG_TRY(launch_gather_rows(d_tgt, d, p->flag_src + f0, cnt, p->fb_rows, st));
+        { SSG_PROF("sqdist_exact", st); SSG_TRY(launch_sqdist_exact(p->fb_rows, cnt, d_src, ns, d, p->dmat, (size_t)ns, st)); }
+        { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)ns, cnt, ns, p->fb_f32, nullptr, st)); }
+        SSG_TRY(launch_scatter_f32(p->fb_f32, cnt, 1, 1, p->flag_src + f0, p->rowmin, 1, st));
+        if (cnt < FB_ROWS && f0 + cnt < nsrc) f0 -= (FB_ROWS - cnt);   // capacity-limited batch: continue after it
+    }
+    for (int f0 = 0; f0 < ntgt; f0 += FB_ROWS) {
+        int cnt = ntgt - f0 < FB_ROWS ? ntgt - f0 : FB_ROWS;
+        const int cap = (int)(p->dmat_elems / (size_t)n);
+        if (cnt > cap) cnt = cap;
+        SSG_TRY(launch_gather_rows(d_tgt, d, p->flag_tgt + f0, cnt, p->fb_rows, st));
+        { SSG_PROF("sqdist_exact", st); SSG_TRY(launch_sqdist_exact(p->fb_rows, cnt, d_tgt, n, d, p->dmat, (size_t)n, st)); }
+        float* fmax = p->cand_val;   // reuse: [cnt] exact row maxima
+        { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, cnt, n, nullptr, fmax, st)); }
+        SSG_TRY(launch_scatter_f32(fmax, cnt, 1, 1, p->flag_tgt + f0, p->rowmax, 1, st));
+        if (want_rank) {
+            { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, cnt, n, fmax, k1p, false, p->fb_i32, p->fb_f32,
+                                      SSG_RANK_STRIDE, st)); }
+            SSG_TRY(launch_scatter_f32((const float*)p->fb_i32, cnt, k1p, SSG_RANK_STRIDE, p->flag_tgt + f0,
+                                       (float*)p->rank, SSG_RANK_STRIDE, st));
+            SSG_TRY(launch_scatter_f32(p->fb_f32, cnt, k1p, SSG_RANK_STRIDE, p->flag_tgt + f0, p->rank_val,
+                                       SSG_RANK_STRIDE, st));
+        }
+        if (d_euclid)   // exact rows replace the approximate ones
+            SSG_TRY(launch_scatter_f32(p->dmat, cnt, n, n, p->flag_tgt + f0, d_euclid, n, st));
+        if (cnt < FB_ROWS && f0 + cnt < ntgt) f0 -= (FB_ROWS - cnt);
+    }
+    h_flags[0] = nsrc + ntgt;
+    SSG_CUDA_TRY(cudaMemcpyAsync(p->flagged, h_flags, sizeof(int), cudaMemcpyHostToDevice, st));
+    { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
+    return SSG_OK;
+}
+
 // stages (i)-(iv): source vector, squared distance, row normaliser, leading k1+1 rank columns
-static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+static int distance_stages_exact(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
                            int k1, int dist_mode, float* d_euclid, bool want_rank, cudaStream_t st) {
     const int k1p = k1 + 1;
     // (i) rerank.py:36-40
@@ -156,28 +308,37 @@ static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const
         const int rows_blk = (int)(p->dmat_elems / (size_t)ns < (size_t)n ? p->dmat_elems / (size_t)ns : (size_t)n);
         for (int r0 = 0; r0 < n; r0 += rows_blk) {
             const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
-            SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_src, ns, d, dist_mode, st));
-            SSG_TRY(launch_row_minmax(p->dmat, (size_t)ns, rows, ns, p->rowmin + r0, nullptr, st));
+            { SSG_PROF("sqdist_exact", st); SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_src, ns, d, dist_mode, st)); }
+            { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)ns, rows, ns, p->rowmin + r0, nullptr, st)); }
         }
-        SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st));
+        { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
     }
     // (ii)-(iv) rerank.py:61-70
     {
         const int rows_blk = (int)(p->dmat_elems / (size_t)n < (size_t)n ? p->dmat_elems / (size_t)n : (size_t)n);
         for (int r0 = 0; r0 < n; r0 += rows_blk) {
             const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
-            SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_tgt, n, d, dist_mode, st));
-            SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, rows, n, nullptr, p->rowmax + r0, st));
+            { SSG_PROF("sqdist_exact", st); SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_tgt, n, d, dist_mode, st)); }
+            { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, rows, n, nullptr, p->rowmax + r0, st)); }
             if (want_rank)
-                SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, p->rowmax + r0, k1p, false,
+                { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, p->rowmax + r0, k1p, false,
                                           p->rank + (size_t)r0 * SSG_RANK_STRIDE,
-                                          p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, SSG_RANK_STRIDE, st));
+                                          p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, SSG_RANK_STRIDE, st)); }
             if (d_euclid)
                 SSG_CUDA_TRY(cudaMemcpyAsync(d_euclid + (size_t)r0 * n, p->dmat, sizeof(float) * (size_t)rows * n,
                                              cudaMemcpyDeviceToDevice, st));
         }
     }
     return SSG_OK;
+}
+
+static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                           int k1, int dist_mode, float* d_euclid, bool want_rank, cudaStream_t st) {
+    if (dist_mode == SSG_DIST_EXACT)
+        return distance_stages_exact(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, want_rank, st);
+    if (dist_mode == SSG_DIST_TENSOR)
+        return distance_stages_tensor(p, d_src, ns, d_tgt, n, d, k1, d_euclid, want_rank, st);
+    return ssg_set_error(SSG_ERR_INVALID, "rerank: unknown dist_mode %d", dist_mode);
 }
 
 extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
@@ -192,12 +353,12 @@ extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, co
     SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
     SSG_TRY(distance_stages(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, true, st));
     // (v) rerank.py:74-92
-    SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st));
-    SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, p->v_idx, SSG_V_STRIDE, p->v_cnt, 0, p->v_val, SSG_V_STRIDE, st));
-    SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st));
+    { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
+    { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, p->v_idx, SSG_V_STRIDE, p->v_cnt, 0, p->v_val, SSG_V_STRIDE, st)); }
+    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st)); }
     // (vi) rerank.py:94-98  (k2 == 1: V is used as it is)
     if (k2 != 1) {
-        SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st));
+        { SSG_PROF("query_expand", st); SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st)); }
     } else {
         SSG_CUDA_TRY(cudaMemcpy2DAsync(p->q_idx, sizeof(int) * SSG_VQ_STRIDE, p->v_idx, sizeof(int) * SSG_V_STRIDE,
                                        sizeof(int) * SSG_V_STRIDE, n, cudaMemcpyDeviceToDevice, st));
@@ -206,9 +367,9 @@ extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, co
         SSG_CUDA_TRY(cudaMemcpyAsync(p->q_cnt, p->v_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
     }
     // (vii)-(viii) rerank.py:101-122
-    SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st));
-    SSG_TRY(launch_jaccard_final(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
-                                 d_final, st));
+    { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
+    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
+                                 d_final, st)); }
     p->last_n = n;
     return SSG_OK;
 }

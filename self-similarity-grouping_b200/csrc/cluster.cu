@@ -199,12 +199,12 @@ static int eps_run(ssg_cluster_plan* p, const T* D, int n, double rho, cudaStrea
     SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
     const int grid = (n + 1) / 2;
     for (int pass = 0; pass < 6; ++pass) {
-        eps_hist_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, pass, p->state, p->hist);
+        { SSG_PROF("eps_hist", st); eps_hist_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, pass, p->state, p->hist); }
         SSG_CHECK_LAUNCH();
         eps_pick_kernel<<<1, 1024, 0, st>>>(p->hist, p->state, pass, rho);
         SSG_CHECK_LAUNCH();
     }
-    eps_sum_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, p->state, p->partial);
+    { SSG_PROF("eps_sum", st); eps_sum_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, p->state, p->partial); }
     SSG_CHECK_LAUNCH();
     eps_final_kernel<<<1, 1024, 0, st>>>(p->partial, grid, p->state, p->eps_out);
     SSG_CHECK_LAUNCH();
@@ -327,14 +327,15 @@ template <typename T>
 static int dbscan_run(ssg_cluster_plan* p, const T* D, int n, double eps, int min_samples,
                       int64_t* labels, cudaStream_t st) {
     SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
-    db_count_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->cnt);
+    { SSG_PROF("dbscan_count", st); db_count_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->cnt); }
     SSG_CHECK_LAUNCH();
     SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
-    db_fill_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags);
+    { SSG_PROF("dbscan_fill", st); db_fill_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags); }
     SSG_CHECK_LAUNCH();
     db_init_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(n, p->cnt, min_samples, p->parent, p->core);
     SSG_CHECK_LAUNCH();
     const int wgrid = ssg_cdiv(n, DB_NT / 32);
+    SSG_PROF("dbscan_label", st);
     db_union_kernel<<<wgrid, DB_NT, 0, st>>>(n, p->rowptr, p->nbr, p->core, p->parent);
     SSG_CHECK_LAUNCH();
     db_flatten_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(n, p->core, p->parent, p->isroot);

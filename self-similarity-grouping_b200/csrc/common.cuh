@@ -25,6 +25,18 @@ int ssg_set_error(int code, const char* fmt, ...);
 
 #define SSG_CHECK_LAUNCH() SSG_CUDA_TRY(cudaGetLastError())
 
+namespace ssg {
+// RAII CUDA-event timer around a group of launches on one stream (no-op unless ssg_profile_enable(1)).
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t st);
+    ~ProfScope();
+    const char* name_;
+    cudaStream_t st_;
+    void* e0_;
+};
+}  // namespace ssg
+#define SSG_PROF(name, st) ssg::ProfScope prof_scope__(name, st)
+
 static inline int ssg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__

@@ -1,0 +1,386 @@
+// ResNet-50 trunk building blocks (reid/models/resnet.py:86-134 with torchvision's Bottleneck graph):
+// every convolution runs on the tcgen05 GEMM of gemm_tc.cuh — 1x1 as a plain GEMM over NHWC pixels, 3x3 as an
+// implicit GEMM whose A tiles are shifted TMA boxes (halo zero-filled by TMA), stride-2 through parity planes —
+// with eval-mode BatchNorm folded into the bf16 weights and bias/residual/ReLU fused in the epilogue.
+// The rest are small HBM-bound helpers: weight folding, stem im2col, max-pool, parity split, pooled tail.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "gemm_tc.cuh"
+#include "conv.h"
+
+namespace ssg {
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue: out[row, col] = bf16( relu?( acc + bias[col] (+ residual[row, col]) ) ), NHWC ([M, Cout] row-major)
+// ---------------------------------------------------------------------------------------------------
+struct EpiConv {
+    const float* bias;            // [Cout]
+    const __nv_bfloat16* res;     // [M, Cout] or nullptr
+    __nv_bfloat16* out;           // [M, Cout]
+    int ldc;                      // Cout
+    int relu;
+    __device__ __forceinline__ void operator()(int row, int col0, int ncols, const uint32_t (&acc)[32]) const {
+        // ncols is always 32 here (Cout % 64 == 0)
+        __nv_bfloat16* o = out + (size_t)row * ldc + col0;
+        const __nv_bfloat16* r = res ? res + (size_t)row * ldc + col0 : nullptr;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // 8 channels (16 bytes of bf16) per iteration
+            float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + 8 * q);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + 8 * q + 4);
+            v[0] = __uint_as_float(acc[8 * q + 0]) + b0.x; v[1] = __uint_as_float(acc[8 * q + 1]) + b0.y;
+            v[2] = __uint_as_float(acc[8 * q + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * q + 3]) + b0.w;
+            v[4] = __uint_as_float(acc[8 * q + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * q + 5]) + b1.y;
+            v[6] = __uint_as_float(acc[8 * q + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * q + 7]) + b1.w;
+            if (r) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(r + 8 * q);
+                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(rp[e]);
+                    v[2 * e] += f.x;
+                    v[2 * e + 1] += f.y;
+                }
+            }
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            uint4 pk;
+            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            *reinterpret_cast<uint4*>(o + 8 * q) = pk;
+        }
+    }
+};
+
+static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, int k, const EpiConv& epi,
+                         cudaStream_t st) {
+    if (cout % 128 == 0) return tc::launch_gemm_op<128, EpiConv>(A, m, w, cout, k, epi, st);
+    if (cout % 64 == 0) return tc::launch_gemm_op<64, EpiConv>(A, m, w, cout, k, epi, st);
+    return ssg_set_error(SSG_ERR_INVALID, "conv: Cout=%d must be a multiple of 64", cout);
+}
+
+// 1x1 convolution (or any [M,K] x [Cout,K]^T product) on NHWC pixels.
+int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int cout, const void* residual,
+            int relu, void* y, cudaStream_t st) {
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 0;
+    A.cblks = cin / tc::BK;
+    A.taps = 1;
+    A.tiles_per_img = 1;
+    SSG_TRY(make_tmap_2d_bf16(&A.map[0], x, (uint64_t)m, (uint64_t)cin, (uint64_t)cin, tc::BM));
+    EpiConv epi{bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, cout, relu};
+    return gemm_dispatch(A, m, w, cout, cin, epi, st);
+}
+
+// tile geometry of a 128-pixel M tile on an [H, W] output map (W divides 128, H*W multiple or divisor of 128)
+static int tile_geometry(int H, int W, int* bw, int* bh, int* bb, int* tiles_per_img) {
+    if (W <= 0 || 128 % W) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: width %d does not divide 128", W);
+    *bw = W;
+    if (H * W >= 128) {
+        if ((H * W) % 128) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: map %dx%d not tileable", H, W);
+        *bh = 128 / W; *bb = 1; *tiles_per_img = H * W / 128;
+    } else {
+        if (128 % (H * W)) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: map %dx%d not tileable", H, W);
+        *bh = H; *bb = 128 / (H * W); *tiles_per_img = 1;
+    }
+    return SSG_OK;
+}
+
+// 3x3 convolution, padding 1.  stride 1: x is [B,H,W,C] NHWC.  stride 2: x points to the four parity planes
+// [4][B,H/2,W/2,C] produced by parity_split (plane = (h&1)*2 + (w&1)); H, W are the OUTPUT map size either way.
+int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout,
+            int relu, void* y, cudaStream_t st) {
+    if (cin % 64) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: Cin=%d must be a multiple of 64", cin);
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 1;
+    A.cblks = cin / tc::BK;
+    A.taps = 9;
+    int bw;
+    SSG_TRY(tile_geometry(H, W, &bw, &A.bh, &A.bb, &A.tiles_per_img));
+    const size_t plane_elems = (size_t)B * H * W * cin;
+    const int nplanes = stride == 2 ? 4 : 1;
+    for (int pl = 0; pl < nplanes; ++pl)
+        SSG_TRY(make_tmap_nhwc_bf16(&A.map[pl], (const __nv_bfloat16*)x + pl * plane_elems, B, H, W, cin, bw,
+                                    A.bh, A.bb));
+    for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) {
+            const int t = kh * 3 + kw;
+            if (stride == 1) {
+                A.tap_plane[t] = 0; A.tap_dh[t] = (signed char)(kh - 1); A.tap_dw[t] = (signed char)(kw - 1);
+            } else {
+                // input row 2h+kh-1: kh=0 -> odd plane, h-1; kh=1 -> even plane, h; kh=2 -> odd plane, h
+                const int ph = kh == 1 ? 0 : 1, pw = kw == 1 ? 0 : 1;
+                A.tap_plane[t] = (signed char)(ph * 2 + pw);
+                A.tap_dh[t] = (signed char)(kh == 0 ? -1 : 0);
+                A.tap_dw[t] = (signed char)(kw == 0 ? -1 : 0);
+            }
+        }
+    const int m = B * H * W;
+    EpiConv epi{bias, nullptr, (__nv_bfloat16*)y, cout, relu};
+    return gemm_dispatch(A, m, w, cout, 9 * cin, epi, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight ingest: fold eval-mode BatchNorm into the convolution (torch: y = (conv(x) - mean)/sqrt(var+eps)*g + b)
+//   w'[co][kh][kw][ci] = bf16( w[co][ci][kh][kw] * g/sqrt(var+eps) ),  bias'[co] = b - mean*g/sqrt(var+eps)
+// K is padded with zeros up to kpad (stem: 147 -> 192).
+// ---------------------------------------------------------------------------------------------------
+__global__ void fold_bn_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int kpad,
+                               __nv_bfloat16* __restrict__ wout, float* __restrict__ bout) {
+    const int co = blockIdx.x;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    if (threadIdx.x == 0) bout[co] = beta[co] - mean[co] * scale;
+    const int kk = kh * kw * cin;
+    for (int k = threadIdx.x; k < kpad; k += blockDim.x) {
+        float v = 0.f;
+        if (k < kk) {
+            const int ci = k % cin, t = k / cin, x = t % kw, y = t / kw;
+            v = w[(((size_t)co * cin + ci) * kh + y) * kw + x] * scale;
+        }
+        wout[(size_t)co * kpad + k] = __float2bfloat16_rn(v);
+    }
+}
+
+int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
+            const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st) {
+    fold_bn_kernel<<<cout, 256, 0, st>>>(w, cout, cin, kh, kw, gamma, beta, mean, var, eps, kpad,
+                                         (__nv_bfloat16*)wout, bout);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stem im2col: fp32 NCHW images [n,3,256,128] -> bf16 [2n*128*64, 192] patches of the 7x7 stride-2 pad-3 conv
+// (K order (kh, kw, ci), zero padded 147 -> 192).  Rows [0, n*8192) are the images, rows [n*8192, 2n*8192) the
+// horizontally flipped images (reid/evaluators.py:12-16 fliplr folded into the load index).
+// One CTA per output row segment: (image, oh) -> 64 output pixels x 192.
+// ---------------------------------------------------------------------------------------------------
+constexpr int STEM_K = 147, STEM_KPAD = 192;
+
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bfloat16* __restrict__ out) {
+    constexpr int H = 256, W = 128, OW = 64, OH = 128;
+    __shared__ float rows[3][7][W + 6];            // 7 input rows x 3 channels, with the 3-pixel halo
+    const int oh = blockIdx.x % OH;
+    const int im = blockIdx.x / OH;                // 0 .. (flip_too ? 2n : n)
+    const bool flipped = im >= n;
+    const int src = flipped ? im - n : im;
+    const float* base = img + (size_t)src * 3 * H * W;
+    for (int e = threadIdx.x; e < 3 * 7 * (W + 6); e += 256) {
+        const int xw = e % (W + 6), t = e / (W + 6), ky = t % 7, c = t / 7;
+        const int ih = oh * 2 - 3 + ky, iw = xw - 3;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = base[((size_t)c * H + ih) * W + (flipped ? W - 1 - iw : iw)];
+        rows[c][ky][xw] = v;
+    }
+    __syncthreads();
+    __nv_bfloat16* orow = out + ((size_t)im * OH + oh) * OW * STEM_KPAD;
+    for (int e = threadIdx.x; e < OW * (STEM_KPAD / 2); e += 256) {
+        const int kp = e % (STEM_KPAD / 2), ow = e / (STEM_KPAD / 2);
+        float v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = kp * 2 + h;
+            float val = 0.f;
+            if (k < STEM_K) {
+                const int c = k % 3, t = k / 3, kx = t % 7, ky = t / 7;
+                val = rows[c][ky][ow * 2 + kx];
+            }
+            v[h] = val;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)ow * STEM_KPAD + kp * 2) = __floats2bfloat162_rn(v[0], v[1]);
+    }
+}
+
+int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st) {
+    const int images = flip_too ? 2 * n : n;
+    stem_im2col_kernel<<<images * 128, 256, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 pad 1 on NHWC bf16: [B,H,W,C] -> [B,H/2,W/2,C]; 8 channels (16 bytes) per thread
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    const int OH = H / 2, OW = W / 2, CV = C / 8;
+    const size_t total = (size_t)B * OH * OW * CV;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(e % CV);
+        size_t t = e / CV;
+        const int ow = (int)(t % OW); t /= OW;
+        const int oh = (int)(t % OH);
+        const int b = (int)(t / OH);
+        float m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ih = oh * 2 - 1 + ky;
+            if (ih < 0 || ih >= H) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iw = ow * 2 - 1 + kx;
+                if (iw < 0 || iw >= W) continue;
+                const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cv * 8);
+                const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(p[q]);
+                    m[2 * q] = fmaxf(m[2 * q], f.x);
+                    m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
+                }
+            }
+        }
+        uint4 o;
+        __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) po[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
+        *reinterpret_cast<uint4*>(y + (((size_t)b * OH + oh) * OW + ow) * C + cv * 8) = o;
+    }
+}
+
+int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st) {
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8);
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    maxpool3x3s2_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, (__nv_bfloat16*)y);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// parity split for the stride-2 convolutions: x [B,H,W,C] -> planes [P][B,H/2,W/2,C], plane = (h&1)*2 + (w&1);
+// nplanes = 1 keeps only the (even, even) plane (the 1x1 stride-2 downsample branch).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+parity_split_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, int nplanes,
+                    __nv_bfloat16* __restrict__ y) {
+    const int OH = H / 2, OW = W / 2, CV = C / 8;
+    const size_t plane = (size_t)B * OH * OW * CV;
+    const size_t total = plane * nplanes;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int pl = (int)(e / plane);
+        size_t t = e % plane;
+        const int cv = (int)(t % CV); t /= CV;
+        const int ow = (int)(t % OW); t /= OW;
+        const int oh = (int)(t % OH);
+        const int b = (int)(t / OH);
+        const int ih = oh * 2 + (pl >> 1), iw = ow * 2 + (pl & 1);
+        reinterpret_cast<uint4*>(y)[e] =
+            *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cv * 8);
+    }
+}
+
+int parity_split(const void* x, int B, int H, int W, int C, int nplanes, void* y, cudaStream_t st) {
+    const size_t total = (size_t)B * (H / 2) * (W / 2) * (C / 8) * nplanes;
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    parity_split_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, nplanes, (__nv_bfloat16*)y);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pooled tail (resnet.py:93-111 + evaluators.py:29-46): layer4 map [2n,8,4,2048] (images then flipped images)
+//   bank 0 = global average, bank 1+s = average of rows [h//S*s, h//S*(s+1)) (S = num_split > 1);
+//   out = pool(img) + pool(flipped img); list mode: each bank / its own L2 norm -> feat[bank][row0+i][2048];
+//   eval mode: one norm over the concatenated banks -> feat[row0+i][(S+1)*2048].
+// One CTA per image, 256 threads x 8 channels.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pooled_tail_kernel(const __nv_bfloat16* __restrict__ x, int n, int num_split, int eval_mode, int flip_too,
+                   float* __restrict__ feat, size_t bank_stride, int row0) {
+    constexpr int H = 8, W = 4, C = 2048;
+    const int i = blockIdx.x;
+    const int c0 = threadIdx.x * 8;
+    const int nb = num_split > 1 ? num_split + 1 : 1;
+    const int step = num_split > 1 ? H / num_split : H;
+    float acc[5][8];
+#pragma unroll
+    for (int b = 0; b < 5; ++b)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[b][q] = 0.f;
+    // avg_pool2d = sum / area in float32; (pool(a) + pool(b)) as the reference adds the two passes
+    for (int pass = 0; pass < (flip_too ? 2 : 1); ++pass) {
+        const __nv_bfloat16* img = x + ((size_t)(pass * n + i) * H * W) * C + c0;
+        float g[8], s[4][8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { g[q] = 0.f; s[0][q] = s[1][q] = s[2][q] = s[3][q] = 0.f; }
+        for (int h = 0; h < H; ++h) {
+            float r[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = 0.f;
+            for (int w = 0; w < W; ++w) {
+                const uint4 v = *reinterpret_cast<const uint4*>(img + ((size_t)h * W + w) * C);
+                const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __bfloat1622float2(p[q]);
+                    r[2 * q] += f.x;
+                    r[2 * q + 1] += f.y;
+                }
+            }
+            const int sb = h / step;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                g[q] += r[q];
+                if (num_split > 1 && sb < num_split && sb < 4) s[sb][q] += r[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            acc[0][q] += g[q] / (float)(H * W);
+            for (int b = 1; b < nb; ++b) acc[b][q] += s[b - 1][q] / (float)(step * W);
+        }
+    }
+    // L2 norms
+    __shared__ float red[5][8];
+    float ss[5];
+    for (int b = 0; b < nb; ++b) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += acc[b][q] * acc[b][q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        ss[b] = t;
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int b = 0; b < nb; ++b) red[b][threadIdx.x >> 5] = ss[b];
+    __syncthreads();
+    float norm[5], all = 0.f;
+    for (int b = 0; b < nb; ++b) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[b][w];
+        all += t;
+        norm[b] = sqrtf(t);
+    }
+    const float norm_all = sqrtf(all);
+    for (int b = 0; b < nb; ++b) {
+        float* o = eval_mode ? feat + ((size_t)(row0 + i) * nb + b) * C + c0
+                             : feat + (size_t)b * bank_stride + (size_t)(row0 + i) * C + c0;
+        const float dv = eval_mode ? norm_all : norm[b];
+        float4 o0, o1;
+        o0.x = acc[b][0] / dv; o0.y = acc[b][1] / dv; o0.z = acc[b][2] / dv; o0.w = acc[b][3] / dv;
+        o1.x = acc[b][4] / dv; o1.y = acc[b][5] / dv; o1.z = acc[b][6] / dv; o1.w = acc[b][7] / dv;
+        *reinterpret_cast<float4*>(o) = o0;
+        *reinterpret_cast<float4*>(o + 4) = o1;
+    }
+}
+
+int pooled_tail(const void* x, int n, int num_split, int eval_mode, int flip_too, float* feat, size_t bank_stride,
+                int row0, cudaStream_t st) {
+    if (num_split < 1 || num_split > 4) return ssg_set_error(SSG_ERR_INVALID, "num_split=%d out of range", num_split);
+    pooled_tail_kernel<<<n, 256, 0, st>>>((const __nv_bfloat16*)x, n, num_split, eval_mode, flip_too, feat, bank_stride,
+                                          row0);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // namespace ssg

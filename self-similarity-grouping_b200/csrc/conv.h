@@ -1,0 +1,18 @@
+// Convolution-path launchers (conv.cu), used by embed.cu.  All activations are NHWC bf16 on the device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ssg {
+int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int cout, const void* residual,
+            int relu, void* y, cudaStream_t st);
+int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout,
+            int relu, void* y, cudaStream_t st);
+int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
+            const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st);
+int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);
+int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st);
+int parity_split(const void* x, int B, int H, int W, int C, int nplanes, void* y, cudaStream_t st);
+int pooled_tail(const void* x, int n, int num_split, int eval_mode, int flip_too, float* feat, size_t bank_stride,
+                int row0, cudaStream_t st);
+}  // namespace ssg

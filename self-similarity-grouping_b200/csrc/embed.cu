@@ -1,0 +1,247 @@
+// Embedding plan: the ResNet-50 trunk of reid/models/resnet.py:86-111 (torchvision Bottleneck graph, stride on
+// the 3x3 conv) + flip test-time augmentation and L2 normalisation of reid/evaluators.py:18-60, as one
+// device-resident forward over a batch of images.  Weights are ingested from the live torch module's
+// state_dict (BatchNorm folded, bf16, [Cout][kh][kw][Cin]); activations are NHWC bf16, accumulation fp32.
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "common.cuh"
+#include "conv.h"
+
+using namespace ssg;
+
+namespace {
+struct LayerSpec {
+    int cin, cout, k, stride;
+    char conv_key[48], bn_key[48];
+};
+
+// canonical layer order: stem, then per block conv1, conv2, conv3, [downsample]
+std::vector<LayerSpec> build_specs() {
+    std::vector<LayerSpec> v;
+    LayerSpec s{3, 64, 7, 2, "conv1", "bn1"};
+    v.push_back(s);
+    const int blocks[4] = {3, 4, 6, 3};
+    int cin = 64;
+    for (int L = 0; L < 4; ++L) {
+        const int mid = 64 << L, out = mid * 4;
+        for (int b = 0; b < blocks[L]; ++b) {
+            const int stride = (b == 0 && L > 0) ? 2 : 1;
+            LayerSpec c1{cin, mid, 1, 1, "", ""}, c2{mid, mid, 3, stride, "", ""}, c3{mid, out, 1, 1, "", ""};
+            snprintf(c1.conv_key, 48, "layer%d.%d.conv1", L + 1, b); snprintf(c1.bn_key, 48, "layer%d.%d.bn1", L + 1, b);
+            snprintf(c2.conv_key, 48, "layer%d.%d.conv2", L + 1, b); snprintf(c2.bn_key, 48, "layer%d.%d.bn2", L + 1, b);
+            snprintf(c3.conv_key, 48, "layer%d.%d.conv3", L + 1, b); snprintf(c3.bn_key, 48, "layer%d.%d.bn3", L + 1, b);
+            v.push_back(c1); v.push_back(c2); v.push_back(c3);
+            if (b == 0) {
+                LayerSpec ds{cin, out, 1, stride, "", ""};
+                snprintf(ds.conv_key, 48, "layer%d.%d.downsample.0", L + 1, b);
+                snprintf(ds.bn_key, 48, "layer%d.%d.downsample.1", L + 1, b);
+                v.push_back(ds);
+            }
+            cin = out;
+        }
+    }
+    return v;
+}
+const std::vector<LayerSpec>& specs() {
+    static std::vector<LayerSpec> s = build_specs();
+    return s;
+}
+int kpad_of(const LayerSpec& s) {
+    const int k = s.k * s.k * s.cin;
+    return (k + 63) / 64 * 64;
+}
+}  // namespace
+
+struct ssg_embed_plan {
+    int device, batch_max;
+    size_t bytes;
+    std::vector<void*> w;        // bf16 [cout, kpad]
+    std::vector<float*> b;       // fp32 [cout]
+    std::vector<char> loaded;
+    void *col, *stem, *x, *y, *ds, *t1, *t2, *planes, *xs;
+};
+
+static int ealloc(void** p, size_t bytes, size_t* total) {
+    SSG_CUDA_TRY(cudaMalloc(p, bytes ? bytes : 16));
+    *total += bytes;
+    return SSG_OK;
+}
+
+extern "C" int ssg_embed_num_layers(void) { return (int)specs().size(); }
+
+extern "C" int ssg_embed_layer_info(int idx, int* cin, int* cout, int* ksize, int* stride, char* conv_key,
+                                    char* bn_key, size_t cap) {
+    if (idx < 0 || idx >= (int)specs().size()) return ssg_set_error(SSG_ERR_INVALID, "layer index %d", idx);
+    const LayerSpec& s = specs()[idx];
+    if (cin) *cin = s.cin;
+    if (cout) *cout = s.cout;
+    if (ksize) *ksize = s.k;
+    if (stride) *stride = s.stride;
+    if (conv_key && cap) { strncpy(conv_key, s.conv_key, cap - 1); conv_key[cap - 1] = 0; }
+    if (bn_key && cap) { strncpy(bn_key, s.bn_key, cap - 1); bn_key[cap - 1] = 0; }
+    return SSG_OK;
+}
+
+extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
+    if (!p) return SSG_OK;
+    cudaSetDevice(p->device);
+    for (void* q : p->w) if (q) cudaFree(q);
+    for (float* q : p->b) if (q) cudaFree(q);
+    void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs};
+    for (void* q : bufs) if (q) cudaFree(q);
+    delete p;
+    return SSG_OK;
+}
+
+extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch_max, int height, int width) {
+    if (!out || batch_max <= 0) return ssg_set_error(SSG_ERR_INVALID, "embed_plan_create: bad arguments");
+    if (height != 256 || width != 128)
+        return ssg_set_error(SSG_ERR_UNSUPPORTED, "embed: only 256x128 inputs are supported (got %dx%d)", height, width);
+    SSG_CUDA_TRY(cudaSetDevice(device));
+    ssg_embed_plan* p = new ssg_embed_plan();
+    p->device = device; p->batch_max = batch_max; p->bytes = 0;
+    p->col = p->stem = p->x = p->y = p->ds = p->t1 = p->t2 = p->planes = p->xs = nullptr;
+    const auto& sp = specs();
+    p->w.assign(sp.size(), nullptr);
+    p->b.assign(sp.size(), nullptr);
+    p->loaded.assign(sp.size(), 0);
+    int rc = SSG_OK;
+    for (size_t i = 0; i < sp.size() && rc == SSG_OK; ++i) {
+        rc = ealloc(&p->w[i], (size_t)sp[i].cout * kpad_of(sp[i]) * 2, &p->bytes);
+        if (rc == SSG_OK) rc = ealloc((void**)&p->b[i], sizeof(float) * sp[i].cout, &p->bytes);
+    }
+    const size_t nb = (size_t)batch_max * 2;       // images + flipped images
+    const size_t px = 2;                           // bytes per bf16
+#define A(ptr, elems) if (rc == SSG_OK) rc = ealloc(&(ptr), (elems) * px, &p->bytes)
+    A(p->col, nb * 8192 * 192);
+    A(p->stem, nb * 8192 * 64);
+    A(p->x, nb * 2048 * 256);
+    A(p->y, nb * 2048 * 256);
+    A(p->ds, nb * 2048 * 256);
+    A(p->t1, nb * 2048 * 128);
+    A(p->t2, nb * 2048 * 64);
+    A(p->planes, nb * 2048 * 128);
+    A(p->xs, nb * 512 * 256);
+#undef A
+    if (rc != SSG_OK) { ssg_embed_plan_destroy(p); return rc; }
+    *out = p;
+    return SSG_OK;
+}
+
+extern "C" size_t ssg_embed_plan_bytes(const ssg_embed_plan* p) { return p ? p->bytes : 0; }
+
+extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w, const float* d_gamma,
+                                    const float* d_beta, const float* d_mean, const float* d_var, float eps,
+                                    void* stream) {
+    if (!p || idx < 0 || idx >= (int)specs().size() || !d_w || !d_gamma || !d_beta || !d_mean || !d_var)
+        return ssg_set_error(SSG_ERR_INVALID, "embed_load_layer: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    const LayerSpec& s = specs()[idx];
+    SSG_TRY(fold_bn(d_w, s.cout, s.cin, s.k, s.k, d_gamma, d_beta, d_mean, d_var, eps, kpad_of(s), p->w[idx],
+                    p->b[idx], (cudaStream_t)stream));
+    p->loaded[idx] = 1;
+    return SSG_OK;
+}
+
+extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n, int num_split, int eval_mode,
+                                 int flip, float* d_feat, size_t bank_stride, int row0, void* stream) {
+    if (!p || !d_images || !d_feat || n <= 0 || n > p->batch_max)
+        return ssg_set_error(SSG_ERR_INVALID, "embed_forward: bad arguments (n=%d, batch_max=%d)", n, p ? p->batch_max : -1);
+    for (size_t i = 0; i < p->loaded.size(); ++i)
+        if (!p->loaded[i]) return ssg_set_error(SSG_ERR_INVALID, "embed_forward: layer %zu (%s) not loaded", i, specs()[i].conv_key);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const auto& sp = specs();
+    const int NB = flip ? 2 * n : n;
+    int li = 0;
+    // stem: 7x7/2 conv as im2col + GEMM (K 147 -> 192), then 3x3/2 max-pool
+    { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
+    { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv1x1(p->col, NB * 8192, 192, p->w[0], p->b[0], 64, nullptr, 1, p->stem, st)); }
+    { SSG_PROF("maxpool", st); SSG_TRY(maxpool3x3s2(p->stem, NB, 128, 64, 64, p->x, st)); }
+    li = 1;
+    int H = 64, W = 32, C = 64;
+    void *x = p->x, *y = p->y;
+    const int blocks[4] = {3, 4, 6, 3};
+    for (int L = 0; L < 4; ++L) {
+        const int mid = 64 << L, outc = mid * 4;
+        for (int b = 0; b < blocks[L]; ++b) {
+            const int stride = (b == 0 && L > 0) ? 2 : 1;
+            const int OH = H / stride, OW = W / stride;
+            const int i1 = li, i2 = li + 1, i3 = li + 2, id = li + 3;
+            li += (b == 0) ? 4 : 3;
+            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
+            if (stride == 2) {
+                { SSG_PROF("parity_split", st); SSG_TRY(parity_split(p->t1, NB, H, W, mid, 4, p->planes, st)); }
+                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+            } else {
+                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, H, W, mid, 1, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+            }
+            const void* res = x;
+            if (b == 0) {
+                if (stride == 2) {
+                    { SSG_PROF("parity_split", st); SSG_TRY(parity_split(x, NB, H, W, C, 1, p->xs, st)); }
+                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->xs, NB * OH * OW, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
+                } else {
+                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
+                }
+                res = p->ds;
+            }
+            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->t2, NB * OH * OW, mid, p->w[i3], p->b[i3], outc, res, 1, y, st)); }
+            void* t = x; x = y; y = t;
+            H = OH; W = OW; C = outc;
+        }
+    }
+    (void)sp;
+    { SSG_PROF("pooled_tail", st); SSG_TRY(pooled_tail(x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, st)); }
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------- building blocks
+// The individual operators of the trunk, exported so that each can be parity-tested in isolation
+// (tests/test_gpu_embed.py) and reused by callers that bring their own graph.  NHWC bf16 activations.
+extern "C" int ssg_op_conv(const void* d_x, int B, int H, int W, int cin, int ksize, int stride, const void* d_w,
+                           const float* d_bias, int cout, const void* d_res, int relu, void* d_y, void* d_scratch,
+                           void* stream) {
+    if (!d_x || !d_w || !d_bias || !d_y || (stride != 1 && stride != 2) || (ksize != 1 && ksize != 3))
+        return ssg_set_error(SSG_ERR_INVALID, "op_conv: bad arguments");
+    if (stride == 2 && !d_scratch) return ssg_set_error(SSG_ERR_INVALID, "op_conv: stride 2 needs scratch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ksize == 1) {
+        if (stride == 1) return conv1x1(d_x, B * H * W, cin, d_w, d_bias, cout, d_res, relu, d_y, st);
+        SSG_TRY(parity_split(d_x, B, H, W, cin, 1, d_scratch, st));
+        return conv1x1(d_scratch, B * (H / 2) * (W / 2), cin, d_w, d_bias, cout, d_res, relu, d_y, st);
+    }
+    if (d_res) return ssg_set_error(SSG_ERR_INVALID, "op_conv: residual is only fused into 1x1 convolutions");
+    if (stride == 1) return conv3x3(d_x, B, H, W, cin, 1, d_w, d_bias, cout, relu, d_y, st);
+    SSG_TRY(parity_split(d_x, B, H, W, cin, 4, d_scratch, st));
+    return conv3x3(d_scratch, B, H / 2, W / 2, cin, 2, d_w, d_bias, cout, relu, d_y, st);
+}
+
+extern "C" int ssg_op_fold_bn(const float* d_w, int cout, int cin, int ksize, const float* d_gamma,
+                              const float* d_beta, const float* d_mean, const float* d_var, float eps, int kpad,
+                              void* d_wout, float* d_bout, void* stream) {
+    if (!d_w || !d_wout || !d_bout || kpad < ksize * ksize * cin)
+        return ssg_set_error(SSG_ERR_INVALID, "op_fold_bn: bad arguments");
+    return fold_bn(d_w, cout, cin, ksize, ksize, d_gamma, d_beta, d_mean, d_var, eps, kpad, d_wout, d_bout,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int ssg_op_stem(const float* d_images, int n, int flip, const void* d_w, const float* d_bias,
+                           void* d_col, void* d_conv_out, void* d_pool_out, void* stream) {
+    if (!d_images || !d_w || !d_bias || !d_col || !d_conv_out || n <= 0)
+        return ssg_set_error(SSG_ERR_INVALID, "op_stem: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int NB = flip ? 2 * n : n;
+    SSG_TRY(stem_im2col(d_images, n, flip, d_col, st));
+    SSG_TRY(conv1x1(d_col, NB * 8192, 192, d_w, d_bias, 64, nullptr, 1, d_conv_out, st));
+    if (d_pool_out) SSG_TRY(maxpool3x3s2(d_conv_out, NB, 128, 64, 64, d_pool_out, st));
+    return SSG_OK;
+}
+
+extern "C" int ssg_op_pooled_tail(const void* d_x, int n, int num_split, int eval_mode, int flip, float* d_feat,
+                                  size_t bank_stride, int row0, void* stream) {
+    if (!d_x || !d_feat || n <= 0) return ssg_set_error(SSG_ERR_INVALID, "op_pooled_tail: bad arguments");
+    return pooled_tail(d_x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, (cudaStream_t)stream);
+}

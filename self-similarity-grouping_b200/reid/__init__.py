@@ -1,0 +1,22 @@
+"""Drop-in ``reid`` package for the pseudo-label hot path of SHI-Labs/Self-Similarity-Grouping.
+
+Put ``self-similarity-grouping_b200/`` ahead of the reference on ``sys.path`` and the unmodified
+``selftraining.py`` picks up these modules for everything on the hot path:
+
+    from reid import models                                   -> reid/models (same factory, same module tree)
+    from reid.evaluators import Evaluator, extract_features   -> CUDA trunk (libssg_b200)
+    from sklearn.cluster import DBSCAN
+    from reid.rerank import *                                 -> CUDA re_ranking, and a CUDA ``DBSCAN`` that
+                                                                 shadows sklearn's in the driver's namespace
+
+Only the hot path lives here; datasets, trainers, losses and the evaluation metrics are the
+reference's own and out of scope.
+"""
+from . import feature_extraction  # noqa: F401
+from . import models  # noqa: F401
+from . import evaluators  # noqa: F401
+from . import rerank  # noqa: F401
+from . import rerank_initial  # noqa: F401
+from . import cluster  # noqa: F401
+
+__version__ = '0.2.0'

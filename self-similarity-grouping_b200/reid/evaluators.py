@@ -1,0 +1,66 @@
+"""Drop-in for reid/evaluators.py of the reference: extract_features (18-60), pairwise_distance (63-85),
+fliplr (12-16) and the Evaluator wrapper.  The CMC/mAP scoring of Evaluator.evaluate (evaluate_all, 88-133) is the
+reference's evaluation_metrics package — outside the pseudo-label hot path."""
+from collections import OrderedDict  # noqa: F401
+
+import torch
+
+from ssg_b200.embed import extract_features  # noqa: F401  (evaluators.py:18)
+
+
+def fliplr(img):
+    '''flip horizontal (evaluators.py:12-16)'''
+    inv_idx = torch.arange(img.size(3) - 1, -1, -1).long()
+    return img.index_select(3, inv_idx)
+
+
+def pairwise_distance(features, query=None, gallery=None, metric=None):
+    """evaluators.py:63-85.  Returns a CPU float32 tensor like the reference; the GEMM runs on the GPU."""
+    from ssg_b200 import _lib
+    dev = _lib.require_cuda()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        if query is None and gallery is None:
+            n = len(features)
+            x = torch.cat(list(features.values())).view(n, -1)
+            if metric is not None:
+                x = metric.transform(x)
+            x = x.to(dev)
+            dist = torch.pow(x, 2).sum(dim=1, keepdim=True) * 2
+            dist = dist.expand(n, n) - 2 * torch.mm(x, x.t())
+            return dist.cpu()
+        x = torch.cat([features[f].unsqueeze(0) for f, _, _ in query], 0)
+        y = torch.cat([features[f].unsqueeze(0) for f, _, _ in gallery], 0)
+        m, n = x.size(0), y.size(0)
+        x, y = x.view(m, -1), y.view(n, -1)
+        if metric is not None:
+            x, y = metric.transform(x), metric.transform(y)
+        x, y = x.to(dev), y.to(dev)
+        dist = torch.pow(x, 2).sum(dim=1, keepdim=True).expand(m, n) + \
+            torch.pow(y, 2).sum(dim=1, keepdim=True).expand(n, m).t()
+        dist = torch.addmm(dist, x, y.t(), beta=1, alpha=-2)
+        return dist.cpu()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+class Evaluator(object):
+    def __init__(self, model, print_freq):
+        super(Evaluator, self).__init__()
+        self.model = model
+        self.print_freq = print_freq
+
+    def distmat(self, data_loader, query, gallery, metric=None):
+        features, _ = extract_features(self.model, data_loader, print_freq=self.print_freq)
+        return pairwise_distance(features, query, gallery, metric=metric)
+
+    def evaluate(self, data_loader, query, gallery, metric=None):
+        distmat = self.distmat(data_loader, query, gallery, metric)
+        try:
+            from reid_reference_metrics import evaluate_all   # the reference's evaluation_metrics, if on the path
+        except ImportError:
+            raise NotImplementedError(
+                "Evaluator.evaluate: CMC/mAP scoring (reid/evaluation_metrics) is outside the pseudo-label hot "
+                "path; use Evaluator.distmat() and the reference's evaluate_all on the returned matrix")
+        return evaluate_all(distmat, query=query, gallery=gallery)

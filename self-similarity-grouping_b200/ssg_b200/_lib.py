@@ -42,6 +42,25 @@ PROTOTYPES = {
     "ssg_dbscan_core_mask": (c_int, [c_void_p, c_void_p, c_int]),
     "ssg_eps_estimate_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, P(c_double), P(c_ll)]),
     "ssg_dbscan_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, P(c_int)]),
+    "ssg_embed_num_layers": (c_int, []),
+    "ssg_embed_layer_info": (c_int, [c_int, P(c_int), P(c_int), P(c_int), P(c_int), ctypes.c_char_p, ctypes.c_char_p,
+                                     c_size_t]),
+    "ssg_embed_plan_create": (c_int, [P(c_void_p), c_int, c_int, c_int, c_int]),
+    "ssg_embed_plan_destroy": (c_int, [c_void_p]),
+    "ssg_embed_plan_bytes": (c_size_t, [c_void_p]),
+    "ssg_embed_load_layer": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     ctypes.c_float, c_void_p]),
+    "ssg_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ssg_op_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                            c_int, c_void_p, c_void_p, c_void_p]),
+    "ssg_op_fold_bn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                               c_int, c_void_p, c_void_p, c_void_p]),
+    "ssg_op_stem": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ssg_op_pooled_tail": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ssg_profile_enable": (c_int, [c_int]),
+    "ssg_profile_reset": (c_int, []),
+    "ssg_profile_collect": (c_int, []),
+    "ssg_profile_entry": (c_int, [c_int, ctypes.c_char_p, c_size_t, P(c_double), P(c_ll)]),
 }
 
 _lib = None
@@ -86,6 +105,24 @@ def require_cuda(device=None):
         raise SsgError("ssg_b200 needs a CUDA device (sm_100); there is no CPU fallback")
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
     return dev
+
+
+def profile(on=None, reset=False):
+    """Enable/disable the library's per-kernel CUDA-event timers; returns {name: (ms, launches)}."""
+    lib = load()
+    if reset:
+        lib.ssg_profile_reset()
+    if on is not None:
+        lib.ssg_profile_enable(int(bool(on)))
+        return {}
+    n = lib.ssg_profile_collect()
+    out = {}
+    buf = ctypes.create_string_buffer(64)
+    for i in range(n):
+        ms, cnt = c_double(), c_ll()
+        check(lib.ssg_profile_entry(i, buf, 64, ctypes.byref(ms), ctypes.byref(cnt)))
+        out[buf.value.decode()] = (ms.value, cnt.value)
+    return out
 
 
 def stream_ptr():
