@@ -74,6 +74,13 @@ int ssg_rerank_host(ssg_rerank_plan* plan, const float* h_src, int ns, const flo
                     int k1, int k2, double lambda_value, int dist_mode, int no_rerank, double* h_final,
                     float* h_euclid);
 
+/* reid/rerank_initial.py:40-99 re_ranking_init(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3) (also
+ * reid/rerank.py:171-234): float32 k-reciprocal re-ranking on precomputed SIMILARITY blocks (device, row-major
+ * [q,g], [q,q], [g,g]); d_out is [q,g] float32.  Needs (q+g) <= n_max of the plan.  Ties are ordered by index
+ * (the reference's argpartition leaves them unspecified). */
+int ssg_rerank_init(ssg_rerank_plan* plan, const float* d_qg, const float* d_qq, const float* d_gg, int q, int g,
+                    int k1, int k2, double lambda_value, float* d_out, void* stream);
+
 /* Intermediate results of the last ssg_rerank_run, copied to the host (stage-isolated parity tests). */
 #define SSG_STAGE_VEC 0       /* float  [n]        normalised source vector v (rerank.py:36-40)     */
 #define SSG_STAGE_ROWMAX 1    /* float  [n]        row maximum of the squared distance (rerank.py:68) */
@@ -126,7 +133,8 @@ int ssg_dbscan_host(ssg_cluster_plan* plan, const void* h_dist, int dtype, int n
  *   deliver them) -> per image the (num_split>1 ? num_split+1 : 1) pooled 2048-d banks of
  *   model(x) + model(fliplr(x)) (flip != 0), L2-normalised:
  *     eval_mode == 0 : d_feat[bank * bank_stride + (row0+i) * 2048 + c]      (each bank normalised alone)
- *     eval_mode != 0 : d_feat[((row0+i) * banks + bank) * 2048 + c]           (one norm over the concatenation)
+ *     eval_mode & 1  : d_feat[((row0+i) * banks + bank) * 2048 + c]           (one norm over the concatenation)
+ *     eval_mode & 2  : skip the L2 normalisation (raw pooled banks, what one model(x) call returns)
  *   Convolutions run in bf16 with fp32 accumulation on the tcgen05 tensor cores; eval-mode BatchNorm is
  *   folded into the weights when a layer is loaded.
  * Layers are indexed in a fixed order (stem, then conv1, conv2, conv3[, downsample] per bottleneck);

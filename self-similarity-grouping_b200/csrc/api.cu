@@ -413,6 +413,41 @@ extern "C" int ssg_rerank_host(ssg_rerank_plan* p, const float* h_src, int ns, c
     return SSG_OK;
 }
 
+// reid/rerank_initial.py:40-99 on precomputed similarity blocks (device float32, row-major).
+extern "C" int ssg_rerank_init(ssg_rerank_plan* p, const float* d_qg, const float* d_qq, const float* d_gg, int q,
+                               int g, int k1, int k2, double lambda_value, float* d_out, void* stream) {
+    if (!p || !d_qg || !d_qq || !d_gg || !d_out || q <= 0 || g <= 0)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_init: bad arguments");
+    const int n = q + g;
+    if (n > p->n_max || (size_t)n * n > p->dmat_elems)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_init: q+g=%d exceeds the plan (n_max=%d)", n, p->n_max);
+    if (k1 < 1 || k1 > 31 || k2 < 1 || k2 > 8) return ssg_set_error(SSG_ERR_INVALID, "rerank_init: k1/k2 out of range");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k1p = k1 + 1, khp = (int)rint(k1 / 2.0) + 1;
+    { SSG_PROF("init_assemble", st); SSG_TRY(launch_init_assemble(d_qg, d_qq, d_gg, q, g, p->dmat, st)); }
+    { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, n, n, nullptr, p->rowmax, st)); }
+    { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, n, n, p->rowmax, k1p, false, p->rank, p->rank_val,
+                                      SSG_RANK_STRIDE, st)); }
+    { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
+    SSG_TRY(launch_gather_row_vals(p->dmat, (size_t)n, n, p->v_idx, p->v_cnt, SSG_V_STRIDE, p->v_val, st));
+    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st)); }
+    if (k2 != 1) {
+        { SSG_PROF("query_expand", st); SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st)); }
+    } else {
+        SSG_CUDA_TRY(cudaMemcpy2DAsync(p->q_idx, sizeof(int) * SSG_VQ_STRIDE, p->v_idx, sizeof(int) * SSG_V_STRIDE,
+                                       sizeof(int) * SSG_V_STRIDE, n, cudaMemcpyDeviceToDevice, st));
+        SSG_CUDA_TRY(cudaMemcpy2DAsync(p->q_val, sizeof(float) * SSG_VQ_STRIDE, p->v_val, sizeof(float) * SSG_V_STRIDE,
+                                       sizeof(float) * SSG_V_STRIDE, n, cudaMemcpyDeviceToDevice, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(p->q_cnt, p->v_cnt, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
+    { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
+    { SSG_PROF("jaccard_init", st); SSG_TRY(launch_jaccard_init(n, q, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->dmat, p->rowmax,
+                                        lambda_value, d_out, st)); }
+    p->last_n = n;
+    return SSG_OK;
+}
+
 extern "C" int ssg_rerank_get_stage(ssg_rerank_plan* p, int stage, void* h_dst, size_t bytes) {
     if (!p || !h_dst) return ssg_set_error(SSG_ERR_INVALID, "get_stage: null argument");
     const size_t n = (size_t)p->last_n;

@@ -362,10 +362,12 @@ pooled_tail_kernel(const __nv_bfloat16* __restrict__ x, int n, int num_split, in
         norm[b] = sqrtf(t);
     }
     const float norm_all = sqrtf(all);
+    const bool raw = (eval_mode & 2) != 0;       // bit 1: leave the pooled banks un-normalised (cnn.py:10-23)
+    eval_mode &= 1;
     for (int b = 0; b < nb; ++b) {
         float* o = eval_mode ? feat + ((size_t)(row0 + i) * nb + b) * C + c0
                              : feat + (size_t)b * bank_stride + (size_t)(row0 + i) * C + c0;
-        const float dv = eval_mode ? norm_all : norm[b];
+        const float dv = raw ? 1.0f : (eval_mode ? norm_all : norm[b]);
         float4 o0, o1;
         o0.x = acc[b][0] / dv; o0.y = acc[b][1] / dv; o0.z = acc[b][2] / dv; o0.w = acc[b][3] / dv;
         o1.x = acc[b][4] / dv; o1.y = acc[b][5] / dv; o1.z = acc[b][6] / dv; o1.w = acc[b][7] / dv;

@@ -45,6 +45,12 @@ int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int
 int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                          const int* csc_row, const float* vec, double lambda_value, double* final_dist,
                          cudaStream_t st);
+int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                        const int* csc_row, const float* dmat, const float* rowmax, double lambda_value, float* out,
+                        cudaStream_t st);
+int launch_init_assemble(const float* qg, const float* qq, const float* gg, int q, int g, float* dt, cudaStream_t st);
+int launch_gather_row_vals(const float* M, size_t ld, int rows, const int* idx, const int* cnt, int stride,
+                           float* out, cudaStream_t st);
 int launch_exclusive_scan_i32(const int* in, int* out, int n, cudaStream_t st);  // out has n+1 entries
 
 // cluster.cu (plan-level entry points live there as well)

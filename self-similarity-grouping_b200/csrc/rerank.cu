@@ -364,12 +364,29 @@ int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int
 // ---------------------------------------------------------------------------------------------------
 constexpr int JF_NT = 256;
 
-__global__ void __launch_bounds__(JF_NT)
-jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
-                     const int* __restrict__ q_cnt, const int* __restrict__ colptr,
-                     const int* __restrict__ csc_row, const float* __restrict__ vec, double lambda_value,
-                     float one_minus_lambda, double* __restrict__ final_dist) {
-    extern __shared__ unsigned char jf_smem[];
+// output policies: how a Jaccard value becomes the stored final distance
+struct OutSourceF64 {        // rerank.py:122  final = J*(1-lambda) + (v_i+v_m)*lambda, float64 [n,n]
+    const float* vec; float vi; double lambda_value; float oml; double* out;
+    __device__ __forceinline__ bool wants(int m) const { return true; }
+    __device__ __forceinline__ void store(int m, float J) const {
+        const float Jm = __fmul_rn(J, oml);
+        out[m] = __dadd_rn((double)Jm, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+    }
+};
+struct OutInitF32 {          // rerank_initial.py:94,98  final = J*(1-lambda) + od_norm[i,m]*lambda, float32 [q,g]
+    const float* drow; float rowmax; float lam; float oml; float* out; int q;
+    __device__ __forceinline__ bool wants(int m) const { return m >= q; }
+    __device__ __forceinline__ void store(int m, float J) const {
+        const float od = __fdiv_rn(drow[m], rowmax);
+        out[m - q] = __fadd_rn(__fmul_rn(J, oml), __fmul_rn(od, lam));
+    }
+};
+
+template <class Out>
+__device__ __forceinline__ void jaccard_row(int n, int i, const int* __restrict__ q_idx,
+                                            const float* __restrict__ q_val, const int* __restrict__ q_cnt,
+                                            const int* __restrict__ colptr, const int* __restrict__ csc_row,
+                                            const Out& o, unsigned char* jf_smem) {
     int* si = reinterpret_cast<int*>(jf_smem);                       // [VQ_STRIDE]
     float* sv = reinterpret_cast<float*>(si + SSG_VQ_STRIDE);        // [VQ_STRIDE]
     int* pref = reinterpret_cast<int*>(sv + SSG_VQ_STRIDE);          // [VQ_STRIDE + 1]
@@ -377,21 +394,17 @@ jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restri
     __shared__ int wsum[JF_NT / 32];
     __shared__ int s_carry;
 
-    const int i = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
     const int ci = q_cnt[i];
-    const float vi = vec[i];
-    double* out = final_dist + (size_t)i * n;
     const int nwords = (n + 31) >> 5;
-
     for (int s = tid; s < ci; s += JF_NT) {
         si[s] = q_idx[(size_t)i * SSG_VQ_STRIDE + s];
         sv[s] = q_val[(size_t)i * SSG_VQ_STRIDE + s];
     }
     for (int w = tid; w < nwords; w += JF_NT) bitmap[w] = 0u;
     // base fill (S = 0  ->  J = 1)
-    const double jbase = (double)__fmul_rn(1.0f, one_minus_lambda);
     for (int m = tid; m < n; m += JF_NT)
-        out[m] = __dadd_rn(jbase, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+        if (o.wants(m)) o.store(m, 1.0f);
     if (tid == 0) s_carry = 0;
     __syncthreads();
     // prefix sums of the inverted-list lengths of this row's columns
@@ -418,6 +431,7 @@ jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restri
             if (pref[mid] <= f) lo = mid; else hi = mid - 1;
         }
         const int m = csc_row[colptr[si[lo]] + (f - pref[lo])];
+        if (!o.wants(m)) continue;
         const unsigned bit = 1u << (m & 31);
         const unsigned old = atomicOr(&bitmap[m >> 5], bit);
         if (old & bit) continue;          // another thread owns column m
@@ -441,17 +455,49 @@ jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restri
             }
         }
         float J = __fsub_rn(1.0f, __fdiv_rn(S, __fsub_rn(2.0f, S)));
-        if (J < 0.f) J = 0.f;
-        const float Jm = __fmul_rn(J, one_minus_lambda);
-        out[m] = __dadd_rn((double)Jm, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+        o.store(m, J);
     }
+}
+
+__global__ void __launch_bounds__(JF_NT)
+jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+                     const int* __restrict__ q_cnt, const int* __restrict__ colptr,
+                     const int* __restrict__ csc_row, const float* __restrict__ vec, double lambda_value,
+                     float one_minus_lambda, double* __restrict__ final_dist) {
+    extern __shared__ unsigned char jf_smem[];
+    const int i = blockIdx.x;
+    // rerank.py:117-118 clamps J < 0 to 0; J = 1 - S/(2-S) with 0 <= S <= 1(+rounding) cannot go below -1e-7,
+    // and the clamp is applied inside store through fmaxf
+    struct Clamp : OutSourceF64 {
+        __device__ __forceinline__ void store(int m, float J) const { OutSourceF64::store(m, fmaxf(J, 0.f)); }
+    };
+    Clamp o;
+    o.vec = vec; o.vi = vec[i]; o.lambda_value = lambda_value; o.oml = one_minus_lambda;
+    o.out = final_dist + (size_t)i * n;
+    jaccard_row(n, i, q_idx, q_val, q_cnt, colptr, csc_row, o, jf_smem);
+}
+
+// rerank_initial.py:85-98: only the first `q` rows, no clamp, float32, columns [q, n)
+__global__ void __launch_bounds__(JF_NT)
+jaccard_init_kernel(int n, int q, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+                    const int* __restrict__ q_cnt, const int* __restrict__ colptr, const int* __restrict__ csc_row,
+                    const float* __restrict__ dmat, const float* __restrict__ rowmax, float lam, float oml,
+                    float* __restrict__ out) {
+    extern __shared__ unsigned char jf_smem[];
+    const int i = blockIdx.x;
+    OutInitF32 o{dmat + (size_t)i * n, rowmax[i], lam, oml, out + (size_t)i * (n - q), q};
+    jaccard_row(n, i, q_idx, q_val, q_cnt, colptr, csc_row, o, jf_smem);
+}
+
+static size_t jaccard_smem(int n) {
+    return sizeof(int) * SSG_VQ_STRIDE + sizeof(float) * SSG_VQ_STRIDE + sizeof(int) * (SSG_VQ_STRIDE + 1) +
+           sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
 }
 
 int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                          const int* csc_row, const float* vec, double lambda_value, double* final_dist,
                          cudaStream_t st) {
-    const size_t smem = sizeof(int) * SSG_VQ_STRIDE + sizeof(float) * SSG_VQ_STRIDE +
-                        sizeof(int) * (SSG_VQ_STRIDE + 1) + sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
+    const size_t smem = jaccard_smem(n);
     if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
     SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
@@ -459,6 +505,56 @@ int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int*
     const float oml = (float)(1.0 - lambda_value);
     jaccard_final_kernel<<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value,
                                                  oml, final_dist);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                        const int* csc_row, const float* dmat, const float* rowmax, double lambda_value, float* out,
+                        cudaStream_t st) {
+    const size_t smem = jaccard_smem(n);
+    if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
+    SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jaccard_init_kernel<<<q, JF_NT, smem, st>>>(n, q, q_idx, q_val, q_cnt, colptr, csc_row, dmat, rowmax,
+                                                (float)lambda_value, (float)(1.0 - lambda_value), out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// re_ranking_init front end (rerank_initial.py:43-48): D'[r,c] = 2 - 2*S[c,r] with S = [[qq, qg],[qg^T, gg]]
+// (the reference normalises by the column max and transposes; D' is that transpose before the division).
+// ---------------------------------------------------------------------------------------------------
+__global__ void init_assemble_kernel(const float* __restrict__ qg, const float* __restrict__ qq,
+                                     const float* __restrict__ gg, int q, int g, float* __restrict__ dt) {
+    const int n = q + g;
+    const size_t total = (size_t)n * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / n), c = (int)(e % n);     // D'[r,c] = od[c,r]
+        float s;
+        if (c < q) s = r < q ? qq[(size_t)c * q + r] : qg[(size_t)c * g + (r - q)];
+        else       s = r < q ? qg[(size_t)r * g + (c - q)] : gg[(size_t)(c - q) * g + (r - q)];
+        dt[e] = __fsub_rn(2.0f, __fmul_rn(2.0f, s));
+    }
+}
+int launch_init_assemble(const float* qg, const float* qq, const float* gg, int q, int g, float* dt, cudaStream_t st) {
+    const size_t total = (size_t)(q + g) * (q + g);
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    init_assemble_kernel<<<grid, 256, 0, st>>>(qg, qq, gg, q, g, dt);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// v_val[i, s] = M[i, v_idx[i, s]]
+__global__ void gather_row_vals_kernel(const float* __restrict__ M, size_t ld, const int* __restrict__ idx,
+                                       const int* __restrict__ cnt, int stride, float* __restrict__ out) {
+    const int i = blockIdx.x;
+    for (int s = threadIdx.x; s < cnt[i]; s += blockDim.x)
+        out[(size_t)i * stride + s] = M[(size_t)i * ld + idx[(size_t)i * stride + s]];
+}
+int launch_gather_row_vals(const float* M, size_t ld, int rows, const int* idx, const int* cnt, int stride,
+                           float* out, cudaStream_t st) {
+    gather_row_vals_kernel<<<rows, 64, 0, st>>>(M, ld, idx, cnt, stride, out);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -33,6 +33,8 @@ PROTOTYPES = {
                                c_int, c_void_p, c_void_p, c_void_p]),
     "ssg_rerank_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double,
                                 c_int, c_int, c_void_p, c_void_p]),
+    "ssg_rerank_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p,
+                                c_void_p]),
     "ssg_rerank_get_stage": (c_int, [c_void_p, c_int, c_void_p, c_size_t]),
     "ssg_cluster_plan_create": (c_int, [P(c_void_p), c_int, c_int, c_ll]),
     "ssg_cluster_plan_destroy": (c_int, [c_void_p]),

@@ -105,6 +105,18 @@ class EmbedPlan(object):
         return out
 
 
+    def forward_raw(self, images, num_split=1):
+        """One forward without flip and without normalisation: [banks, n, 2048] pooled banks (cnn.py:16)."""
+        import torch
+        images = images.contiguous()
+        n = images.shape[0]
+        banks = num_split + 1 if num_split > 1 else 1
+        out = torch.empty((banks, n, 2048), dtype=torch.float32, device=images.device)
+        _lib.check(_lib.load().ssg_embed_forward(self._h, images.data_ptr(), n, int(num_split), 2, 0,
+                                                 out.data_ptr(), out.stride(0), 0, _lib.stream_ptr()))
+        return out
+
+
 def get_plan(batch_max=256, device=None):
     dev = _lib.require_cuda(device)
     plan = _plans.get(dev.index)

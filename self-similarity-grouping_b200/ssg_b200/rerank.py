@@ -126,6 +126,26 @@ def re_ranking(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.
     return plan.run_host(src, tgt, k1, k2, lambda_value, dist_mode, no_rerank, want_euclid=True)
 
 
+def re_ranking_init_blocks(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
+    """reid/rerank_initial.py:40 re_ranking_init on similarity blocks (numpy or CUDA tensors).
+    Returns a numpy float32 [q,g] array for numpy inputs, a CUDA tensor for CUDA inputs."""
+    import torch
+    dev = _lib.require_cuda()
+    host = not (hasattr(q_g_dist, "is_cuda") and q_g_dist.is_cuda)
+
+    def dv(a):
+        if hasattr(a, "is_cuda"):
+            return a.to(dev, dtype=torch.float32).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    qg, qq, gg = dv(q_g_dist), dv(q_q_dist), dv(g_g_dist)
+    q, g = qg.shape
+    plan = get_plan(q + g, 1, 64, dev.index)
+    out = torch.empty((q, g), dtype=torch.float32, device=dev)
+    _lib.check(_lib.load().ssg_rerank_init(plan._h, qg.data_ptr(), qq.data_ptr(), gg.data_ptr(), q, g, int(k1),
+                                           int(k2), float(lambda_value), out.data_ptr(), _lib.stream_ptr()))
+    return out.cpu().numpy() if host else out
+
+
 def sqdist(x, y, mode=_lib.DIST_EXACT):
     """Squared Euclidean distance matrix of two float32 CUDA tensors (ssg_sqdist)."""
     import torch

@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads without a GPU and exports exactly what include/ssg_b200.h declares;
+host-side logic that needs no device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "ssg_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ssg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssg_b200 import _lib
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    # the ctypes prototype table mirrors the header one to one
+    assert sorted(_lib.PROTOTYPES.keys()) == declared
+    assert lib.ssg_version() >= 100
+
+
+def test_constants_match_header():
+    from ssg_b200 import _lib
+    with open(os.path.join(ROOT, "include", "ssg_b200.h")) as f:
+        src = f.read()
+    defs = dict(re.findall(r"#define\s+(SSG_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", src))
+    assert int(defs["SSG_RANK_STRIDE"]) == _lib.RANK_STRIDE
+    assert int(defs["SSG_V_STRIDE"]) == _lib.V_STRIDE and int(defs["SSG_VQ_STRIDE"]) == _lib.VQ_STRIDE
+    assert int(defs["SSG_ERR_CAPACITY"]) == _lib.ERR_CAPACITY and int(defs["SSG_DIST_TENSOR"]) == _lib.DIST_TENSOR
+    assert int(defs["SSG_STAGE_FLAGGED"]) == _lib.STAGE_FLAGGED and int(defs["SSG_F64"]) == _lib.F64
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ssg_b200
+    from ssg_b200 import _lib
+    x = np.zeros((8, 16), np.float32)
+    with pytest.raises(_lib.SsgError):
+        ssg_b200.re_ranking(x, x)
+    with pytest.raises(_lib.SsgError):
+        ssg_b200.DBSCAN(eps=0.5, min_samples=4, metric="precomputed").fit_predict(np.zeros((4, 4)))
+    with pytest.raises(_lib.SsgError):
+        ssg_b200.eps_estimate(np.zeros((4, 4)), 0.1)
+
+
+def test_embed_layer_table_is_torchvision_resnet50():
+    import torchvision
+    from ssg_b200 import embed
+    table = embed.layer_table()
+    assert len(table) == 53
+    sd = torchvision.models.resnet50(weights=None).state_dict()
+    convs = [k[:-len(".weight")] for k, v in sd.items() if v.dim() == 4]
+    assert sorted(t[5] for t in table) == sorted(convs)
+    macs = 0
+    for _, cin, cout, k, stride, ck, bk in table:
+        assert tuple(sd[ck + ".weight"].shape) == (cout, cin, k, k)
+        assert sd[bk + ".running_var"].shape[0] == cout
+    # 2 669 150 208 conv MACs per 256x128 image
+    H, W = 256, 128
+    sizes = {}
+    x = (H // 2, W // 2)
+    for _, cin, cout, k, stride, ck, bk in table:
+        if ck == "conv1":
+            macs += x[0] * x[1] * cout * cin * k * k
+            cur = (x[0] // 2, x[1] // 2)
+            sizes["in"] = cur
+            continue
+        name = ck.split(".")
+        if name[2] == "conv1":
+            block_in = sizes["in"]
+            o = block_in
+        elif name[2] == "conv2":
+            o = (sizes["in"][0] // stride, sizes["in"][1] // stride)
+            sizes["mid"] = o
+        elif name[2] == "conv3":
+            o = sizes["mid"]
+        else:
+            o = sizes["mid"]
+        macs += o[0] * o[1] * cout * cin * k * k
+        if name[2] == "conv3" and not any(t[5] == ".".join(name[:2]) + ".downsample.0" for t in table):
+            sizes["in"] = sizes["mid"]
+        if name[2] == "downsample":
+            sizes["in"] = sizes["mid"]
+    assert macs == 2669150208
+
+
+def test_keep_mask_and_dbscan_params():
+    import ssg_b200
+    m = ssg_b200.generate_keep_mask([np.array([0, -1, 2, 3]), np.array([1, 1, -1, 0])])
+    assert m.tolist() == [True, False, False, True]
+    est = ssg_b200.DBSCAN(eps=0.3, min_samples=4, metric="precomputed", n_jobs=8)
+    assert est.get_params()["eps"] == 0.3 and est.set_params(eps=0.5).eps == 0.5
+    with pytest.raises(ValueError):
+        ssg_b200.DBSCAN(metric="euclidean").fit(np.zeros((3, 3)))
+
+
+def test_reid_drop_in_surface():
+    import inspect
+    import reid
+    import reid.evaluators, reid.rerank, reid.rerank_initial, reid.feature_extraction, reid.models  # noqa: E401
+    sig = inspect.signature(reid.rerank.re_ranking)
+    assert list(sig.parameters)[:8] == ["input_feature_source", "input_feature", "k1", "k2", "lambda_value",
+                                        "MemorySave", "Minibatch", "no_rerank"]
+    assert sig.parameters["k1"].default == 20 and sig.parameters["lambda_value"].default == 0.2
+    assert list(inspect.signature(reid.evaluators.extract_features).parameters) == \
+        ["model", "data_loader", "print_freq", "for_eval", "metric"]
+    assert list(inspect.signature(reid.rerank_initial.re_ranking_init).parameters) == \
+        ["q_g_dist", "q_q_dist", "g_g_dist", "k1", "k2", "lambda_value"]
+    assert list(inspect.signature(reid.feature_extraction.extract_cnn_feature).parameters) == \
+        ["model", "inputs", "for_eval", "modules"]
+    # `from reid.rerank import *` must shadow sklearn's DBSCAN in the driver namespace (selftraining.py:27-28)
+    ns = {}
+    exec("from sklearn.cluster import DBSCAN\nfrom reid.rerank import *", ns)
+    assert ns["DBSCAN"].__module__.startswith("ssg_b200")
+    m = reid.models.create("resnet50", num_classes=0, num_split=2, pretrained=False)
+    keys = set(m.state_dict().keys())
+    assert "base.layer4.2.conv3.weight" in keys and "feat.weight" in keys and "feat_bn.running_mean" in keys

@@ -145,3 +145,22 @@ def test_full_size_properties(ssg):
     od = np.power(cdist(tgt[rows], tgt).astype(np.float32), 2).astype(np.float32)
     odn = od / od.max(axis=1, keepdims=True)
     assert np.array_equal(np.argsort(odn, kind="stable")[:, :21], rank[rows, :21])
+
+
+def test_re_ranking_init_against_reference_golden(ssg, golden_dir):
+    """reid/rerank_initial.py:40 (blocks) and reid/rerank.py:171 (features) through the drop-in modules."""
+    import reid.rerank
+    import reid.rerank_initial
+    g = np.load(os.path.join(golden_dir, "rerank_init_q40_g90.npz"))
+    qf, gf = g["qf"], g["gf"]
+    out = reid.rerank_initial.re_ranking_init(qf @ gf.T, qf @ qf.T, gf @ gf.T)
+    assert out.shape == (40, 90) and out.dtype == np.float32
+    np.testing.assert_allclose(out, g["final"], rtol=0, atol=1e-5)
+    out2 = reid.rerank.re_ranking_init(qf, gf)
+    np.testing.assert_allclose(out2, g["final"], rtol=0, atol=1e-4)   # GPU GEMM vs np.dot in the similarities
+    for lam, k2 in ((0.1, 6), (0.5, 1)):
+        f, _ = O.synth_features(300, 128, 9, per_cluster=10)
+        q_, g_ = f[:100], f[100:]
+        want = O.re_ranking_init(q_ @ g_.T, q_ @ q_.T, g_ @ g_.T, k2=k2, lambda_value=lam)
+        got = reid.rerank_initial.re_ranking_init(q_ @ g_.T, q_ @ q_.T, g_ @ g_.T, k2=k2, lambda_value=lam)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
