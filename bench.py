@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--banks", type=int, default=3)
     ap.add_argument("--dist-mode", default="tensor", choices=["tensor", "exact"])
     ap.add_argument("--cpu-sample", type=int, default=1280, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-embed-sample", type=int, default=64, help="images of the bounded CPU embedding sample")
+    ap.add_argument("--batch", type=int, default=256, help="images per embedding batch")
+    ap.add_argument("--features-only", action="store_true", help="skip the embedding stage (synthetic features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -129,6 +132,21 @@ def cpu_cycle_sample(n_sample, d=D, seed=0, mode="ref"):
     return time.perf_counter() - t0, kind
 
 
+def cpu_embed_sample(n_img, seed=1234):
+    """reid/evaluators.py:18-60 on the host cores (torch CPU fp32, all threads): n_img images, num_split=2."""
+    import torch
+    from oracle import resnet_oracle as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = R.build_model(2, 0)
+    imgs = R.synth_images(n_img, seed)
+    names = ["i%d" % i for i in range(n_img)]
+    batches = [(imgs[i:i + 32], names[i:i + 32], [0] * len(names[i:i + 32]), [0] * len(names[i:i + 32]))
+               for i in range(0, n_img, 32)]
+    t0 = time.perf_counter()
+    R.extract_features(model, batches, for_eval=False)
+    return time.perf_counter() - t0
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -143,6 +161,7 @@ def run_reference_arm(args):
         times.append(t)
     sec = sum(times) / len(times)
     val = n_s * n_s / sec / 1e6
+    esec = cpu_embed_sample(args.cpu_embed_sample)
     sample = "1 bank, N=Ns=%d rows of the %d-row workload, d=%d, fp16 reference arithmetic" % (n_s, args.n, D)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -152,6 +171,8 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "embed": {"value": args.cpu_embed_sample / esec, "unit": "images/s (two forward passes per image)",
+                  "cores": os.cpu_count(), "sample": "%d images, torch CPU fp32, all host threads" % args.cpu_embed_sample},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -189,7 +210,7 @@ def main():
     import torch
     import torch.distributed as dist
     import ssg_b200
-    from ssg_b200 import _lib
+    from ssg_b200 import _lib, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,28 +221,51 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     mode = _lib.DIST_TENSOR if args.dist_mode == "tensor" else _lib.DIST_EXACT
     n, banks = args.n, args.banks
-
-    # every rank owns an independent target set of the same shape (weak scaling, no data-path collective)
-    tgt = [synth_bank(n, D, 1000 * rank + 10 + b, 0.5, dev) for b in range(banks)]
-    src = [synth_bank(n, D, 1000 * rank + 20 + b, 0.6, dev) for b in range(banks)]
+    num_split = banks - 1 if banks > 1 else 1
+    with_embed = not args.features_only
     pairs_per_step = float(banks) * n * n
 
-    def step_device():
-        return ssg_b200.pseudo_label_cycle(src, tgt, LAMBDA, RHO, dist_mode=mode, device=local)
+    # every rank owns an independent target/source set of the same shape (weak scaling, no data-path collective)
+    if with_embed:
+        model = synth.build_model(num_split, 0)
+        tgt_img, _ = synth.synth_images(n, 1234 + 100 * rank, dev)
+        src_img, _ = synth.synth_images(n, 4321 + 100 * rank, dev)
+        plan_e = ssg_b200.embed.get_plan(args.batch, local)
+        plan_e.load_model(model)
+    else:
+        tgt_f = [synth_bank(n, D, 1000 * rank + 10 + b, 0.5, dev) for b in range(banks)]
+        src_f = [synth_bank(n, D, 1000 * rank + 20 + b, 0.6, dev) for b in range(banks)]
 
-    # host-resident copies for the end-to-end measurement (pinned)
-    tgt_h = [t.cpu().pin_memory() for t in tgt]
-    src_h = [s.cpu().pin_memory() for s in src]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    stage_ms = {"embed": 0.0, "rerank": 0.0}
 
-    def step_e2e():
-        return ssg_b200.pseudo_label_cycle(src_h, tgt_h, LAMBDA, RHO, dist_mode=mode, device=local)
+    def cycle(tgt_in, src_in, record):
+        """selftraining.py:196-218: embed source + target sets, then re-rank / eps / DBSCAN per bank."""
+        if record:
+            ev[0].record()
+        if with_embed:
+            tf = ssg_b200.embed_images(model, tgt_in, num_split, False, args.batch, local)
+            sf = ssg_b200.embed_images(model, src_in, num_split, False, args.batch, local)
+            tfl, sfl = [tf[b] for b in range(banks)], [sf[b] for b in range(banks)]
+        else:
+            tfl, sfl = tgt_in, src_in
+        if record:
+            ev[1].record()
+        out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local)
+        if record:
+            ev[2].record()
+            torch.cuda.synchronize()
+            stage_ms["embed"] += ev[0].elapsed_time(ev[1])
+            stage_ms["rerank"] += ev[1].elapsed_time(ev[2])
+        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
+    def timed(tgt_in, src_in, steps, profile=False):
+        stage_ms["embed"] = stage_ms["rerank"] = 0.0
         barrier()
         if profile:
             _lib.profile(reset=True)
@@ -230,43 +274,63 @@ def main():
         e0.record()
         out = None
         for _ in range(steps):
-            out = fn()
+            out = cycle(tgt_in, src_in, True)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        t = torch.tensor([e0.elapsed_time(e1), stage_ms["embed"], stage_ms["rerank"]], device=dev)
         if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         prof = {}
         if profile:
             prof = _lib.profile()
             _lib.profile(on=False)
-        return float(ms.item()), out, prof
+        return [float(v) for v in t.tolist()], out, prof
 
+    dev_in = (tgt_img, src_img) if with_embed else (tgt_f, src_f)
     for _ in range(max(args.warmup, 3)):
-        step_device()
+        cycle(dev_in[0], dev_in[1], False)
     clocks = ClockSampler(local)
-    ms_dev, out, prof = timed(step_device, args.steps, profile=True)
+    (ms_dev, ms_embed, ms_rerank), out, prof = timed(dev_in[0], dev_in[1], args.steps, profile=True)
     clk = clocks.stop()
-    for _ in range(1):
-        step_e2e()
-    ms_e2e, out_e2e, _ = timed(step_e2e, args.steps)
+
+    # end to end through the host-buffer API: pinned host inputs, copies inside the timed region
+    if with_embed:
+        host_in = (tgt_img.cpu().pin_memory(), src_img.cpu().pin_memory())
+        h2d = 2 * n * 3 * 256 * 128 * 4
+    else:
+        host_in = ([t.cpu().pin_memory() for t in tgt_f], [t.cpu().pin_memory() for t in src_f])
+        h2d = 2 * banks * n * D * 4
+    cycle(host_in[0], host_in[1], False)
+    (ms_e2e, ms_e2e_embed, ms_e2e_rerank), out_e2e, _ = timed(host_in[0], host_in[1], args.steps)
 
     labels, eps_list, keep = out
-    value = pairs_per_step * world * args.steps / (ms_dev / 1e3) / 1e6
-    e2e_value = pairs_per_step * world * args.steps / (ms_e2e / 1e3) / 1e6
+    k = args.steps
+    value = pairs_per_step * world * k / (ms_rerank / 1e3) / 1e6
+    e2e_value = pairs_per_step * world * k / (ms_e2e_rerank / 1e3) / 1e6
 
     line = None
     if rank == 0:
         peaks = load_peaks()
-        # dominant kernel of the step
         launches = sum(v[1] for v in prof.values())
-        kern_ms = {k: v[0] for k, v in prof.items()}
+        kern_ms = {kk: v[0] for kk, v in prof.items()}
         top = max(kern_ms, key=kern_ms.get) if kern_ms else None
         roof = None
-        if top in ALGO:
+        conv_names = ("conv1x1_tc", "conv3x3_tc", "conv_stem_tc")
+        if top in conv_names:
+            # the three conv groups are one kernel template (gemm_kernel<BN, EpiConv>): rate them together
+            conv_ms = sum(prof[c][0] for c in conv_names if c in prof)
+            flops = 2.0 * 2669150208 * 2 * (2 * n) * k          # conv MACs x2 flops x2 passes x (tgt+src) images
+            ach = flops / (conv_ms / 1e3) / 1e12
+            roof = {"kernel": "gemm_kernel<EpiConv> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)"
+                              % sum(prof[c][1] for c in conv_names if c in prof),
+                    "bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tensor"], "traffic": None, "ms_per_step": conv_ms / k,
+                    "peak_source": peaks["source"],
+                    "note": "algorithmic flops = 2 x 2 669 150 208 conv MACs per image-pass (SURVEY.md 8d), summed over "
+                            "all conv launches of the step"}
+        elif top in ALGO:
             bound, fn = ALGO[top]
             per_launch_ms = prof[top][0] / prof[top][1]
-            # all the big launches of this path cover the whole N x N (or N x Ns) problem of one bank
             work = fn(n, n, D)
             if bound == "tensor":
                 ach = work / (per_launch_ms / 1e3) / 1e12
@@ -289,25 +353,45 @@ def main():
                    "seconds": sec,
                    "sample": "1 bank, N=Ns=%d rows of the %d-row workload (re_ranking fp16 reference arithmetic + eps + "
                              "sklearn DBSCAN n_jobs=8); numpy/scipy parts are single-threaded" % (args.cpu_sample, n)}
+            if with_embed:
+                esec = cpu_embed_sample(args.cpu_embed_sample)
+                cpu["embed"] = {"value": args.cpu_embed_sample / esec, "unit": "images/s", "cores": os.cpu_count(),
+                                "sample": "%d images, torch CPU fp32 ResNet-50 x2 passes, all host threads"
+                                          % args.cpu_embed_sample}
+        embed = None
+        if with_embed:
+            img_per_s = 2.0 * n * world * k / (ms_embed / 1e3)
+            flops = 2.0 * 2669150208 * 2 * (2 * n) * k
+            embed = {"value": img_per_s, "unit": "images/s (source + target sets; two forward passes per image)",
+                     "ms_per_step": ms_embed / k, "images_per_step": 2 * n,
+                     "tensor_tflops_algorithmic": flops / (ms_embed / 1e3) / 1e12,
+                     "frac_of_measured_bf16_peak": flops / (ms_embed / 1e3) / 1e12 / peaks["tensor"],
+                     "e2e_value": 2.0 * n * world * k / (ms_e2e_embed / 1e3), "batch": args.batch}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64 (bf16x3 tensor-core candidates, exact f64 re-score)"
-            if mode == _lib.DIST_TENSOR else "f32/f64 (exact f64 distances)",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / k, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("bf16 conv (fp32 accumulate) + " if with_embed else "") +
+                     ("f32/f64 re-rank (bf16x3 tensor-core candidates, exact f64 re-score)"
+                      if mode == _lib.DIST_TENSOR else "f32/f64 re-rank (exact f64 distances)"),
             "data": "synthetic",
-            "config": {"workload": "configs[1]: N=Ns=%d, %d banks x 2048-d (num_split=2), re-rank k1=20 k2=6 lambda=0.1 + "
-                                   "eps rho=1.6e-3 + DBSCAN min_samples=4; features device-resident; embed stage not "
-                                   "built yet" % (n, banks),
-                       "l2": "inputs (%.0f MB of features, %.1f GB distance block) exceed the 126 MB L2"
-                             % (2 * banks * n * D * 4 / 1e6, n * n * 4 / 1e9),
+            "config": {"workload": "configs[1]: N=Ns=%d synthetic 256x128 images, random-init ResNet-50 (num_split=%d -> %d "
+                                   "banks x 2048-d): embed source+target sets (flip TTA) -> per bank re-rank k1=20 k2=6 "
+                                   "lambda=0.1 -> eps rho=1.6e-3 -> DBSCAN min_samples=4%s"
+                                   % (n, num_split, banks, "" if with_embed else "; EMBED SKIPPED (--features-only)"),
+                       "l2": "inputs exceed the 126 MB L2 (%.1f GB of images, %.1f GB distance block per bank)"
+                             % (2 * n * 3 * 256 * 128 * 4 / 1e9, n * n * 4 / 1e9),
+                       "value_is": "Mpairs/s of the re-rank+eps+DBSCAN stage inside the full step; embed stage under 'embed'; "
+                                   "ms_per_step is the whole cycle",
                        "parallelism": "%d independent replicas (one target set per GPU)" % world,
                        "dist_mode": args.dist_mode},
-            "embed": None,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": 2 * banks * n * D * 4, "d2h_bytes_per_step": banks * n * 8,
-                    "api": "ssg_b200.pseudo_label_cycle(host pinned features) -> host labels"},
+            "embed": embed,
+            "rerank": {"value": value, "unit": UNIT, "ms_per_step": ms_rerank / k},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / k, "rerank_ms_per_step": ms_e2e_rerank / k,
+                    "embed_ms_per_step": ms_e2e_embed / k, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": banks * n * 8,
+                    "api": "ssg_b200.embed_images(pinned host images) + ssg_b200.pseudo_label_cycle -> host labels"},
             "gpu_launches": int(launches),
-            "kernels_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
+            "kernels_ms_per_step": {kk: round(v[0] / k, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "result": {"clusters": [int(l.max()) + 1 for l in labels], "eps": [round(e, 6) for e in eps_list],
                        "kept_images": int(keep.sum())},

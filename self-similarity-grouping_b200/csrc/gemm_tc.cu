@@ -92,15 +92,44 @@ int tc_num_sms(int* out) {
 // ---------------------------------------------------------------------------------------------------
 // x (fp32 [n,d]) -> bf16 hi/lo split laid out as [n, 3d]: which = 0: [hi|hi|lo] (A side), 1: [hi|lo|hi] (B side);
 // also the squared norm (fp64 accumulate, rounded to fp32).
+// column mean of x [n,d] (float64 partial sums over 64 interleaved row groups, deterministic)
+constexpr int MEAN_GROUPS = 64;
 __global__ void __launch_bounds__(256)
-split_bf16x3_kernel(const float* __restrict__ x, int n, int d, int which, __nv_bfloat16* __restrict__ out,
-                    float* __restrict__ norm2) {
+col_partial_kernel(const float* __restrict__ x, int n, int d, double* __restrict__ partial) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= d) return;
+    double acc = 0.0;
+    for (int r = blockIdx.y; r < n; r += MEAN_GROUPS) acc += (double)x[(size_t)r * d + c];
+    partial[(size_t)blockIdx.y * d + c] = acc;
+}
+__global__ void __launch_bounds__(256)
+col_mean_kernel(const double* __restrict__ partial, int n, int d, float* __restrict__ mean) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= d) return;
+    double acc = 0.0;
+    for (int g = 0; g < MEAN_GROUPS; ++g) acc += partial[(size_t)g * d + c];
+    mean[c] = (float)(acc / (double)n);
+}
+int launch_col_mean(const float* x, int n, int d, double* partial, float* mean, cudaStream_t st) {
+    dim3 grid(ssg_cdiv(d, 256), MEAN_GROUPS);
+    col_partial_kernel<<<grid, 256, 0, st>>>(x, n, d, partial);
+    SSG_CHECK_LAUNCH();
+    col_mean_kernel<<<ssg_cdiv(d, 256), 256, 0, st>>>(partial, n, d, mean);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// `centre` (optional, [d]) is subtracted first: distances are translation invariant, and centred operands make the
+// approximation error proportional to the spread of the data instead of its absolute norm.
+__global__ void __launch_bounds__(256)
+split_bf16x3_kernel(const float* __restrict__ x, int n, int d, int which, const float* __restrict__ centre,
+                    __nv_bfloat16* __restrict__ out, float* __restrict__ norm2) {
     const int i = blockIdx.x;
     const float* row = x + (size_t)i * d;
     __nv_bfloat16* o = out + (size_t)i * 3 * d;
     double acc = 0.0;
     for (int k = threadIdx.x; k < d; k += 256) {
-        const float v = row[k];
+        const float v = centre ? __fsub_rn(row[k], centre[k]) : row[k];
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
         o[k] = hi;
@@ -118,9 +147,10 @@ split_bf16x3_kernel(const float* __restrict__ x, int n, int d, int which, __nv_b
     if (threadIdx.x == 0 && norm2) norm2[i] = (float)sh[0];
 }
 
-int launch_split_bf16x3(const float* x, int n, int d, int which, void* out_bf16, float* norm2, cudaStream_t st) {
+int launch_split_bf16x3(const float* x, int n, int d, int which, const float* centre, void* out_bf16, float* norm2,
+                        cudaStream_t st) {
     if (n <= 0) return SSG_OK;
-    split_bf16x3_kernel<<<n, 256, 0, st>>>(x, n, d, which, (__nv_bfloat16*)out_bf16, norm2);
+    split_bf16x3_kernel<<<n, 256, 0, st>>>(x, n, d, which, centre, (__nv_bfloat16*)out_bf16, norm2);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -168,8 +198,8 @@ int launch_sqdist_tensor(const float* X, int nx, const float* Y, int ny, int d, 
     SSG_CUDA_TRY(cudaMallocAsync(&by, (size_t)ny * 3 * d * 2, st));
     SSG_CUDA_TRY(cudaMallocAsync((void**)&na, sizeof(float) * nx, st));
     SSG_CUDA_TRY(cudaMallocAsync((void**)&nb, sizeof(float) * ny, st));
-    int rc = launch_split_bf16x3(X, nx, d, 0, ax, na, st);
-    if (rc == SSG_OK) rc = launch_split_bf16x3(Y, ny, d, 1, by, nb, st);
+    int rc = launch_split_bf16x3(X, nx, d, 0, nullptr, ax, na, st);
+    if (rc == SSG_OK) rc = launch_split_bf16x3(Y, ny, d, 1, nullptr, by, nb, st);
     if (rc == SSG_OK) rc = launch_gemm_dist(ax, na, nx, by, nb, ny, 3 * d, out, ldo, st);
     cudaFreeAsync(ax, st);
     cudaFreeAsync(by, st);

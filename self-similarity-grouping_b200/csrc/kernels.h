@@ -30,7 +30,9 @@ int launch_pair_exact(const float* A, int rows, const float* B, int d, const int
 // gemm_tc.cu
 int launch_sqdist_tensor(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
                          cudaStream_t st);
-int launch_split_bf16x3(const float* x, int n, int d, int which, void* out_bf16, float* norm2, cudaStream_t st);
+int launch_split_bf16x3(const float* x, int n, int d, int which, const float* centre, void* out_bf16, float* norm2,
+                        cudaStream_t st);
+int launch_col_mean(const float* x, int n, int d, double* partial, float* mean, cudaStream_t st);
 int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_split, const float* nb, int n,
                      int k, float* out, size_t ldc, cudaStream_t st);
 

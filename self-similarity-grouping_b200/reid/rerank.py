@@ -33,4 +33,4 @@ def re_ranking_init(query_feature, gallery_feature, k1=20, k2=6, lambda_value=0.
         q_g, q_q, g_g = q @ g.t(), q @ q.t(), g @ g.t()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    return _init(q_g, q_q, g_g, k1=k1, k2=k2, lambda_value=lambda_value)
+    return _init(q_g, q_q, g_g, k1=k1, k2=k2, lambda_value=lambda_value).cpu().numpy()
