@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="images per embedding batch")
     ap.add_argument("--features-only", action="store_true", help="skip the embedding stage (synthetic features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replicas", action="store_true",
+                    help="N>1: independent replicas (weak scaling) instead of sharding one cycle over the GPUs")
+    ap.add_argument("--quick", action="store_true",
+                    help="profiling runs (ncu): exactly --warmup warm-up steps, no e2e leg, no CPU baseline")
     return ap.parse_args()
 
 
@@ -225,11 +229,29 @@ def main():
     with_embed = not args.features_only
     pairs_per_step = float(banks) * n * n
 
-    # every rank owns an independent target/source set of the same shape (weak scaling, no data-path collective)
+    # N>1 default: ONE cycle sharded over the ranks (strong scaling): image shards -> all-gather of the feature banks
+    # (NCCL) -> row-block distance stage + table gather -> bank-parallel finish (ssg_b200.dist).  --replicas: every rank
+    # owns an independent set of the same shape (weak scaling, no data-path collective).
+    sharded = world > 1 and not args.replicas
+    if sharded and not with_embed:
+        raise SystemExit("--features-only is a single-GPU / --replicas mode")
     if with_embed:
         model = synth.build_model(num_split, 0)
-        tgt_img, _ = synth.synth_images(n, 1234 + 100 * rank, dev)
-        src_img, _ = synth.synth_images(n, 4321 + 100 * rank, dev)
+        if sharded:
+            from ssg_b200 import dist as sdist
+            comm = sdist.Comm()
+            backend = sdist.CudaBackend(local, mode, args.batch)
+            lo, hi = sdist.shard_bounds(n, world, rank)
+            tgt_full, _ = synth.synth_images(n, 1234, dev)          # same seeds on every rank: one global data set
+            tgt_img = tgt_full[lo:hi].clone()
+            del tgt_full
+            src_full, _ = synth.synth_images(n, 4321, dev)
+            src_img = src_full[lo:hi].clone()
+            del src_full
+            torch.cuda.empty_cache()
+        else:
+            tgt_img, _ = synth.synth_images(n, 1234 + 100 * rank, dev)
+            src_img, _ = synth.synth_images(n, 4321 + 100 * rank, dev)
         plan_e = ssg_b200.embed.get_plan(args.batch, local)
         plan_e.load_model(model)
     else:
@@ -251,7 +273,11 @@ def main():
             tfl, sfl = tgt_in, src_in
         if record:
             ev[1].record()
-        out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local)
+        if sharded:
+            out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, RHO, backend=backend,
+                                                   comm=comm, features=(tf, sf))
+        else:
+            out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local)
         if record:
             ev[2].record()
             torch.cuda.synchronize()
@@ -287,16 +313,25 @@ def main():
         return [float(v) for v in t.tolist()], out, prof
 
     dev_in = (tgt_img, src_img) if with_embed else (tgt_f, src_f)
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm):
         cycle(dev_in[0], dev_in[1], False)
     clocks = ClockSampler(local)
     (ms_dev, ms_embed, ms_rerank), out, prof = timed(dev_in[0], dev_in[1], args.steps, profile=True)
     clk = clocks.stop()
 
     # end to end through the host-buffer API: pinned host inputs, copies inside the timed region
+    if args.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": ms_dev / args.steps, "embed_ms": ms_embed / args.steps,
+                              "rerank_ms": ms_rerank / args.steps,
+                              "kernels_ms_per_step": {kk: round(v[0] / args.steps, 4) for kk, v in prof.items()}}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if with_embed:
         host_in = (tgt_img.cpu().pin_memory(), src_img.cpu().pin_memory())
-        h2d = 2 * n * 3 * 256 * 128 * 4
+        h2d = (tgt_img.shape[0] + src_img.shape[0]) * 3 * 256 * 128 * 4      # per rank
     else:
         host_in = ([t.cpu().pin_memory() for t in tgt_f], [t.cpu().pin_memory() for t in src_f])
         h2d = 2 * banks * n * D * 4
@@ -305,8 +340,9 @@ def main():
 
     labels, eps_list, keep = out
     k = args.steps
-    value = pairs_per_step * world * k / (ms_rerank / 1e3) / 1e6
-    e2e_value = pairs_per_step * world * k / (ms_e2e_rerank / 1e3) / 1e6
+    units = 1 if sharded else world          # sharded: all ranks together process ONE data set
+    value = pairs_per_step * units * k / (ms_rerank / 1e3) / 1e6
+    e2e_value = pairs_per_step * units * k / (ms_e2e_rerank / 1e3) / 1e6
 
     line = None
     if rank == 0:
@@ -319,7 +355,7 @@ def main():
         if top in conv_names:
             # the three conv groups are one kernel template (gemm_kernel<BN, EpiConv>): rate them together
             conv_ms = sum(prof[c][0] for c in conv_names if c in prof)
-            flops = 2.0 * 2669150208 * 2 * (2 * n) * k          # conv MACs x2 flops x2 passes x (tgt+src) images
+            flops = 2.0 * 2669150208 * 2 * (2 * n) * k * (1.0 / world if sharded else 1.0)   # rank 0's share
             ach = flops / (conv_ms / 1e3) / 1e12
             roof = {"kernel": "gemm_kernel<EpiConv> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)"
                               % sum(prof[c][1] for c in conv_names if c in prof),
@@ -360,17 +396,17 @@ def main():
                                           % args.cpu_embed_sample}
         embed = None
         if with_embed:
-            img_per_s = 2.0 * n * world * k / (ms_embed / 1e3)
-            flops = 2.0 * 2669150208 * 2 * (2 * n) * k
+            img_per_s = 2.0 * n * units * k / (ms_embed / 1e3)
+            flops = 2.0 * 2669150208 * 2 * (2 * n) * k * units / world   # per GPU
             embed = {"value": img_per_s, "unit": "images/s (source + target sets; two forward passes per image)",
                      "ms_per_step": ms_embed / k, "images_per_step": 2 * n,
                      "tensor_tflops_algorithmic": flops / (ms_embed / 1e3) / 1e12,
                      "frac_of_measured_bf16_peak": flops / (ms_embed / 1e3) / 1e12 / peaks["tensor"],
-                     "e2e_value": 2.0 * n * world * k / (ms_e2e_embed / 1e3), "batch": args.batch}
+                     "e2e_value": 2.0 * n * units * k / (ms_e2e_embed / 1e3), "batch": args.batch}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": k,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / k, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "warmup": n_warm, "ms_per_step": ms_dev / k, "higher_is_better": True,
+            "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": ("bf16 conv (fp32 accumulate) + " if with_embed else "") +
                      ("f32/f64 re-rank (bf16x3 tensor-core candidates, exact f64 re-score)"
                       if mode == _lib.DIST_TENSOR else "f32/f64 re-rank (exact f64 distances)"),
@@ -383,7 +419,9 @@ def main():
                              % (2 * n * 3 * 256 * 128 * 4 / 1e9, n * n * 4 / 1e9),
                        "value_is": "Mpairs/s of the re-rank+eps+DBSCAN stage inside the full step; embed stage under 'embed'; "
                                    "ms_per_step is the whole cycle",
-                       "parallelism": "%d independent replicas (one target set per GPU)" % world,
+                       "parallelism": ("one cycle sharded over %d GPUs: image shards, NCCL all-gather of the feature banks, "
+                                       "row-block distance stage, bank-parallel finish" % world) if sharded else
+                                      "%d independent replicas (one target set per GPU)" % world,
                        "dist_mode": args.dist_mode},
             "embed": embed,
             "rerank": {"value": value, "unit": UNIT, "ms_per_step": ms_rerank / k},

@@ -69,6 +69,20 @@ size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* plan);
 int ssg_rerank_run(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d,
                    int k1, int k2, double lambda_value, int dist_mode, double* d_final,
                    float* d_euclid, void* stream);
+/* The same computation in two halves, for row-block sharding across GPUs:
+ *   ssg_rerank_distance_rows : stages (i)-(iv) for target rows [row0, row0+rows): fills those rows of the plan's
+ *                              tables (row minimum over the sources, row maximum, k1+1 leading rank columns and
+ *                              their normalised distances).  d_euclid (optional) is the full [n,n] matrix; only the
+ *                              rows of the block are written.
+ *   ssg_rerank_tables        : device pointers of the tables (rowmin float[n], rowmax float[n], rank int32[n,32],
+ *                              rank_val float[n,32]) so that the caller can all-gather the row blocks in place.
+ *   ssg_rerank_finish        : everything after the tables are complete (source vector, stages (v)-(viii)). */
+int ssg_rerank_distance_rows(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                             int k1, int dist_mode, int row0, int rows, float* d_euclid, void* stream);
+int ssg_rerank_tables(ssg_rerank_plan* plan, float** d_rowmin, float** d_rowmax, int** d_rank, float** d_rank_val);
+int ssg_rerank_finish(ssg_rerank_plan* plan, const float* d_tgt, int n, int d, int k1, int k2, double lambda_value,
+                      double* d_final, void* stream);
+
 /* Host in / host out (the literal drop-in of re_ranking): copies features up, results down. */
 int ssg_rerank_host(ssg_rerank_plan* plan, const float* h_src, int ns, const float* h_tgt, int n, int d,
                     int k1, int k2, double lambda_value, int dist_mode, int no_rerank, double* h_final,

@@ -204,7 +204,8 @@ static int ensure_tensor_buffers(ssg_rerank_plan* p) {
 // Tensor distance mode: bf16x3 tcgen05 GEMM for the bulk, exact float64 re-scoring of the candidates, exact
 // fallback for the rows whose result the error bound cannot certify.  Synchronises the stream once (flag counts).
 static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
-                                  int k1, float* d_euclid, bool want_rank, cudaStream_t st) {
+                                  int k1, float* d_euclid, bool want_rank, int row_begin, int row_end,
+                                  cudaStream_t st) {
     if (d % 8) return ssg_set_error(SSG_ERR_INVALID, "tensor distance mode needs d %% 8 == 0 (d=%d)", d);
     SSG_TRY(ensure_tensor_buffers(p));
     const int k1p = k1 + 1;
@@ -225,8 +226,8 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
     {
         const int rows_blk = (int)(p->dmat_elems / (size_t)ns < (size_t)n ? p->dmat_elems / (size_t)ns : (size_t)n);
         const int ke = ns < CAND_EXT ? ns : CAND_EXT;
-        for (int r0 = 0; r0 < n; r0 += rows_blk) {
-            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+        for (int r0 = row_begin; r0 < row_end; r0 += rows_blk) {
+            const int rows = row_end - r0 < rows_blk ? row_end - r0 : rows_blk;
             { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_sb, p->norm_s, ns, k3,
                                      p->dmat, (size_t)ns, st)); }
             { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)ns, rows, ns, nullptr, ke, false, p->cand_idx, p->cand_val,
@@ -242,8 +243,8 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
         const int rows_blk = (int)(p->dmat_elems / (size_t)n < (size_t)n ? p->dmat_elems / (size_t)n : (size_t)n);
         const int ke = n < CAND_EXT ? n : CAND_EXT;
         const int kc = n < CAND_K ? n : CAND_K;
-        for (int r0 = 0; r0 < n; r0 += rows_blk) {
-            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+        for (int r0 = row_begin; r0 < row_end; r0 += rows_blk) {
+            const int rows = row_end - r0 < rows_blk ? row_end - r0 : rows_blk;
             { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_tb, p->norm_t, n, k3,
                                      p->dmat, (size_t)n, st)); }
             { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, nullptr, ke, true, p->cand_idx, p->cand_val,
@@ -305,29 +306,28 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
     }
     h_flags[0] = nsrc + ntgt;
     SSG_CUDA_TRY(cudaMemcpyAsync(p->flagged, h_flags, sizeof(int), cudaMemcpyHostToDevice, st));
-    { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
     return SSG_OK;
 }
 
 // stages (i)-(iv): source vector, squared distance, row normaliser, leading k1+1 rank columns
 static int distance_stages_exact(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
-                           int k1, int dist_mode, float* d_euclid, bool want_rank, cudaStream_t st) {
+                           int k1, int dist_mode, float* d_euclid, bool want_rank, int row_begin, int row_end,
+                                 cudaStream_t st) {
     const int k1p = k1 + 1;
     // (i) rerank.py:36-40
     {
         const int rows_blk = (int)(p->dmat_elems / (size_t)ns < (size_t)n ? p->dmat_elems / (size_t)ns : (size_t)n);
-        for (int r0 = 0; r0 < n; r0 += rows_blk) {
-            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+        for (int r0 = row_begin; r0 < row_end; r0 += rows_blk) {
+            const int rows = row_end - r0 < rows_blk ? row_end - r0 : rows_blk;
             { SSG_PROF("sqdist_exact", st); SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_src, ns, d, dist_mode, st)); }
             { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)ns, rows, ns, p->rowmin + r0, nullptr, st)); }
         }
-        { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
     }
     // (ii)-(iv) rerank.py:61-70
     {
         const int rows_blk = (int)(p->dmat_elems / (size_t)n < (size_t)n ? p->dmat_elems / (size_t)n : (size_t)n);
-        for (int r0 = 0; r0 < n; r0 += rows_blk) {
-            const int rows = n - r0 < rows_blk ? n - r0 : rows_blk;
+        for (int r0 = row_begin; r0 < row_end; r0 += rows_blk) {
+            const int rows = row_end - r0 < rows_blk ? row_end - r0 : rows_blk;
             { SSG_PROF("sqdist_exact", st); SSG_TRY(dist_block(p, d_tgt + (size_t)r0 * d, rows, d_tgt, n, d, dist_mode, st)); }
             { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, rows, n, nullptr, p->rowmax + r0, st)); }
             if (want_rank)
@@ -342,26 +342,51 @@ static int distance_stages_exact(ssg_rerank_plan* p, const float* d_src, int ns,
     return SSG_OK;
 }
 
+// rows [row_begin, row_end) of: rowmin (source term, before exp/normalisation), rowmax, rank, rank_val
+// (d_euclid, when given, is indexed by the absolute row)
 static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
-                           int k1, int dist_mode, float* d_euclid, bool want_rank, cudaStream_t st) {
+                           int k1, int dist_mode, float* d_euclid, bool want_rank, int row_begin, int row_end,
+                           cudaStream_t st) {
     if (dist_mode == SSG_DIST_EXACT)
-        return distance_stages_exact(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, want_rank, st);
+        return distance_stages_exact(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, want_rank, row_begin, row_end, st);
     if (dist_mode == SSG_DIST_TENSOR)
-        return distance_stages_tensor(p, d_src, ns, d_tgt, n, d, k1, d_euclid, want_rank, st);
+        return distance_stages_tensor(p, d_src, ns, d_tgt, n, d, k1, d_euclid, want_rank, row_begin, row_end, st);
     return ssg_set_error(SSG_ERR_INVALID, "rerank: unknown dist_mode %d", dist_mode);
 }
 
-extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
-                              int k1, int k2, double lambda_value, int dist_mode, double* d_final,
-                              float* d_euclid, void* stream) {
-    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
+extern "C" int ssg_rerank_distance_rows(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n,
+                                        int d, int k1, int dist_mode, int row0, int rows, float* d_euclid,
+                                        void* stream) {
+    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, 1));
+    if (row0 < 0 || rows < 0 || row0 + rows > n)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_distance_rows: rows [%d,%d) outside [0,%d)", row0, row0 + rows, n);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
+    if (rows == 0) return SSG_OK;
+    return distance_stages(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, true, row0, row0 + rows, st);
+}
+
+extern "C" int ssg_rerank_tables(ssg_rerank_plan* p, float** d_rowmin, float** d_rowmax, int** d_rank,
+                                 float** d_rank_val) {
+    if (!p) return ssg_set_error(SSG_ERR_INVALID, "rerank_tables: null plan");
+    if (d_rowmin) *d_rowmin = p->rowmin;
+    if (d_rowmax) *d_rowmax = p->rowmax;
+    if (d_rank) *d_rank = p->rank;
+    if (d_rank_val) *d_rank_val = p->rank_val;
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_finish(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2,
+                                 double lambda_value, double* d_final, void* stream) {
+    SSG_TRY(check_run_args(p, d_tgt, 1, d_tgt, n, d, k1, k2));
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
     SSG_CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int k1p = k1 + 1;
     const int khp = (int)rint(k1 / 2.0) + 1;   // int(np.around(k1/2)) + 1, rerank.py:83
-    SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
-    SSG_TRY(distance_stages(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, true, st));
+    // (i, tail) rerank.py:38-40: v = 1 - exp(-rowmin); v /= max(v)
+    { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
     // (v) rerank.py:74-92
     { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
     { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, p->v_idx, SSG_V_STRIDE, p->v_cnt, 0, p->v_val, SSG_V_STRIDE, st)); }
@@ -382,6 +407,15 @@ extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, co
                                  d_final, st)); }
     p->last_n = n;
     return SSG_OK;
+}
+
+extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
+                              int k1, int k2, double lambda_value, int dist_mode, double* d_final,
+                              float* d_euclid, void* stream) {
+    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
+    if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
+    SSG_TRY(ssg_rerank_distance_rows(p, d_src, ns, d_tgt, n, d, k1, dist_mode, 0, n, d_euclid, stream));
+    return ssg_rerank_finish(p, d_tgt, n, d, k1, k2, lambda_value, d_final, stream);
 }
 
 static int grow(void** ptr, size_t* have, size_t need) {
@@ -411,7 +445,7 @@ extern "C" int ssg_rerank_host(ssg_rerank_plan* p, const float* h_src, int ns, c
         // rerank.py:65-66: the source term is still computed before the early return; only
         // euclidean_dist is handed back.
         SSG_TRY(distance_stages(p, p->io_src, ns, p->io_tgt, n, d, k1, dist_mode, h_euclid ? p->io_euclid : nullptr,
-                                false, st));
+                                false, 0, n, st));
     } else {
         SSG_TRY(ssg_rerank_run(p, p->io_src, ns, p->io_tgt, n, d, k1, k2, lambda_value, dist_mode, p->io_final,
                                h_euclid ? p->io_euclid : nullptr, st));

@@ -23,6 +23,7 @@ struct ssg_cluster_plan {
     unsigned long long* state;     // [8]: 0 prefix key, 1 remaining, 2 top_num, 3 M, 4 done-flag
     double* partial;               // [n_max]
     double* eps_out;               // [2]: eps, (unused)
+    double* list;                  // [EPS_LIST_CAP] values of the threshold bin (3-pass eps)
     // dbscan
     int* cnt;                      // [n_max]
     int* rowptr;                   // [n_max+1]
@@ -46,6 +47,7 @@ template <> __device__ __forceinline__ double ld_as_double<float>(const float* p
 // ----------------------------------------------------------------------------------------------- eps
 constexpr int EPS_NT = 256;
 constexpr int EPS_BINS = 4096;
+constexpr int EPS_LIST_CAP = 1 << 20;
 // pass p looks at key bits [shift, shift+width)
 __constant__ int c_eps_shift[6] = {52, 40, 28, 16, 4, 0};
 __constant__ int c_eps_width[6] = {12, 12, 12, 12, 12, 4};
@@ -191,6 +193,142 @@ eps_final_kernel(const double* __restrict__ partial, int nparts, const unsigned 
             eps_out[0] = (sh[0] + (double)state[1] * thr) / (double)top;
         }
     }
+}
+
+// ---- 3-pass variant: two histogram passes fix the leading 24 key bits of the threshold; the third pass sums every
+// entry below that 24-bit bin and gathers the (few) entries inside it; the order statistic is finished on that list.
+template <typename T>
+__global__ void __launch_bounds__(EPS_NT)
+eps_gather_kernel(const T* __restrict__ D, int n, unsigned long long* __restrict__ state, double* __restrict__ list,
+                  double* __restrict__ partial) {
+    const unsigned long long pre = state[0] >> 40;
+    double acc = 0.0;
+    if (state[2] > 0) {
+        for (int half = 0; half < 2; ++half) {
+            const int i = half == 0 ? (int)blockIdx.x : n - 1 - (int)blockIdx.x;
+            if (half == 1 && i <= (int)blockIdx.x) break;
+            const T* row = D + (size_t)i * n;
+            for (int j = i + 1 + threadIdx.x; j < n; j += EPS_NT) {
+                const double v = ld_as_double<T>(row, j);
+                if (v == 0.0) continue;
+                const unsigned long long h = f64_key(v) >> 40;
+                if (h < pre) acc += v;
+                else if (h == pre) {
+                    const unsigned long long pos = atomicAdd(&state[5], 1ull);
+                    if (pos < (unsigned long long)EPS_LIST_CAP) list[pos] = v; else state[6] = 1ull;
+                }
+            }
+        }
+    }
+    __shared__ double sh[EPS_NT];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = EPS_NT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// single CTA: finish the radix select (40 low key bits, 4 passes) on the gathered list, then the mean.
+__global__ void __launch_bounds__(1024)
+eps_list_finish_kernel(const double* __restrict__ list, unsigned long long* __restrict__ state,
+                       const double* __restrict__ partial, int nparts, double* __restrict__ eps_out) {
+    __shared__ unsigned int hist[EPS_BINS];
+    __shared__ unsigned long long s_prefix, s_rem;
+    __shared__ double sh[1024];
+    const int tid = threadIdx.x;
+    const unsigned long long top = state[2];
+    if (top == 0) {
+        if (tid == 0) eps_out[0] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    if (state[6]) return;                         // list overflow: the host falls back to the 6-pass path
+    const int L = (int)state[5];
+    if (tid == 0) { s_prefix = state[0]; s_rem = state[1]; }
+    __syncthreads();
+    const int shifts[4] = {28, 16, 4, 0};
+    const int widths[4] = {12, 12, 12, 4};
+    for (int p = 0; p < 4; ++p) {
+        for (int b = tid; b < EPS_BINS; b += 1024) hist[b] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const int shift = shifts[p], hs = shifts[p] + widths[p];
+        const unsigned mask = (1u << widths[p]) - 1u;
+        for (int e = tid; e < L; e += 1024) {
+            const unsigned long long k = f64_key(list[e]);
+            if ((k >> hs) == (prefix >> hs)) atomicAdd(&hist[(unsigned)(k >> shift) & mask], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long c = 0, rem = s_rem;
+            for (int b = 0; b < EPS_BINS; ++b) {
+                const unsigned long long hb = hist[b];
+                if (c < rem && rem <= c + hb) { s_prefix = prefix | ((unsigned long long)b << shift); s_rem = rem - c; break; }
+                c += hb;
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long thr = s_prefix;
+    // The list is filled through an atomic cursor, so its order differs from run to run; all its entries share sign
+    // and exponent (equal leading 24 key bits), so their sum is taken exactly on the integer mantissas and is
+    // therefore independent of the order: eps is bit-reproducible.
+    unsigned __int128 isum = 0;
+    for (int e = tid; e < L; e += 1024) {
+        const double v = list[e];
+        if (f64_key(v) < thr) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+            const unsigned long long ex = (bits >> 52) & 0x7ffull;
+            isum += (unsigned __int128)((bits & 0xfffffffffffffull) | (ex ? (1ull << 52) : 0ull));
+        }
+    }
+    __shared__ unsigned long long sh_lo[1024], sh_hi[1024];
+    sh_lo[tid] = (unsigned long long)isum;
+    sh_hi[tid] = (unsigned long long)(isum >> 64);
+    double acc = 0.0;
+    for (int i = tid; i < nparts; i += 1024) acc += partial[i];
+    sh[tid] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (tid < o) {
+            sh[tid] += sh[tid + o];
+            const unsigned __int128 a = ((unsigned __int128)sh_hi[tid] << 64) | sh_lo[tid];
+            const unsigned __int128 b = ((unsigned __int128)sh_hi[tid + o] << 64) | sh_lo[tid + o];
+            const unsigned __int128 c = a + b;
+            sh_lo[tid] = (unsigned long long)c;
+            sh_hi[tid] = (unsigned long long)(c >> 64);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double tv = f64_from_key(thr);
+        const unsigned long long tb = (unsigned long long)__double_as_longlong(tv);
+        const int ex = (int)((tb >> 52) & 0x7ffull);
+        const int e2 = (ex ? ex : 1) - 1075;                         // value = mantissa * 2^e2
+        double lsum = ldexp((double)sh_hi[0], 64 + e2) + ldexp((double)sh_lo[0], e2);
+        if (tb >> 63) lsum = -lsum;
+        state[0] = thr; state[1] = s_rem;
+        eps_out[0] = (sh[0] + lsum + (double)s_rem * tv) / (double)top;
+    }
+}
+
+template <typename T>
+static int eps_run3(ssg_cluster_plan* p, const T* D, int n, double rho, cudaStream_t st) {
+    SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
+    const int grid = (n + 1) / 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        { SSG_PROF("eps_hist", st); eps_hist_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, pass, p->state, p->hist); }
+        SSG_CHECK_LAUNCH();
+        eps_pick_kernel<<<1, 1024, 0, st>>>(p->hist, p->state, pass, rho);
+        SSG_CHECK_LAUNCH();
+    }
+    { SSG_PROF("eps_gather", st); eps_gather_kernel<T><<<grid, EPS_NT, 0, st>>>(D, n, p->state, p->list, p->partial); }
+    SSG_CHECK_LAUNCH();
+    eps_list_finish_kernel<<<1, 1024, 0, st>>>(p->list, p->state, p->partial, grid, p->eps_out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
 }
 
 template <typename T>
@@ -373,6 +511,7 @@ extern "C" int ssg_cluster_plan_create(ssg_cluster_plan** out, int device, int n
     A(p->state, sizeof(unsigned long long) * 8);
     A(p->partial, sizeof(double) * n);
     A(p->eps_out, sizeof(double) * 2);
+    A(p->list, sizeof(double) * EPS_LIST_CAP);
     A(p->cnt, sizeof(int) * n);
     A(p->rowptr, sizeof(int) * (n + 1));
     A(p->nbr, sizeof(int) * (size_t)max_neighbors);
@@ -390,7 +529,7 @@ extern "C" int ssg_cluster_plan_create(ssg_cluster_plan** out, int device, int n
 extern "C" int ssg_cluster_plan_destroy(ssg_cluster_plan* p) {
     if (!p) return SSG_OK;
     cudaSetDevice(p->device);
-    void* ptrs[] = {p->hist, p->state, p->partial, p->eps_out, p->cnt, p->rowptr, p->nbr, p->parent,
+    void* ptrs[] = {p->hist, p->state, p->partial, p->eps_out, p->list, p->cnt, p->rowptr, p->nbr, p->parent,
                     p->isroot, p->cid, p->core, p->flags, p->staging};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
@@ -405,13 +544,21 @@ extern "C" int ssg_eps_estimate(ssg_cluster_plan* p, const void* d_dist, int dty
         return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
     SSG_CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (dtype == SSG_F64) SSG_TRY(eps_run<double>(p, (const double*)d_dist, n, rho, st));
-    else if (dtype == SSG_F32) SSG_TRY(eps_run<float>(p, (const float*)d_dist, n, rho, st));
-    else return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: dtype %d", dtype);
+    if (dtype != SSG_F64 && dtype != SSG_F32) return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: dtype %d", dtype);
+    if (dtype == SSG_F64) SSG_TRY(eps_run3<double>(p, (const double*)d_dist, n, rho, st));
+    else SSG_TRY(eps_run3<float>(p, (const float*)d_dist, n, rho, st));
     unsigned long long hs[8];
     SSG_CUDA_TRY(cudaMemcpyAsync(h_eps, p->eps_out, sizeof(double), cudaMemcpyDeviceToHost, st));
     SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
     SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (hs[6]) {
+        // more than EPS_LIST_CAP entries share the threshold's leading 24 key bits (massive ties): full radix select
+        if (dtype == SSG_F64) SSG_TRY(eps_run<double>(p, (const double*)d_dist, n, rho, st));
+        else SSG_TRY(eps_run<float>(p, (const float*)d_dist, n, rho, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(h_eps, p->eps_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (h_top_num) *h_top_num = (long long)hs[2];
     return SSG_OK;
 }

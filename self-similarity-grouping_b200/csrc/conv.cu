@@ -13,55 +13,21 @@
 namespace ssg {
 
 // ---------------------------------------------------------------------------------------------------
-// epilogue: out[row, col] = bf16( relu?( acc + bias[col] (+ residual[row, col]) ) ), NHWC ([M, Cout] row-major)
+// epilogue: out[row, col] = bf16( relu?( acc + bias[col] (+ residual[row, col]) ) ), NHWC ([M, Cout] row-major),
+// staged through shared memory and written / prefetched by TMA (tc::StagedEpi in gemm_tc.cuh).
 // ---------------------------------------------------------------------------------------------------
-struct EpiConv {
-    const float* bias;            // [Cout]
-    const __nv_bfloat16* res;     // [M, Cout] or nullptr
-    __nv_bfloat16* out;           // [M, Cout]
-    int ldc;                      // Cout
-    int relu;
-    __device__ __forceinline__ void operator()(int row, int col0, int ncols, const uint32_t (&acc)[32]) const {
-        // ncols is always 32 here (Cout % 64 == 0)
-        __nv_bfloat16* o = out + (size_t)row * ldc + col0;
-        const __nv_bfloat16* r = res ? res + (size_t)row * ldc + col0 : nullptr;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // 8 channels (16 bytes of bf16) per iteration
-            float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + 8 * q);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + 8 * q + 4);
-            v[0] = __uint_as_float(acc[8 * q + 0]) + b0.x; v[1] = __uint_as_float(acc[8 * q + 1]) + b0.y;
-            v[2] = __uint_as_float(acc[8 * q + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * q + 3]) + b0.w;
-            v[4] = __uint_as_float(acc[8 * q + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * q + 5]) + b1.y;
-            v[6] = __uint_as_float(acc[8 * q + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * q + 7]) + b1.w;
-            if (r) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(r + 8 * q);
-                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 f = __bfloat1622float2(rp[e]);
-                    v[2 * e] += f.x;
-                    v[2 * e + 1] += f.y;
-                }
-            }
-            if (relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            uint4 pk;
-            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            *reinterpret_cast<uint4*>(o + 8 * q) = pk;
-        }
-    }
-};
-
-static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, int k, const EpiConv& epi,
-                         cudaStream_t st) {
-    if (cout % 128 == 0) return tc::launch_gemm_op<128, EpiConv>(A, m, w, cout, k, epi, st);
-    if (cout % 64 == 0) return tc::launch_gemm_op<64, EpiConv>(A, m, w, cout, k, epi, st);
-    return ssg_set_error(SSG_ERR_INVALID, "conv: Cout=%d must be a multiple of 64", cout);
+static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, int k, const float* bias,
+                         const void* residual, int relu, void* y, cudaStream_t st) {
+    if (cout % 64) return ssg_set_error(SSG_ERR_INVALID, "conv: Cout=%d must be a multiple of 64", cout);
+    tc::StagedEpi epi;
+    memset(&epi, 0, sizeof(epi));
+    epi.bias = bias;
+    epi.relu = relu;
+    epi.has_res = residual != nullptr;
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapR, residual ? residual : y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
+    return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
 }
 
 // 1x1 convolution (or any [M,K] x [Cout,K]^T product) on NHWC pixels.
@@ -74,8 +40,7 @@ int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int
     A.taps = 1;
     A.tiles_per_img = 1;
     SSG_TRY(make_tmap_2d_bf16(&A.map[0], x, (uint64_t)m, (uint64_t)cin, (uint64_t)cin, tc::BM));
-    EpiConv epi{bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, cout, relu};
-    return gemm_dispatch(A, m, w, cout, cin, epi, st);
+    return gemm_dispatch(A, m, w, cout, cin, bias, residual, relu, y, st);
 }
 
 // tile geometry of a 128-pixel M tile on an [H, W] output map (W divides 128, H*W multiple or divisor of 128)
@@ -123,8 +88,7 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
             }
         }
     const int m = B * H * W;
-    EpiConv epi{bias, nullptr, (__nv_bfloat16*)y, cout, relu};
-    return gemm_dispatch(A, m, w, cout, 9 * cin, epi, st);
+    return gemm_dispatch(A, m, w, cout, 9 * cin, bias, nullptr, relu, y, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -166,44 +130,46 @@ int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamm
 // ---------------------------------------------------------------------------------------------------
 constexpr int STEM_K = 147, STEM_KPAD = 192;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(192)
 stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bfloat16* __restrict__ out) {
-    constexpr int H = 256, W = 128, OW = 64, OH = 128;
-    __shared__ float rows[3][7][W + 6];            // 7 input rows x 3 channels, with the 3-pixel halo
+    constexpr int H = 256, W = 128, OW = 64, OH = 128, RW = W + 6;
+    __shared__ float rows[3 * 7 * RW];             // 7 input rows x 3 channels, with the 3-pixel halo
     const int oh = blockIdx.x % OH;
     const int im = blockIdx.x / OH;                // 0 .. (flip_too ? 2n : n)
     const bool flipped = im >= n;
     const int src = flipped ? im - n : im;
     const float* base = img + (size_t)src * 3 * H * W;
-    for (int e = threadIdx.x; e < 3 * 7 * (W + 6); e += 256) {
-        const int xw = e % (W + 6), t = e / (W + 6), ky = t % 7, c = t / 7;
+    for (int e = threadIdx.x; e < 3 * 7 * RW; e += 192) {
+        const int xw = e % RW, t = e / RW, ky = t % 7, c = t / 7;
         const int ih = oh * 2 - 3 + ky, iw = xw - 3;
         float v = 0.f;
         if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = base[((size_t)c * H + ih) * W + (flipped ? W - 1 - iw : iw)];
-        rows[c][ky][xw] = v;
+        rows[e] = v;
     }
     __syncthreads();
-    __nv_bfloat16* orow = out + ((size_t)im * OH + oh) * OW * STEM_KPAD;
-    for (int e = threadIdx.x; e < OW * (STEM_KPAD / 2); e += 256) {
-        const int kp = e % (STEM_KPAD / 2), ow = e / (STEM_KPAD / 2);
-        float v[2];
+    // thread = (pair of K columns, output-pixel parity): the K -> (c, ky, kx) decode is done once per thread
+    const int kp = threadIdx.x % (STEM_KPAD / 2), par = threadIdx.x / (STEM_KPAD / 2);
+    int off[2];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k = kp * 2 + h;
-            float val = 0.f;
-            if (k < STEM_K) {
-                const int c = k % 3, t = k / 3, kx = t % 7, ky = t / 7;
-                val = rows[c][ky][ow * 2 + kx];
-            }
-            v[h] = val;
+    for (int h = 0; h < 2; ++h) {
+        const int k = kp * 2 + h;
+        off[h] = -1;
+        if (k < STEM_K) {
+            const int c = k % 3, t = k / 3, kx = t % 7, ky = t / 7;
+            off[h] = (c * 7 + ky) * RW + kx;
         }
-        *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)ow * STEM_KPAD + kp * 2) = __floats2bfloat162_rn(v[0], v[1]);
+    }
+    __nv_bfloat16* orow = out + ((size_t)im * OH + oh) * OW * STEM_KPAD + kp * 2;
+    for (int ow = par; ow < OW; ow += 2) {
+        const float v0 = off[0] >= 0 ? rows[off[0] + ow * 2] : 0.f;
+        const float v1 = off[1] >= 0 ? rows[off[1] + ow * 2] : 0.f;
+        *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)ow * STEM_KPAD) = __floats2bfloat162_rn(v0, v1);
     }
 }
 
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st) {
     const int images = flip_too ? 2 * n : n;
-    stem_im2col_kernel<<<images * 128, 256, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);
+    stem_im2col_kernel<<<images * 128, 192, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -278,54 +278,82 @@ int launch_row_select(const float* M, size_t ld, int rows, int cols, const float
 // (cnt == nullptr -> fixed_cnt).  One CTA per row, the row staged in shared memory as float64, one
 // thread per pair walking its partner row sequentially (cdist order, see sqdist_exact).
 // ---------------------------------------------------------------------------------------------------
+// v2 layout: a CTA owns PE_ROWS rows and PE_KP pair slots per row (thread = (row, slot)); the row block is staged
+// through shared memory in PE_CHUNK-wide float64 chunks, every thread carries its accumulator across the chunks, so
+// the summation order per pair is still strictly k = 0..d-1.  All 256 threads stay busy even for 8 pairs per row.
+constexpr int PE_KP = 8, PE_ROWS = 32, PE_CHUNK = 128;
+
 __global__ void __launch_bounds__(256)
-pair_exact_kernel(const float* __restrict__ A, const float* __restrict__ B, int d,
+pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict__ B, int d,
                   const int* __restrict__ idx, int idx_stride, const int* __restrict__ cnt,
                   int fixed_cnt, float* __restrict__ out, int out_stride) {
-    extern __shared__ double sa[];
-    const int i = blockIdx.x;
-    const float* a = A + (size_t)i * d;
-    for (int k = threadIdx.x; k < d; k += blockDim.x) sa[k] = (double)a[k];
+    __shared__ double sa[PE_ROWS][PE_CHUNK];
+    __shared__ int s_maxcnt;
+    const int r_in = threadIdx.x / PE_KP, slot = threadIdx.x % PE_KP;
+    const int row = blockIdx.x * PE_ROWS + r_in;
+    const int c = row < rows ? (cnt ? cnt[row] : fixed_cnt) : 0;
+    if (threadIdx.x == 0) s_maxcnt = 0;
     __syncthreads();
-    const int c = cnt ? cnt[i] : fixed_cnt;
+    if (slot == 0) atomicMax(&s_maxcnt, c);
+    __syncthreads();
+    const int maxcnt = s_maxcnt;
     const bool vec_ok = (d & 3) == 0;
-    for (int sidx = threadIdx.x; sidx < c; sidx += blockDim.x) {
-        const int m = idx[(size_t)i * idx_stride + sidx];
-        if (m < 0) { out[(size_t)i * out_stride + sidx] = INFINITY; continue; }
-        const float* b = B + (size_t)m * d;
+    for (int sbase = 0; sbase < maxcnt; sbase += PE_KP) {
+        const int sidx = sbase + slot;
+        const bool active = sidx < c;
+        int m = -1;
+        if (active) m = idx[(size_t)row * idx_stride + sidx];
+        const float* b = B + (size_t)(m < 0 ? 0 : m) * d;
         double acc = 0.0;
-        if (vec_ok) {
-            for (int k = 0; k < d; k += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(b + k);
-                double df;
-                df = __dsub_rn(sa[k], (double)t.x);     acc = __dadd_rn(acc, __dmul_rn(df, df));
-                df = __dsub_rn(sa[k + 1], (double)t.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                df = __dsub_rn(sa[k + 2], (double)t.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                df = __dsub_rn(sa[k + 3], (double)t.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
+        for (int k0 = 0; k0 < d; k0 += PE_CHUNK) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < PE_ROWS * PE_CHUNK; e += 256) {
+                const int rr = e / PE_CHUNK, kk = e % PE_CHUNK;
+                const int gr = blockIdx.x * PE_ROWS + rr;
+                sa[rr][kk] = (gr < rows && k0 + kk < d) ? (double)A[(size_t)gr * d + k0 + kk] : 0.0;
             }
-        } else {
-            for (int k = 0; k < d; ++k) {
-                const double df = __dsub_rn(sa[k], (double)b[k]);
-                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            __syncthreads();
+            if (active && m >= 0) {
+                const int kend = min(PE_CHUNK, d - k0);
+                const double* ar = sa[r_in];
+                if (vec_ok) {
+                    for (int k = 0; k < kend; k += 8) {          // 8 floats = one 32-byte sector of the partner row
+                        const float4 t0 = *reinterpret_cast<const float4*>(b + k0 + k);
+                        float4 t1 = t0;
+                        const bool two = k + 4 < kend;
+                        if (two) t1 = *reinterpret_cast<const float4*>(b + k0 + k + 4);
+                        double df;
+                        df = __dsub_rn(ar[k], (double)t0.x);     acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        df = __dsub_rn(ar[k + 1], (double)t0.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        df = __dsub_rn(ar[k + 2], (double)t0.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        df = __dsub_rn(ar[k + 3], (double)t0.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        if (two) {
+                            df = __dsub_rn(ar[k + 4], (double)t1.x); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                            df = __dsub_rn(ar[k + 5], (double)t1.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                            df = __dsub_rn(ar[k + 6], (double)t1.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                            df = __dsub_rn(ar[k + 7], (double)t1.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < kend; ++k) {
+                        const double df = __dsub_rn(ar[k], (double)b[k0 + k]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                }
             }
         }
-        out[(size_t)i * out_stride + sidx] = finish_sqdist(acc);
+        if (active) out[(size_t)row * out_stride + sidx] = m < 0 ? INFINITY : finish_sqdist(acc);
     }
 }
 
 int launch_pair_exact(const float* A, int rows, const float* B, int d, const int* idx, int idx_stride,
                       const int* cnt, int fixed_cnt, float* out, int out_stride, cudaStream_t st) {
     if (rows <= 0) return SSG_OK;
-    const size_t smem = (size_t)d * sizeof(double);
-    if (smem > 200 * 1024) return ssg_set_error(SSG_ERR_INVALID, "pair_exact: d=%d too large", d);
-    if (smem > 48 * 1024)   // per-device attribute: set on every launch that needs it (cheap host call)
-        SSG_CUDA_TRY(cudaFuncSetAttribute(pair_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)smem));
-    pair_exact_kernel<<<rows, 256, smem, st>>>(A, B, d, idx, idx_stride, cnt, fixed_cnt, out, out_stride);
+    pair_exact_kernel<<<ssg_cdiv(rows, PE_ROWS), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt, fixed_cnt, out,
+                                                              out_stride);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // Tensor distance mode: candidates picked on the approximate matrix are re-scored exactly; each result

@@ -9,6 +9,7 @@
 // the fp32 features are represented to ~2^-17 relative: the result is an approximation (|err| ~1e-5) that is
 // only used to pick candidates; api.cu re-scores candidates exactly (DESIGN.md "tensor distance mode").
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -184,7 +185,12 @@ struct EpiDist {
 int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_split, const float* nb, int n,
                      int k, float* out, size_t ldc, cudaStream_t st) {
     EpiDist epi{na, nb, out, ldc};
-    return tc::launch_gemm<128, EpiDist>(a_split, m, b_split, n, k, epi, st);
+    // 128x256 tiles halve the shared-memory operand traffic per MMA (128x128 is smem-bandwidth bound); the
+    // environment switch exists for A/B measurements only
+    static int bn = 0;
+    if (!bn) { const char* e = getenv("SSG_GEMM_BN"); bn = e ? atoi(e) : 256; }
+    if (bn == 128 || n < 256) return tc::launch_gemm<128, EpiDist>(a_split, m, b_split, n, k, epi, st);
+    return tc::launch_gemm<256, EpiDist>(a_split, m, b_split, n, k, epi, st);
 }
 
 // Stand-alone ssg_sqdist(mode = TENSOR): split both operands into scratch memory, run the GEMM.

@@ -3,6 +3,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda_bf16.h>
 
 namespace ssg {
 
@@ -33,21 +34,44 @@ struct AOperand {
     signed char tap_plane[9], tap_dh[9], tap_dw[9];
 };
 
-template <int BN>
+// Staged epilogue (bf16 output through shared memory + TMA store, residual tile fetched by TMA): parameters.
+struct StagedEpi {
+    CUtensorMap mapC;      // output  [M, N] bf16, box 64 cols x 128 rows, 128B swizzle
+    CUtensorMap mapR;      // residual, same geometry (valid when has_res)
+    const float* bias;     // [N]
+    int relu;
+    int has_res;
+};
+
+template <int BN, bool STAGED>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN <= 64) ? 8 : (BN <= 128 ? 6 : 4);
-    static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // barriers + alignment slack
+    static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
+    static constexpr int C_BYTES = STAGED ? (BN / 64) * SUB_BYTES : 0;
+    static constexpr int STAGES = STAGED ? (BN <= 64 ? 5 : 3) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
+    static constexpr int C_OFFSET = STAGES * STAGE_BYTES;        // output staging, then 2 residual staging buffers
+    static constexpr int BAR_OFFSET = C_OFFSET + 3 * C_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
 };
 
-template <int BN, class Epi>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int BN, class Epi, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N,
-            int num_k_blocks, Epi epi) {
-    using L = SmemLayout<BN>;
+            int num_k_blocks, const __grid_constant__ Epi epi) {
+    using L = SmemLayout<BN, STAGED>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ unsigned char smem_raw[];
@@ -56,7 +80,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;           // [2] residual tile landed (staged epilogue, double buffered)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
@@ -67,6 +92,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        mbar_init(&res_bar[0], 1);
+        mbar_init(&res_bar[1], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -153,24 +180,118 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         const int q = warp & 3;               // TMEM lane quarter this warp may access
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            int m_blk, n_blk;
-            tile_coords(t, m_blk, n_blk);
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after();
-            const int row = m_blk * BM + q * 32 + lane;
+        if constexpr (!STAGED) {
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const int row = m_blk * BM + q * 32 + lane;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                tmem_ld_wait();
-                const int col0 = n_blk * BN + c * 32;
-                if (row < M && col0 < N) epi(row, col0, min(32, N - col0), v);
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                    tmem_ld_wait();
+                    const int col0 = n_blk * BN + c * 32;
+                    if (row < M && col0 < N) epi(row, col0, min(32, N - col0), v);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        } else {
+            // bf16 output staged in 128B-swizzled shared memory and written by TMA (full-line, asynchronous stores), one
+            // 64-column sub-tile at a time so that the store of one sub-tile overlaps the math of the next; the residual
+            // tile is fetched by TMA one tile ahead (double buffered).
+            constexpr int NSUB = BN / 64;
+            unsigned char* c_s = smem + L::C_OFFSET;
+            unsigned char* r_s = c_s + L::C_BYTES;                    // 2 buffers of C_BYTES
+            const bool leader = (warp == 2 && lane == 0);
+            const int r_in = q * 32 + lane;                           // row inside the tile
+            const uint32_t row_off = (uint32_t)r_in * 128u;
+            const uint32_t sw = (uint32_t)(r_in & 7);
+            auto load_residual = [&](int tile, int buf) {
+                int mb, nb;
+                tile_coords(tile, mb, nb);
+                mbar_arrive_expect_tx(&res_bar[buf], L::C_BYTES);
+#pragma unroll
+                for (int j = 0; j < NSUB; ++j)
+                    tma_load_2d(r_s + buf * L::C_BYTES + j * L::SUB_BYTES, &epi.mapR, &res_bar[buf], nb * BN + j * 64,
+                                mb * BM);
+            };
+            if (leader && epi.has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                const int rb = it & 1;
+                // the other residual buffer was last read by tile it-1, which every thread has left: prefetch tile it+1
+                if (leader && epi.has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                if (epi.has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
+                const unsigned char* rbuf = r_s + rb * L::C_BYTES;
+#pragma unroll 1
+                for (int j = 0; j < NSUB; ++j) {
+                    // sub-buffer j is free once the store issued for it one tile ago has been read out
+                    if (leader) tma_store_wait_read<NSUB - 1>();
+                    epi_bar_sync();
+                    unsigned char* csub = c_s + j * L::SUB_BYTES + row_off;
+                    const unsigned char* rsub = rbuf + j * L::SUB_BYTES + row_off;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = 2 * j + h;
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                        tmem_ld_wait();
+                        const int col0 = n_blk * BN + c * 32;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {                 // 8 columns = one 16-byte chunk
+                            const uint32_t chunk = ((uint32_t)(h * 4 + g) ^ sw) << 4;
+                            float f[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(epi.bias + col0 + 8 * g);
+                            const float4 b1 = *reinterpret_cast<const float4*>(epi.bias + col0 + 8 * g + 4);
+                            f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+                            if (epi.has_res) {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(rsub + chunk);
+                                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 ff = __bfloat1622float2(rp[e]);
+                                    f[2 * e] += ff.x;
+                                    f[2 * e + 1] += ff.y;
+                                }
+                            }
+                            if (epi.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                            }
+                            uint4 pk;
+                            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            *reinterpret_cast<uint4*>(csub + chunk) = pk;
+                        }
+                    }
+                    if (j == NSUB - 1) {                               // accumulator drained: MMAs may reuse it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    fence_proxy_async();                               // smem writes -> visible to the TMA engine
+                    epi_bar_sync();
+                    if (leader) {
+                        tma_store_2d(&epi.mapC, c_s + j * L::SUB_BYTES, n_blk * BN + j * 64, m_blk * BM);
+                        tma_store_commit();
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (leader) tma_store_wait_all();
         }
     }
     tc_fence_before();
@@ -179,9 +300,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 }
 
 // Launch with a fully prepared A operand.
-template <int BN, class Epi>
+template <int BN, class Epi, bool STAGED = false>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, STAGED>;
     if (k % BK) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of %d", k, BK);
     CUtensorMap mapB;
     SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
@@ -189,7 +310,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = tiles < sms ? tiles : sms;
-    auto kern = gemm_kernel<BN, Epi>;
+    auto kern = gemm_kernel<BN, Epi, STAGED>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, k / BK, epi);
     SSG_CHECK_LAUNCH();
@@ -206,7 +327,7 @@ int launch_gemm(const void* a, int m, const void* b, int n, int k, const Epi& ep
     A.taps = 1;
     A.tiles_per_img = 1;
     SSG_TRY(make_tmap_2d_bf16(&A.map[0], a, (uint64_t)m, (uint64_t)k, (uint64_t)k, BM));
-    return launch_gemm_op<BN, Epi>(A, m, b, n, k, epi, st);
+    return launch_gemm_op<BN, Epi, false>(A, m, b, n, k, epi, st);
 }
 
 }  // namespace tc

@@ -18,5 +18,6 @@ from . import evaluators  # noqa: F401
 from . import rerank  # noqa: F401
 from . import rerank_initial  # noqa: F401
 from . import cluster  # noqa: F401
+from . import eug  # noqa: F401
 
 __version__ = '0.2.0'

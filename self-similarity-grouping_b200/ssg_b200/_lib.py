@@ -31,6 +31,10 @@ PROTOTYPES = {
     "ssg_rerank_plan_bytes": (c_size_t, [c_void_p]),
     "ssg_rerank_run": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double,
                                c_int, c_void_p, c_void_p, c_void_p]),
+    "ssg_rerank_distance_rows": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
+    "ssg_rerank_tables": (c_int, [c_void_p, P(c_void_p), P(c_void_p), P(c_void_p), P(c_void_p)]),
+    "ssg_rerank_finish": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_void_p]),
     "ssg_rerank_host": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double,
                                 c_int, c_int, c_void_p, c_void_p]),
     "ssg_rerank_init": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p,

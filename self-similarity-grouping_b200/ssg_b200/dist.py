@@ -1,0 +1,184 @@
+"""Multi-GPU pseudo-label cycle: one process per GPU (torch.distributed, NCCL over NVLink), SURVEY.md §8e.
+
+Sharding of ONE cycle over `world` ranks:
+  1. embed   : rank r embeds the contiguous image shard [lo_r, hi_r) of the target and of the source set;
+  2. exchange: all-gather of the feature banks ([banks, N, 2048] float32 on every rank) — the one real exchange step;
+  3. re-rank : for every bank, rank r computes the distance stages (GEMM, candidate selection, exact re-scoring) for
+               its row block [lo_r, hi_r) only (ssg_rerank_distance_rows), the small per-row tables (row min / max,
+               21 rank columns) are all-gathered (~4.4 MB per bank), and the owner rank (bank % world) runs the cheap
+               remaining stages (k-reciprocal encoding ... final distance), eps and DBSCAN;
+  4. labels  : broadcast from the owners (N int64 per bank).
+
+All collectives go through a small `Comm` wrapper, and all compute through a `backend` object, so that the sharding
+logic itself is exercised on CPU with the gloo backend (tests/test_dist_gloo.py) against a fake backend.
+"""
+import numpy as np
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous balanced shard [lo, hi) of n rows for `rank`: the first n % world ranks get one extra row."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_shard(n, world):
+    return (int(n) + int(world) - 1) // int(world)
+
+
+class Comm(object):
+    """torch.distributed wrapper with row-block all-gather for uneven shards (pad to the largest shard)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.rank = dist.get_rank(group) if self.on else 0
+
+    def all_gather_rows(self, local, n_total, dim=0):
+        """local: this rank's rows [lo, hi) along `dim` -> tensor with all n_total rows along `dim` on every rank."""
+        import torch
+        if self.world == 1:
+            return local
+        m = max_shard(n_total, self.world)
+        loc = local.movedim(dim, 0).contiguous()
+        pad = torch.zeros((m,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
+        pad[: loc.shape[0]] = loc
+        out = torch.empty((self.world * m,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=loc.device)
+        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(n_total, self.world, r)
+            parts.append(out[r * m: r * m + (hi - lo)])
+        return torch.cat(parts, 0).movedim(0, dim).contiguous()
+
+    def all_gather_rows_inplace(self, full, n_total):
+        """full: [n_total, ...] tensor whose rows [lo_r, hi_r) are valid on rank r -> all rows valid everywhere."""
+        if self.world == 1:
+            return full
+        lo, hi = shard_bounds(n_total, self.world, self.rank)
+        full.copy_(self.all_gather_rows(full[lo:hi], n_total, 0))
+        return full
+
+    def broadcast(self, t, src):
+        if self.world > 1:
+            self.dist.broadcast(t, src=src, group=self.group)
+        return t
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+
+
+class CudaBackend(object):
+    """The real compute: libssg_b200 through the plans of ssg_b200.{embed,rerank,cluster}."""
+
+    def __init__(self, device=None, dist_mode=None, batch=256):
+        from . import _lib
+        from .cycle import _dist_mode
+        self._lib = _lib
+        self.dev = _lib.require_cuda(device)
+        self.mode = _dist_mode(dist_mode)
+        self.batch = batch
+
+    def embed(self, model, images, num_split):
+        from .embed import embed_images
+        return embed_images(model, images, num_split, False, self.batch, self.dev.index)   # [banks, n_local, 2048]
+
+    def plan(self, n, ns, d):
+        from .rerank import get_plan
+        return get_plan(n, ns, d, self.dev.index)
+
+    def distance_rows(self, plan, src, tgt, k1, row0, rows):
+        L = self._lib
+        L.check(L.load().ssg_rerank_distance_rows(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), tgt.shape[0],
+                                                  tgt.shape[1], int(k1), self.mode, int(row0), int(rows), None,
+                                                  L.stream_ptr()))
+
+    def tables(self, plan, n):
+        """Zero-copy torch views of the plan's per-row tables: rowmin [n], rowmax [n], rank [n,32], rank_val [n,32]."""
+        import ctypes
+        import torch
+        L = self._lib
+        ptrs = [ctypes.c_void_p() for _ in range(4)]
+        L.check(L.load().ssg_rerank_tables(plan._h, *[ctypes.byref(p) for p in ptrs]))
+        specs = [((n,), "<f4"), ((n,), "<f4"), ((n, L.RANK_STRIDE), "<i4"), ((n, L.RANK_STRIDE), "<f4")]
+        return [torch.as_tensor(_DevArray(p.value, shape, ts), device=self.dev) for p, (shape, ts) in zip(ptrs, specs)]
+
+    def finish(self, plan, tgt, k1, k2, lambda_value, final):
+        L = self._lib
+        L.check(L.load().ssg_rerank_finish(plan._h, tgt.data_ptr(), tgt.shape[0], tgt.shape[1], int(k1), int(k2),
+                                           float(lambda_value), final.data_ptr(), L.stream_ptr()))
+
+    def new_final(self, n):
+        import torch
+        return torch.empty((n, n), dtype=torch.float64, device=self.dev)
+
+    def eps(self, final, rho):
+        from .cluster import get_plan
+        return get_plan(final.shape[0], self.dev.index).eps(final, rho)[0]
+
+    def dbscan(self, final, eps, min_samples):
+        from .cluster import _with_capacity_retry
+        n = final.shape[0]
+        return _with_capacity_retry(n, self.dev.index, lambda p: p.dbscan(final, eps, min_samples)[0])
+
+
+class _DevArray(object):
+    """Minimal __cuda_array_interface__ holder for a raw device pointer owned by a plan."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_split=2, lambda_value=0.1, rho=1.6e-3,
+                               eps_list=None, min_samples=4, k1=20, k2=6, backend=None, comm=None, features=None):
+    """Run one pseudo-label cycle sharded over the ranks of `comm`.
+
+    tgt_shard / src_shard: this rank's image rows [shard_bounds(n, world, rank)) (host or device tensors).
+    `features=(tgt_local, src_local)` ([banks, n_local, d] each) skips the embedding (pre-extracted features).
+    Returns (labels_list [np.int64 arrays], eps_list, keep_mask) — identical on every rank.
+    """
+    import torch
+    comm = comm or Comm()
+    backend = backend or CudaBackend()
+    banks = num_split + 1 if num_split > 1 else 1
+    if features is None:
+        tloc = backend.embed(model, tgt_shard, num_split)
+        sloc = backend.embed(model, src_shard, num_split)
+    else:
+        tloc, sloc = features
+    # the one real exchange step: feature banks of every image on every rank
+    tgt = comm.all_gather_rows(tloc, n_tgt, dim=1)
+    src = comm.all_gather_rows(sloc, n_src, dim=1)
+    lo, hi = shard_bounds(n_tgt, comm.world, comm.rank)
+    plan = backend.plan(n_tgt, n_src, tgt.shape[2])
+    final = None
+    labels_dev, eps_out = [], []
+    for b in range(banks):
+        tb, sb = tgt[b].contiguous(), src[b].contiguous()
+        backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
+        for tab in backend.tables(plan, n_tgt):
+            comm.all_gather_rows_inplace(tab, n_tgt)
+        owner = b % comm.world
+        lab = torch.empty((n_tgt,), dtype=torch.int64, device=tb.device)
+        eps_t = torch.zeros((1,), dtype=torch.float64, device=tb.device)
+        if comm.rank == owner:
+            if final is None:
+                final = backend.new_final(n_tgt)
+            backend.finish(plan, tb, k1, k2, lambda_value, final)
+            eps = backend.eps(final, rho) if eps_list is None else float(eps_list[b])
+            lab.copy_(backend.dbscan(final, eps, min_samples))
+            eps_t[0] = eps
+        labels_dev.append(lab)
+        eps_out.append(eps_t)
+    for b in range(banks):
+        comm.broadcast(labels_dev[b], b % comm.world)
+        comm.broadcast(eps_out[b], b % comm.world)
+    labels = [l.cpu().numpy() for l in labels_dev]
+    eps_vals = [float(e.item()) for e in eps_out]
+    keep = ~(np.stack(labels, 0) == -1).any(0)
+    return labels, eps_vals, keep

@@ -214,3 +214,48 @@ def test_trunk_batch_invariance_and_reset_params_regime():
         o = x1[k] + x1f[k]
         want = o / o.norm(dim=1, keepdim=True)
         assert _rel_err(got[k], want) <= 5e-2
+
+
+def test_eug_label_estimation_matches_numpy_restatement():
+    """reid/eug.py:193-253 (both branches) on features extracted by the CUDA trunk, against the reference's numpy
+    arithmetic applied to the same features."""
+    import torch
+    import reid.eug
+    from oracle import resnet_oracle as R, ssg_oracle as O
+    model = R.build_model(1, 0)
+    rng = np.random.RandomState(0)
+    pats = R.synth_images(6, 11)
+    def make(n, seed):
+        g = torch.Generator().manual_seed(seed)
+        lab = torch.randint(0, 6, (n,), generator=g)
+        return pats[lab] + 0.4 * torch.randn(n, 3, 256, 128, generator=g), lab.numpy()
+    l_img, l_lab = make(12, 1)
+    u_img, u_lab = make(20, 2)
+    l_data = [("l%d" % i, int(l_lab[i]), 0) for i in range(12)]
+    u_data = [("u%d" % i, int(u_lab[i]), 0) for i in range(20)]
+    store = {"l": l_img, "u": u_img}
+
+    def loader_factory(dataset, training):
+        imgs = store[dataset[0][0][0]]
+        names = [d[0] for d in dataset]
+        return [(imgs, names, [d[1] for d in dataset], [0] * len(names))]
+
+    for rerank in (False, True):
+        eug = reid.eug.EUG("resnet50", 32, "Weight" if rerank else "Dissimilarity", 0, None, l_data, u_data, None, 20,
+                           pretrained_model=model, rerank=rerank, loader_factory=loader_factory)
+        out = eug.estimate_label()
+        u_f, l_f = eug.get_feature(u_data), eug.get_feature(l_data)
+        if not rerank:
+            labels, scores = out
+            d = np.stack([np.linalg.norm(l_f - uf, axis=1) for uf in u_f])
+            assert np.array_equal(labels, l_lab[d.argmin(1)].astype(np.float64))
+            np.testing.assert_allclose(scores, -d.min(1), atol=1e-5)
+        else:
+            labels, scores, conf = out
+            rr = O.re_ranking_init(u_f @ l_f.T, u_f @ u_f.T, l_f @ l_f.T)
+            idx = rr.argmin(1)
+            assert np.mean(labels == l_lab[idx]) >= 0.9           # near-ties may resolve differently (GPU GEMM vs np.dot)
+            np.testing.assert_allclose(scores, -rr.min(1), atol=2e-4)
+            assert conf.shape == (20,) and np.all(conf <= 1.0)
+        sel = eug.select_top_data(scores, 5)
+        assert sel.sum() == 5 and len(eug.generate_new_train_data(sel, labels)) == 12 + 5
