@@ -18,7 +18,8 @@ namespace tc {
 constexpr int BM = 128;        // UMMA M (one TMEM lane per output row)
 constexpr int BK = 64;         // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // two warps per TMEM lane quarter: each takes every other 32-column chunk
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int GROUP_M = 16;    // tile rasterisation: 16 m-blocks share each B tile while it is L2-hot
 
 // A operand: plain [M,K] matrix (mode 0) or implicit-GEMM view of NHWC activations (mode 1): the K axis runs over
@@ -65,7 +66,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 
 template <int BN, class Epi, bool STAGED>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -91,7 +92,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         tma_prefetch_desc(&A.map[0]);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
         mbar_init(&res_bar[0], 1);
         mbar_init(&res_bar[1], 1);
         fence_barrier_init();
@@ -176,8 +177,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int q = warp & 3;               // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;      // 0/1: which 32-column chunk of every 64 this warp handles
         int acc = 0;
         uint32_t acc_phase = 0;
         if constexpr (!STAGED) {
@@ -188,7 +190,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 tc_fence_after();
                 const int row = m_blk * BM + q * 32 + lane;
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = grp; c < BN / 32; c += 2) {
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                     tmem_ld_wait();
@@ -211,6 +213,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             const int r_in = q * 32 + lane;                           // row inside the tile
             const uint32_t row_off = (uint32_t)r_in * 128u;
             const uint32_t sw = (uint32_t)(r_in & 7);
+            __shared__ float s_bias[BN];
+            const int epi_tid = threadIdx.x - 64;
             auto load_residual = [&](int tile, int buf) {
                 int mb, nb;
                 tile_coords(tile, mb, nb);
@@ -228,6 +232,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 const int rb = it & 1;
                 // the other residual buffer was last read by tile it-1, which every thread has left: prefetch tile it+1
                 if (leader && epi.has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                if (epi_tid < BN) s_bias[epi_tid] = epi.bias[n_blk * BN + epi_tid];   // visible after the next barrier
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 if (epi.has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
@@ -239,19 +244,18 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     epi_bar_sync();
                     unsigned char* csub = c_s + j * L::SUB_BYTES + row_off;
                     const unsigned char* rsub = rbuf + j * L::SUB_BYTES + row_off;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    {
+                        const int h = grp;
                         const int c = 2 * j + h;
                         uint32_t v[32];
                         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                         tmem_ld_wait();
-                        const int col0 = n_blk * BN + c * 32;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {                 // 8 columns = one 16-byte chunk
                             const uint32_t chunk = ((uint32_t)(h * 4 + g) ^ sw) << 4;
                             float f[8];
-                            const float4 b0 = *reinterpret_cast<const float4*>(epi.bias + col0 + 8 * g);
-                            const float4 b1 = *reinterpret_cast<const float4*>(epi.bias + col0 + 8 * g + 4);
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 8 * g);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + c * 32 + 8 * g + 4);
                             f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
                             f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
                             f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
