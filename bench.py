@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--dist-mode", default="tensor", choices=["tensor", "exact"])
     ap.add_argument("--cpu-sample", type=int, default=1280, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-embed-sample", type=int, default=64, help="images of the bounded CPU embedding sample")
-    ap.add_argument("--batch", type=int, default=256, help="images per embedding batch")
+    ap.add_argument("--batch", type=int, default=512, help="images per embedding batch")
     ap.add_argument("--features-only", action="store_true", help="skip the embedding stage (synthetic features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true",

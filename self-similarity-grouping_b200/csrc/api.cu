@@ -160,7 +160,7 @@ static int dist_block(ssg_rerank_plan* p, const float* X, int rows, const float*
 }
 
 constexpr int CAND_STRIDE = 64;   // candidate table row stride
-constexpr int CAND_K = 40;        // nearest-neighbour candidates re-scored per row (k1+1 <= 32 needed)
+constexpr int CAND_K = 32;        // nearest-neighbour candidates re-scored per row (k1+1 <= 32 needed)
 constexpr int CAND_EXT = 8;       // candidates for the row minimum / maximum
 constexpr int FB_ROWS = 1024;     // rows per exact-fallback batch
 // Certified error of the tensor-core squared distance, relative to (|x|^2 + max|y|^2):
@@ -231,7 +231,7 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
             { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_sb, p->norm_s, ns, k3,
                                      p->dmat, (size_t)ns, st)); }
             { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)ns, rows, ns, nullptr, ke, false, p->cand_idx, p->cand_val,
-                                      CAND_STRIDE, st)); }
+                                      CAND_STRIDE, p->cursor, st)); }
             { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_src, d, p->cand_idx, CAND_STRIDE, nullptr, ke,
                                       p->cand_exact, CAND_STRIDE, st)); }
             { SSG_PROF("cand_reduce", st); SSG_TRY(launch_cand_reduce(rows, ns, ke, false, p->cand_exact, p->cand_val, CAND_STRIDE, p->norm_t + r0,
@@ -248,14 +248,14 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
             { SSG_PROF("gemm_dist_tc", st); SSG_TRY(launch_gemm_dist(ta + (size_t)r0 * k3 * 2, p->norm_t + r0, rows, p->split_tb, p->norm_t, n, k3,
                                      p->dmat, (size_t)n, st)); }
             { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, nullptr, ke, true, p->cand_idx, p->cand_val,
-                                      CAND_STRIDE, st)); }
+                                      CAND_STRIDE, p->cursor, st)); }
             { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_tgt, d, p->cand_idx, CAND_STRIDE, nullptr, ke,
                                       p->cand_exact, CAND_STRIDE, st)); }
             { SSG_PROF("cand_reduce", st); SSG_TRY(launch_cand_reduce(rows, n, ke, true, p->cand_exact, p->cand_val, CAND_STRIDE, p->norm_t + r0,
                                        p->norm_max, TENSOR_EPS_REL, p->rowmax + r0, cnt_tgt, p->flag_tgt, r0, st)); }
             if (want_rank) {
                 { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, nullptr, kc, false, p->cand_idx, p->cand_val,
-                                          CAND_STRIDE, st)); }
+                                          CAND_STRIDE, p->cursor, st)); }
                 { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt + (size_t)r0 * d, rows, d_tgt, d, p->cand_idx, CAND_STRIDE, nullptr,
                                           kc, p->cand_exact, CAND_STRIDE, st)); }
                 { SSG_PROF("rank_finalize", st); SSG_TRY(launch_rank_finalize(rows, n, kc, k1p < kc ? k1p : kc, p->cand_idx, p->cand_val,
@@ -294,7 +294,7 @@ static int distance_stages_tensor(ssg_rerank_plan* p, const float* d_src, int ns
         SSG_TRY(launch_scatter_f32(fmax, cnt, 1, 1, p->flag_tgt + f0, p->rowmax, 1, st));
         if (want_rank) {
             { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, cnt, n, fmax, k1p, false, p->fb_i32, p->fb_f32,
-                                      SSG_RANK_STRIDE, st)); }
+                                      SSG_RANK_STRIDE, p->cursor, st)); }
             SSG_TRY(launch_scatter_f32((const float*)p->fb_i32, cnt, k1p, SSG_RANK_STRIDE, p->flag_tgt + f0,
                                        (float*)p->rank, SSG_RANK_STRIDE, st));
             SSG_TRY(launch_scatter_f32(p->fb_f32, cnt, k1p, SSG_RANK_STRIDE, p->flag_tgt + f0, p->rank_val,
@@ -333,7 +333,7 @@ static int distance_stages_exact(ssg_rerank_plan* p, const float* d_src, int ns,
             if (want_rank)
                 { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, rows, n, p->rowmax + r0, k1p, false,
                                           p->rank + (size_t)r0 * SSG_RANK_STRIDE,
-                                          p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, SSG_RANK_STRIDE, st)); }
+                                          p->rank_val + (size_t)r0 * SSG_RANK_STRIDE, SSG_RANK_STRIDE, p->cursor, st)); }
             if (d_euclid)
                 SSG_CUDA_TRY(cudaMemcpyAsync(d_euclid + (size_t)r0 * n, p->dmat, sizeof(float) * (size_t)rows * n,
                                              cudaMemcpyDeviceToDevice, st));
@@ -389,8 +389,18 @@ extern "C" int ssg_rerank_finish(ssg_rerank_plan* p, const float* d_tgt, int n, 
     { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
     // (v) rerank.py:74-92
     { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
-    { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, p->v_idx, SSG_V_STRIDE, p->v_cnt, 0, p->v_val, SSG_V_STRIDE, st)); }
-    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st)); }
+    {
+        // entries of R*(i) inside row i's own rank columns already have their exact normalised distance; only the
+        // expansion entries are re-scored (scratch: the not-yet-used expanded-row buffers, each [n, VQ_STRIDE])
+        int* todo_idx = p->q_idx;
+        int* todo_slot = p->csc_row;
+        float* todo_od = p->q_val;
+        int* todo_cnt = p->q_cnt;
+        { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_classify(p->rank, p->rank_val, n, k1p, p->v_idx, p->v_cnt, p->v_val, todo_idx, todo_slot, todo_cnt, st)); }
+        { SSG_PROF("pair_exact", st); SSG_TRY(launch_pair_exact(d_tgt, n, d_tgt, d, todo_idx, SSG_V_STRIDE, todo_cnt, 0, todo_od, SSG_V_STRIDE, st)); }
+        { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_scatter(p->rowmax, n, todo_od, todo_slot, todo_cnt, p->v_val, st)); }
+    }
+    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, 1, st)); }
     // (vi) rerank.py:94-98  (k2 == 1: V is used as it is)
     if (k2 != 1) {
         { SSG_PROF("query_expand", st); SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st)); }
@@ -472,10 +482,10 @@ extern "C" int ssg_rerank_init(ssg_rerank_plan* p, const float* d_qg, const floa
     { SSG_PROF("init_assemble", st); SSG_TRY(launch_init_assemble(d_qg, d_qq, d_gg, q, g, p->dmat, st)); }
     { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, n, n, nullptr, p->rowmax, st)); }
     { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, n, n, p->rowmax, k1p, false, p->rank, p->rank_val,
-                                      SSG_RANK_STRIDE, st)); }
+                                      SSG_RANK_STRIDE, p->cursor, st)); }
     { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
     SSG_TRY(launch_gather_row_vals(p->dmat, (size_t)n, n, p->v_idx, p->v_cnt, SSG_V_STRIDE, p->v_val, st));
-    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, st)); }
+    { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, 0, st)); }
     if (k2 != 1) {
         { SSG_PROF("query_expand", st); SSG_TRY(launch_query_expand(p->rank, n, k2, p->v_idx, p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, st)); }
     } else {

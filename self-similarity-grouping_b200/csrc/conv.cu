@@ -4,6 +4,7 @@
 // with eval-mode BatchNorm folded into the bf16 weights and bias/residual/ReLU fused in the epilogue.
 // The rest are small HBM-bound helpers: weight folding, stem im2col, max-pool, parity split, pooled tail.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -26,6 +27,11 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     epi.has_res = residual != nullptr;
     SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
     SSG_TRY(make_tmap_2d_bf16(&epi.mapR, residual ? residual : y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    // 128x256 tiles for the K-heavy convolutions without a residual (SSG_CONV_BN256=0 disables, for A/B runs)
+    static int bn256 = -1;
+    if (bn256 < 0) { const char* e = getenv("SSG_CONV_BN256"); bn256 = e ? atoi(e) : 1; }
+    if (bn256 && !residual && cout % 256 == 0 && k >= 256)
+        return tc::launch_gemm_op<256, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
 }
@@ -39,6 +45,7 @@ int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int
     A.cblks = cin / tc::BK;
     A.taps = 1;
     A.tiles_per_img = 1;
+    A.hmul = 1;
     SSG_TRY(make_tmap_2d_bf16(&A.map[0], x, (uint64_t)m, (uint64_t)cin, (uint64_t)cin, tc::BM));
     return gemm_dispatch(A, m, w, cout, cin, bias, residual, relu, y, st);
 }
@@ -57,8 +64,32 @@ static int tile_geometry(int H, int W, int* bw, int* bh, int* bb, int* tiles_per
     return SSG_OK;
 }
 
-// 3x3 convolution, padding 1.  stride 1: x is [B,H,W,C] NHWC.  stride 2: x points to the four parity planes
-// [4][B,H/2,W/2,C] produced by parity_split (plane = (h&1)*2 + (w&1)); H, W are the OUTPUT map size either way.
+// stride-2 convolutions read the un-split input through element-strided TMA boxes unless SSG_S2_PLANES=1
+bool s2_strided_tma() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SSG_S2_PLANES"); v = (e && atoi(e)) ? 0 : 1; }
+    return v != 0;
+}
+
+// 1x1 stride-2 convolution straight from x [B,2H,2W,C] (H, W = output size): implicit mode with a single tap.
+int conv1x1_s2(const void* x, int B, int H, int W, int cin, const void* w, const float* bias, int cout, int relu,
+               void* y, cudaStream_t st) {
+    if (cin % 64) return ssg_set_error(SSG_ERR_INVALID, "conv1x1_s2: Cin=%d must be a multiple of 64", cin);
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 1;
+    A.cblks = cin / tc::BK;
+    A.taps = 1;
+    A.hmul = 2;
+    int bw;
+    SSG_TRY(tile_geometry(H, W, &bw, &A.bh, &A.bb, &A.tiles_per_img));
+    SSG_TRY(make_tmap_nhwc_bf16(&A.map[0], x, B, 2 * H, 2 * W, cin, bw, A.bh, A.bb, 2));
+    return gemm_dispatch(A, B * H * W, w, cout, cin, bias, nullptr, relu, y, st);
+}
+
+// 3x3 convolution, padding 1; H, W are the OUTPUT map size.  stride 1: x is [B,H,W,C] NHWC.
+// stride 2: x is the input [B,2H,2W,C] read through stride-2 TMA boxes (default), or — SSG_S2_PLANES=1 — the four
+// parity planes [4][B,H,W,C] produced by parity_split (plane = (h&1)*2 + (w&1)).
 int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout,
             int relu, void* y, cudaStream_t st) {
     if (cin % 64) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: Cin=%d must be a multiple of 64", cin);
@@ -70,14 +101,20 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
     int bw;
     SSG_TRY(tile_geometry(H, W, &bw, &A.bh, &A.bb, &A.tiles_per_img));
     const size_t plane_elems = (size_t)B * H * W * cin;
-    const int nplanes = stride == 2 ? 4 : 1;
-    for (int pl = 0; pl < nplanes; ++pl)
-        SSG_TRY(make_tmap_nhwc_bf16(&A.map[pl], (const __nv_bfloat16*)x + pl * plane_elems, B, H, W, cin, bw,
-                                    A.bh, A.bb));
+    const bool strided = stride == 2 && s2_strided_tma();
+    A.hmul = strided ? 2 : 1;
+    if (strided) {
+        SSG_TRY(make_tmap_nhwc_bf16(&A.map[0], x, B, 2 * H, 2 * W, cin, bw, A.bh, A.bb, 2));
+    } else {
+        const int nplanes = stride == 2 ? 4 : 1;
+        for (int pl = 0; pl < nplanes; ++pl)
+            SSG_TRY(make_tmap_nhwc_bf16(&A.map[pl], (const __nv_bfloat16*)x + pl * plane_elems, B, H, W, cin, bw,
+                                        A.bh, A.bb));
+    }
     for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) {
             const int t = kh * 3 + kw;
-            if (stride == 1) {
+            if (stride == 1 || strided) {
                 A.tap_plane[t] = 0; A.tap_dh[t] = (signed char)(kh - 1); A.tap_dw[t] = (signed char)(kw - 1);
             } else {
                 // input row 2h+kh-1: kh=0 -> odd plane, h-1; kh=1 -> even plane, h; kh=2 -> odd plane, h

@@ -6,6 +6,9 @@
 namespace ssg {
 int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int cout, const void* residual,
             int relu, void* y, cudaStream_t st);
+bool s2_strided_tma();
+int conv1x1_s2(const void* x, int B, int H, int W, int cin, const void* w, const float* bias, int cout, int relu,
+               void* y, cudaStream_t st);
 int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout,
             int relu, void* y, cudaStream_t st);
 int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,

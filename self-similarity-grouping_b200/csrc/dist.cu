@@ -160,7 +160,9 @@ __device__ __forceinline__ uint32_t sel_key(float v, bool largest) {
 
 __global__ void __launch_bounds__(SEL_NT)
 row_select_kernel(const float* __restrict__ M, size_t ld, int cols, const float* __restrict__ scale,
-                  int K, bool largest, int* __restrict__ out_idx, float* __restrict__ out_val, int out_stride) {
+                  int K, bool largest, int* __restrict__ out_idx, float* __restrict__ out_val, int out_stride,
+                  const int* __restrict__ row_done) {
+    if (row_done && row_done[blockIdx.x]) return;     // already served by the sampled fast path
     __shared__ int hist[SEL_BINS];
     __shared__ int wsum[SEL_NT / 32];
     __shared__ uint32_t s_prefix;
@@ -263,12 +265,100 @@ row_select_kernel(const float* __restrict__ M, size_t ld, int cols, const float*
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// row_select, sampled fast path: a sorted 512-element sample of the row gives a pivot that is, with overwhelming
+// probability, above the K-th smallest element and below ~2 % of the row; ONE pass over the row then collects
+// everything <= pivot into shared memory, and the K smallest by (value, index) are ranked there.  Rows for which
+// the pivot turns out too low (fewer than K collected) or too high (list overflow) are left to the radix-select
+// kernel above (row_done[row] = 0), so the result is always exact.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SMP_N = 512;
+constexpr int SMP_CAP = 1024;
+
+__global__ void __launch_bounds__(SEL_NT)
+row_select_sampled_kernel(const float* __restrict__ M, size_t ld, int cols, const float* __restrict__ scale,
+                          int K, bool largest, int* __restrict__ out_idx, float* __restrict__ out_val,
+                          int out_stride, int* __restrict__ row_done) {
+    __shared__ uint32_t samp[SMP_N];
+    __shared__ uint32_t l_key[SMP_CAP];
+    __shared__ int l_idx[SMP_CAP];
+    __shared__ int s_cnt;
+    const int row_id = blockIdx.x, tid = threadIdx.x;
+    const float* row = M + (size_t)row_id * ld;
+    const bool scaled = scale != nullptr;
+    const float s = scaled ? scale[row_id] : 1.0f;
+    const int Keff = min(K, cols);
+    if (cols <= SMP_CAP / 2) {                   // short rows: not worth sampling
+        if (tid == 0) row_done[row_id] = 0;
+        return;
+    }
+    for (int t = tid; t < SMP_N; t += SEL_NT) {
+        const int j = (int)(((long long)t * cols) / SMP_N);
+        samp[t] = sel_key(sel_value(row, j, scaled, s), largest);
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    for (int k = 2; k <= SMP_N; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < SMP_N; t += SEL_NT) {
+                const int p = t ^ j;
+                if (p > t) {
+                    const uint32_t a = samp[t], b = samp[p];
+                    const bool up = (t & k) == 0;
+                    if ((a > b) == up) { samp[t] = b; samp[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // expected rank of the K-th smallest in the sample is K*SMP_N/cols; take 3x that plus a safety margin
+    int pi = (int)(((long long)Keff * SMP_N * 3 + cols - 1) / cols) + 6;
+    if (pi > SMP_N - 1) pi = SMP_N - 1;
+    const uint32_t pivot = samp[pi];
+    for (int j = tid; j < cols; j += SEL_NT) {
+        const uint32_t k = sel_key(sel_value(row, j, scaled, s), largest);
+        if (k <= pivot) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < SMP_CAP) { l_key[pos] = k; l_idx[pos] = j; }
+        }
+    }
+    __syncthreads();
+    const int c = s_cnt;
+    if (c > SMP_CAP || c < Keff) {
+        if (tid == 0) row_done[row_id] = 0;
+        return;
+    }
+    // rank by (key, index) among the c collected elements; ranks < Keff are the answer
+    for (int e = tid; e < c; e += SEL_NT) {
+        const uint32_t k = l_key[e];
+        const int ix = l_idx[e];
+        int r = 0;
+        for (int q = 0; q < c; ++q) {
+            const uint32_t kq = l_key[q];
+            r += (kq < k) || (kq == k && l_idx[q] < ix);
+        }
+        if (r < Keff) {
+            out_idx[(size_t)row_id * out_stride + r] = ix;
+            out_val[(size_t)row_id * out_stride + r] = sel_value(row, ix, scaled, s);
+        }
+    }
+    for (int q = Keff + tid; q < K; q += SEL_NT) {
+        out_idx[(size_t)row_id * out_stride + q] = -1;
+        out_val[(size_t)row_id * out_stride + q] = INFINITY;
+    }
+    if (tid == 0) row_done[row_id] = 1;
+}
+
 int launch_row_select(const float* M, size_t ld, int rows, int cols, const float* scale, int K, bool largest,
-                      int* out_idx, float* out_val, int out_stride, cudaStream_t st) {
+                      int* out_idx, float* out_val, int out_stride, int* row_done, cudaStream_t st) {
     if (K < 1 || K > SEL_KMAX || K > out_stride)
         return ssg_set_error(SSG_ERR_INVALID, "row_select: K=%d out of range", K);
     if (rows <= 0) return SSG_OK;
-    row_select_kernel<<<rows, SEL_NT, 0, st>>>(M, ld, cols, scale, K, largest, out_idx, out_val, out_stride);
+    if (row_done)
+        row_select_sampled_kernel<<<rows, SEL_NT, 0, st>>>(M, ld, cols, scale, K, largest, out_idx, out_val, out_stride,
+                                                          row_done);
+    row_select_kernel<<<rows, SEL_NT, 0, st>>>(M, ld, cols, scale, K, largest, out_idx, out_val, out_stride, row_done);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -172,7 +172,9 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
             const int i1 = li, i2 = li + 1, i3 = li + 2, id = li + 3;
             li += (b == 0) ? 4 : 3;
             { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
-            if (stride == 2) {
+            if (stride == 2 && s2_strided_tma()) {
+                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+            } else if (stride == 2) {
                 { SSG_PROF("parity_split", st); SSG_TRY(parity_split(p->t1, NB, H, W, mid, 4, p->planes, st)); }
                 { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
             } else {
@@ -180,7 +182,9 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
             }
             const void* res = x;
             if (b == 0) {
-                if (stride == 2) {
+                if (stride == 2 && s2_strided_tma()) {
+                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1_s2(x, NB, OH, OW, C, p->w[id], p->b[id], outc, 0, p->ds, st)); }
+                } else if (stride == 2) {
                     { SSG_PROF("parity_split", st); SSG_TRY(parity_split(x, NB, H, W, C, 1, p->xs, st)); }
                     { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->xs, NB * OH * OW, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
                 } else {
@@ -210,11 +214,13 @@ extern "C" int ssg_op_conv(const void* d_x, int B, int H, int W, int cin, int ks
     cudaStream_t st = (cudaStream_t)stream;
     if (ksize == 1) {
         if (stride == 1) return conv1x1(d_x, B * H * W, cin, d_w, d_bias, cout, d_res, relu, d_y, st);
+        if (s2_strided_tma() && !d_res) return conv1x1_s2(d_x, B, H / 2, W / 2, cin, d_w, d_bias, cout, relu, d_y, st);
         SSG_TRY(parity_split(d_x, B, H, W, cin, 1, d_scratch, st));
         return conv1x1(d_scratch, B * (H / 2) * (W / 2), cin, d_w, d_bias, cout, d_res, relu, d_y, st);
     }
     if (d_res) return ssg_set_error(SSG_ERR_INVALID, "op_conv: residual is only fused into 1x1 convolutions");
     if (stride == 1) return conv3x3(d_x, B, H, W, cin, 1, d_w, d_bias, cout, relu, d_y, st);
+    if (s2_strided_tma()) return conv3x3(d_x, B, H / 2, W / 2, cin, 2, d_w, d_bias, cout, relu, d_y, st);
     SSG_TRY(parity_split(d_x, B, H, W, cin, 4, d_scratch, st));
     return conv3x3(d_scratch, B, H / 2, W / 2, cin, 2, d_w, d_bias, cout, relu, d_y, st);
 }

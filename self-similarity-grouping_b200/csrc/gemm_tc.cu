@@ -59,16 +59,18 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 
 // 4-D bf16 NHWC activation [B, H, W, C] seen as dims (C, W, H, B); box = (64, bw, bh, bb): one box is a
 // [bb*bh*bw, 64] K-major tile of an implicit-GEMM A operand; out-of-bounds (halo) elements are zero-filled.
+// `stride` (1 or 2) is the element stride of the W and H traversal: a stride-2 box of extent (2bw, 2bh) delivers
+// every other pixel, i.e. the bw x bh input pixels a stride-2 convolution tap needs — no parity-split copy.
 int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
-                        uint32_t bw, uint32_t bh, uint32_t bb) {
+                        uint32_t bw, uint32_t bh, uint32_t bb, uint32_t stride) {
     PFN_encodeTiled enc;
     SSG_TRY(get_encode(&enc));
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (C * 2) % 16)
         return ssg_set_error(SSG_ERR_INVALID, "tensor map: NHWC base/channel pitch must be 16-byte aligned");
     cuuint64_t dims[4] = {C, W, H, B};
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
-    cuuint32_t box[4] = {64, bw, bh, bb};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t box[4] = {64, bw * stride, bh * stride, bb};
+    cuuint32_t estr[4] = {1, stride, stride, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

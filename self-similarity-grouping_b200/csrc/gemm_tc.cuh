@@ -10,7 +10,7 @@ namespace ssg {
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows);
 int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
-                        uint32_t bw, uint32_t bh, uint32_t bb);
+                        uint32_t bw, uint32_t bh, uint32_t bb, uint32_t stride = 1);
 int tc_num_sms(int* out);
 
 namespace tc {
@@ -32,6 +32,7 @@ struct AOperand {
     int taps;
     int bh, bb;            // box rows / images per 128-pixel tile
     int tiles_per_img;     // >= 1
+    int hmul;              // input rows per output row (2 for stride-2 boxes read straight from the input map)
     signed char tap_plane[9], tap_dh[9], tap_dw[9];
 };
 
@@ -44,16 +45,23 @@ struct StagedEpi {
     int has_res;
 };
 
+// BN <= 128 (staged): one output sub-buffer per 64-column sub-tile + two residual tile buffers, 3-5 operand stages.
+// BN == 256 (staged): K-heavy convolutions without residual: a ring of two output sub-buffers, no residual staging,
+//                     4 operand stages (128x256 tiles halve the shared-memory operand traffic per MMA).
 template <int BN, bool STAGED>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
-    static constexpr int C_BYTES = STAGED ? (BN / 64) * SUB_BYTES : 0;
-    static constexpr int STAGES = STAGED ? (BN <= 64 ? 5 : 3) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
+    static constexpr int NSUB = BN / 64;
+    static constexpr int NBUF = NSUB > 2 ? 2 : NSUB;             // output sub-buffers
+    static constexpr bool HAS_R = BN <= 128;                     // residual staging available
+    static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
+    static constexpr int R_BYTES = (STAGED && HAS_R) ? NSUB * SUB_BYTES : 0;   // one residual tile
+    static constexpr int STAGES = STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
     static constexpr int C_OFFSET = STAGES * STAGE_BYTES;        // output staging, then 2 residual staging buffers
-    static constexpr int BAR_OFFSET = C_OFFSET + 3 * C_BYTES;
+    static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + 2 * R_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
 };
 
@@ -137,7 +145,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     } else {
                         const int tap = kb / A.cblks, cb = kb - tap * A.cblks;
                         tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
-                                    h0 + A.tap_dh[tap], b0);
+                                    h0 * A.hmul + A.tap_dh[tap], b0);
                     }
                     tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -206,9 +214,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             // bf16 output staged in 128B-swizzled shared memory and written by TMA (full-line, asynchronous stores), one
             // 64-column sub-tile at a time so that the store of one sub-tile overlaps the math of the next; the residual
             // tile is fetched by TMA one tile ahead (double buffered).
-            constexpr int NSUB = BN / 64;
+            constexpr int NSUB = L::NSUB, NBUF = L::NBUF;
             unsigned char* c_s = smem + L::C_OFFSET;
-            unsigned char* r_s = c_s + L::C_BYTES;                    // 2 buffers of C_BYTES
+            unsigned char* r_s = c_s + L::C_BYTES;                    // 2 buffers of R_BYTES (BN <= 128)
+            const bool has_res = L::HAS_R && epi.has_res;
             const bool leader = (warp == 2 && lane == 0);
             const int r_in = q * 32 + lane;                           // row inside the tile
             const uint32_t row_off = (uint32_t)r_in * 128u;
@@ -218,31 +227,31 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             auto load_residual = [&](int tile, int buf) {
                 int mb, nb;
                 tile_coords(tile, mb, nb);
-                mbar_arrive_expect_tx(&res_bar[buf], L::C_BYTES);
+                mbar_arrive_expect_tx(&res_bar[buf], L::R_BYTES);
 #pragma unroll
                 for (int j = 0; j < NSUB; ++j)
-                    tma_load_2d(r_s + buf * L::C_BYTES + j * L::SUB_BYTES, &epi.mapR, &res_bar[buf], nb * BN + j * 64,
+                    tma_load_2d(r_s + buf * L::R_BYTES + j * L::SUB_BYTES, &epi.mapR, &res_bar[buf], nb * BN + j * 64,
                                 mb * BM);
             };
-            if (leader && epi.has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+            if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 const int rb = it & 1;
                 // the other residual buffer was last read by tile it-1, which every thread has left: prefetch tile it+1
-                if (leader && epi.has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                if (leader && has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
                 if (epi_tid < BN) s_bias[epi_tid] = epi.bias[n_blk * BN + epi_tid];   // visible after the next barrier
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-                if (epi.has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
-                const unsigned char* rbuf = r_s + rb * L::C_BYTES;
+                if (has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
+                const unsigned char* rbuf = r_s + rb * L::R_BYTES;
 #pragma unroll 1
                 for (int j = 0; j < NSUB; ++j) {
                     // sub-buffer j is free once the store issued for it one tile ago has been read out
-                    if (leader) tma_store_wait_read<NSUB - 1>();
+                    if (leader) tma_store_wait_read<NBUF - 1>();
                     epi_bar_sync();
-                    unsigned char* csub = c_s + j * L::SUB_BYTES + row_off;
+                    unsigned char* csub = c_s + (j % NBUF) * L::SUB_BYTES + row_off;
                     const unsigned char* rsub = rbuf + j * L::SUB_BYTES + row_off;
                     {
                         const int h = grp;
@@ -260,7 +269,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                             f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
                             f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
                             f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
-                            if (epi.has_res) {
+                            if (has_res) {
                                 const uint4 rr = *reinterpret_cast<const uint4*>(rsub + chunk);
                                 const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
@@ -289,7 +298,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     fence_proxy_async();                               // smem writes -> visible to the TMA engine
                     epi_bar_sync();
                     if (leader) {
-                        tma_store_2d(&epi.mapC, c_s + j * L::SUB_BYTES, n_blk * BN + j * 64, m_blk * BM);
+                        tma_store_2d(&epi.mapC, c_s + (j % NBUF) * L::SUB_BYTES, n_blk * BN + j * 64, m_blk * BM);
                         tma_store_commit();
                     }
                 }
@@ -330,6 +339,7 @@ int launch_gemm(const void* a, int m, const void* b, int n, int k, const Epi& ep
     A.cblks = k / BK;
     A.taps = 1;
     A.tiles_per_img = 1;
+    A.hmul = 1;
     SSG_TRY(make_tmap_2d_bf16(&A.map[0], a, (uint64_t)m, (uint64_t)k, (uint64_t)k, BM));
     return launch_gemm_op<BN, Epi, false>(A, m, b, n, k, epi, st);
 }

@@ -12,7 +12,7 @@ int launch_sqdist_exact(const float* X, int nx, const float* Y, int ny, int d, f
 int launch_row_minmax(const float* M, size_t ld, int rows, int cols, float* rmin, float* rmax,
                       cudaStream_t st);
 int launch_row_select(const float* M, size_t ld, int rows, int cols, const float* scale, int K, bool largest,
-                      int* out_idx, float* out_val, int out_stride, cudaStream_t st);
+                      int* out_idx, float* out_val, int out_stride, int* row_done, cudaStream_t st);
 int launch_cand_reduce(int rows, int cols, int K, bool is_max, const float* exact, const float* cand_approx,
                        int stride, const float* norm_row, const float* norm_other_max, float eps_rel, float* out,
                        int* flag_cnt, int* flag_rows, int row_offset, cudaStream_t st);
@@ -39,7 +39,12 @@ int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_
 // rerank.cu
 int launch_source_vector(const float* rowmin, int n, float* vec, float* scratch, cudaStream_t st);
 int launch_krecip_build(const int* rank, int n, int k1p, int khp, int* v_idx, int* v_cnt, cudaStream_t st);
-int launch_krecip_weights(const float* rowmax, int n, const int* v_cnt, float* v_val, cudaStream_t st);
+int launch_krecip_weights(const float* rowmax, int n, const int* v_cnt, float* v_val, int normalised,
+                          cudaStream_t st);
+int launch_krecip_classify(const int* rank, const float* rank_val, int n, int k1p, const int* v_idx, const int* v_cnt,
+                           float* v_val, int* todo_idx, int* todo_slot, int* todo_cnt, cudaStream_t st);
+int launch_krecip_scatter(const float* rowmax, int n, const float* todo_od, const int* todo_slot, const int* todo_cnt,
+                          float* v_val, cudaStream_t st);
 int launch_query_expand(const int* rank, int n, int k2, const int* v_idx, const float* v_val,
                         const int* v_cnt, int* q_idx, float* q_val, int* q_cnt, cudaStream_t st);
 int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int* colptr, int* cursor,

@@ -206,9 +206,60 @@ __device__ float np_pairwise_sum_f32(const float* a, int n) {
     return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
 }
 
+// Most entries of R*(i) are members of row i's own leading rank columns, whose exact normalised distance is already in
+// the rank table: copy those, and list only the remaining (expansion) entries for exact re-scoring.
+__global__ void __launch_bounds__(256)
+krecip_classify_kernel(const int* __restrict__ rank, const float* __restrict__ rank_val, int k1p,
+                       const int* __restrict__ v_idx, const int* __restrict__ v_cnt, float* __restrict__ v_val,
+                       int* __restrict__ todo_idx, int* __restrict__ todo_slot, int* __restrict__ todo_cnt) {
+    __shared__ int s_rank[32];
+    __shared__ float s_rv[32];
+    __shared__ int s_n;
+    const int i = blockIdx.x, s = threadIdx.x;
+    if (s < 32) { s_rank[s] = s < k1p ? rank[(size_t)i * SSG_RANK_STRIDE + s] : -2; s_rv[s] = rank_val[(size_t)i * SSG_RANK_STRIDE + s]; }
+    if (s == 0) s_n = 0;
+    __syncthreads();
+    const int c = v_cnt[i];
+    if (s < c) {
+        const int m = v_idx[(size_t)i * SSG_V_STRIDE + s];
+        int hit = -1;
+        for (int q = 0; q < k1p; ++q) if (s_rank[q] == m) hit = q;
+        if (hit >= 0) {
+            v_val[(size_t)i * SSG_V_STRIDE + s] = s_rv[hit];
+        } else {
+            const int t = atomicAdd(&s_n, 1);            // order inside the todo list is irrelevant
+            todo_idx[(size_t)i * SSG_V_STRIDE + t] = m;
+            todo_slot[(size_t)i * SSG_V_STRIDE + t] = s;
+        }
+    }
+    __syncthreads();
+    if (s == 0) todo_cnt[i] = s_n;
+}
+__global__ void __launch_bounds__(256)
+krecip_scatter_kernel(const float* __restrict__ rowmax, const float* __restrict__ todo_od,
+                      const int* __restrict__ todo_slot, const int* __restrict__ todo_cnt, float* __restrict__ v_val) {
+    const int i = blockIdx.x, t = threadIdx.x;
+    if (t < todo_cnt[i])
+        v_val[(size_t)i * SSG_V_STRIDE + todo_slot[(size_t)i * SSG_V_STRIDE + t]] =
+            __fdiv_rn(todo_od[(size_t)i * SSG_V_STRIDE + t], rowmax[i]);
+}
+int launch_krecip_classify(const int* rank, const float* rank_val, int n, int k1p, const int* v_idx, const int* v_cnt,
+                           float* v_val, int* todo_idx, int* todo_slot, int* todo_cnt, cudaStream_t st) {
+    krecip_classify_kernel<<<n, 256, 0, st>>>(rank, rank_val, k1p, v_idx, v_cnt, v_val, todo_idx, todo_slot, todo_cnt);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int launch_krecip_scatter(const float* rowmax, int n, const float* todo_od, const int* todo_slot, const int* todo_cnt,
+                          float* v_val, cudaStream_t st) {
+    krecip_scatter_kernel<<<n, 256, 0, st>>>(rowmax, todo_od, todo_slot, todo_cnt, v_val);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// `normalised` != 0: v_val already holds d2/rowmax on entry (else the squared distance d2).
 __global__ void __launch_bounds__(128)
 krecip_weights_kernel(const float* __restrict__ rowmax, int n, const int* __restrict__ v_cnt,
-                      float* __restrict__ v_val) {
+                      float* __restrict__ v_val, int normalised) {
     __shared__ float w[4][SSG_V_STRIDE];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + wid;
@@ -216,7 +267,7 @@ krecip_weights_kernel(const float* __restrict__ rowmax, int n, const int* __rest
     const int c = v_cnt[i];
     const float mx = rowmax[i];
     float* row = v_val + (size_t)i * SSG_V_STRIDE;
-    for (int s = lane; s < c; s += 32) w[wid][s] = expf(-__fdiv_rn(row[s], mx));
+    for (int s = lane; s < c; s += 32) w[wid][s] = expf(-(normalised ? row[s] : __fdiv_rn(row[s], mx)));
     __syncwarp();
     float sum = 0.f;
     if (lane == 0) sum = np_pairwise_sum_f32(w[wid], c);
@@ -224,8 +275,9 @@ krecip_weights_kernel(const float* __restrict__ rowmax, int n, const int* __rest
     for (int s = lane; s < c; s += 32) row[s] = __fdiv_rn(w[wid][s], sum);
 }
 
-int launch_krecip_weights(const float* rowmax, int n, const int* v_cnt, float* v_val, cudaStream_t st) {
-    krecip_weights_kernel<<<ssg_cdiv(n, 4), 128, 0, st>>>(rowmax, n, v_cnt, v_val);
+int launch_krecip_weights(const float* rowmax, int n, const int* v_cnt, float* v_val, int normalised,
+                          cudaStream_t st) {
+    krecip_weights_kernel<<<ssg_cdiv(n, 4), 128, 0, st>>>(rowmax, n, v_cnt, v_val, normalised);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -11,6 +11,9 @@ fi
 # full-set capture: the distance GEMM (2 launches) and one whole batch of the convolution GEMMs (53 launches)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -c 2 -o gpurun_out/${TAG}_gemm_dist \
     python bench.py --quick --steps 1 --warmup 0 --features-only > gpurun_out/${TAG}_gemm_dist.out 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 53 -c 53 -o gpurun_out/${TAG}_gemm_conv \
-    python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_gemm_conv.out 2>&1
+# (reports are ~1.4 MB per launch and gpurun_out/ is capped at 64 MiB: stem + layer1 + start of layer2, then layer4)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 53 -c 16 -o gpurun_out/${TAG}_gemm_conv_l1 \
+    python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_gemm_conv_l1.out 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 96 -c 10 -o gpurun_out/${TAG}_gemm_conv_l4 \
+    python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_gemm_conv_l4.out 2>&1
 ls -la gpurun_out/ | tail -8
