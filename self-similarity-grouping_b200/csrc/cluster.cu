@@ -68,23 +68,30 @@ eps_hist_kernel(const T* __restrict__ D, int n, int pass, const unsigned long lo
         const int i = half == 0 ? (int)blockIdx.x : n - 1 - (int)blockIdx.x;
         if (half == 1 && i <= (int)blockIdx.x) break;
         const T* row = D + (size_t)i * n;
-        for (int j0 = i + 1; j0 < n; j0 += EPS_NT) {
-            const int j = j0 + threadIdx.x;
-            bool in = false;
-            unsigned bin = 0;
-            if (j < n) {
-                const double v = ld_as_double<T>(row, j);
+        for (int jb = i + 1; jb < n; jb += EPS_NT * 4) {
+            // 4 independent loads in flight per thread (the scan is latency bound otherwise)
+            double vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = jb + u * EPS_NT + threadIdx.x;
+                vv[u] = j < n ? ld_as_double<T>(row, j) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double v = vv[u];
+                bool in = false;
+                unsigned bin = 0;
                 if (v != 0.0) {
                     const unsigned long long k = f64_key(v);
                     in = (pass == 0) || ((k >> hs) == (prefix >> hs));
                     bin = (unsigned)(k >> shift) & mask;
                 }
-            }
-            // warp-aggregated shared-memory histogram (the values are heavily clustered)
-            const unsigned act = __ballot_sync(0xffffffffu, in);
-            if (in) {
-                const unsigned peers = __match_any_sync(act, bin);
-                if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+                // warp-aggregated shared-memory histogram (the values are heavily clustered)
+                const unsigned act = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+                }
             }
         }
     }
@@ -208,14 +215,23 @@ eps_gather_kernel(const T* __restrict__ D, int n, unsigned long long* __restrict
             const int i = half == 0 ? (int)blockIdx.x : n - 1 - (int)blockIdx.x;
             if (half == 1 && i <= (int)blockIdx.x) break;
             const T* row = D + (size_t)i * n;
-            for (int j = i + 1 + threadIdx.x; j < n; j += EPS_NT) {
-                const double v = ld_as_double<T>(row, j);
-                if (v == 0.0) continue;
-                const unsigned long long h = f64_key(v) >> 40;
-                if (h < pre) acc += v;
-                else if (h == pre) {
-                    const unsigned long long pos = atomicAdd(&state[5], 1ull);
-                    if (pos < (unsigned long long)EPS_LIST_CAP) list[pos] = v; else state[6] = 1ull;
+            for (int jb = i + 1 + threadIdx.x; jb < n; jb += EPS_NT * 4) {
+                double vv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = jb + u * EPS_NT;
+                    vv[u] = j < n ? ld_as_double<T>(row, j) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {      // same element order per thread as a plain strided loop
+                    const double v = vv[u];
+                    if (v == 0.0) continue;
+                    const unsigned long long h = f64_key(v) >> 40;
+                    if (h < pre) acc += v;
+                    else if (h == pre) {
+                        const unsigned long long pos = atomicAdd(&state[5], 1ull);
+                        if (pos < (unsigned long long)EPS_LIST_CAP) list[pos] = v; else state[6] = 1ull;
+                    }
                 }
             }
         }

@@ -316,11 +316,24 @@ row_select_sampled_kernel(const float* __restrict__ M, size_t ld, int cols, cons
     int pi = (int)(((long long)Keff * SMP_N * 3 + cols - 1) / cols) + 6;
     if (pi > SMP_N - 1) pi = SMP_N - 1;
     const uint32_t pivot = samp[pi];
-    for (int j = tid; j < cols; j += SEL_NT) {
-        const uint32_t k = sel_key(sel_value(row, j, scaled, s), largest);
-        if (k <= pivot) {
-            const int pos = atomicAdd(&s_cnt, 1);
-            if (pos < SMP_CAP) { l_key[pos] = k; l_idx[pos] = j; }
+    // the row is streamed with 8 independent loads in flight per thread (the loop is latency bound otherwise)
+    for (int j0 = tid; j0 < cols; j0 += SEL_NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * SEL_NT;
+            v[u] = j < cols ? row[j] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u * SEL_NT;
+            if (j < cols) {
+                const uint32_t k = sel_key(scaled ? __fdiv_rn(v[u], s) : v[u], largest);
+                if (k <= pivot) {
+                    const int pos = atomicAdd(&s_cnt, 1);
+                    if (pos < SMP_CAP) { l_key[pos] = k; l_idx[pos] = j; }
+                }
+            }
         }
     }
     __syncthreads();
