@@ -173,7 +173,7 @@ int ssg_embed_forward(ssg_embed_plan* plan, const float* d_images, int n, int nu
  *                   (+ ReLU).  H, W are the INPUT map size; stride 2 needs a scratch buffer of the input's size.
  *                   3x3 needs W (output) to divide 128 and H*W (output) to be a multiple or a divisor of 128.
  *   ssg_op_fold_bn: fp32 [cout,cin,k,k] conv weight + BatchNorm statistics -> bf16 [cout,kpad] + fp32 bias.
- *   ssg_op_stem   : 7x7/2 conv (K padded 147->192) + ReLU on fp32 NCHW images (and their mirror images when
+ *   ssg_op_stem   : 7x7/2 conv (K padded 147->192: d_w is bf16 [64,192], d_col scratch bf16 [images*8192,192]) + ReLU on fp32 NCHW images (and their mirror images when
  *                   flip != 0), optionally followed by the 3x3/2 max-pool.
  *   ssg_op_pooled_tail : global + stripe average pools, flip sum, L2 normalisation (see ssg_embed_forward). */
 int ssg_op_conv(const void* d_x, int B, int H, int W, int cin, int ksize, int stride, const void* d_w,

@@ -275,3 +275,51 @@ def synth_features(n, d=2048, seed=0, per_cluster=20, noise=0.5):
     f = centres[lab] + noise * rng.randn(n, d)
     f /= np.linalg.norm(f, axis=1, keepdims=True)
     return f.astype(np.float32), lab
+
+
+# ----------------------------------------------------------------------------- evaluation metrics (row f2)
+def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, first_match_break=False):
+    """reid/evaluation_metrics/ranking.py:18-79 (separate_camera_set=False, single_gallery_shot=False)."""
+    distmat = np.asarray(distmat)
+    m, n = distmat.shape
+    query_ids, gallery_ids = np.asarray(query_ids), np.asarray(gallery_ids)
+    query_cams, gallery_cams = np.asarray(query_cams), np.asarray(gallery_cams)
+    indices = np.argsort(distmat, axis=1, kind="stable")
+    matches = (gallery_ids[indices] == query_ids[:, np.newaxis])
+    ret = np.zeros(topk)
+    num_valid_queries = 0
+    for i in range(m):
+        valid = ((gallery_ids[indices[i]] != query_ids[i]) | (gallery_cams[indices[i]] != query_cams[i]))
+        if not np.any(matches[i, valid]):
+            continue
+        index = np.nonzero(matches[i, valid])[0]
+        delta = 1. / len(index)
+        for j, k in enumerate(index):
+            if k - j >= topk:
+                break
+            if first_match_break:
+                ret[k - j] += 1
+                break
+            ret[k - j] += delta
+        num_valid_queries += 1
+    return ret.cumsum() / num_valid_queries
+
+
+def mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams):
+    """reid/evaluation_metrics/ranking.py:82-115 (sklearn average_precision_score per query)."""
+    from sklearn.metrics import average_precision_score
+    distmat = np.asarray(distmat)
+    m, n = distmat.shape
+    query_ids, gallery_ids = np.asarray(query_ids), np.asarray(gallery_ids)
+    query_cams, gallery_cams = np.asarray(query_cams), np.asarray(gallery_cams)
+    indices = np.argsort(distmat, axis=1, kind="stable")
+    matches = (gallery_ids[indices] == query_ids[:, np.newaxis])
+    aps = []
+    for i in range(m):
+        valid = ((gallery_ids[indices[i]] != query_ids[i]) | (gallery_cams[indices[i]] != query_cams[i]))
+        y_true = matches[i, valid]
+        y_score = -distmat[i][indices[i]][valid]
+        if not np.any(y_true):
+            continue
+        aps.append(average_precision_score(y_true, y_score))
+    return np.mean(aps)

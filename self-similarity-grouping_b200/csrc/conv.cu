@@ -42,12 +42,45 @@ int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int
     tc::AOperand A;
     memset(&A, 0, sizeof(A));
     A.mode = 0;
-    A.cblks = cin / tc::BK;
+    A.cblks = (cin + tc::BK - 1) / tc::BK;
     A.taps = 1;
     A.tiles_per_img = 1;
     A.hmul = 1;
     SSG_TRY(make_tmap_2d_bf16(&A.map[0], x, (uint64_t)m, (uint64_t)cin, (uint64_t)cin, tc::BM));
     return gemm_dispatch(A, m, w, cout, cin, bias, residual, relu, y, st);
+}
+
+static int tile_geometry(int H, int W, int* bw, int* bh, int* bb, int* tiles_per_img);
+static inline int tile_geometry_fwd(int H, int W, int* bw, int* bh, int* bb, int* t) { return tile_geometry(H, W, bw, bh, bb, t); }
+
+// Bottleneck tail of a first block, fused: y = relu( conv3(t2) + downsample(x) ) as ONE GEMM whose K axis is the
+// concatenation [mid | cin]: K blocks < mid/64 read t2 [M, mid], the rest read x — as a plain [M, cin] matrix
+// (stride 1) or through stride-2 single-tap TMA boxes of x [B,2H,2W,cin] (stride 2).  w = [cout, mid + cin] (conv3 and
+// downsample weights side by side), bias = bias3 + bias_ds.  The downsample output never touches memory.
+int conv_fused_ds(const void* t2, const void* x, int B, int H, int W, int mid, int cin, int stride, const void* w,
+                  const float* bias, int cout, void* y, cudaStream_t st) {
+    if (mid % 64 || cin % 64) return ssg_set_error(SSG_ERR_INVALID, "conv_fused_ds: channels must be multiples of 64");
+    const int m = B * H * W;
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 0;
+    A.cblks = mid / tc::BK;
+    A.taps = 1;
+    A.tiles_per_img = 1;
+    A.hmul = 1;
+    A.kb_split = mid / tc::BK;
+    SSG_TRY(make_tmap_2d_bf16(&A.map[0], t2, (uint64_t)m, (uint64_t)mid, (uint64_t)mid, tc::BM));
+    if (stride == 1) {
+        A.mode1 = 0;
+        SSG_TRY(make_tmap_2d_bf16(&A.map[1], x, (uint64_t)m, (uint64_t)cin, (uint64_t)cin, tc::BM));
+    } else {
+        A.mode1 = 1;
+        A.hmul = 2;
+        int bw;
+        SSG_TRY(tile_geometry_fwd(H, W, &bw, &A.bh, &A.bb, &A.tiles_per_img));
+        SSG_TRY(make_tmap_nhwc_bf16(&A.map[1], x, B, 2 * H, 2 * W, cin, bw, A.bh, A.bb, 2));
+    }
+    return gemm_dispatch(A, m, w, cout, mid + cin, bias, nullptr, 1, y, st);
 }
 
 // tile geometry of a 128-pixel M tile on an [H, W] output map (W divides 128, H*W multiple or divisor of 128)
@@ -151,6 +184,16 @@ __global__ void fold_bn_kernel(const float* __restrict__ w, int cout, int cin, i
     }
 }
 
+__global__ void vec_add_f32_kernel(const float* a, const float* b, int n, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+int vec_add_f32(const float* a, const float* b, int n, float* out, cudaStream_t st) {
+    vec_add_f32_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(a, b, n, out);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
 int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
             const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st) {
     fold_bn_kernel<<<cout, 256, 0, st>>>(w, cout, cin, kh, kw, gamma, beta, mean, var, eps, kpad,
@@ -165,7 +208,8 @@ int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamm
 // horizontally flipped images (reid/evaluators.py:12-16 fliplr folded into the load index).
 // One CTA per output row segment: (image, oh) -> 64 output pixels x 192.
 // ---------------------------------------------------------------------------------------------------
-constexpr int STEM_K = 147, STEM_KPAD = 192;
+constexpr int STEM_K = 147, STEM_KPAD = 192;   // 384-byte rows: every 128-byte TMA box row is cache-line aligned (a 152-wide
+                                                // buffer is 20 % smaller but its misaligned rows doubled the GEMM's A traffic)
 
 __global__ void __launch_bounds__(192)
 stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bfloat16* __restrict__ out) {
@@ -176,7 +220,7 @@ stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bflo
     const bool flipped = im >= n;
     const int src = flipped ? im - n : im;
     const float* base = img + (size_t)src * 3 * H * W;
-    for (int e = threadIdx.x; e < 3 * 7 * RW; e += 192) {
+    for (int e = threadIdx.x; e < 3 * 7 * RW; e += STEM_KPAD) {
         const int xw = e % RW, t = e / RW, ky = t % 7, c = t / 7;
         const int ih = oh * 2 - 3 + ky, iw = xw - 3;
         float v = 0.f;
@@ -206,7 +250,7 @@ stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bflo
 
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st) {
     const int images = flip_too ? 2 * n : n;
-    stem_im2col_kernel<<<images * 128, 192, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);
+    stem_im2col_kernel<<<images * 128, STEM_KPAD, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

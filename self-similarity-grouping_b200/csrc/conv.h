@@ -9,8 +9,11 @@ int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int
 bool s2_strided_tma();
 int conv1x1_s2(const void* x, int B, int H, int W, int cin, const void* w, const float* bias, int cout, int relu,
                void* y, cudaStream_t st);
+int conv_fused_ds(const void* t2, const void* x, int B, int H, int W, int mid, int cin, int stride, const void* w,
+                  const float* bias, int cout, void* y, cudaStream_t st);
 int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout,
             int relu, void* y, cudaStream_t st);
+int vec_add_f32(const float* a, const float* b, int n, float* out, cudaStream_t st);
 int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
             const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st);
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);

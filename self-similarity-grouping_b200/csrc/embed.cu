@@ -3,6 +3,7 @@
 // device-resident forward over a batch of images.  Weights are ingested from the live torch module's
 // state_dict (BatchNorm folded, bf16, [Cout][kh][kw][Cin]); activations are NHWC bf16, accumulation fp32.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -50,7 +51,7 @@ const std::vector<LayerSpec>& specs() {
 }
 int kpad_of(const LayerSpec& s) {
     const int k = s.k * s.k * s.cin;
-    return (k + 63) / 64 * 64;
+    return (k + 63) / 64 * 64;   // whole K blocks (stem: 147 -> 192); the GEMM itself also accepts K % 8 == 0
 }
 }  // namespace
 
@@ -60,6 +61,9 @@ struct ssg_embed_plan {
     std::vector<void*> w;        // bf16 [cout, kpad]
     std::vector<float*> b;       // fp32 [cout]
     std::vector<char> loaded;
+    void* wf[4];                 // fused [conv3 | downsample] weights of the first block of each layer
+    float* bf[4];                // fused bias
+    bool fused_ready;
     void *col, *stem, *x, *y, *ds, *t1, *t2, *planes, *xs;
 };
 
@@ -88,6 +92,7 @@ extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
     if (!p) return SSG_OK;
     cudaSetDevice(p->device);
     for (void* q : p->w) if (q) cudaFree(q);
+    for (int L = 0; L < 4; ++L) { if (p->wf[L]) cudaFree(p->wf[L]); if (p->bf[L]) cudaFree(p->bf[L]); }
     for (float* q : p->b) if (q) cudaFree(q);
     void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs};
     for (void* q : bufs) if (q) cudaFree(q);
@@ -107,10 +112,21 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     p->w.assign(sp.size(), nullptr);
     p->b.assign(sp.size(), nullptr);
     p->loaded.assign(sp.size(), 0);
+    p->fused_ready = false;
+    for (int L = 0; L < 4; ++L) { p->wf[L] = nullptr; p->bf[L] = nullptr; }
     int rc = SSG_OK;
     for (size_t i = 0; i < sp.size() && rc == SSG_OK; ++i) {
         rc = ealloc(&p->w[i], (size_t)sp[i].cout * kpad_of(sp[i]) * 2, &p->bytes);
         if (rc == SSG_OK) rc = ealloc((void**)&p->b[i], sizeof(float) * sp[i].cout, &p->bytes);
+    }
+    {   // fused first-block tails: [outc, mid + cin]
+        int cin = 64;
+        for (int L = 0; L < 4 && rc == SSG_OK; ++L) {
+            const int mid = 64 << L, outc = mid * 4;
+            rc = ealloc(&p->wf[L], (size_t)outc * (mid + cin) * 2, &p->bytes);
+            if (rc == SSG_OK) rc = ealloc((void**)&p->bf[L], sizeof(float) * outc, &p->bytes);
+            cin = outc;
+        }
     }
     const size_t nb = (size_t)batch_max * 2;       // images + flipped images
     const size_t px = 2;                           // bytes per bf16
@@ -142,6 +158,7 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
     SSG_TRY(fold_bn(d_w, s.cout, s.cin, s.k, s.k, d_gamma, d_beta, d_mean, d_var, eps, kpad_of(s), p->w[idx],
                     p->b[idx], (cudaStream_t)stream));
     p->loaded[idx] = 1;
+    p->fused_ready = false;
     return SSG_OK;
 }
 
@@ -155,6 +172,25 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
     cudaStream_t st = (cudaStream_t)stream;
     const auto& sp = specs();
     const int NB = flip ? 2 * n : n;
+    static int fuse_ds = -1;
+    if (fuse_ds < 0) { const char* e = getenv("SSG_FUSE_DS"); fuse_ds = e ? atoi(e) : 1; }
+    if (fuse_ds && !p->fused_ready) {
+        // [conv3 | downsample] weights side by side along K, biases added (first block of every layer)
+        int idx = 1, cin = 64;
+        const int nblk[4] = {3, 4, 6, 3};
+        for (int L = 0; L < 4; ++L) {
+            const int mid = 64 << L, outc = mid * 4, i3 = idx + 2, id = idx + 3;
+            const size_t pitch = (size_t)(mid + cin) * 2;
+            SSG_CUDA_TRY(cudaMemcpy2DAsync(p->wf[L], pitch, p->w[i3], (size_t)mid * 2, (size_t)mid * 2, outc,
+                                           cudaMemcpyDeviceToDevice, st));
+            SSG_CUDA_TRY(cudaMemcpy2DAsync((char*)p->wf[L] + (size_t)mid * 2, pitch, p->w[id], (size_t)cin * 2,
+                                           (size_t)cin * 2, outc, cudaMemcpyDeviceToDevice, st));
+            SSG_TRY(vec_add_f32(p->b[i3], p->b[id], outc, p->bf[L], st));
+            idx += 4 + 3 * (nblk[L] - 1);
+            cin = outc;
+        }
+        p->fused_ready = true;
+    }
     int li = 0;
     // stem: 7x7/2 conv as im2col + GEMM (K 147 -> 192), then 3x3/2 max-pool
     { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
@@ -179,6 +215,12 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
                 { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
             } else {
                 { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, H, W, mid, 1, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+            }
+            if (b == 0 && fuse_ds) {
+                { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv_fused_ds(p->t2, x, NB, OH, OW, mid, C, stride, p->wf[L], p->bf[L], outc, y, st)); }
+                void* t = x; x = y; y = t;
+                H = OH; W = OW; C = outc;
+                continue;
             }
             const void* res = x;
             if (b == 0) {

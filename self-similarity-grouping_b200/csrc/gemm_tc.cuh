@@ -33,6 +33,8 @@ struct AOperand {
     int bh, bb;            // box rows / images per 128-pixel tile
     int tiles_per_img;     // >= 1
     int hmul;              // input rows per output row (2 for stride-2 boxes read straight from the input map)
+    int kb_split;          // > 0: K blocks >= kb_split come from a second source, map[1] (K-concatenated GEMM)
+    int mode1;             // second source: 0 = plain [M,K1] matrix, 1 = single-tap implicit view (uses bh/bb/hmul)
     signed char tap_plane[9], tap_dh[9], tap_dw[9];
 };
 
@@ -131,7 +133,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 int b0 = 0, h0 = 0;
-                if (A.mode == 1) {
+                if (A.mode == 1 || (A.kb_split > 0 && A.mode1 == 1)) {
                     if (A.bb > 1) { b0 = m_blk * A.bb; }
                     else { b0 = m_blk / A.tiles_per_img; h0 = (m_blk % A.tiles_per_img) * A.bh; }
                 }
@@ -140,7 +142,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     unsigned char* sa = smem + stage * L::STAGE_BYTES;
                     unsigned char* sb = sa + L::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (A.mode == 0) {
+                    if (A.kb_split > 0 && kb >= A.kb_split) {
+                        const int kb2 = kb - A.kb_split;
+                        if (A.mode1 == 0) tma_load_2d(sa, &A.map[1], &full_bar[stage], kb2 * BK, m_blk * BM);
+                        else tma_load_4d(sa, &A.map[1], &full_bar[stage], kb2 * BK, 0, h0 * A.hmul, b0);
+                    } else if (A.mode == 0) {
                         tma_load_2d(sa, &A.map[0], &full_bar[stage], kb * BK, m_blk * BM);
                     } else {
                         const int tap = kb / A.cblks, cb = kb - tap * A.cblks;
@@ -316,7 +322,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 template <int BN, class Epi, bool STAGED = false>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
     using L = SmemLayout<BN, STAGED>;
-    if (k % BK) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of %d", k, BK);
+    // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
+    if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;
     SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
     int sms = 0;
@@ -325,7 +332,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     const int grid = tiles < sms ? tiles : sms;
     auto kern = gemm_kernel<BN, Epi, STAGED>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, k / BK, epi);
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, (k + BK - 1) / BK, epi);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

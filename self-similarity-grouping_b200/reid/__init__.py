@@ -12,6 +12,7 @@ Put ``self-similarity-grouping_b200/`` ahead of the reference on ``sys.path`` an
 Only the hot path lives here; datasets, trainers, losses and the evaluation metrics are the
 reference's own and out of scope.
 """
+from . import evaluation_metrics  # noqa: F401
 from . import feature_extraction  # noqa: F401
 from . import models  # noqa: F401
 from . import evaluators  # noqa: F401

@@ -1,6 +1,6 @@
 """Drop-in for reid/evaluators.py of the reference: extract_features (18-60), pairwise_distance (63-85),
-fliplr (12-16) and the Evaluator wrapper.  The CMC/mAP scoring of Evaluator.evaluate (evaluate_all, 88-133) is the
-reference's evaluation_metrics package — outside the pseudo-label hot path."""
+fliplr (12-16), evaluate_all (88-133) and the Evaluator wrapper (183-192); CMC / mAP are scored on the GPU by
+reid/evaluation_metrics/ranking.py."""
 from collections import OrderedDict  # noqa: F401
 
 import torch
@@ -45,6 +45,29 @@ def pairwise_distance(features, query=None, gallery=None, metric=None):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def evaluate_all(distmat, query=None, gallery=None, query_ids=None, gallery_ids=None, query_cams=None,
+                 gallery_cams=None, cmc_topk=(1, 5, 10)):
+    """evaluators.py:88-133: mean AP + the 'market1501' CMC protocol, same prints, returns CMC top-1."""
+    from .evaluation_metrics import cmc, mean_ap
+    if query is not None and gallery is not None:
+        query_ids = [pid for _, pid, _ in query]
+        gallery_ids = [pid for _, pid, _ in gallery]
+        query_cams = [cam for _, _, cam in query]
+        gallery_cams = [cam for _, _, cam in gallery]
+    else:
+        assert (query_ids is not None and gallery_ids is not None
+                and query_cams is not None and gallery_cams is not None)
+    mAP = mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams)
+    print('Mean AP: {:4.1%}'.format(mAP))
+    cmc_configs = {'market1501': dict(separate_camera_set=False, single_gallery_shot=False, first_match_break=True)}
+    cmc_scores = {name: cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, **params)
+                  for name, params in cmc_configs.items()}
+    print('CMC Scores{:>12}'.format('market1501'))
+    for k in cmc_topk:
+        print('top-{:<4}{:12.1%}'.format(k, cmc_scores['market1501'][k - 1]))
+    return cmc_scores['market1501'][0]
+
+
 class Evaluator(object):
     def __init__(self, model, print_freq):
         super(Evaluator, self).__init__()
@@ -56,11 +79,5 @@ class Evaluator(object):
         return pairwise_distance(features, query, gallery, metric=metric)
 
     def evaluate(self, data_loader, query, gallery, metric=None):
-        distmat = self.distmat(data_loader, query, gallery, metric)
-        try:
-            from reid_reference_metrics import evaluate_all   # the reference's evaluation_metrics, if on the path
-        except ImportError:
-            raise NotImplementedError(
-                "Evaluator.evaluate: CMC/mAP scoring (reid/evaluation_metrics) is outside the pseudo-label hot "
-                "path; use Evaluator.distmat() and the reference's evaluate_all on the returned matrix")
-        return evaluate_all(distmat, query=query, gallery=gallery)
+        """evaluators.py:189-192."""
+        return evaluate_all(self.distmat(data_loader, query, gallery, metric), query=query, gallery=gallery)

@@ -118,3 +118,23 @@ def test_full_size_cycle_labels(ssg):
     want = DBSCAN(eps=eps, min_samples=4, metric="precomputed", n_jobs=8).fit_predict(fh)
     assert np.array_equal(labels.cpu().numpy(), want)
     assert ncl == want.max() + 1 and ncl > 100
+
+
+@pytest.mark.parametrize("m,n,nid,quant", [(60, 300, 25, False), (120, 500, 40, True)])
+def test_cmc_and_mean_ap_match_reference_restatement(m, n, nid, quant):
+    """reid/evaluation_metrics/ranking.py on the GPU vs the numpy + sklearn restatement (quantised distances = ties)."""
+    import torch
+    from reid.evaluation_metrics import cmc, mean_ap
+    rng = np.random.RandomState(m)
+    qid, gid = rng.randint(0, nid, m), rng.randint(0, nid, n)
+    qcam, gcam = rng.randint(0, 3, m), rng.randint(0, 3, n)
+    d = rng.rand(m, n).astype(np.float32) + 0.5 * (qid[:, None] != gid[None, :])
+    if quant:
+        d = np.round(d * 20) / 20
+    dist = torch.from_numpy(d)
+    want_map = O.mean_ap(d, qid, gid, qcam, gcam)
+    assert abs(mean_ap(dist, qid, gid, qcam, gcam) - want_map) < 1e-9
+    if not quant:      # with tied distances the rank order of ties is unspecified in the reference (np.argsort)
+        for fmb in (True, False):
+            got = cmc(dist, qid, gid, qcam, gcam, topk=50, first_match_break=fmb)
+            np.testing.assert_allclose(got, O.cmc(d, qid, gid, qcam, gcam, topk=50, first_match_break=fmb), atol=1e-12)

@@ -17,3 +17,8 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 96 -c 10 -o gpurun_out/${TAG}_gemm_conv_l4 \
     python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_gemm_conv_l4.out 2>&1
 ls -la gpurun_out/ | tail -8
+# re-rank side kernels (one bank): select / rescoring / eps / Jaccard / DBSCAN scans
+if [ "${3:-}" = "rerank" ]; then
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'row_select|pair_exact|eps_hist|eps_gather|jaccard_final|db_count|db_fill' -c 14 -o gpurun_out/${TAG}_rerank \
+    python bench.py --quick --steps 1 --warmup 0 --features-only --banks 1 > gpurun_out/${TAG}_rerank.out 2>&1
+fi
