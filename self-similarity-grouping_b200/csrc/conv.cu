@@ -248,6 +248,82 @@ stem_im2col_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bflo
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// stem without an im2col buffer: (1) stem_prep: fp32 NCHW image -> bf16 P [images][256][144 px][4 ch] (3 zero px on
+// the left, zeros on the right, zero 4th channel; mirror images appended when flip_too); (2) implicit GEMM whose K
+// block kh is one overlapping-window TMA box of P (make_tmap_stem_windows): K = 7 x 64 (16 px x 4 ch per kernel row,
+// of which 7 x 3 carry weights).
+// ---------------------------------------------------------------------------------------------------
+constexpr int STEM_WP = 144;
+
+__global__ void __launch_bounds__(256)
+stem_prep_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bfloat16* __restrict__ P) {
+    constexpr int H = 256, W = 128;
+    const int images = flip_too ? 2 * n : n;
+    const size_t total = (size_t)images * H * STEM_WP;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(e % STEM_WP);
+        const size_t t = e / STEM_WP;
+        const int ih = (int)(t % H), im = (int)(t / H);
+        const bool flipped = im >= n;
+        const float* base = img + (size_t)(flipped ? im - n : im) * 3 * H * W;
+        const int iw = p - 3;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (iw >= 0 && iw < W) {
+            const int sw = flipped ? W - 1 - iw : iw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = base[((size_t)c * H + ih) * W + sw];
+        }
+        uint2 pk;
+        *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(v[2], 0.f);
+        reinterpret_cast<uint2*>(P)[e] = pk;
+    }
+}
+
+int stem_prep(const float* img, int n, int flip_too, void* P, cudaStream_t st) {
+    const size_t total = (size_t)(flip_too ? 2 * n : n) * 256 * STEM_WP;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    stem_prep_kernel<<<grid, 256, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)P);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// weights for the window GEMM: w'[co][kh][px 0..15][c 0..3] = w[co][c][kh][px] * bn_scale for px < 7, c < 3, else 0
+__global__ void fold_bn_stem_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ wout,
+                                    float* __restrict__ bout) {
+    const int co = blockIdx.x;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    if (threadIdx.x == 0) bout[co] = beta[co] - mean[co] * scale;
+    for (int k = threadIdx.x; k < 7 * 64; k += blockDim.x) {
+        const int c = k & 3, px = (k >> 2) & 15, kh = k >> 6;
+        float v = 0.f;
+        if (c < 3 && px < 7) v = w[(((size_t)co * 3 + c) * 7 + kh) * 7 + px] * scale;
+        wout[(size_t)co * 448 + k] = __float2bfloat16_rn(v);
+    }
+}
+int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 void* wout, float* bout, cudaStream_t st) {
+    fold_bn_stem_kernel<<<64, 256, 0, st>>>(w, gamma, beta, mean, var, eps, (__nv_bfloat16*)wout, bout);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// the window GEMM: P [images][256][144][4] -> relu(conv7x7/2 + bias) as NHWC bf16 [images,128,64,64]
+int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t st) {
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 2;
+    A.cblks = 1;
+    A.taps = 7;
+    A.tiles_per_img = 64;
+    A.hmul = 1;
+    SSG_TRY(make_tmap_stem_windows(&A.map[0], P, (uint64_t)images));
+    return gemm_dispatch(A, images * 8192, w448, 64, 448, bias, nullptr, 1, y, st);
+}
+
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st) {
     const int images = flip_too ? 2 * n : n;
     stem_im2col_kernel<<<images * 128, STEM_KPAD, 0, st>>>(img, n, flip_too, (__nv_bfloat16*)out);

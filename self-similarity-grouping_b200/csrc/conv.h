@@ -16,6 +16,10 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
 int vec_add_f32(const float* a, const float* b, int n, float* out, cudaStream_t st);
 int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
             const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st);
+int stem_prep(const float* img, int n, int flip_too, void* P, cudaStream_t st);
+int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 void* wout, float* bout, cudaStream_t st);
+int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t st);
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);
 int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st);
 int parity_split(const void* x, int B, int H, int W, int C, int nplanes, void* y, cudaStream_t st);

@@ -273,7 +273,7 @@ row_select_kernel(const float* __restrict__ M, size_t ld, int cols, const float*
 // the pivot turns out too low (fewer than K collected) or too high (list overflow) are left to the radix-select
 // kernel above (row_done[row] = 0), so the result is always exact.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SMP_N = 512;
+constexpr int SMP_N = 256;
 constexpr int SMP_CAP = 1024;
 
 __global__ void __launch_bounds__(SEL_NT)
@@ -313,7 +313,7 @@ row_select_sampled_kernel(const float* __restrict__ M, size_t ld, int cols, cons
         }
     }
     // expected rank of the K-th smallest in the sample is K*SMP_N/cols; take 3x that plus a safety margin
-    int pi = (int)(((long long)Keff * SMP_N * 3 + cols - 1) / cols) + 6;
+    int pi = (int)(((long long)Keff * SMP_N * 2 + cols - 1) / cols) + 5;
     if (pi > SMP_N - 1) pi = SMP_N - 1;
     const uint32_t pivot = samp[pi];
     // the row is streamed with 8 independent loads in flight per thread (the loop is latency bound otherwise)
@@ -342,19 +342,77 @@ row_select_sampled_kernel(const float* __restrict__ M, size_t ld, int cols, cons
         if (tid == 0) row_done[row_id] = 0;
         return;
     }
-    // rank by (key, index) among the c collected elements; ranks < Keff are the answer
+    // K smallest of the c collected (key, index) pairs: 3-pass radix select on the 32-bit keys inside shared memory,
+    // ties at the threshold key resolved by index, then the K survivors are rank-sorted (K^2 comparisons only).
+    __shared__ int hist[SEL_BINS];
+    __shared__ int wsum2[SEL_NT / 32];
+    __shared__ uint32_t s_prefix2;
+    __shared__ int s_rem2, s_nsel;
+    __shared__ uint32_t c_key[SEL_KMAX];
+    __shared__ int c_idx[SEL_KMAX];
+    if (tid == 0) { s_prefix2 = 0u; s_rem2 = Keff; s_nsel = 0; }
+    const int shifts[3] = {21, 10, 0};
+    const int widths[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+        for (int bq = tid; bq < SEL_BINS; bq += SEL_NT) hist[bq] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix2;
+        const int shift = shifts[p], width = widths[p];
+        const uint32_t mask = (1u << width) - 1u;
+        for (int e = tid; e < c; e += SEL_NT) {
+            const uint32_t k = l_key[e];
+            if (p == 0 || ((k >> (shift + width)) == (prefix >> (shift + width)))) atomicAdd(&hist[(k >> shift) & mask], 1);
+        }
+        __syncthreads();
+        constexpr int PER = SEL_BINS / SEL_NT;
+        int local[PER], sum = 0;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) { local[q] = hist[tid * PER + q]; sum += local[q]; }
+        int total;
+        const int excl = block_exclusive_scan<SEL_NT>(sum, wsum2, total);
+        const int rem = s_rem2;
+        __syncthreads();
+        if (excl < rem && rem <= excl + sum) {
+            int cc = excl;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) {
+                if (cc < rem && rem <= cc + local[q]) {
+                    s_prefix2 = prefix | ((uint32_t)(tid * PER + q) << shift);
+                    s_rem2 = rem - cc;
+                }
+                cc += local[q];
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t thr = s_prefix2;        // key of the Keff-th smallest
+    const int take_ties = s_rem2;          // how many entries with key == thr belong to the answer (lowest indices)
     for (int e = tid; e < c; e += SEL_NT) {
         const uint32_t k = l_key[e];
-        const int ix = l_idx[e];
+        bool take = k < thr;
+        if (k == thr) {
+            const int ix = l_idx[e];
+            int r = 0;
+            for (int q = 0; q < c; ++q) r += (l_key[q] == thr && l_idx[q] < ix);   // ties are rare: short loop in practice
+            take = r < take_ties;
+        }
+        if (take) {
+            const int pos = atomicAdd(&s_nsel, 1);
+            c_key[pos] = k;
+            c_idx[pos] = l_idx[e];
+        }
+    }
+    __syncthreads();
+    if (tid < Keff) {
+        const uint32_t k = c_key[tid];
+        const int ix = c_idx[tid];
         int r = 0;
-        for (int q = 0; q < c; ++q) {
-            const uint32_t kq = l_key[q];
-            r += (kq < k) || (kq == k && l_idx[q] < ix);
+        for (int q = 0; q < Keff; ++q) {
+            const uint32_t kq = c_key[q];
+            r += (kq < k) || (kq == k && c_idx[q] < ix);
         }
-        if (r < Keff) {
-            out_idx[(size_t)row_id * out_stride + r] = ix;
-            out_val[(size_t)row_id * out_stride + r] = sel_value(row, ix, scaled, s);
-        }
+        out_idx[(size_t)row_id * out_stride + r] = ix;
+        out_val[(size_t)row_id * out_stride + r] = sel_value(row, ix, scaled, s);
     }
     for (int q = Keff + tid; q < K; q += SEL_NT) {
         out_idx[(size_t)row_id * out_stride + q] = -1;
@@ -381,19 +439,20 @@ int launch_row_select(const float* M, size_t ld, int rows, int cols, const float
 // (cnt == nullptr -> fixed_cnt).  One CTA per row, the row staged in shared memory as float64, one
 // thread per pair walking its partner row sequentially (cdist order, see sqdist_exact).
 // ---------------------------------------------------------------------------------------------------
-// v2 layout: a CTA owns PE_ROWS rows and PE_KP pair slots per row (thread = (row, slot)); the row block is staged
-// through shared memory in PE_CHUNK-wide float64 chunks, every thread carries its accumulator across the chunks, so
-// the summation order per pair is still strictly k = 0..d-1.  All 256 threads stay busy even for 8 pairs per row.
-constexpr int PE_KP = 8, PE_ROWS = 32, PE_CHUNK = 128;
-
-__global__ void __launch_bounds__(256)
+// v3 layout: a CTA owns ROWS rows; thread = (row, slot) with KP slots per row, and every thread carries PPT
+// independent accumulator chains (pair slots slot, slot+KP, ...): the float64 add chain of one pair is strictly
+// sequential (k = 0..d-1, cdist order), so instruction-level parallelism has to come from different pairs.  The row
+// block is staged through shared memory in CHUNK-wide float64 chunks shared by all the pairs of a row.
+template <int KP, int PPT, int ROWS, int CHUNK>
+__global__ void __launch_bounds__(KP * ROWS)
 pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict__ B, int d,
                   const int* __restrict__ idx, int idx_stride, const int* __restrict__ cnt,
                   int fixed_cnt, float* __restrict__ out, int out_stride) {
-    __shared__ double sa[PE_ROWS][PE_CHUNK];
+    constexpr int NT = KP * ROWS;
+    __shared__ double sa[ROWS][CHUNK];
     __shared__ int s_maxcnt;
-    const int r_in = threadIdx.x / PE_KP, slot = threadIdx.x % PE_KP;
-    const int row = blockIdx.x * PE_ROWS + r_in;
+    const int r_in = threadIdx.x / KP, slot = threadIdx.x % KP;
+    const int row = blockIdx.x * ROWS + r_in;
     const int c = row < rows ? (cnt ? cnt[row] : fixed_cnt) : 0;
     if (threadIdx.x == 0) s_maxcnt = 0;
     __syncthreads();
@@ -401,59 +460,74 @@ pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict
     __syncthreads();
     const int maxcnt = s_maxcnt;
     const bool vec_ok = (d & 3) == 0;
-    for (int sbase = 0; sbase < maxcnt; sbase += PE_KP) {
-        const int sidx = sbase + slot;
-        const bool active = sidx < c;
-        int m = -1;
-        if (active) m = idx[(size_t)row * idx_stride + sidx];
-        const float* b = B + (size_t)(m < 0 ? 0 : m) * d;
-        double acc = 0.0;
-        for (int k0 = 0; k0 < d; k0 += PE_CHUNK) {
+    for (int sbase = 0; sbase < maxcnt; sbase += KP * PPT) {
+        int m[PPT];
+        const float* b[PPT];
+        double acc[PPT];
+        bool act[PPT];
+#pragma unroll
+        for (int u = 0; u < PPT; ++u) {
+            const int sidx = sbase + slot + u * KP;
+            act[u] = sidx < c;
+            m[u] = act[u] ? idx[(size_t)row * idx_stride + sidx] : -1;
+            b[u] = B + (size_t)(m[u] < 0 ? 0 : m[u]) * d;
+            acc[u] = 0.0;
+        }
+        for (int k0 = 0; k0 < d; k0 += CHUNK) {
             __syncthreads();
-            for (int e = threadIdx.x; e < PE_ROWS * PE_CHUNK; e += 256) {
-                const int rr = e / PE_CHUNK, kk = e % PE_CHUNK;
-                const int gr = blockIdx.x * PE_ROWS + rr;
+            for (int e = threadIdx.x; e < ROWS * CHUNK; e += NT) {
+                const int rr = e / CHUNK, kk = e % CHUNK;
+                const int gr = blockIdx.x * ROWS + rr;
                 sa[rr][kk] = (gr < rows && k0 + kk < d) ? (double)A[(size_t)gr * d + k0 + kk] : 0.0;
             }
             __syncthreads();
-            if (active && m >= 0) {
-                const int kend = min(PE_CHUNK, d - k0);
-                const double* ar = sa[r_in];
-                if (vec_ok) {
-                    for (int k = 0; k < kend; k += 8) {          // 8 floats = one 32-byte sector of the partner row
-                        const float4 t0 = *reinterpret_cast<const float4*>(b + k0 + k);
-                        float4 t1 = t0;
-                        const bool two = k + 4 < kend;
-                        if (two) t1 = *reinterpret_cast<const float4*>(b + k0 + k + 4);
+            const int kend = min(CHUNK, d - k0);
+            const double* ar = sa[r_in];
+            if (vec_ok) {
+                for (int k = 0; k < kend; k += 4) {
+                    float4 t[PPT];
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u)
+                        t[u] = (act[u] && m[u] >= 0) ? *reinterpret_cast<const float4*>(b[u] + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const double a0 = ar[k], a1 = ar[k + 1], a2 = ar[k + 2], a3 = ar[k + 3];
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
                         double df;
-                        df = __dsub_rn(ar[k], (double)t0.x);     acc = __dadd_rn(acc, __dmul_rn(df, df));
-                        df = __dsub_rn(ar[k + 1], (double)t0.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                        df = __dsub_rn(ar[k + 2], (double)t0.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                        df = __dsub_rn(ar[k + 3], (double)t0.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                        if (two) {
-                            df = __dsub_rn(ar[k + 4], (double)t1.x); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                            df = __dsub_rn(ar[k + 5], (double)t1.y); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                            df = __dsub_rn(ar[k + 6], (double)t1.z); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                            df = __dsub_rn(ar[k + 7], (double)t1.w); acc = __dadd_rn(acc, __dmul_rn(df, df));
-                        }
+                        df = __dsub_rn(a0, (double)t[u].x); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a1, (double)t[u].y); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a2, (double)t[u].z); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a3, (double)t[u].w); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
                     }
-                } else {
-                    for (int k = 0; k < kend; ++k) {
-                        const double df = __dsub_rn(ar[k], (double)b[k0 + k]);
-                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                }
+            } else {
+                for (int k = 0; k < kend; ++k) {
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        if (act[u] && m[u] >= 0) {
+                            const double df = __dsub_rn(ar[k], (double)b[u][k0 + k]);
+                            acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        }
                     }
                 }
             }
         }
-        if (active) out[(size_t)row * out_stride + sidx] = m < 0 ? INFINITY : finish_sqdist(acc);
+#pragma unroll
+        for (int u = 0; u < PPT; ++u)
+            if (act[u]) out[(size_t)row * out_stride + sbase + slot + u * KP] = m[u] < 0 ? INFINITY : finish_sqdist(acc[u]);
     }
 }
 
 int launch_pair_exact(const float* A, int rows, const float* B, int d, const int* idx, int idx_stride,
                       const int* cnt, int fixed_cnt, float* out, int out_stride, cudaStream_t st) {
     if (rows <= 0) return SSG_OK;
-    pair_exact_kernel<<<ssg_cdiv(rows, PE_ROWS), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt, fixed_cnt, out,
-                                                              out_stride);
+    if (!cnt && fixed_cnt <= 8) {
+        // few pairs per row (row min / max candidates): 2 threads x 4 chains per row, 128 rows per CTA
+        pair_exact_kernel<2, 4, 128, 32><<<ssg_cdiv(rows, 128), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt, fixed_cnt,
+                                                                           out, out_stride);
+    } else {
+        pair_exact_kernel<8, 4, 32, 128><<<ssg_cdiv(rows, 32), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt, fixed_cnt,
+                                                                          out, out_stride);
+    }
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "conv.h"
+#include "gemm_tc.cuh"
 
 using namespace ssg;
 
@@ -64,6 +65,10 @@ struct ssg_embed_plan {
     void* wf[4];                 // fused [conv3 | downsample] weights of the first block of each layer
     float* bf[4];                // fused bias
     bool fused_ready;
+    void* w_stem448;             // stem weights for the overlapping-window GEMM [64, 7*64]
+    float* b_stem448;
+    void* stemP;                 // padded 4-channel bf16 input [2*batch][256][144][4]
+    int stem_windows;            // 1: window GEMM (no im2col), 0: im2col + GEMM, -1: undecided
     void *col, *stem, *x, *y, *ds, *t1, *t2, *planes, *xs;
 };
 
@@ -94,7 +99,8 @@ extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
     for (void* q : p->w) if (q) cudaFree(q);
     for (int L = 0; L < 4; ++L) { if (p->wf[L]) cudaFree(p->wf[L]); if (p->bf[L]) cudaFree(p->bf[L]); }
     for (float* q : p->b) if (q) cudaFree(q);
-    void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs};
+    void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs, p->w_stem448, p->b_stem448,
+                    p->stemP};
     for (void* q : bufs) if (q) cudaFree(q);
     delete p;
     return SSG_OK;
@@ -114,6 +120,7 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     p->loaded.assign(sp.size(), 0);
     p->fused_ready = false;
     for (int L = 0; L < 4; ++L) { p->wf[L] = nullptr; p->bf[L] = nullptr; }
+    p->w_stem448 = nullptr; p->b_stem448 = nullptr; p->stemP = nullptr; p->stem_windows = -1;
     int rc = SSG_OK;
     for (size_t i = 0; i < sp.size() && rc == SSG_OK; ++i) {
         rc = ealloc(&p->w[i], (size_t)sp[i].cout * kpad_of(sp[i]) * 2, &p->bytes);
@@ -129,6 +136,9 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
         }
     }
     const size_t nb = (size_t)batch_max * 2;       // images + flipped images
+    if (rc == SSG_OK) rc = ealloc(&p->w_stem448, (size_t)64 * 448 * 2, &p->bytes);
+    if (rc == SSG_OK) rc = ealloc((void**)&p->b_stem448, sizeof(float) * 64, &p->bytes);
+    if (rc == SSG_OK) rc = ealloc(&p->stemP, nb * 256 * 144 * 8, &p->bytes);
     const size_t px = 2;                           // bytes per bf16
 #define A(ptr, elems) if (rc == SSG_OK) rc = ealloc(&(ptr), (elems) * px, &p->bytes)
     A(p->col, nb * 8192 * 192);
@@ -157,6 +167,8 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
     const LayerSpec& s = specs()[idx];
     SSG_TRY(fold_bn(d_w, s.cout, s.cin, s.k, s.k, d_gamma, d_beta, d_mean, d_var, eps, kpad_of(s), p->w[idx],
                     p->b[idx], (cudaStream_t)stream));
+    if (idx == 0)
+        SSG_TRY(fold_bn_stem(d_w, d_gamma, d_beta, d_mean, d_var, eps, p->w_stem448, p->b_stem448, (cudaStream_t)stream));
     p->loaded[idx] = 1;
     p->fused_ready = false;
     return SSG_OK;
@@ -193,8 +205,22 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
     }
     int li = 0;
     // stem: 7x7/2 conv as im2col + GEMM (K 147 -> 192), then 3x3/2 max-pool
-    { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
-    { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv1x1(p->col, NB * 8192, 192, p->w[0], p->b[0], 64, nullptr, 1, p->stem, st)); }
+    if (p->stem_windows < 0) {
+        // overlapping-window TMA view of the input (no im2col buffer) unless SSG_STEM_WINDOWS=0 or the driver refuses
+        const char* e = getenv("SSG_STEM_WINDOWS");
+        p->stem_windows = (e && !atoi(e)) ? 0 : 1;
+        if (p->stem_windows) {
+            CUtensorMap probe;
+            if (make_tmap_stem_windows(&probe, p->stemP, 2) != SSG_OK) p->stem_windows = 0;
+        }
+    }
+    if (p->stem_windows) {
+        { SSG_PROF("stem_prep", st); SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st)); }
+        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows(p->stemP, NB, p->w_stem448, p->b_stem448, p->stem, st)); }
+    } else {
+        { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
+        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv1x1(p->col, NB * 8192, 192, p->w[0], p->b[0], 64, nullptr, 1, p->stem, st)); }
+    }
     { SSG_PROF("maxpool", st); SSG_TRY(maxpool3x3s2(p->stem, NB, 128, 64, 64, p->x, st)); }
     li = 1;
     int H = 64, W = 32, C = 64;

@@ -78,6 +78,25 @@ int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t
     return SSG_OK;
 }
 
+// Sliding-window view of the padded 4-channel stem input P [images][256 rows][144 px][4 ch] (bf16): dim0 = 64 elements
+// (16 px x 4 ch) of one window, dim1 = output column (window start advances 2 px = 16 bytes: the windows OVERLAP),
+// dim2 = input row (element stride 2 = one box row per output row), dim3 = image.  One box is the [2 x 64, 64] A tile
+// of one kernel row of the 7x7/2 convolution: no im2col buffer.
+int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images) {
+    PFN_encodeTiled enc;
+    SSG_TRY(get_encode(&enc));
+    cuuint64_t dims[4] = {64, 64, 256, images};
+    cuuint64_t strides[3] = {16, 144 * 8, (cuuint64_t)256 * 144 * 8};
+    cuuint32_t box[4] = {64, 64, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 2, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return ssg_set_error(SSG_ERR_UNSUPPORTED, "overlapping-window tensor map rejected by the driver (%d)", (int)r);
+    return SSG_OK;
+}
+
 int tc_num_sms(int* out) {
     static int cached[64] = {0};
     int dev = 0;

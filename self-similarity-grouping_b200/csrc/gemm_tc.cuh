@@ -11,6 +11,7 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
                       uint32_t box_rows);
 int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                         uint32_t bw, uint32_t bh, uint32_t bb, uint32_t stride = 1);
+int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images);
 int tc_num_sms(int* out);
 
 namespace tc {
@@ -148,6 +149,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         else tma_load_4d(sa, &A.map[1], &full_bar[stage], kb2 * BK, 0, h0 * A.hmul, b0);
                     } else if (A.mode == 0) {
                         tma_load_2d(sa, &A.map[0], &full_bar[stage], kb * BK, m_blk * BM);
+                    } else if (A.mode == 2) {
+                        // stem: K block kb = kernel row kh; tile = output rows (2t, 2t+1) of image m_blk / 64
+                        tma_load_4d(sa, &A.map[0], &full_bar[stage], 0, 0, 4 * (m_blk & 63) + kb - 3, m_blk >> 6);
                     } else {
                         const int tap = kb / A.cblks, cb = kb - tap * A.cblks;
                         tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
