@@ -304,11 +304,36 @@ __global__ void fold_bn_stem_kernel(const float* __restrict__ w, const float* __
         wout[(size_t)co * 448 + k] = __float2bfloat16_rn(v);
     }
 }
+// 64-byte-row variant: w'[co][kh 0..7][px 0..7][c 0..3] (kh = 7, px = 7 and c = 3 are zero)  ->  K = 256
+__global__ void fold_bn_stem64_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                      const float* __restrict__ var, float eps, __nv_bfloat16* __restrict__ wout) {
+    const int co = blockIdx.x;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) {
+        const int c = k & 3, px = (k >> 2) & 7, kh = k >> 5;
+        float v = 0.f;
+        if (c < 3 && px < 7 && kh < 7) v = w[(((size_t)co * 3 + c) * 7 + kh) * 7 + px] * scale;
+        wout[(size_t)co * 256 + k] = __float2bfloat16_rn(v);
+    }
+}
 int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-                 void* wout, float* bout, cudaStream_t st) {
+                 void* wout, float* bout, void* wout64, cudaStream_t st) {
     fold_bn_stem_kernel<<<64, 256, 0, st>>>(w, gamma, beta, mean, var, eps, (__nv_bfloat16*)wout, bout);
     SSG_CHECK_LAUNCH();
+    fold_bn_stem64_kernel<<<64, 256, 0, st>>>(w, gamma, var, eps, (__nv_bfloat16*)wout64);
+    SSG_CHECK_LAUNCH();
     return SSG_OK;
+}
+int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st) {
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 3;
+    A.cblks = 1;
+    A.taps = 8;
+    A.tiles_per_img = 64;
+    A.hmul = 1;
+    SSG_TRY(make_tmap_stem_windows64(&A.map[0], P, (uint64_t)images));
+    return gemm_dispatch(A, images * 8192, w256, 64, 256, bias, nullptr, 1, y, st);
 }
 
 // the window GEMM: P [images][256][144][4] -> relu(conv7x7/2 + bias) as NHWC bf16 [images,128,64,64]

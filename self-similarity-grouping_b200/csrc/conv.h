@@ -18,7 +18,8 @@ int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamm
             const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st);
 int stem_prep(const float* img, int n, int flip_too, void* P, cudaStream_t st);
 int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
-                 void* wout, float* bout, cudaStream_t st);
+                 void* wout, float* bout, void* wout64, cudaStream_t st);
+int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st);
 int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t st);
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);
 int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st);

@@ -66,6 +66,7 @@ struct ssg_embed_plan {
     float* bf[4];                // fused bias
     bool fused_ready;
     void* w_stem448;             // stem weights for the overlapping-window GEMM [64, 7*64]
+    void* w_stem256;             // ... 64-byte-row variant [64, 8*32]
     float* b_stem448;
     void* stemP;                 // padded 4-channel bf16 input [2*batch][256][144][4]
     int stem_windows;            // 1: window GEMM (no im2col), 0: im2col + GEMM, -1: undecided
@@ -99,7 +100,7 @@ extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
     for (void* q : p->w) if (q) cudaFree(q);
     for (int L = 0; L < 4; ++L) { if (p->wf[L]) cudaFree(p->wf[L]); if (p->bf[L]) cudaFree(p->bf[L]); }
     for (float* q : p->b) if (q) cudaFree(q);
-    void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs, p->w_stem448, p->b_stem448,
+    void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs, p->w_stem448, p->w_stem256, p->b_stem448,
                     p->stemP};
     for (void* q : bufs) if (q) cudaFree(q);
     delete p;
@@ -120,7 +121,7 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     p->loaded.assign(sp.size(), 0);
     p->fused_ready = false;
     for (int L = 0; L < 4; ++L) { p->wf[L] = nullptr; p->bf[L] = nullptr; }
-    p->w_stem448 = nullptr; p->b_stem448 = nullptr; p->stemP = nullptr; p->stem_windows = -1;
+    p->w_stem448 = nullptr; p->w_stem256 = nullptr; p->b_stem448 = nullptr; p->stemP = nullptr; p->stem_windows = -1;
     int rc = SSG_OK;
     for (size_t i = 0; i < sp.size() && rc == SSG_OK; ++i) {
         rc = ealloc(&p->w[i], (size_t)sp[i].cout * kpad_of(sp[i]) * 2, &p->bytes);
@@ -137,6 +138,7 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     }
     const size_t nb = (size_t)batch_max * 2;       // images + flipped images
     if (rc == SSG_OK) rc = ealloc(&p->w_stem448, (size_t)64 * 448 * 2, &p->bytes);
+    if (rc == SSG_OK) rc = ealloc(&p->w_stem256, (size_t)64 * 256 * 2, &p->bytes);
     if (rc == SSG_OK) rc = ealloc((void**)&p->b_stem448, sizeof(float) * 64, &p->bytes);
     if (rc == SSG_OK) rc = ealloc(&p->stemP, nb * 256 * 144 * 8, &p->bytes);
     const size_t px = 2;                           // bytes per bf16
@@ -168,7 +170,8 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
     SSG_TRY(fold_bn(d_w, s.cout, s.cin, s.k, s.k, d_gamma, d_beta, d_mean, d_var, eps, kpad_of(s), p->w[idx],
                     p->b[idx], (cudaStream_t)stream));
     if (idx == 0)
-        SSG_TRY(fold_bn_stem(d_w, d_gamma, d_beta, d_mean, d_var, eps, p->w_stem448, p->b_stem448, (cudaStream_t)stream));
+        SSG_TRY(fold_bn_stem(d_w, d_gamma, d_beta, d_mean, d_var, eps, p->w_stem448, p->b_stem448, p->w_stem256,
+                             (cudaStream_t)stream));
     p->loaded[idx] = 1;
     p->fused_ready = false;
     return SSG_OK;
@@ -208,13 +211,17 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
     if (p->stem_windows < 0) {
         // overlapping-window TMA view of the input (no im2col buffer) unless SSG_STEM_WINDOWS=0 or the driver refuses
         const char* e = getenv("SSG_STEM_WINDOWS");
-        p->stem_windows = (e && !atoi(e)) ? 0 : 1;
+        // 2 (default): 8-pixel windows, 64-byte swizzle; 1: 16-pixel windows, 128-byte swizzle; 0: im2col + GEMM
+        p->stem_windows = e ? atoi(e) : 2;
         if (p->stem_windows) {
             CUtensorMap probe;
             if (make_tmap_stem_windows(&probe, p->stemP, 2) != SSG_OK) p->stem_windows = 0;
         }
     }
-    if (p->stem_windows) {
+    if (p->stem_windows == 2) {
+        { SSG_PROF("stem_prep", st); SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st)); }
+        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, p->stem, st)); }
+    } else if (p->stem_windows == 1) {
         { SSG_PROF("stem_prep", st); SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st)); }
         { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows(p->stemP, NB, p->w_stem448, p->b_stem448, p->stem, st)); }
     } else {

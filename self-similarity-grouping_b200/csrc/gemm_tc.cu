@@ -97,6 +97,36 @@ int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images) 
     return SSG_OK;
 }
 
+// 64-byte-swizzle variants for the stem: 8-pixel windows (32 elements = 64 B per row) halve the L2 traffic of the
+// overlapping-window view; the weight matrix is cut into matching [rows, 32] boxes.
+int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images) {
+    PFN_encodeTiled enc;
+    SSG_TRY(get_encode(&enc));
+    cuuint64_t dims[4] = {32, 64, 256, images};
+    cuuint64_t strides[3] = {16, 144 * 8, (cuuint64_t)256 * 144 * 8};
+    cuuint32_t box[4] = {32, 64, 4, 1};
+    cuuint32_t estr[4] = {1, 1, 2, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return ssg_set_error(SSG_ERR_UNSUPPORTED, "overlapping-window (64B) tensor map rejected by the driver (%d)", (int)r);
+    return SSG_OK;
+}
+int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    PFN_encodeTiled enc;
+    SSG_TRY(get_encode(&enc));
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return ssg_set_error(SSG_ERR_CUDA, "cuTensorMapEncodeTiled(sw64) failed (%d)", (int)r);
+    return SSG_OK;
+}
+
 int tc_num_sms(int* out) {
     static int cached[64] = {0};
     int dev = 0;

@@ -12,6 +12,8 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                         uint32_t bw, uint32_t bh, uint32_t bb, uint32_t stride = 1);
 int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images);
+int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images);
+int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int tc_num_sms(int* out);
 
 namespace tc {
@@ -149,6 +151,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         else tma_load_4d(sa, &A.map[1], &full_bar[stage], kb2 * BK, 0, h0 * A.hmul, b0);
                     } else if (A.mode == 0) {
                         tma_load_2d(sa, &A.map[0], &full_bar[stage], kb * BK, m_blk * BM);
+                    } else if (A.mode == 3) {
+                        // stem, 64-byte rows: the stage holds two kernel rows (kh = 2kb, 2kb+1) as two [128 x 64 B] halves
+                        const int ih = 4 * (m_blk & 63) + 2 * kb - 3;
+                        tma_load_4d(sa, &A.map[0], &full_bar[stage], 0, 0, ih, m_blk >> 6);
+                        tma_load_4d(sa + L::A_BYTES / 2, &A.map[0], &full_bar[stage], 0, 0, ih + 1, m_blk >> 6);
                     } else if (A.mode == 2) {
                         // stem: K block kb = kernel row kh; tile = output rows (2t, 2t+1) of image m_blk / 64
                         tma_load_4d(sa, &A.map[0], &full_bar[stage], 0, 0, 4 * (m_blk & 63) + kb - 3, m_blk >> 6);
@@ -157,7 +164,12 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
                                     h0 * A.hmul + A.tap_dh[tap], b0);
                     }
-                    tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
+                    if (A.mode == 3) {
+                        tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
+                        tma_load_2d(sb + L::B_BYTES / 2, &mapB, &full_bar[stage], kb * BK + 32, n_blk * BN);
+                    } else {
+                        tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -179,12 +191,23 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t sb = sa + L::A_BYTES;
-                    const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sb);
+                    if (A.mode == 3) {
+                        // two half-stages of 64-byte-swizzled rows, two 16-element K steps each
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 bytes (16 bf16) inside the swizzle row: +2 in the (addr >> 4) field
-                        umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                 (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t da = make_desc_k_sw64(sa + (k >> 1) * (L::A_BYTES / 2));
+                            const uint64_t db = make_desc_k_sw64(sb + (k >> 1) * (L::B_BYTES / 2));
+                            umma_f16(d_tmem, da + (uint64_t)(2 * (k & 1)), db + (uint64_t)(2 * (k & 1)), idesc,
+                                     (kb > 0 || k > 0) ? 1u : 0u);
+                        }
+                    } else {
+                        const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 32 bytes (16 bf16) inside the swizzle row: +2 in the (addr >> 4) field
+                            umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                     (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);                        // smem slot free once the MMAs retire
                     if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
@@ -329,7 +352,8 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;
-    SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
+    if (A.mode == 3) SSG_TRY(make_tmap_2d_bf16_sw64(&mapB, b, (uint64_t)n, (uint64_t)k, BN));
+    else SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
     int sms = 0;
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);

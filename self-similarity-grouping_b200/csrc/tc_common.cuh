@@ -127,6 +127,16 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2u << 61;
     return d;
 }
+// Same, 64-byte swizzle (rows of 32 bf16 = 64 B): SBO = 512 B (8 rows x 64 B), layout SWIZZLE_64B (4).
+__device__ __forceinline__ uint64_t make_desc_k_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+    d |= (uint64_t)1u << 16;
+    d |= (uint64_t)(512u >> 4) << 32;
+    d |= (uint64_t)1u << 46;
+    d |= (uint64_t)4u << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16: D = F32, A = B = BF16, both K-major, dense.
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);

@@ -100,3 +100,42 @@ def test_tensor_mode_full_size_matches_exact(ssg):
     assert np.array_equal(plan.stage(_lib.STAGE_RANK, n)[:, :21], rank_ex[:, :21])
     assert torch.equal(f_tc, f_ex)
     print("flagged rows:", int(plan.stage(_lib.STAGE_FLAGGED, n)[0]))
+
+
+def test_duke_size_row_blocked_path(ssg):
+    """N = 36 411 (DukeMTMC shape, BASELINE.json configs[3]): the fp32 distance matrix (5.3 GB) exceeds the 4 GiB
+    distance block, so the distance stages run in row blocks; size-independent properties + sampled rows vs cdist."""
+    import torch
+    from scipy.spatial.distance import cdist
+    from ssg_b200 import _lib
+    n, d, lam = 36411, 2048, 0.1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    c = n // 20
+    centres = torch.randn(c, d, generator=g, device="cuda")
+    lab = torch.randint(0, c, (n,), generator=g, device="cuda")
+    t = centres[lab] + 0.5 * torch.randn(n, d, generator=g, device="cuda")
+    t = (t / t.norm(dim=1, keepdim=True)).contiguous()
+    s = centres[torch.randint(0, c, (n,), generator=g, device="cuda")] + 0.6 * torch.randn(n, d, generator=g, device="cuda")
+    s = (s / s.norm(dim=1, keepdim=True)).contiguous()
+    plan = ssg.RerankPlan(n, n, d)
+    _, f = plan.run(s, t, lambda_value=lam, dist_mode=_lib.DIST_TENSOR)
+    torch.cuda.synchronize()
+    rank = plan.stage(_lib.STAGE_RANK, n)
+    assert np.array_equal(rank[:, 0], np.arange(n))
+    rows = np.arange(0, n, n // 48)[:48]
+    th = t.cpu().numpy()
+    od = np.power(cdist(th[rows], th).astype(np.float32), 2).astype(np.float32)
+    odn = od / od.max(axis=1, keepdims=True)
+    assert np.array_equal(np.argsort(odn, kind="stable")[:, :21], rank[rows, :21])
+    assert np.array_equal(plan.stage(_lib.STAGE_ROWMAX, n)[rows], od.max(axis=1))
+    # symmetric on a sampled block (a full transpose of the 10.6 GB matrix is not needed)
+    blk = torch.arange(0, n, 37, device="cuda")
+    sub = f.index_select(0, blk).index_select(1, blk)
+    assert torch.equal(sub, sub.t())
+    cplan = ssg.ClusterPlan(n)
+    eps, top = cplan.eps(f, 1.6e-3)
+    assert top == 1060580                                  # SURVEY.md §8 table: round(rho * M) at N = 36 411
+    labels, ncl = cplan.dbscan(f, eps, 4)
+    assert ncl > 500 and int((labels >= 0).sum()) > n // 2
+    del f, plan, cplan
+    torch.cuda.empty_cache()
