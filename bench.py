@@ -432,7 +432,9 @@ def main():
             "kernels_ms_per_step": {kk: round(v[0] / k, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
             "result": {"clusters": [int(l.max()) + 1 for l in labels], "eps": [round(e, 6) for e in eps_list],
-                       "kept_images": int(keep.sum())},
+                       "kept_images": int(keep.sum()),
+                       "rows_recomputed_exactly_last_bank": int(ssg_b200.rerank.get_plan(n, n, D, local).stage(
+                           _lib.STAGE_FLAGGED, n)[0]) if mode == _lib.DIST_TENSOR else None},
         }
     if world > 1:
         dist.barrier()
