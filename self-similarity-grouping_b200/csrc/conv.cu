@@ -158,6 +158,23 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
             }
         }
     const int m = B * H * W;
+    // few-channel stride-1 convolutions (layer 1: C = 64) are L2-bandwidth bound when every tap re-reads the map:
+    // share the three kernel rows of a kernel column through one haloed TMA box (SSG_CONV_KHS=0 disables)
+    static int khs = -1;
+    if (khs < 0) { const char* e = getenv("SSG_CONV_KHS"); khs = e ? atoi(e) : 1; }
+    if (khs && stride == 1 && cin == 64 && cout == 64 && A.bb == 1 && (A.bh + 2) * bw == 192 && (bw * 128) % 1024 == 0) {
+        // (the haloed box must fill the 192-row stage buffer exactly: the TMA transaction count is fixed at compile time)
+        A.khs_row_bytes = bw * 128;
+        SSG_TRY(make_tmap_nhwc_bf16(&A.map[0], x, B, H, W, cin, bw, A.bh + 2, 1));
+        tc::StagedEpi epi;
+        memset(&epi, 0, sizeof(epi));
+        epi.bias = bias;
+        epi.relu = relu;
+        epi.has_res = 0;
+        SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+        SSG_TRY(make_tmap_2d_bf16(&epi.mapR, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+        return tc::launch_gemm_op<64, tc::StagedEpi, true, true>(A, m, w, cout, 9 * cin, epi, st);
+    }
     return gemm_dispatch(A, m, w, cout, 9 * cin, bias, nullptr, relu, y, st);
 }
 

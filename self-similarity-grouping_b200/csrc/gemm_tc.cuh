@@ -38,6 +38,7 @@ struct AOperand {
     int hmul;              // input rows per output row (2 for stride-2 boxes read straight from the input map)
     int kb_split;          // > 0: K blocks >= kb_split come from a second source, map[1] (K-concatenated GEMM)
     int mode1;             // second source: 0 = plain [M,K1] matrix, 1 = single-tap implicit view (uses bh/bb/hmul)
+    int khs_row_bytes;     // KHS kernels: bytes of one image row of the tile in the haloed A buffer (bw * 128)
     signed char tap_plane[9], tap_dh[9], tap_dw[9];
 };
 
@@ -53,10 +54,15 @@ struct StagedEpi {
 // BN <= 128 (staged): one output sub-buffer per 64-column sub-tile + two residual tile buffers, 3-5 operand stages.
 // BN == 256 (staged): K-heavy convolutions without residual: a ring of two output sub-buffers, no residual staging,
 //                     4 operand stages (128x256 tiles halve the shared-memory operand traffic per MMA).
-template <int BN, bool STAGED>
+// KHS ("kernel-row sharing", 3x3 stride-1 convolutions with few channels): one stage holds the input rows of a tile
+// plus a one-row halo above and below ((bh+2)*bw <= 192 pixel rows) for one kernel column, and the three weight
+// tiles of that column; the three kernel rows are three MMAs whose A descriptors start kh*bw rows into the same
+// buffer — the activation is read 3 times from L2 instead of 9.
+template <int BN, bool STAGED, bool KHS = false>
 struct SmemLayout {
-    static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int A_BYTES = (KHS ? 192 : BM) * BK * 2;
+    static constexpr int B_TILE = BN * BK * 2;
+    static constexpr int B_BYTES = (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
@@ -64,7 +70,7 @@ struct SmemLayout {
     static constexpr bool HAS_R = BN <= 128;                     // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && HAS_R) ? NSUB * SUB_BYTES : 0;   // one residual tile
-    static constexpr int STAGES = STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4));
+    static constexpr int STAGES = KHS ? 3 : (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int C_OFFSET = STAGES * STAGE_BYTES;        // output staging, then 2 residual staging buffers
     static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + 2 * R_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
@@ -81,11 +87,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 
-template <int BN, class Epi, bool STAGED>
+template <int BN, class Epi, bool STAGED, bool KHS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N,
             int num_k_blocks, const __grid_constant__ Epi epi) {
-    using L = SmemLayout<BN, STAGED>;
+    using L = SmemLayout<BN, STAGED, KHS>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ unsigned char smem_raw[];
@@ -145,6 +151,17 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     unsigned char* sa = smem + stage * L::STAGE_BYTES;
                     unsigned char* sb = sa + L::A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if constexpr (KHS) {
+                        // stage kb = (kernel column kw, channel block cb): rows h0-1 .. h0+bh of the tile's image
+                        const int kw = kb / A.cblks, cb = kb - kw * A.cblks;
+                        tma_load_4d(sa, &A.map[0], &full_bar[stage], cb * BK, kw - 1, h0 - 1, b0);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+                            tma_load_2d(sb + kh * L::B_TILE, &mapB, &full_bar[stage], ((kh * 3 + kw) * A.cblks + cb) * BK,
+                                        n_blk * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (A.kb_split > 0 && kb >= A.kb_split) {
                         const int kb2 = kb - A.kb_split;
                         if (A.mode1 == 0) tma_load_2d(sa, &A.map[1], &full_bar[stage], kb2 * BK, m_blk * BM);
@@ -191,7 +208,18 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
                     const uint32_t sb = sa + L::A_BYTES;
-                    if (A.mode == 3) {
+                    if constexpr (KHS) {
+                        // three kernel rows out of one haloed buffer: A starts kh*bw pixel rows (kh*bw*128 B) in
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint64_t da = make_desc_k_sw128(sa + (uint32_t)(kh * A.khs_row_bytes));
+                            const uint64_t db = make_desc_k_sw128(sb + (uint32_t)(kh * L::B_TILE));
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k)
+                                umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                         (kb > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                        }
+                    } else if (A.mode == 3) {
                         // two half-stages of 64-byte-swizzled rows, two 16-element K steps each
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -346,9 +374,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 }
 
 // Launch with a fully prepared A operand.
-template <int BN, class Epi, bool STAGED = false>
+template <int BN, class Epi, bool STAGED = false, bool KHS = false>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGED>;
+    using L = SmemLayout<BN, STAGED, KHS>;
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;
@@ -358,9 +386,10 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = tiles < sms ? tiles : sms;
-    auto kern = gemm_kernel<BN, Epi, STAGED>;
+    auto kern = gemm_kernel<BN, Epi, STAGED, KHS>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, (k + BK - 1) / BK, epi);
+    // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, KHS ? (k / BK) / 3 : (k + BK - 1) / BK, epi);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
