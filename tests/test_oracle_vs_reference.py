@@ -48,3 +48,20 @@ def test_reference_model_matches_oracle_model():
         b = o(x, False)[0]
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_evaluation_metrics_restatement_matches_reference():
+    """oracle cmc / mean_ap (row f2) against reid/evaluation_metrics/ranking.py of the unmodified reference."""
+    ref = refshim.load_reference()
+    with refshim._reference_on_path():
+        import reid.evaluation_metrics as rem
+    rng = np.random.RandomState(0)
+    m, n = 40, 200
+    qid, gid = rng.randint(0, 20, m), rng.randint(0, 20, n)
+    qc, gc = rng.randint(0, 3, m), rng.randint(0, 3, n)
+    d = rng.rand(m, n).astype(np.float32) + 0.5 * (qid[:, None] != gid[None, :])
+    assert rem.mean_ap(d, qid, gid, qc, gc) == O.mean_ap(d, qid, gid, qc, gc)
+    for fmb in (True, False):
+        a = rem.cmc(d, qid, gid, qc, gc, first_match_break=fmb)
+        b = O.cmc(d, qid, gid, qc, gc, first_match_break=fmb)
+        assert np.array_equal(a, b)
