@@ -357,10 +357,20 @@ def main():
             conv_ms = sum(prof[c][0] for c in conv_names if c in prof)
             flops = 2.0 * 2669150208 * 2 * (2 * n) * k * (1.0 / world if sharded else 1.0)   # rank 0's share
             ach = flops / (conv_ms / 1e3) / 1e12
-            roof = {"kernel": "gemm_kernel<EpiConv> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)"
+            # DRAM traffic of the same launches, from the committed ncu capture of one embedding batch (not re-measured
+            # here: a number printed under a profiler is never a bench value, but the byte counts are clock independent)
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "r01_final_conv_traffic.json")
+            if os.path.isfile(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                batches = 2.0 * n * (1.0 / world if sharded else 1.0) / tj["batch_images"]
+                traffic = {"bytes_per_step": tj["dram_bytes_per_batch"] * batches, "source": "profiles/r01_final_conv_traffic.json",
+                           "algorithmic_note": "see DESIGN.md 3.1: the convolution path is HBM bound in its 1x1 layers"}
+            roof = {"kernel": "gemm_kernel<StagedEpi> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)"
                               % sum(prof[c][1] for c in conv_names if c in prof),
                     "bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tensor"], "traffic": None, "ms_per_step": conv_ms / k,
+                    "frac": ach / peaks["tensor"], "traffic": traffic, "ms_per_step": conv_ms / k,
                     "peak_source": peaks["source"],
                     "note": "algorithmic flops = 2 x 2 669 150 208 conv MACs per image-pass (SURVEY.md 8d), summed over "
                             "all conv launches of the step"}

@@ -3,10 +3,11 @@
 Sharding of ONE cycle over `world` ranks:
   1. embed   : rank r embeds the contiguous image shard [lo_r, hi_r) of the target and of the source set;
   2. exchange: all-gather of the feature banks ([banks, N, 2048] float32 on every rank) — the one real exchange step;
-  3. re-rank : for every bank, rank r computes the distance stages (GEMM, candidate selection, exact re-scoring) for
-               its row block [lo_r, hi_r) only (ssg_rerank_distance_rows), the small per-row tables (row min / max,
-               21 rank columns) are all-gathered (~4.4 MB per bank), and the owner rank (bank % world) runs the cheap
-               remaining stages (k-reciprocal encoding ... final distance), eps and DBSCAN;
+  3. re-rank : phase A, for every bank, rank r computes the distance stages (GEMM, candidate selection, exact
+               re-scoring) for its row block [lo_r, hi_r) only (ssg_rerank_distance_rows) and the small per-row tables
+               (row min / max, 21 rank columns; ~4.4 MB per bank) are all-gathered; phase B, the owner ranks
+               (bank % world) run the cheap remaining stages (k-reciprocal encoding ... final distance), eps and DBSCAN
+               of their banks in parallel;
   4. labels  : broadcast from the owners (N int64 per bank).
 
 All collectives go through a small `Comm` wrapper, and all compute through a `backend` object, so that the sharding
@@ -156,17 +157,28 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
     src = comm.all_gather_rows(sloc, n_src, dim=1)
     lo, hi = shard_bounds(n_tgt, comm.world, comm.rank)
     plan = backend.plan(n_tgt, n_src, tgt.shape[2])
+    # phase A — all ranks, bank after bank: row-block distance stage, then all-gather of the per-row tables; the owner
+    # of a bank keeps a copy of its tables (the plan holds one set).  Phase B — the owners finish their banks in
+    # parallel (k-reciprocal encoding ... final distance, eps, DBSCAN); nobody waits for an owner between banks.
+    saved = []
+    bank_t = []
+    for b in range(banks):
+        tb, sb = tgt[b].contiguous(), src[b].contiguous()
+        bank_t.append(tb)
+        backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
+        tabs = backend.tables(plan, n_tgt)
+        for tab in tabs:
+            comm.all_gather_rows_inplace(tab, n_tgt)
+        saved.append([t.clone() for t in tabs] if comm.rank == b % comm.world else None)
     final = None
     labels_dev, eps_out = [], []
     for b in range(banks):
-        tb, sb = tgt[b].contiguous(), src[b].contiguous()
-        backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
-        for tab in backend.tables(plan, n_tgt):
-            comm.all_gather_rows_inplace(tab, n_tgt)
-        owner = b % comm.world
+        tb = bank_t[b]
         lab = torch.empty((n_tgt,), dtype=torch.int64, device=tb.device)
         eps_t = torch.zeros((1,), dtype=torch.float64, device=tb.device)
-        if comm.rank == owner:
+        if comm.rank == b % comm.world:
+            for dst, keep in zip(backend.tables(plan, n_tgt), saved[b]):
+                dst.copy_(keep)
             if final is None:
                 final = backend.new_final(n_tgt)
             backend.finish(plan, tb, k1, k2, lambda_value, final)

@@ -29,6 +29,7 @@ class FakePlan(object):
         self.rank = torch.full((n, 32), -1, dtype=torch.int32)
         self.rank_val = torch.zeros(n, 32)
         self.src = None
+        self.src_by_tgt = {}
 
 
 class OracleBackend(object):
@@ -54,6 +55,7 @@ class OracleBackend(object):
         import torch
         from scipy.spatial.distance import cdist
         plan.src = src
+        plan.src_by_tgt[tgt.data_ptr()] = src
         t, s = tgt.numpy(), src.numpy()
         blk = slice(row0, row0 + rows)
         st = np.power(cdist(t[blk], s), 2).astype(np.float32)
@@ -72,7 +74,8 @@ class OracleBackend(object):
     def finish(self, plan, tgt, k1, k2, lambda_value, final):
         import torch
         st = {}
-        _, f = O.re_ranking(plan.src.numpy(), tgt.numpy(), k1, k2, lambda_value, mode="f32", stages=st)
+        src = plan.src_by_tgt[tgt.data_ptr()]          # phase B runs after all banks' distance stages
+        _, f = O.re_ranking(src.numpy(), tgt.numpy(), k1, k2, lambda_value, mode="f32", stages=st)
         # the gathered tables must be exactly what a single process computes
         assert np.array_equal(plan.rank[:, :k1 + 1].numpy(), st["rank"][:, :k1 + 1])
         assert np.array_equal(plan.rowmax.numpy(), st["od"].max(0))

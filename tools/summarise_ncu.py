@@ -77,5 +77,34 @@ def full(path):
     print("units: " + ", ".join("%s=%s" % (k, rd[1][cols[k]]) for k in KEYS if k in cols))
 
 
+def traffic(path):
+    """DRAM bytes + time of every convolution GEMM launch of one embedding batch -> JSON on stdout."""
+    import json
+    with open(path, newline="") as f:
+        lines = [l for l in f if not l.startswith("==")]
+    rd = csv.reader(lines)
+    header = next(rd)
+    per = defaultdict(dict)
+    order = []
+    for r in rd:
+        row = dict(zip(header, r))
+        i = row["ID"]
+        if i not in per:
+            order.append(i)
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+                 "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}.get(u, 1)
+        per[i][row["Metric Name"]] = v * scale
+        per[i]["kernel"] = short(row["Kernel Name"])
+    launches_ = [{"kernel": per[i]["kernel"], "us": per[i].get("gpu__time_duration.sum", 0.0),
+                  "dram_read": per[i].get("dram__bytes_read.sum", 0.0), "dram_write": per[i].get("dram__bytes_write.sum", 0.0)}
+                 for i in order]
+    out = {"launches": len(launches_), "batch_images": 512,
+           "dram_bytes_per_batch": sum(l["dram_read"] + l["dram_write"] for l in launches_),
+           "us_per_batch": sum(l["us"] for l in launches_), "per_launch": launches_}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
