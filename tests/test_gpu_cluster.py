@@ -138,3 +138,33 @@ def test_cmc_and_mean_ap_match_reference_restatement(m, n, nid, quant):
         for fmb in (True, False):
             got = cmc(dist, qid, gid, qcam, gcam, topk=50, first_match_break=fmb)
             np.testing.assert_allclose(got, O.cmc(d, qid, gid, qcam, gcam, topk=50, first_match_break=fmb), atol=1e-12)
+
+
+def test_dbscan_and_eps_property_based(ssg):
+    """Property test: random symmetric matrices with heavy ties (quantised values, non-zero diagonal),
+    random eps / min_samples / rho — labels, core samples and eps must equal sklearn / numpy every time."""
+    from hypothesis import given, settings, strategies as st
+    from sklearn.cluster import DBSCAN
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(n=st.integers(1, 150), seed=st.integers(0, 10 ** 6), levels=st.integers(2, 40),
+           eps_q=st.integers(0, 40), min_samples=st.integers(1, 7), rho=st.floats(0.001, 1.0))
+    def run(n, seed, levels, eps_q, min_samples, rho):
+        rng = np.random.RandomState(seed)
+        A = rng.randint(0, levels, (n, n)).astype(np.float64) / levels
+        D = np.minimum(A, A.T)
+        np.fill_diagonal(D, rng.randint(0, levels, n) / levels)
+        eps = eps_q / 40.0
+        want = DBSCAN(eps=eps, min_samples=min_samples, metric="precomputed").fit(D)
+        got = ssg.DBSCAN(eps=eps, min_samples=min_samples, metric="precomputed").fit(D)
+        assert np.array_equal(got.labels_, want.labels_)
+        assert np.array_equal(got.core_sample_indices_, want.core_sample_indices_)
+        tri = np.triu(D, 1)
+        tri = np.sort(tri[np.nonzero(tri)], axis=None)
+        top = int(np.round(rho * tri.size))
+        e = ssg.eps_estimate(D, rho)
+        if top == 0:
+            assert np.isnan(e)
+        else:
+            assert abs(e - tri[:top].mean()) <= 1e-12 * max(abs(tri[:top].mean()), 1e-300)
+    run()
