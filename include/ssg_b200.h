@@ -187,6 +187,25 @@ int ssg_op_pooled_tail(const void* d_x, int n, int num_split, int eval_mode, int
                        size_t bank_stride, int row0, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fine-tune loss: reid/loss/triplet.py:11-77 TripletLoss(margin, num_instances, use_semi)
+ * .forward(inputs, targets, epoch) with w = None, as called per feature bank by reid/trainers.py:257-271
+ * (FinedTrainer2._forward).  The batch is P = n / num_instances identities x num_instances consecutive rows.
+ *   forward : d_x fp32 [n,d] (16-byte aligned), d_targets int64 [n]  ->  d_loss_prec fp32 [2] = {loss, prec};
+ *             d_dist fp32 [n,n] (the clamped pairwise distances, triplet.py:27-31) and d_coef fp32 [n,n]
+ *             ((d loss / d dist) / dist, consumed by backward) are caller-allocated.  use_semi != 0: every
+ *             (anchor, later row of its group) pair with the anchor's closest other-label row (triplet.py:49-56);
+ *             use_semi == 0: per row the farthest same-label and closest other-label rows (triplet.py:57-60).
+ *             d_status int32 [2]: {1 if some anchor has no other-label row in the batch (the reference raises
+ *             there; the loss is then NaN), that anchor's index}.  n <= 4096.
+ *   backward: d_grad_x fp32 [n,d] = *d_grad_loss (device scalar, NULL = 1) * d loss / d x.
+ * Deterministic (fixed reduction order); ties between candidate negatives take the lowest index.
+ * ------------------------------------------------------------------------------------------------ */
+int ssg_triplet_forward(const float* d_x, const int64_t* d_targets, int n, int d, int num_instances, float margin,
+                        int use_semi, float* d_dist, float* d_coef, float* d_loss_prec, int* d_status, void* stream);
+int ssg_triplet_backward(const float* d_x, int n, int d, const float* d_coef, const float* d_grad_loss,
+                         float* d_grad_x, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-kernel CUDA-event timers (the reference only has wall-clock AverageMeters, reid/utils/meters.py:4-23,
  * printed from reid/evaluators.py:48-57).  Disabled by default; when enabled every kernel group launched by
  * this library is bracketed by events on its own stream.  collect() synchronises the device, accumulates

@@ -12,7 +12,7 @@ import warnings
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import refshim, ssg_oracle as O, resnet_oracle as R  # noqa: E402
+from oracle import refshim, ssg_oracle as O, resnet_oracle as R, triplet_oracle as TO  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -82,6 +82,32 @@ def embed_case(name, n_img, seed_img):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def triplet_cases(name):
+    """reid/loss/triplet.py TripletLoss of the unmodified reference on CPU (forward + autograd backward)."""
+    import torch
+    refshim.load_reference()
+    with refshim._reference_on_path():
+        import reid.loss.triplet as T
+    out = dict(versions=versions())
+    cases = [  # P, K, d, seed, margin, use_semi, extra rows, sep
+        (4, 4, 32, 0, 0.5, 1, 0, 1.0), (16, 4, 2048, 1, 0.5, 1, 0, 0.2), (16, 4, 512, 2, 0.0, 1, 3, 0.3),
+        (8, 8, 256, 3, 0.3, 0, 0, 0.5), (32, 4, 512, 5, 0.5, 1, 0, 0.15), (5, 3, 77, 6, 0.3, 1, 2, 0.4)]
+    out["cases"] = np.array(cases, dtype=np.float64)
+    for ci, (P, K, d, seed, margin, semi, extra, sep) in enumerate(cases):
+        x, t = TO.synth_batch(P, K, d, seed, sep, extra)
+        xt = torch.from_numpy(x).requires_grad_(True)
+        crit = T.TripletLoss(margin=margin, num_instances=K, use_semi=bool(semi))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            loss, prec = crit(xt, torch.from_numpy(t), 0)
+        loss.backward()
+        out["x_%d" % ci], out["t_%d" % ci] = x, t
+        out["loss_%d" % ci], out["prec_%d" % ci] = np.float32(loss.item()), np.float32(float(prec))
+        out["grad_%d" % ci] = xt.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, [float(out["loss_%d" % c]) for c in range(len(cases))])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     rerank_case("rerank_n160_d256.npz", 160, 150, 256, seed=3, lam=0.1, rhos=[1.6e-3, 1.6e-2, 5e-2])
@@ -90,3 +116,4 @@ if __name__ == "__main__":
                 noise=0.0)   # noise 0 => duplicate features: exact ties everywhere
     rerank_init_case("rerank_init_q40_g90.npz", 40, 90, 512, seed=5)
     embed_case("embed_4img.npz", 4, 1234)
+    triplet_cases("triplet_cases.npz")

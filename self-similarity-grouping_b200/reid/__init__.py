@@ -9,8 +9,11 @@ Put ``self-similarity-grouping_b200/`` ahead of the reference on ``sys.path`` an
     from reid.rerank import *                                 -> CUDA re_ranking, and a CUDA ``DBSCAN`` that
                                                                  shadows sklearn's in the driver's namespace
 
-Only the hot path lives here; datasets, trainers, losses and the evaluation metrics are the
-reference's own and out of scope.
+    from reid.loss import TripletLoss                         -> CUDA triplet loss (row f1)
+    from reid.trainers import FinedTrainer2                   -> the fine-tune step over it
+
+Only the hot path and its "next" rows live here; datasets, samplers, the other trainers/losses and
+checkpoint I/O are the reference's own and out of scope.
 """
 from . import evaluation_metrics  # noqa: F401
 from . import feature_extraction  # noqa: F401
@@ -20,5 +23,7 @@ from . import rerank  # noqa: F401
 from . import rerank_initial  # noqa: F401
 from . import cluster  # noqa: F401
 from . import eug  # noqa: F401
+from . import loss  # noqa: F401
+from . import trainers  # noqa: F401
 
 __version__ = '0.2.0'

@@ -8,6 +8,7 @@ from .rerank import RerankPlan, re_ranking, re_ranking_device, sqdist  # noqa: F
 from .cluster import ClusterPlan, DBSCAN, eps_estimate, dbscan_labels  # noqa: F401
 
 from .embed import EmbedPlan, embed_images, extract_features  # noqa: F401
+from .triplet import triplet_loss  # noqa: F401
 from .cycle import pseudo_label_cycle, compute_dist, generate_selflabel, generate_keep_mask  # noqa: F401
 
 __version__ = "0.1.0"

@@ -63,6 +63,9 @@ PROTOTYPES = {
                                c_int, c_void_p, c_void_p, c_void_p]),
     "ssg_op_stem": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssg_op_pooled_tail": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ssg_triplet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "ssg_triplet_backward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssg_profile_enable": (c_int, [c_int]),
     "ssg_profile_reset": (c_int, []),
     "ssg_profile_collect": (c_int, []),
