@@ -166,6 +166,14 @@ int ssg_embed_load_layer(ssg_embed_plan* plan, int idx, const float* d_w, const 
                          const float* d_beta, const float* d_mean, const float* d_var, float eps, void* stream);
 int ssg_embed_forward(ssg_embed_plan* plan, const float* d_images, int n, int num_split, int eval_mode, int flip,
                       float* d_feat, size_t bank_stride, int row0, void* stream);
+/* The same from raw pixels: d_images_u8 is uint8 HWC [n,256,128,3] (a decoded, resized RGB
+ * image as PIL hands it over); the loader's ToTensor + Normalize of selftraining.py:36-45 -- x/255, then
+ * (x - mean[c]) / std[c], IEEE float32 in that order -- run on the device on the way to bf16, so the features are
+ * bit-identical to ssg_embed_forward on the normalised float32 tensor while 4x fewer bytes cross PCIe.
+ * h_mean / h_std: HOST float[3]. */
+int ssg_embed_forward_u8(ssg_embed_plan* plan, const uint8_t* d_images_u8, const float* h_mean, const float* h_std,
+                         int n, int num_split, int eval_mode, int flip, float* d_feat, size_t bank_stride, int row0,
+                         void* stream);
 
 /* Building blocks of the trunk (NHWC bf16 activations, weights bf16 [cout][k][k][cin] with BatchNorm folded):
  * exported for stage-isolated parity tests and for callers with their own graph.

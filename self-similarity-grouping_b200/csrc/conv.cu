@@ -298,6 +298,48 @@ stem_prep_kernel(const float* __restrict__ img, int n, int flip_too, __nv_bfloat
     }
 }
 
+// The same for raw pixels: img uint8 HWC [n][256][128][3] as the decoder delivers them; the
+// loader's ToTensor + Normalize (selftraining.py:36-45: x/255, then (x - mean)/std, IEEE fp32 in that order) happen
+// here on the way to bf16, so a quarter of the bytes cross PCIe and no fp32 image is ever materialised.
+struct StemNorm { float mean[3], std[3]; };
+
+__global__ void __launch_bounds__(256)
+stem_prep_u8_kernel(const uint8_t* __restrict__ img, int n, int flip_too, StemNorm nm, __nv_bfloat16* __restrict__ P) {
+    constexpr int H = 256, W = 128;
+    const int images = flip_too ? 2 * n : n;
+    const size_t total = (size_t)images * H * STEM_WP;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(e % STEM_WP);
+        const size_t t = e / STEM_WP;
+        const int ih = (int)(t % H), im = (int)(t / H);
+        const bool flipped = im >= n;
+        const int iw = p - 3;
+        float v[3] = {0.f, 0.f, 0.f};
+        if (iw >= 0 && iw < W) {
+            const int sw = flipped ? W - 1 - iw : iw;
+            const uint8_t* px = img + (((size_t)(flipped ? im - n : im) * H + ih) * W + sw) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[c], 255.f), nm.mean[c]), nm.std[c]);
+        }
+        uint2 pk;
+        *reinterpret_cast<__nv_bfloat162*>(&pk.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&pk.y) = __floats2bfloat162_rn(v[2], 0.f);
+        reinterpret_cast<uint2*>(P)[e] = pk;
+    }
+}
+
+int stem_prep_u8(const uint8_t* img, int n, int flip_too, const float* mean, const float* std, void* P,
+                 cudaStream_t st) {
+    StemNorm nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean[c]; nm.std[c] = std[c]; }
+    const size_t total = (size_t)(flip_too ? 2 * n : n) * 256 * STEM_WP;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    stem_prep_u8_kernel<<<grid, 256, 0, st>>>(img, n, flip_too, nm, (__nv_bfloat16*)P);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
 int stem_prep(const float* img, int n, int flip_too, void* P, cudaStream_t st) {
     const size_t total = (size_t)(flip_too ? 2 * n : n) * 256 * STEM_WP;
     const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);

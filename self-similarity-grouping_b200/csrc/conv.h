@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 namespace ssg {
 int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int cout, const void* residual,
@@ -17,6 +18,8 @@ int vec_add_f32(const float* a, const float* b, int n, float* out, cudaStream_t 
 int fold_bn(const float* w, int cout, int cin, int kh, int kw, const float* gamma, const float* beta,
             const float* mean, const float* var, float eps, int kpad, void* wout, float* bout, cudaStream_t st);
 int stem_prep(const float* img, int n, int flip_too, void* P, cudaStream_t st);
+int stem_prep_u8(const uint8_t* img, int n, int flip_too, const float* mean, const float* std, void* P,
+                 cudaStream_t st);
 int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                  void* wout, float* bout, void* wout64, cudaStream_t st);
 int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st);

@@ -177,9 +177,12 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
     return SSG_OK;
 }
 
-extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n, int num_split, int eval_mode,
-                                 int flip, float* d_feat, size_t bank_stride, int row0, void* stream) {
-    if (!p || !d_images || !d_feat || n <= 0 || n > p->batch_max)
+// One forward over a batch; the images come either as fp32 NCHW (d_images) or as raw uint8 HWC pixels (d_u8 with the
+// loader's per-channel mean / std).
+static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const uint8_t* d_u8, const float* mean,
+                              const float* stdv, int n, int num_split, int eval_mode, int flip, float* d_feat,
+                              size_t bank_stride, int row0, void* stream) {
+    if (!p || (!d_images && !d_u8) || !d_feat || n <= 0 || n > p->batch_max)
         return ssg_set_error(SSG_ERR_INVALID, "embed_forward: bad arguments (n=%d, batch_max=%d)", n, p ? p->batch_max : -1);
     for (size_t i = 0; i < p->loaded.size(); ++i)
         if (!p->loaded[i]) return ssg_set_error(SSG_ERR_INVALID, "embed_forward: layer %zu (%s) not loaded", i, specs()[i].conv_key);
@@ -218,12 +221,17 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
             if (make_tmap_stem_windows(&probe, p->stemP, 2) != SSG_OK) p->stem_windows = 0;
         }
     }
-    if (p->stem_windows == 2) {
-        { SSG_PROF("stem_prep", st); SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st)); }
-        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, p->stem, st)); }
-    } else if (p->stem_windows == 1) {
-        { SSG_PROF("stem_prep", st); SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st)); }
-        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows(p->stemP, NB, p->w_stem448, p->b_stem448, p->stem, st)); }
+    if (d_u8 && !p->stem_windows)
+        return ssg_set_error(SSG_ERR_UNSUPPORTED, "embed_forward_u8 needs the window stem (SSG_STEM_WINDOWS != 0)");
+    if (p->stem_windows) {
+        {
+            SSG_PROF("stem_prep", st);
+            if (d_u8) SSG_TRY(stem_prep_u8(d_u8, n, flip, mean, stdv, p->stemP, st));
+            else SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st));
+        }
+        SSG_PROF("conv_stem_tc", st);
+        if (p->stem_windows == 2) SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, p->stem, st));
+        else SSG_TRY(conv_stem_windows(p->stemP, NB, p->w_stem448, p->b_stem448, p->stem, st));
     } else {
         { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
         { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv1x1(p->col, NB * 8192, 192, p->w[0], p->b[0], 64, nullptr, 1, p->stem, st)); }
@@ -275,6 +283,23 @@ extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n
     (void)sp;
     { SSG_PROF("pooled_tail", st); SSG_TRY(pooled_tail(x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, st)); }
     return SSG_OK;
+}
+
+extern "C" int ssg_embed_forward(ssg_embed_plan* p, const float* d_images, int n, int num_split, int eval_mode,
+                                 int flip, float* d_feat, size_t bank_stride, int row0, void* stream) {
+    if (!d_images) return ssg_set_error(SSG_ERR_INVALID, "embed_forward: null images");
+    return embed_forward_impl(p, d_images, nullptr, nullptr, nullptr, n, num_split, eval_mode, flip, d_feat,
+                              bank_stride, row0, stream);
+}
+
+extern "C" int ssg_embed_forward_u8(ssg_embed_plan* p, const uint8_t* d_images_u8, const float* h_mean,
+                                    const float* h_std, int n, int num_split, int eval_mode, int flip, float* d_feat,
+                                    size_t bank_stride, int row0, void* stream) {
+    if (!d_images_u8 || !h_mean || !h_std) return ssg_set_error(SSG_ERR_INVALID, "embed_forward_u8: null argument");
+    for (int c = 0; c < 3; ++c)
+        if (!(h_std[c] != 0.f)) return ssg_set_error(SSG_ERR_INVALID, "embed_forward_u8: std[%d] is zero", c);
+    return embed_forward_impl(p, nullptr, d_images_u8, h_mean, h_std, n, num_split, eval_mode, flip, d_feat,
+                              bank_stride, row0, stream);
 }
 
 // ---------------------------------------------------------------------------------------- building blocks

@@ -57,6 +57,8 @@ PROTOTYPES = {
     "ssg_embed_load_layer": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      ctypes.c_float, c_void_p]),
     "ssg_embed_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_void_p]),
+    "ssg_embed_forward_u8": (c_int, [c_void_p, c_void_p, P(ctypes.c_float), P(ctypes.c_float), c_int, c_int, c_int,
+                                     c_int, c_void_p, c_size_t, c_int, c_void_p]),
     "ssg_op_conv": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p,
                             c_int, c_void_p, c_void_p, c_void_p]),
     "ssg_op_fold_bn": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float,

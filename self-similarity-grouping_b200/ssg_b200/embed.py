@@ -8,6 +8,9 @@ import numpy as np
 from . import _lib
 
 _plans = {}
+# the normaliser of the reference's loaders (selftraining.py:36-37)
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 def layer_table():
@@ -86,12 +89,15 @@ class EmbedPlan(object):
         return getattr(m, "num_split", 1)
 
     # ---- forward
-    def forward(self, images, num_split=1, for_eval=False, flip=True, out=None, row0=0):
-        """images: float32 CUDA tensor [n,3,256,128] (n <= batch_max).
+    def forward(self, images, num_split=1, for_eval=False, flip=True, out=None, row0=0, mean=IMAGENET_MEAN,
+                std=IMAGENET_STD):
+        """images: float32 CUDA tensor [n,3,256,128], already normalised (what the reference's loader yields), or raw
+        pixels as a uint8 CUDA tensor [n,256,128,3] that are normalised on the device with ``mean`` / ``std``
+        (n <= batch_max).
         list mode  -> out [banks, rows, 2048] (bank b of image i at out[b, row0+i]);
         eval mode  -> out [rows, banks*2048]."""
         import torch
-        assert images.is_cuda and images.dtype == torch.float32 and images.dim() == 4
+        assert images.is_cuda and images.dim() == 4
         images = images.contiguous()
         n = images.shape[0]
         banks = num_split + 1 if num_split > 1 else 1
@@ -99,6 +105,17 @@ class EmbedPlan(object):
             out = torch.empty((n, banks * 2048) if for_eval else (banks, n, 2048), dtype=torch.float32,
                               device=images.device)
         bank_stride = 0 if for_eval else out.stride(0)
+        if images.dtype == torch.uint8:
+            if tuple(images.shape[1:]) != (256, 128, 3):
+                raise ValueError("uint8 images must be HWC [n,256,128,3], got %s" % (tuple(images.shape),))
+            c3 = ctypes.c_float * 3
+            _lib.check(_lib.load().ssg_embed_forward_u8(self._h, images.data_ptr(), c3(*mean), c3(*std), n,
+                                                        int(num_split), int(bool(for_eval)), int(bool(flip)),
+                                                        out.data_ptr(), bank_stride, int(row0), _lib.stream_ptr()))
+            return out
+        if images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 256, 128):
+            raise ValueError("images must be float32 [n,3,256,128] or uint8 [n,256,128,3], got %s %s"
+                             % (images.dtype, tuple(images.shape)))
         _lib.check(_lib.load().ssg_embed_forward(self._h, images.data_ptr(), n, int(num_split), int(bool(for_eval)),
                                                  int(bool(flip)), out.data_ptr(), bank_stride, int(row0),
                                                  _lib.stream_ptr()))
@@ -127,9 +144,11 @@ def get_plan(batch_max=256, device=None):
     return plan
 
 
-def embed_images(model, images, num_split=None, for_eval=False, batch=256, device=None, out_device=True):
-    """Embed a whole image tensor ([N,3,256,128], host (ideally pinned) or device) in batches with copy/compute
-    overlap.  Returns a CUDA tensor: [banks, N, 2048] (list mode) or [N, banks*2048] (eval mode)."""
+def embed_images(model, images, num_split=None, for_eval=False, batch=256, device=None, out_device=True,
+                 mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Embed a whole image tensor (normalised float32 [N,3,256,128] or raw uint8 [N,256,128,3]; host (ideally
+    pinned) or device) in batches with copy/compute overlap.  Returns a CUDA tensor: [banks, N, 2048] (list mode)
+    or [N, banks*2048] (eval mode)."""
     import torch
     dev = _lib.require_cuda(device)
     plan = get_plan(batch, dev.index)
@@ -140,11 +159,11 @@ def embed_images(model, images, num_split=None, for_eval=False, batch=256, devic
     out = torch.empty((N, banks * 2048) if for_eval else (banks, N, 2048), dtype=torch.float32, device=dev)
     if images.is_cuda:
         for r0 in range(0, N, batch):
-            plan.forward(images[r0:r0 + batch], num_split, for_eval, True, out, r0)
+            plan.forward(images[r0:r0 + batch], num_split, for_eval, True, out, r0, mean, std)
         return out
     copy_stream = torch.cuda.Stream(device=dev)
     compute = torch.cuda.current_stream(dev)
-    bufs = [torch.empty((batch,) + tuple(images.shape[1:]), dtype=torch.float32, device=dev) for _ in range(2)]
+    bufs = [torch.empty((batch,) + tuple(images.shape[1:]), dtype=images.dtype, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
     starts = list(range(0, N, batch))
@@ -157,7 +176,7 @@ def embed_images(model, images, num_split=None, for_eval=False, batch=256, devic
             bufs[slot][:n].copy_(images[r0:r0 + n], non_blocking=True)
             ready[slot].record(copy_stream)
         compute.wait_event(ready[slot])
-        plan.forward(bufs[slot][:n], num_split, for_eval, True, out, r0)
+        plan.forward(bufs[slot][:n], num_split, for_eval, True, out, r0, mean, std)
         freed[slot].record(compute)
     return out
 
@@ -184,7 +203,9 @@ def extract_features(model, data_loader, print_freq=20, for_eval=True, metric=No
         if plan is None or plan.batch_max < imgs.shape[0]:
             plan = get_plan(max(256, imgs.shape[0]), dev.index)
             plan.load_model(model)
-        x = imgs.to(dev, dtype=torch.float32, non_blocking=True)
+        # raw uint8 HWC batches (row f5: a loader that stops after Resize) are normalised on the device
+        x = imgs.to(dev, non_blocking=True) if imgs.dtype == torch.uint8 else \
+            imgs.to(dev, dtype=torch.float32, non_blocking=True)
         o = plan.forward(x, num_split, for_eval=not list_mode, flip=True)
         # list mode: [banks, n, 2048] (each bank normalised alone) -> [n, banks, 2048]; else [n, banks*2048]
         chunks.append(o.permute(1, 0, 2).reshape(o.shape[1], -1) if list_mode else o)

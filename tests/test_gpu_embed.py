@@ -261,3 +261,34 @@ def test_eug_label_estimation_matches_numpy_restatement():
             assert conf.shape == (20,) and np.all(conf <= 1.0 + 1e-5) and np.all(np.isfinite(conf))
         sel = eug.select_top_data(scores, 5)
         assert sel.sum() == 5 and len(eug.generate_new_train_data(sel, labels)) == 12 + 5
+
+
+def test_uint8_pixels_give_bit_identical_features():
+    """Row f5: raw uint8 HWC pixels normalised on the device (ssg_embed_forward_u8) == the loader's ToTensor +
+    Normalize on the CPU (selftraining.py:36-45) followed by the float32 path, bit for bit; also through
+    embed_images (host uint8 tensor, a quarter of the H2D bytes) and the drop-in extract_features."""
+    import torch
+    import ssg_b200
+    from ssg_b200.embed import IMAGENET_MEAN, IMAGENET_STD
+    from oracle import resnet_oracle as R
+    model = R.build_model(2, 0)
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (5, 256, 128, 3), dtype=torch.uint8, generator=g)
+    u8[0, :, 0, :] = 0
+    u8[0, :, 127, :] = 255                              # image borders + extreme values
+    mean, std = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1), torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    f32 = u8.permute(0, 3, 1, 2).to(torch.float32).div(255).sub_(mean).div_(std).contiguous()   # T.ToTensor, T.Normalize
+    plan = ssg_b200.EmbedPlan(16)
+    plan.load_model(model)
+    a = plan.forward(f32.cuda(), 2).clone()
+    b = plan.forward(u8.cuda(), 2).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    c = ssg_b200.embed_images(model, u8.pin_memory(), batch=4)       # 2 batches through the copy/compute overlap
+    assert torch.equal(c, a)
+    names = ["u%d" % i for i in range(5)]
+    fa, _ = ssg_b200.extract_features(model, [(f32, names, [0] * 5, [0] * 5)], for_eval=True)
+    fb, _ = ssg_b200.extract_features(model, [(u8, names, [0] * 5, [0] * 5)], for_eval=True)
+    assert all(torch.equal(fa[k], fb[k]) for k in names)
+    with pytest.raises(ValueError):
+        plan.forward(u8.permute(0, 3, 1, 2).contiguous().cuda(), 2)  # CHW uint8 is not a supported layout
