@@ -32,6 +32,17 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     if (bn256 < 0) { const char* e = getenv("SSG_CONV_BN256"); bn256 = e ? atoi(e) : 1; }
     if (bn256 && !residual && cout % 256 == 0 && k >= 256)
         return tc::launch_gemm_op<256, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
+    // ... and WITH a residual (the conv3 of layers 3 and 4): 128x256 tiles with a residual sub-tile ring
+    // (SSG_CONV_BN256_RES=0 falls back to 128x128 tiles with a whole-tile residual double buffer)
+    static int bn256_res = -1;
+    if (bn256_res < 0) { const char* e = getenv("SSG_CONV_BN256_RES"); bn256_res = e ? atoi(e) : 1; }
+    if (bn256_res && residual && cout % 256 == 0 && k >= 256)
+        return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_RRING>(A, m, w, cout, k, epi, st);
+    // the stem (mode 3: N = 64, K = 256) keeps its weights resident in shared memory (SSG_STEM_BRES=0 disables)
+    static int stem_bres = -1;
+    if (stem_bres < 0) { const char* e = getenv("SSG_STEM_BRES"); stem_bres = e ? atoi(e) : 1; }
+    if (stem_bres && A.mode == 3 && cout == 64 && k == tc::BRES_K)
+        return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_BRES>(A, m, w, cout, k, epi, st);
     if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
 }
@@ -420,6 +431,9 @@ int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t s
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    // one thread = one output pixel x 8 channels.  Window coordinates are CLAMPED into the map instead of skipped: a
+    // duplicate tap cannot change a maximum, and the nine 16-byte loads become unconditional and independent (all in
+    // flight at once); the maximum is taken on packed bf16 pairs (exact, no float round trip).
     const int OH = H / 2, OW = W / 2, CV = C / 8;
     const size_t total = (size_t)B * OH * OW * CV;
     for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -428,29 +442,25 @@ maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, int B, int H, int W, in
         const int ow = (int)(t % OW); t /= OW;
         const int oh = (int)(t % OH);
         const int b = (int)(t / OH);
-        float m[8];
+        const __nv_bfloat16* base = x + (size_t)b * H * W * C + cv * 8;
+        uint4 v[9];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
         for (int ky = 0; ky < 3; ++ky) {
-            const int ih = oh * 2 - 1 + ky;
-            if (ih < 0 || ih >= H) continue;
-            for (int kx = 0; kx < 3; ++kx) {
-                const int iw = ow * 2 - 1 + kx;
-                if (iw < 0 || iw >= W) continue;
-                const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cv * 8);
-                const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+            const int ih = min(max(oh * 2 - 1 + ky, 0), H - 1);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __bfloat1622float2(p[q]);
-                    m[2 * q] = fmaxf(m[2 * q], f.x);
-                    m[2 * q + 1] = fmaxf(m[2 * q + 1], f.y);
-                }
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iw = min(max(ow * 2 - 1 + kx, 0), W - 1);
+                v[ky * 3 + kx] = *reinterpret_cast<const uint4*>(base + ((size_t)ih * W + iw) * C);
             }
         }
-        uint4 o;
+        uint4 o = v[0];
         __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) po[q] = __floats2bfloat162_rn(m[2 * q], m[2 * q + 1]);
+        for (int k = 1; k < 9; ++k) {
+            const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v[k]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) po[q] = __hmax2(po[q], p[q]);
+        }
         *reinterpret_cast<uint4*>(y + (((size_t)b * OH + oh) * OW + ow) * C + cv * 8) = o;
     }
 }

@@ -58,22 +58,39 @@ struct StagedEpi {
 // plus a one-row halo above and below ((bh+2)*bw <= 192 pixel rows) for one kernel column, and the three weight
 // tiles of that column; the three kernel rows are three MMAs whose A descriptors start kh*bw rows into the same
 // buffer — the activation is read 3 times from L2 instead of 9.
-template <int BN, bool STAGED, bool KHS = false>
+// VAR (kernel variant, staged epilogue only):
+//   VAR_BRES  (stem, BN = 64, K = 256): the whole B operand (the 32 KB of stem weights) is loaded ONCE per CTA into a
+//             resident region and the operand stages carry A only (8 stages of 16 KB): the per-tile weight re-load was a
+//             third of the kernel's L2 -> shared-memory traffic.
+//   VAR_RRING (BN = 256 WITH a residual): 3 operand stages, and the residual arrives through a ring of three 64-column
+//             sub-tile buffers fetched by TMA two sub-tiles ahead (a whole-tile double buffer does not fit next to
+//             128x256 operand stages).
+constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2;
+constexpr int BRES_K = 256;
+
+template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
 struct SmemLayout {
+    static constexpr bool BRES = VAR == VAR_BRES, RRING = VAR == VAR_RRING;
     static constexpr int A_BYTES = (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int B_BYTES = (KHS ? 3 : 1) * B_TILE;
+    static constexpr int B_BYTES = BRES ? 0 : (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
     static constexpr int NBUF = NSUB > 2 ? 2 : NSUB;             // output sub-buffers
-    static constexpr bool HAS_R = BN <= 128;                     // residual staging available
+    static constexpr bool HAS_R = BN <= 128 || RRING;            // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
-    static constexpr int R_BYTES = (STAGED && HAS_R) ? NSUB * SUB_BYTES : 0;   // one residual tile
-    static constexpr int STAGES = KHS ? 3 : (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
-    static constexpr int C_OFFSET = STAGES * STAGE_BYTES;        // output staging, then 2 residual staging buffers
-    static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + 2 * R_BYTES;
+    static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
+    static constexpr int RSTAGE_BYTES = RRING ? 3 * SUB_BYTES : 2 * R_BYTES;       // residual staging in total
+    static constexpr int STAGES = BRES ? 8 : RRING ? 3 : KHS ? 3 :
+        (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
+    static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
+    static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : 0;
+    static constexpr int C_OFFSET = BRES_OFFSET + BRES_BYTES;    // output staging, then the residual staging buffers
+    static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + RSTAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
+    static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
+    static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -87,11 +104,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 
-template <int BN, class Epi, bool STAGED, bool KHS = false>
+template <int BN, class Epi, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N,
             int num_k_blocks, const __grid_constant__ Epi epi) {
-    using L = SmemLayout<BN, STAGED, KHS>;
+    using L = SmemLayout<BN, STAGED, KHS, VAR>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ unsigned char smem_raw[];
@@ -100,8 +117,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-    uint64_t* res_bar = tempty_bar + 2;           // [2] residual tile landed (staged epilogue, double buffered)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
+    uint64_t* res_bar = tempty_bar + 2;           // [3] residual tile / sub-tile landed (staged epilogue)
+    uint64_t* bres_bar = res_bar + 3;             // [1] resident B operand landed (VAR_BRES)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
@@ -112,8 +130,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
-        mbar_init(&res_bar[0], 1);
-        mbar_init(&res_bar[1], 1);
+        for (int s = 0; s < 3; ++s) mbar_init(&res_bar[s], 1);
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -138,6 +156,16 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            if constexpr (L::BRES) {
+                // the whole [BN, 256] weight matrix, once: K block kb at kb * B_TILE, two 64-byte-row halves each
+                unsigned char* bres = smem + L::BRES_OFFSET;
+                mbar_arrive_expect_tx(bres_bar, L::BRES_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < BRES_K / BK; ++kb) {
+                    tma_load_2d(bres + kb * L::B_TILE, &mapB, bres_bar, kb * BK, 0);
+                    tma_load_2d(bres + kb * L::B_TILE + L::B_TILE / 2, &mapB, bres_bar, kb * BK + 32, 0);
+                }
+            }
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
@@ -181,9 +209,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
                                     h0 * A.hmul + A.tap_dh[tap], b0);
                     }
-                    if (A.mode == 3) {
+                    if constexpr (L::BRES) {
+                        // weights are resident: the stage carries A only
+                    } else if (A.mode == 3) {
                         tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
-                        tma_load_2d(sb + L::B_BYTES / 2, &mapB, &full_bar[stage], kb * BK + 32, n_blk * BN);
+                        tma_load_2d(sb + L::B_TILE / 2, &mapB, &full_bar[stage], kb * BK + 32, n_blk * BN);
                     } else {
                         tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
                     }
@@ -198,6 +228,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
+        if constexpr (L::BRES) {
+            mbar_wait(bres_bar, 0);                           // resident weights have landed
+            tc_fence_after();
+        }
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
             tc_fence_after();
@@ -207,7 +241,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t sb = sa + L::A_BYTES;
+                    const uint32_t sb = L::BRES ? smem_u32(smem + L::BRES_OFFSET) + (uint32_t)(kb * L::B_TILE)
+                                                : sa + L::A_BYTES;
                     if constexpr (KHS) {
                         // three kernel rows out of one haloed buffer: A starts kh*bw pixel rows (kh*bw*128 B) in
 #pragma unroll
@@ -224,7 +259,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t da = make_desc_k_sw64(sa + (k >> 1) * (L::A_BYTES / 2));
-                            const uint64_t db = make_desc_k_sw64(sb + (k >> 1) * (L::B_BYTES / 2));
+                            const uint64_t db = make_desc_k_sw64(sb + (k >> 1) * (L::B_TILE / 2));
                             umma_f16(d_tmem, da + (uint64_t)(2 * (k & 1)), db + (uint64_t)(2 * (k & 1)), idesc,
                                      (kb > 0 || k > 0) ? 1u : 0u);
                         }
@@ -294,18 +329,37 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     tma_load_2d(r_s + buf * L::R_BYTES + j * L::SUB_BYTES, &epi.mapR, &res_bar[buf], nb * BN + j * 64,
                                 mb * BM);
             };
-            if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+            // VAR_RRING: residual sub-tile s (s counts this CTA's 64-column sub-tiles: tile it, sub-tile j -> it*NSUB + j)
+            // lives in ring slot s % 3 and is fetched two sub-tiles ahead
+            auto load_residual_sub = [&](int s) {
+                const int tile = (int)blockIdx.x + (s / NSUB) * (int)gridDim.x;
+                if (tile >= num_tiles) return;
+                int mb, nb;
+                tile_coords(tile, mb, nb);
+                const int slot = s % 3;
+                mbar_arrive_expect_tx(&res_bar[slot], L::SUB_BYTES);
+                tma_load_2d(r_s + slot * L::SUB_BYTES, &epi.mapR, &res_bar[slot], nb * BN + (s % NSUB) * 64, mb * BM);
+            };
+            if constexpr (L::RRING) {
+                if (leader && has_res) { load_residual_sub(0); load_residual_sub(1); }
+            } else {
+                if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+            }
             int it = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 const int rb = it & 1;
-                // the other residual buffer was last read by tile it-1, which every thread has left: prefetch tile it+1
-                if (leader && has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                if constexpr (!L::RRING) {
+                    // the other residual buffer was last read by tile it-1, which every thread has left: prefetch tile it+1
+                    if (leader && has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                }
                 if (epi_tid < BN) s_bias[epi_tid] = epi.bias[n_blk * BN + epi_tid];   // visible after the next barrier
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
-                if (has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
+                if constexpr (!L::RRING) {
+                    if (has_res) mbar_wait(&res_bar[rb], (uint32_t)((it >> 1) & 1));
+                }
                 const unsigned char* rbuf = r_s + rb * L::R_BYTES;
 #pragma unroll 1
                 for (int j = 0; j < NSUB; ++j) {
@@ -314,6 +368,14 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     epi_bar_sync();
                     unsigned char* csub = c_s + (j % NBUF) * L::SUB_BYTES + row_off;
                     const unsigned char* rsub = rbuf + j * L::SUB_BYTES + row_off;
+                    if constexpr (L::RRING) {
+                        const int s = it * NSUB + j;
+                        // every epilogue thread is past the barrier above, i.e. done with sub-tile s-1: its ring slot
+                        // (s+2) % 3 == (s-1) % 3 is free for the sub-tile two ahead
+                        if (leader && has_res) load_residual_sub(s + 2);
+                        if (has_res) mbar_wait(&res_bar[s % 3], (uint32_t)((s / 3) & 1));
+                        rsub = r_s + (s % 3) * L::SUB_BYTES + row_off;
+                    }
                     {
                         const int h = grp;
                         const int c = 2 * j + h;
@@ -374,9 +436,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 }
 
 // Launch with a fully prepared A operand.
-template <int BN, class Epi, bool STAGED = false, bool KHS = false>
+template <int BN, class Epi, bool STAGED = false, bool KHS = false, int VAR = VAR_NONE>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGED, KHS>;
+    using L = SmemLayout<BN, STAGED, KHS, VAR>;
+    if (VAR == VAR_BRES && (A.mode != 3 || n != BN || k != BRES_K))
+        return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;
@@ -386,7 +450,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     const int grid = tiles < sms ? tiles : sms;
-    auto kern = gemm_kernel<BN, Epi, STAGED, KHS>;
+    auto kern = gemm_kernel<BN, Epi, STAGED, KHS, VAR>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks
     kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, KHS ? (k / BK) / 3 : (k + BK - 1) / BK, epi);

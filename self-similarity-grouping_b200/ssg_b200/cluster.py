@@ -150,6 +150,14 @@ class DBSCAN(object):
         if sample_weight is not None:
             raise ValueError("ssg_b200.DBSCAN does not support sample_weight")
         eps = float(self.eps)
+        # sklearn validates at fit(): eps is a real in (0, inf) -- NaN (an empty rho-slice, selftraining.py:293) and
+        # 0 are rejected with InvalidParameterError, a ValueError -- and min_samples an integer >= 1
+        if not (eps > 0.0) or eps == float("inf"):
+            raise ValueError("The 'eps' parameter of DBSCAN must be a float in the range (0.0, inf). Got %r instead."
+                             % (self.eps,))
+        if int(self.min_samples) != self.min_samples or self.min_samples < 1:
+            raise ValueError("The 'min_samples' parameter of DBSCAN must be an int in the range [1, inf). Got %r "
+                             "instead." % (self.min_samples,))
         if isinstance(X, np.ndarray) or not hasattr(X, "is_cuda"):
             X = np.asarray(X)
             if X.dtype == np.float32 and not isinstance(self.eps, np.floating):

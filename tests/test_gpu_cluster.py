@@ -148,7 +148,7 @@ def test_dbscan_and_eps_property_based(ssg):
 
     @settings(max_examples=60, deadline=None, derandomize=True)
     @given(n=st.integers(1, 150), seed=st.integers(0, 10 ** 6), levels=st.integers(2, 40),
-           eps_q=st.integers(0, 40), min_samples=st.integers(1, 7), rho=st.floats(0.001, 1.0))
+           eps_q=st.integers(1, 40), min_samples=st.integers(1, 7), rho=st.floats(0.001, 1.0))
     def run(n, seed, levels, eps_q, min_samples, rho):
         rng = np.random.RandomState(seed)
         A = rng.randint(0, levels, (n, n)).astype(np.float64) / levels
@@ -168,3 +168,9 @@ def test_dbscan_and_eps_property_based(ssg):
         else:
             assert abs(e - tri[:top].mean()) <= 1e-12 * max(abs(tri[:top].mean()), 1e-300)
     run()
+    D = np.zeros((4, 4))
+    for bad in (0.0, -1.0, float("nan")):            # sklearn: InvalidParameterError (a ValueError) at fit()
+        with pytest.raises(ValueError):
+            DBSCAN(eps=bad, min_samples=4, metric="precomputed").fit(D)
+        with pytest.raises(ValueError):
+            ssg.DBSCAN(eps=bad, min_samples=4, metric="precomputed").fit(D)

@@ -59,6 +59,8 @@ CONV_CASES = [
     (8, 8, 4, 512, 512, 3, 1, False), (5, 8, 4, 512, 512, 3, 1, False),
     (2, 64, 32, 128, 128, 3, 2, False), (2, 32, 16, 256, 256, 3, 2, False), (4, 16, 8, 512, 512, 3, 2, False),
     (2, 64, 32, 256, 512, 1, 2, False), (4, 16, 8, 1024, 2048, 1, 2, False), (4, 8, 4, 2048, 512, 1, 1, False),
+    # conv3 of layers 3 / 4: 128x256 tiles with the residual sub-tile ring (one tile, ragged M, > 148 tiles)
+    (3, 16, 8, 256, 1024, 1, 1, True), (5, 8, 4, 512, 2048, 1, 1, True), (64, 16, 8, 256, 1024, 1, 1, True),
 ]
 
 
