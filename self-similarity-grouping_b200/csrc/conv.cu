@@ -18,13 +18,14 @@ namespace ssg {
 // staged through shared memory and written / prefetched by TMA (tc::StagedEpi in gemm_tc.cuh).
 // ---------------------------------------------------------------------------------------------------
 static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, int k, const float* bias,
-                         const void* residual, int relu, void* y, cudaStream_t st) {
+                         const void* residual, int relu, void* y, cudaStream_t st, void* pool_out = nullptr) {
     if (cout % 64) return ssg_set_error(SSG_ERR_INVALID, "conv: Cout=%d must be a multiple of 64", cout);
     tc::StagedEpi epi;
     memset(&epi, 0, sizeof(epi));
     epi.bias = bias;
     epi.relu = relu;
     epi.has_res = residual != nullptr;
+    epi.pool_out = pool_out;
     SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
     SSG_TRY(make_tmap_2d_bf16(&epi.mapR, residual ? residual : y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
     // 128x256 tiles for the K-heavy convolutions without a residual (SSG_CONV_BN256=0 disables, for A/B runs)
@@ -43,6 +44,7 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     if (stem_bres < 0) { const char* e = getenv("SSG_STEM_BRES"); stem_bres = e ? atoi(e) : 1; }
     if (stem_bres && A.mode == 3 && cout == 64 && k == tc::BRES_K)
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_BRES>(A, m, w, cout, k, epi, st);
+    if (pool_out) return ssg_set_error(SSG_ERR_UNSUPPORTED, "the fused stem max-pool needs the resident-weight stem kernel");
     if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
 }
@@ -106,6 +108,17 @@ static int tile_geometry(int H, int W, int* bw, int* bh, int* bb, int* tiles_per
         *bh = H; *bb = 128 / (H * W); *tiles_per_img = 1;
     }
     return SSG_OK;
+}
+
+// the stem's max-pool runs in the stem kernel's epilogue unless SSG_STEM_POOL=0 (or the resident-weight stem is off)
+bool stem_pool_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SSG_STEM_POOL");
+        const char* b = getenv("SSG_STEM_BRES");
+        v = ((e && !atoi(e)) || (b && !atoi(b))) ? 0 : 1;
+    }
+    return v != 0;
 }
 
 // stride-2 convolutions read the un-split input through element-strided TMA boxes unless SSG_S2_PLANES=1
@@ -394,7 +407,10 @@ int fold_bn_stem(const float* w, const float* gamma, const float* beta, const fl
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
-int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st) {
+// pool_out != NULL: the 3x3/2 max-pool is fused behind the convolution (y is then only a placeholder for the tensor
+// map; the full-resolution map is never written) -- pool_out is [images, 64, 32, 64] NHWC bf16.
+int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st,
+                        void* pool_out) {
     tc::AOperand A;
     memset(&A, 0, sizeof(A));
     A.mode = 3;
@@ -403,7 +419,7 @@ int conv_stem_windows64(const void* P, int images, const void* w256, const float
     A.tiles_per_img = 64;
     A.hmul = 1;
     SSG_TRY(make_tmap_stem_windows64(&A.map[0], P, (uint64_t)images));
-    return gemm_dispatch(A, images * 8192, w256, 64, 256, bias, nullptr, 1, y, st);
+    return gemm_dispatch(A, images * 8192, w256, 64, 256, bias, nullptr, 1, y, st, pool_out);
 }
 
 // the window GEMM: P [images][256][144][4] -> relu(conv7x7/2 + bias) as NHWC bf16 [images,128,64,64]

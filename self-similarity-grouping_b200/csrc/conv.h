@@ -22,7 +22,9 @@ int stem_prep_u8(const uint8_t* img, int n, int flip_too, const float* mean, con
                  cudaStream_t st);
 int fold_bn_stem(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                  void* wout, float* bout, void* wout64, cudaStream_t st);
-int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st);
+int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st,
+                        void* pool_out = nullptr);
+bool stem_pool_fused();
 int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t st);
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);
 int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st);

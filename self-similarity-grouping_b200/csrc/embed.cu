@@ -221,6 +221,7 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
             if (make_tmap_stem_windows(&probe, p->stemP, 2) != SSG_OK) p->stem_windows = 0;
         }
     }
+    bool pooled = false;       // the max-pool already ran inside the stem kernel
     if (d_u8 && !p->stem_windows)
         return ssg_set_error(SSG_ERR_UNSUPPORTED, "embed_forward_u8 needs the window stem (SSG_STEM_WINDOWS != 0)");
     if (p->stem_windows) {
@@ -230,13 +231,15 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
             else SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st));
         }
         SSG_PROF("conv_stem_tc", st);
-        if (p->stem_windows == 2) SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, p->stem, st));
+        pooled = p->stem_windows == 2 && stem_pool_fused();
+        if (p->stem_windows == 2)
+            SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, p->stem, st, pooled ? p->x : nullptr));
         else SSG_TRY(conv_stem_windows(p->stemP, NB, p->w_stem448, p->b_stem448, p->stem, st));
     } else {
         { SSG_PROF("stem_im2col", st); SSG_TRY(stem_im2col(d_images, n, flip, p->col, st)); }
         { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv1x1(p->col, NB * 8192, 192, p->w[0], p->b[0], 64, nullptr, 1, p->stem, st)); }
     }
-    { SSG_PROF("maxpool", st); SSG_TRY(maxpool3x3s2(p->stem, NB, 128, 64, 64, p->x, st)); }
+    if (!pooled) { SSG_PROF("maxpool", st); SSG_TRY(maxpool3x3s2(p->stem, NB, 128, 64, 64, p->x, st)); }
     li = 1;
     int H = 64, W = 32, C = 64;
     void *x = p->x, *y = p->y;

@@ -49,6 +49,7 @@ struct StagedEpi {
     const float* bias;     // [N]
     int relu;
     int has_res;
+    void* pool_out;        // VAR_BRES only: != NULL fuses the 3x3/2 max-pool behind the stem (the conv map is not stored)
 };
 
 // BN <= 128 (staged): one output sub-buffer per 64-column sub-tile + two residual tile buffers, 3-5 operand stages.
@@ -151,6 +152,18 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         n_blk = r / gsz;
     };
 
+    // tile sequence of this CTA: round-robin, except for the stem with the fused max-pool, where a CTA owns whole
+    // images and walks their 64 two-row tiles in order (the pool needs the previous tile's last row)
+    int t_begin = blockIdx.x, t_end = num_tiles, t_step = gridDim.x;
+    if constexpr (SmemLayout<BN, STAGED, KHS, VAR>::BRES) {
+        if (epi.pool_out != nullptr) {
+            const long long images = m_blocks / 64;
+            t_begin = (int)(images * blockIdx.x / gridDim.x) * 64;
+            t_end = (int)(images * (blockIdx.x + 1) / gridDim.x) * 64;
+            t_step = 1;
+        }
+    }
+
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -166,7 +179,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     tma_load_2d(bres + kb * L::B_TILE + L::B_TILE / 2, &mapB, bres_bar, kb * BK + 32, 0);
                 }
             }
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 int b0 = 0, h0 = 0;
@@ -232,7 +245,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             mbar_wait(bres_bar, 0);                           // resident weights have landed
             tc_fence_after();
         }
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = t_begin; t < t_end; t += t_step) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -287,7 +300,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         int acc = 0;
         uint32_t acc_phase = 0;
         if constexpr (!STAGED) {
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 mbar_wait(&tfull_bar[acc], acc_phase);
@@ -329,6 +342,75 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     tma_load_2d(r_s + buf * L::R_BYTES + j * L::SUB_BYTES, &epi.mapR, &res_bar[buf], nb * BN + j * 64,
                                 mb * BM);
             };
+            if constexpr (L::BRES) {
+                if (epi.pool_out != nullptr) {
+                    // ---- stem with the 3x3/2 max-pool fused behind it.  Tile t = conv rows (2tr, 2tr+1) of image b,
+                    // 64 px x 64 ch each, written as bf16 into one of two staging buffers (buffer = tile parity, same
+                    // swizzled layout as for a TMA store); pooled row tr = max over conv rows 2tr-1 (second half of the
+                    // OTHER buffer: the previous tile of the same image), 2tr, 2tr+1 and columns 2pw-1..2pw+1, clamped
+                    // at the borders (a duplicate tap cannot change a maximum).  One thread = one pooled pixel x 8
+                    // channels; the 64 x 32 x 64 pooled map is the only thing stored.
+                    __nv_bfloat16* pool = reinterpret_cast<__nv_bfloat16*>(epi.pool_out);
+                    const int pw = epi_tid >> 3, pch = epi_tid & 7;
+                    int it = 0;
+                    for (int t = t_begin; t < t_end; t += t_step, ++it) {
+                        const int b = t >> 6, tr = t & 63;
+                        if (epi_tid < BN) s_bias[epi_tid] = epi.bias[epi_tid];
+                        mbar_wait(&tfull_bar[acc], acc_phase);
+                        tc_fence_after();
+                        epi_bar_sync();                                  // bias visible; buffer (it & 1) free (see below)
+                        unsigned char* cur = c_s + (it & 1) * L::SUB_BYTES;
+                        const unsigned char* prv = c_s + ((it & 1) ^ 1) * L::SUB_BYTES;
+                        {
+                            uint32_t v[32];
+                            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + grp * 32), v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                const uint32_t chunk = ((uint32_t)(grp * 4 + g) ^ sw) << 4;
+                                uint4 pk;
+                                __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float f0 = fmaxf(__uint_as_float(v[8 * g + 2 * e]) + s_bias[grp * 32 + 8 * g + 2 * e], 0.f);
+                                    const float f1 = fmaxf(__uint_as_float(v[8 * g + 2 * e + 1]) + s_bias[grp * 32 + 8 * g + 2 * e + 1], 0.f);
+                                    pp[e] = __floats2bfloat162_rn(f0, f1);
+                                }
+                                *reinterpret_cast<uint4*>(cur + row_off + chunk) = pk;
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);      // accumulator drained
+                        epi_bar_sync();                                  // the whole conv tile is in `cur`
+                        {
+                            // staging row index: conv row 2tr -> rows 0..63 of cur, 2tr+1 -> rows 64..127 of cur,
+                            // 2tr-1 -> rows 64..127 of prv (tr > 0), else clamp to conv row 0
+                            uint4 m = make_uint4(0u, 0u, 0u, 0u);         // post-ReLU values are >= 0
+                            __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
+#pragma unroll
+                            for (int ry = 0; ry < 3; ++ry) {
+                                const unsigned char* rowbuf = (ry == 0) ? (tr > 0 ? prv + 64 * 128 : cur)
+                                                                        : cur + (ry - 1) * 64 * 128;
+#pragma unroll
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    const int ow = max(2 * pw - 1 + kx, 0);
+                                    const uint4 vv = *reinterpret_cast<const uint4*>(
+                                        rowbuf + ow * 128 + (((uint32_t)pch ^ (uint32_t)(ow & 7)) << 4));
+                                    const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) pm[e] = __hmax2(pm[e], pv[e]);
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(pool + (((size_t)b * 64 + tr) * 32 + pw) * 64 + pch * 8) = m;
+                        }
+                        // buffer `prv` is overwritten by tile it+1 only after the barrier at the top of that tile, which
+                        // every thread reaches after the reads above
+                        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                    }
+                    t_begin = t_end;                                     // nothing left for the generic epilogue below
+                }
+            }
             // VAR_RRING: residual sub-tile s (s counts this CTA's 64-column sub-tiles: tile it, sub-tile j -> it*NSUB + j)
             // lives in ring slot s % 3 and is fetched two sub-tiles ahead
             auto load_residual_sub = [&](int s) {
@@ -346,7 +428,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
             }
             int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            for (int t = t_begin; t < t_end; t += t_step, ++it) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
                 const int rb = it & 1;
@@ -449,7 +531,14 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     int sms = 0;
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
-    const int grid = tiles < sms ? tiles : sms;
+    int grid = tiles < sms ? tiles : sms;
+    if constexpr (VAR == VAR_BRES) {
+        if (epi.pool_out != nullptr) {                      // whole images per CTA
+            if (m % (64 * BM)) return ssg_set_error(SSG_ERR_INVALID, "gemm: fused stem pool needs whole images (M=%d)", m);
+            const int images = m / (64 * BM);
+            grid = images < sms ? images : sms;
+        }
+    }
     auto kern = gemm_kernel<BN, Epi, STAGED, KHS, VAR>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks

@@ -55,8 +55,10 @@ def test_dbscan_everything_is_a_neighbour(ssg):
     D = _sym(300, 3)
     lab = ssg.DBSCAN(eps=2.0, min_samples=4, metric="precomputed").fit_predict(D)
     assert np.array_equal(lab, np.zeros(300, np.int64))
-    lab = ssg.DBSCAN(eps=-1.0, min_samples=4, metric="precomputed").fit_predict(D)
-    assert np.array_equal(lab, -np.ones(300, np.int64))
+    # nothing is a neighbour: the estimator rejects eps <= 0 as sklearn does; the kernel-level entry labels all noise
+    with pytest.raises(ValueError):
+        ssg.DBSCAN(eps=-1.0, min_samples=4, metric="precomputed").fit_predict(D)
+    assert np.array_equal(ssg.dbscan_labels(D, -1.0, 4), -np.ones(300, np.int64))
 
 
 def test_dbscan_on_rerank_output(ssg):

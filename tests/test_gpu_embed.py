@@ -294,3 +294,30 @@ def test_uint8_pixels_give_bit_identical_features():
     assert all(torch.equal(fa[k], fb[k]) for k in names)
     with pytest.raises(ValueError):
         plan.forward(u8.permute(0, 3, 1, 2).contiguous().cuda(), 2)  # CHW uint8 is not a supported layout
+
+
+def test_conv_variants_are_bit_identical(tmp_path):
+    """The default trunk (stem with resident weights + fused max-pool, 128x256 residual-ring tiles) against the plain
+    variants (SSG_STEM_BRES=0 SSG_STEM_POOL=0 SSG_CONV_BN256_RES=0, read once per process -> a subprocess): the same
+    products accumulate in the same order, so the features must agree bit for bit."""
+    import subprocess
+    import sys
+    import torch
+    import ssg_b200
+    from oracle import resnet_oracle as R
+    script = (
+        "import sys, numpy as np, torch\n"
+        "sys.path[:0] = %r\n"
+        "import ssg_b200\n"
+        "from oracle import resnet_oracle as R\n"
+        "plan = ssg_b200.EmbedPlan(16); plan.load_model(R.build_model(2, 0))\n"
+        "out = plan.forward(R.synth_images(9, 11).cuda(), 2); torch.cuda.synchronize()\n"
+        "np.save(sys.argv[1], out.cpu().numpy())\n" % ([p for p in sys.path if p.endswith(("repo", "_b200"))],))
+    env = dict(os.environ, SSG_STEM_BRES="0", SSG_STEM_POOL="0", SSG_CONV_BN256_RES="0")
+    out_file = str(tmp_path / "plain.npy")
+    subprocess.run([sys.executable, "-c", script, out_file], check=True, env=env, timeout=300)
+    plan = ssg_b200.EmbedPlan(16)
+    plan.load_model(R.build_model(2, 0))
+    got = plan.forward(R.synth_images(9, 11).cuda(), 2)
+    torch.cuda.synchronize()
+    assert np.array_equal(got.cpu().numpy(), np.load(out_file))
