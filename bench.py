@@ -41,8 +41,8 @@ def parse():
     ap.add_argument("--n", type=int, default=16702)
     ap.add_argument("--banks", type=int, default=3)
     ap.add_argument("--dist-mode", default="tensor", choices=["tensor", "exact"])
-    ap.add_argument("--cpu-sample", type=int, default=1280, help="rows of the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-embed-sample", type=int, default=64, help="images of the bounded CPU embedding sample")
+    ap.add_argument("--cpu-sample", type=int, default=2560, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-embed-sample", type=int, default=512, help="images of the bounded CPU embedding sample")
     ap.add_argument("--batch", type=int, default=512, help="images per embedding batch")
     ap.add_argument("--features-only", action="store_true", help="skip the embedding stage (synthetic features)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -136,19 +136,24 @@ def cpu_cycle_sample(n_sample, d=D, seed=0, mode="ref"):
     return time.perf_counter() - t0, kind
 
 
-def cpu_embed_sample(n_img, seed=1234):
-    """reid/evaluators.py:18-60 on the host cores (torch CPU fp32, all threads): n_img images, num_split=2."""
+def cpu_embed_sample(n_img, seed=1234, budget_s=10.0):
+    """reid/evaluators.py:18-60 on the host cores (torch CPU fp32, all threads), num_split=2: batches of 32 images
+    until `n_img` images are done or `budget_s` seconds have passed (at least one batch).  -> (seconds, images)."""
     import torch
     from oracle import resnet_oracle as R
     torch.set_num_threads(os.cpu_count() or 1)
     model = R.build_model(2, 0)
-    imgs = R.synth_images(n_img, seed)
-    names = ["i%d" % i for i in range(n_img)]
-    batches = [(imgs[i:i + 32], names[i:i + 32], [0] * len(names[i:i + 32]), [0] * len(names[i:i + 32]))
-               for i in range(0, n_img, 32)]
-    t0 = time.perf_counter()
-    R.extract_features(model, batches, for_eval=False)
-    return time.perf_counter() - t0
+    imgs = R.synth_images(min(n_img, 64), seed)
+    done, t0 = 0, time.perf_counter()
+    while done < n_img:
+        n = min(32, n_img - done)
+        part = imgs[(done % 64):(done % 64) + n]
+        names = ["i%d" % (done + i) for i in range(part.shape[0])]
+        R.extract_features(model, [(part, names, [0] * len(names), [0] * len(names))], for_eval=False)
+        done += part.shape[0]
+        if time.perf_counter() - t0 >= budget_s:
+            break
+    return time.perf_counter() - t0, done
 
 
 def run_reference_arm(args):
@@ -165,7 +170,7 @@ def run_reference_arm(args):
         times.append(t)
     sec = sum(times) / len(times)
     val = n_s * n_s / sec / 1e6
-    esec = cpu_embed_sample(args.cpu_embed_sample)
+    esec, eimgs = cpu_embed_sample(args.cpu_embed_sample)
     sample = "1 bank, N=Ns=%d rows of the %d-row workload, d=%d, fp16 reference arithmetic" % (n_s, args.n, D)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -175,8 +180,8 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "embed": {"value": args.cpu_embed_sample / esec, "unit": "images/s (two forward passes per image)",
-                  "cores": os.cpu_count(), "sample": "%d images, torch CPU fp32, all host threads" % args.cpu_embed_sample},
+        "embed": {"value": eimgs / esec, "unit": "images/s (two forward passes per image)",
+                  "cores": os.cpu_count(), "sample": "%d images, torch CPU fp32, all host threads" % eimgs},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -400,10 +405,9 @@ def main():
                    "sample": "1 bank, N=Ns=%d rows of the %d-row workload (re_ranking fp16 reference arithmetic + eps + "
                              "sklearn DBSCAN n_jobs=8); numpy/scipy parts are single-threaded" % (args.cpu_sample, n)}
             if with_embed:
-                esec = cpu_embed_sample(args.cpu_embed_sample)
-                cpu["embed"] = {"value": args.cpu_embed_sample / esec, "unit": "images/s", "cores": os.cpu_count(),
-                                "sample": "%d images, torch CPU fp32 ResNet-50 x2 passes, all host threads"
-                                          % args.cpu_embed_sample}
+                esec, eimgs = cpu_embed_sample(args.cpu_embed_sample)
+                cpu["embed"] = {"value": eimgs / esec, "unit": "images/s", "cores": os.cpu_count(),
+                                "sample": "%d images, torch CPU fp32 ResNet-50 x2 passes, all host threads" % eimgs}
         embed = None
         if with_embed:
             img_per_s = 2.0 * n * units * k / (ms_embed / 1e3)

@@ -66,12 +66,15 @@ struct StagedEpi {
 //   VAR_RRING (BN = 256 WITH a residual): 3 operand stages, and the residual arrives through a ring of three 64-column
 //             sub-tile buffers fetched by TMA two sub-tiles ahead (a whole-tile double buffer does not fit next to
 //             128x256 operand stages).
+//             (A six-slot ring with two operand stages was measured for the short-K launches and changed nothing:
+//             those are bound by the epilogue, not by HBM latency -- profiles/r01m_conv_variants.md.)
 constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2;
 constexpr int BRES_K = 256;
 
 template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
 struct SmemLayout {
     static constexpr bool BRES = VAR == VAR_BRES, RRING = VAR == VAR_RRING;
+    static constexpr int RSLOTS = 3;                             // residual ring slots (RRING)
     static constexpr int A_BYTES = (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
     static constexpr int B_BYTES = BRES ? 0 : (KHS ? 3 : 1) * B_TILE;
@@ -82,7 +85,7 @@ struct SmemLayout {
     static constexpr bool HAS_R = BN <= 128 || RRING;            // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
-    static constexpr int RSTAGE_BYTES = RRING ? 3 * SUB_BYTES : 2 * R_BYTES;       // residual staging in total
+    static constexpr int RSTAGE_BYTES = RRING ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
     static constexpr int STAGES = BRES ? 8 : RRING ? 3 : KHS ? 3 :
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
@@ -92,6 +95,7 @@ struct SmemLayout {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
     static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
+    static_assert(TOTAL <= 232448, "shared-memory layout exceeds 227 KB");
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -118,8 +122,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
-    uint64_t* res_bar = tempty_bar + 2;           // [3] residual tile / sub-tile landed (staged epilogue)
-    uint64_t* bres_bar = res_bar + 3;             // [1] resident B operand landed (VAR_BRES)
+    uint64_t* res_bar = tempty_bar + 2;           // [6] residual tile / sub-tile landed (staged epilogue)
+    uint64_t* bres_bar = res_bar + 6;             // [1] resident B operand landed (VAR_BRES)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +135,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
-        for (int s = 0; s < 3; ++s) mbar_init(&res_bar[s], 1);
+        for (int s = 0; s < 6; ++s) mbar_init(&res_bar[s], 1);
         mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
@@ -412,18 +416,21 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 }
             }
             // VAR_RRING: residual sub-tile s (s counts this CTA's 64-column sub-tiles: tile it, sub-tile j -> it*NSUB + j)
-            // lives in ring slot s % 3 and is fetched two sub-tiles ahead
+            // lives in ring slot s % RS and is fetched RS - 1 sub-tiles ahead
+            constexpr int RS = L::RSLOTS;
             auto load_residual_sub = [&](int s) {
                 const int tile = (int)blockIdx.x + (s / NSUB) * (int)gridDim.x;
                 if (tile >= num_tiles) return;
                 int mb, nb;
                 tile_coords(tile, mb, nb);
-                const int slot = s % 3;
+                const int slot = s % RS;
                 mbar_arrive_expect_tx(&res_bar[slot], L::SUB_BYTES);
                 tma_load_2d(r_s + slot * L::SUB_BYTES, &epi.mapR, &res_bar[slot], nb * BN + (s % NSUB) * 64, mb * BM);
             };
             if constexpr (L::RRING) {
-                if (leader && has_res) { load_residual_sub(0); load_residual_sub(1); }
+                if (leader && has_res) {
+                    for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
+                }
             } else {
                 if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
             }
@@ -453,10 +460,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     if constexpr (L::RRING) {
                         const int s = it * NSUB + j;
                         // every epilogue thread is past the barrier above, i.e. done with sub-tile s-1: its ring slot
-                        // (s+2) % 3 == (s-1) % 3 is free for the sub-tile two ahead
-                        if (leader && has_res) load_residual_sub(s + 2);
-                        if (has_res) mbar_wait(&res_bar[s % 3], (uint32_t)((s / 3) & 1));
-                        rsub = r_s + (s % 3) * L::SUB_BYTES + row_off;
+                        // (s + RS - 1) % RS == (s - 1) % RS is free for the sub-tile RS - 1 ahead
+                        if (leader && has_res) load_residual_sub(s + RS - 1);
+                        if (has_res) mbar_wait(&res_bar[s % RS], (uint32_t)((s / RS) & 1));
+                        rsub = r_s + (s % RS) * L::SUB_BYTES + row_off;
                     }
                     {
                         const int h = grp;
