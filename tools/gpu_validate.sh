@@ -1,14 +1,18 @@
 #!/bin/bash
-# One-call GPU validation (run under gpurun, ONE GPU): new-row tests, the default bench line, the whole -m gpu suite,
-# the conv DRAM-traffic capture and smoke().  Every step has its own timeout and logs under gpurun_out/<tag>_*.
+# One-call GPU validation (run under gpurun, ONE GPU): the whole -m gpu suite, the default bench line, smoke(), the
+# ncu launch list of one full step and the conv DRAM-traffic capture.  Every step has its own timeout and logs under
+# gpurun_out/<tag>_*.
 set -u
-TAG=${1:-r01j}
+TAG=${1:-r01n}
 mkdir -p gpurun_out
 T0=$(date +%s)
 step() { echo "== $1  (t=$(( $(date +%s)-T0 ))s)"; }
-step "new tests"; timeout 240 python -m pytest tests/test_gpu_triplet.py "tests/test_gpu_embed.py::test_uint8_pixels_give_bit_identical_features" -x -q > gpurun_out/${TAG}_newtests.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/${TAG}_newtests.log
-step "bench"; timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "rc=$?"; head -c 1200 gpurun_out/${TAG}_bench.json; echo
-step "gpu suite"; timeout 420 python -m pytest tests -m gpu -x -q --durations=12 > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "rc=$?"; tail -22 gpurun_out/${TAG}_gpu_tests.log
-step "traffic"; timeout 150 bash tools/profile.sh ${TAG} traffic > /dev/null 2>&1; echo "rc=$?"
+step "gpu suite"; timeout 420 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${TAG}_gpu_tests.log 2>&1; echo "rc=$?"; tail -14 gpurun_out/${TAG}_gpu_tests.log
+step "bench"; timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "rc=$?"; head -c 700 gpurun_out/${TAG}_bench.json; echo
 step "smoke"; timeout 100 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
+step "launches"; timeout 240 bash tools/profile.sh ${TAG} launches > /dev/null 2>&1; echo "rc=$?"
+step "traffic"; timeout 120 bash tools/profile.sh ${TAG} traffic > /dev/null 2>&1; echo "rc=$?"
+for b in 256 1024; do
+  step "quick batch $b"; timeout 100 python bench.py --quick --steps 2 --warmup 1 --n 4096 --batch $b 2>/dev/null | cut -c1-330
+done
 step "done"
