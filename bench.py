@@ -398,7 +398,7 @@ def main():
                 roof = {"kernel": top, "bound": bound, "achieved": work / (per_launch_ms / 1e3) / 1e12, "peak": None,
                         "unit": "Tflop64/s", "frac": None, "traffic": None, "ms_per_launch": per_launch_ms}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only (the other ranks would idle)
             sec, kind = cpu_cycle_sample(args.cpu_sample)
             cpu = {"value": args.cpu_sample ** 2 / sec / 1e6, "unit": UNIT, "cores": 1, "kind": kind,
                    "seconds": sec,
