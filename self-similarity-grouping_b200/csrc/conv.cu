@@ -17,6 +17,18 @@ namespace ssg {
 // epilogue: out[row, col] = bf16( relu?( acc + bias[col] (+ residual[row, col]) ) ), NHWC ([M, Cout] row-major),
 // staged through shared memory and written / prefetched by TMA (tc::StagedEpi in gemm_tc.cuh).
 // ---------------------------------------------------------------------------------------------------
+// stem kernel variant: 0 = plain (weights re-loaded per tile; SSG_STEM_BRES=0), 1 = resident weights (default),
+// 2 = resident weights + whole-tile parity-plane operand staging (SSG_STEM_PLANES=1)
+static int stem_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* b = getenv("SSG_STEM_BRES");
+        const char* p = getenv("SSG_STEM_PLANES");
+        v = (b && !atoi(b)) ? 0 : ((p && atoi(p)) ? 2 : 1);
+    }
+    return v;
+}
+
 static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, int k, const float* bias,
                          const void* residual, int relu, void* y, cudaStream_t st, void* pool_out = nullptr) {
     if (cout % 64) return ssg_set_error(SSG_ERR_INVALID, "conv: Cout=%d must be a multiple of 64", cout);
@@ -40,10 +52,11 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     if (bn256_res && residual && cout % 256 == 0 && k >= 256)
         return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_RRING>(A, m, w, cout, k, epi, st);
     // the stem (mode 3: N = 64, K = 256) keeps its weights resident in shared memory (SSG_STEM_BRES=0 disables)
-    static int stem_bres = -1;
-    if (stem_bres < 0) { const char* e = getenv("SSG_STEM_BRES"); stem_bres = e ? atoi(e) : 1; }
-    if (stem_bres && A.mode == 3 && cout == 64 && k == tc::BRES_K)
+    if (stem_variant() && A.mode == 3 && cout == 64 && k == tc::BRES_K) {
+        if (stem_variant() == 2)
+            return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_BRESP>(A, m, w, cout, k, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_BRES>(A, m, w, cout, k, epi, st);
+    }
     if (pool_out) return ssg_set_error(SSG_ERR_UNSUPPORTED, "the fused stem max-pool needs the resident-weight stem kernel");
     if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
@@ -115,8 +128,7 @@ bool stem_pool_fused() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SSG_STEM_POOL");
-        const char* b = getenv("SSG_STEM_BRES");
-        v = ((e && !atoi(e)) || (b && !atoi(b))) ? 0 : 1;
+        v = ((e && !atoi(e)) || stem_variant() == 0) ? 0 : 1;
     }
     return v != 0;
 }
@@ -418,7 +430,7 @@ int conv_stem_windows64(const void* P, int images, const void* w256, const float
     A.taps = 8;
     A.tiles_per_img = 64;
     A.hmul = 1;
-    SSG_TRY(make_tmap_stem_windows64(&A.map[0], P, (uint64_t)images));
+    SSG_TRY(make_tmap_stem_windows64(&A.map[0], P, (uint64_t)images, stem_variant() == 2 ? 10 : 4));
     return gemm_dispatch(A, images * 8192, w256, 64, 256, bias, nullptr, 1, y, st, pool_out);
 }
 

@@ -99,12 +99,14 @@ int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images) 
 
 // 64-byte-swizzle variants for the stem: 8-pixel windows (32 elements = 64 B per row) halve the L2 traffic of the
 // overlapping-window view; the weight matrix is cut into matching [rows, 32] boxes.
-int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images) {
+// box_rows = 4: two input rows (r, r+2) per box, one kernel row of a two-row output tile; box_rows = 10: five rows
+// (r, r+2, .., r+8), one parity plane of a whole tile (VAR_BRESP)
+int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images, uint32_t box_rows) {
     PFN_encodeTiled enc;
     SSG_TRY(get_encode(&enc));
     cuuint64_t dims[4] = {32, 64, 256, images};
     cuuint64_t strides[3] = {16, 144 * 8, (cuuint64_t)256 * 144 * 8};
-    cuuint32_t box[4] = {32, 64, 4, 1};
+    cuuint32_t box[4] = {32, 64, box_rows, 1};
     cuuint32_t estr[4] = {1, 1, 2, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

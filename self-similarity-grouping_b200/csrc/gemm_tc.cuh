@@ -12,7 +12,7 @@ int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 int make_tmap_nhwc_bf16(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                         uint32_t bw, uint32_t bh, uint32_t bb, uint32_t stride = 1);
 int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images);
-int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images);
+int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images, uint32_t box_rows = 4);
 int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int tc_num_sms(int* out);
 
@@ -68,14 +68,20 @@ struct StagedEpi {
 //             128x256 operand stages).
 //             (A six-slot ring with two operand stages was measured for the short-K launches and changed nothing:
 //             those are bound by the epilogue, not by HBM latency -- profiles/r01m_conv_variants.md.)
-constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2;
+//   VAR_BRESP (stem, "parity planes"): VAR_BRES whose operand stage is a whole tile: the 10 input rows a two-row output
+//             tile touches are loaded ONCE, as two stride-2 TMA boxes of five rows (even / odd offsets: 2 x 20 KB), and
+//             kernel row kh reads plane kh & 1 starting (kh >> 1) rows in -- 40 KB per tile instead of the 64 KB of eight
+//             per-kernel-row boxes.  Same MMA sequence, hence the same bits.
+constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3;
+constexpr int STEM_ROW_BYTES = 64 * 64;     // one input row of a stem tile in shared memory: 64 windows x 64 B
 constexpr int BRES_K = 256;
 
 template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
 struct SmemLayout {
-    static constexpr bool BRES = VAR == VAR_BRES, RRING = VAR == VAR_RRING;
+    static constexpr bool PLANES = VAR == VAR_BRESP;
+    static constexpr bool BRES = VAR == VAR_BRES || PLANES, RRING = VAR == VAR_RRING;
     static constexpr int RSLOTS = 3;                             // residual ring slots (RRING)
-    static constexpr int A_BYTES = (KHS ? 192 : BM) * BK * 2;
+    static constexpr int A_BYTES = PLANES ? 2 * 5 * STEM_ROW_BYTES : (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
     static constexpr int B_BYTES = BRES ? 0 : (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -86,7 +92,7 @@ struct SmemLayout {
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
     static constexpr int RSTAGE_BYTES = RRING ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
-    static constexpr int STAGES = BRES ? 8 : RRING ? 3 : KHS ? 3 :
+    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KHS ? 3 :
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
     static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : 0;
@@ -213,6 +219,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         else tma_load_4d(sa, &A.map[1], &full_bar[stage], kb2 * BK, 0, h0 * A.hmul, b0);
                     } else if (A.mode == 0) {
                         tma_load_2d(sa, &A.map[0], &full_bar[stage], kb * BK, m_blk * BM);
+                    } else if (L::PLANES) {
+                        // stem, whole tile per stage: input rows r0, r0+2, .., r0+8 (plane 0) and r0+1, .., r0+9 (plane 1)
+                        const int r0 = 4 * (m_blk & 63) - 3;
+                        tma_load_4d(sa, &A.map[0], &full_bar[stage], 0, 0, r0, m_blk >> 6);
+                        tma_load_4d(sa + L::A_BYTES / 2, &A.map[0], &full_bar[stage], 0, 0, r0 + 1, m_blk >> 6);
                     } else if (A.mode == 3) {
                         // stem, 64-byte rows: the stage holds two kernel rows (kh = 2kb, 2kb+1) as two [128 x 64 B] halves
                         const int ih = 4 * (m_blk & 63) + 2 * kb - 3;
@@ -270,6 +281,21 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                             for (int k = 0; k < BK / UMMA_K; ++k)
                                 umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
                                          (kb > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                        }
+                    } else if (L::PLANES) {
+                        // kernel row kh: output rows (0, 1) of the tile read plane rows (kh >> 1, (kh >> 1) + 1) of plane
+                        // kh & 1 -- 128 contiguous 64-byte rows; weights of kernel row kh sit kh * 4 KB into the
+                        // resident B operand.  Same (kh, k-step) order as the per-kernel-row stages.
+                        const uint32_t bres = smem_u32(smem + L::BRES_OFFSET);
+#pragma unroll
+                        for (int kh = 0; kh < 8; ++kh) {
+                            const uint64_t da = make_desc_k_sw64(sa + (uint32_t)((kh & 1) * (L::A_BYTES / 2) +
+                                                                              (kh >> 1) * STEM_ROW_BYTES));
+                            const uint64_t db = make_desc_k_sw64(bres + (uint32_t)(kh * (L::B_TILE / 2)));
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks)
+                                umma_f16(d_tmem, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc,
+                                         (kh > 0 || ks > 0) ? 1u : 0u);
                         }
                     } else if (A.mode == 3) {
                         // two half-stages of 64-byte-swizzled rows, two 16-element K steps each
@@ -528,7 +554,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 template <int BN, class Epi, bool STAGED = false, bool KHS = false, int VAR = VAR_NONE>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
     using L = SmemLayout<BN, STAGED, KHS, VAR>;
-    if (VAR == VAR_BRES && (A.mode != 3 || n != BN || k != BRES_K))
+    if ((VAR == VAR_BRES || VAR == VAR_BRESP) && (A.mode != 3 || n != BN || k != BRES_K))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
@@ -539,7 +565,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);
     int grid = tiles < sms ? tiles : sms;
-    if constexpr (VAR == VAR_BRES) {
+    if constexpr (VAR == VAR_BRES || VAR == VAR_BRESP) {
         if (epi.pool_out != nullptr) {                      // whole images per CTA
             if (m % (64 * BM)) return ssg_set_error(SSG_ERR_INVALID, "gemm: fused stem pool needs whole images (M=%d)", m);
             const int images = m / (64 * BM);
@@ -549,7 +575,8 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     auto kern = gemm_kernel<BN, Epi, STAGED, KHS, VAR>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks
-    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, KHS ? (k / BK) / 3 : (k + BK - 1) / BK, epi);
+    // VAR_BRESP: the whole K range of a tile rides in one stage
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, L::PLANES ? 1 : KHS ? (k / BK) / 3 : (k + BK - 1) / BK, epi);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
