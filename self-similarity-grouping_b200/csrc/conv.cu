@@ -17,14 +17,14 @@ namespace ssg {
 // epilogue: out[row, col] = bf16( relu?( acc + bias[col] (+ residual[row, col]) ) ), NHWC ([M, Cout] row-major),
 // staged through shared memory and written / prefetched by TMA (tc::StagedEpi in gemm_tc.cuh).
 // ---------------------------------------------------------------------------------------------------
-// stem kernel variant: 0 = plain (weights re-loaded per tile; SSG_STEM_BRES=0), 1 = resident weights (default),
-// 2 = resident weights + whole-tile parity-plane operand staging (SSG_STEM_PLANES=1)
+// stem kernel variant: 0 = plain (weights re-loaded per tile; SSG_STEM_BRES=0), 1 = resident weights, one TMA box per
+// kernel row (SSG_STEM_PLANES=0), 2 = resident weights + whole-tile parity-plane operand staging (default)
 static int stem_variant() {
     static int v = -1;
     if (v < 0) {
         const char* b = getenv("SSG_STEM_BRES");
         const char* p = getenv("SSG_STEM_PLANES");
-        v = (b && !atoi(b)) ? 0 : ((p && atoi(p)) ? 2 : 1);
+        v = (b && !atoi(b)) ? 0 : ((p && !atoi(p)) ? 1 : 2);
     }
     return v;
 }

@@ -297,9 +297,10 @@ def test_uint8_pixels_give_bit_identical_features():
 
 
 def test_conv_variants_are_bit_identical(tmp_path):
-    """The default trunk (stem with resident weights + fused max-pool, 128x256 residual-ring tiles) against the plain
-    variants (SSG_STEM_BRES=0 SSG_STEM_POOL=0 SSG_CONV_BN256_RES=0, read once per process -> a subprocess): the same
-    products accumulate in the same order, so the features must agree bit for bit."""
+    """The default trunk (stem with resident weights, parity-plane operand staging and fused max-pool; 128x256
+    residual-ring tiles) against the plain variants (SSG_STEM_BRES=0 SSG_STEM_POOL=0 SSG_CONV_BN256_RES=0, read once
+    per process -> a subprocess): the same products accumulate in the same order, so the features must agree bit for
+    bit."""
     import subprocess
     import sys
     import torch
