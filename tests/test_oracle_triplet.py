@@ -65,3 +65,27 @@ def test_oracle_matches_reference_live(P, K, d, seed, margin, semi, extra):
     l, p, g = TO.triplet_loss(x, t, K, margin, semi, with_grad=True)
     assert abs(l - loss.item()) <= RTOL * max(1.0, abs(l)) and abs(p - float(prec)) < 1e-6
     assert np.abs(g - xt.grad.numpy()).max() <= RTOL * np.abs(g).max()
+
+
+def test_oracle_gradient_is_the_derivative_of_the_oracle_loss():
+    """Central finite differences of the restated loss (float64 evaluation of the same expression) against the analytic
+    gradient the CUDA kernels are compared with: the mining is piecewise constant, so away from ties they must agree."""
+    x, t = TO.synth_batch(4, 3, 6, 21, 0.4, extra=1)
+
+    def loss64(xx):
+        sq = (xx * xx).sum(1)
+        d = np.sqrt(np.maximum(sq[:, None] + sq[None, :] - 2.0 * xx @ xx.T, 1e-12))
+        a, p, m = TO.mine(d, t, 3, True)
+        return np.maximum(d[a, p] - d[a, m] + 0.5, 0.0).mean()
+
+    _, _, g = TO.triplet_loss(x, t, 3, 0.5, True, with_grad=True)
+    x64 = x.astype(np.float64)
+    h = 1e-6
+    num = np.zeros_like(x64)
+    for i in range(x64.shape[0]):
+        for j in range(x64.shape[1]):
+            xp, xm = x64.copy(), x64.copy()
+            xp[i, j] += h
+            xm[i, j] -= h
+            num[i, j] = (loss64(xp) - loss64(xm)) / (2 * h)
+    assert np.abs(num - g).max() <= 1e-5 * max(np.abs(num).max(), 1.0)
