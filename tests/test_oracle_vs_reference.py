@@ -65,3 +65,25 @@ def test_evaluation_metrics_restatement_matches_reference():
         a = rem.cmc(d, qid, gid, qc, gc, first_match_break=fmb)
         b = O.cmc(d, qid, gid, qc, gc, first_match_break=fmb)
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["f32", "ref"])
+@pytest.mark.parametrize("n,ns,d,seed,noise", [(90, 70, 64, 0, 0.5), (150, 120, 256, 1, 0.5), (64, 40, 32, 2, 0.0)])
+def test_rerank_plain_restatement_bit_exact(mode, n, ns, d, seed, noise):
+    """Row f4 (oracle only so far): reid/rerank_plain.py:127-178 through neighbour lists / set intersections, against
+    the unmodified reference (dense boolean matrix + scipy's boolean Jaccard); noise 0 = duplicate features = ties at
+    the k-th distance."""
+    import contextlib
+    import os
+    from oracle import rerank_plain_oracle as P
+    refshim.load_reference()
+    with refshim._reference_on_path():
+        import reid.rerank_plain as RP
+    tgt, _ = O.synth_features(n, d, seed, noise=noise)
+    src, _ = O.synth_features(ns, d, seed + 9)
+    ctx = refshim.f32_stable(RP) if mode == "f32" else contextlib.nullcontext()
+    with ctx, contextlib.redirect_stdout(open(os.devnull, "w")):
+        want, again = RP.re_ranking(src, tgt, k=20, lambda_value=0.1)
+    assert want is again
+    got = P.re_ranking_plain(src, tgt, 20, 0.1, mode)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
