@@ -306,6 +306,7 @@ def test_conv_variants_are_bit_identical(tmp_path):
     import torch
     import ssg_b200
     from oracle import resnet_oracle as R
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = (
         "import sys, numpy as np, torch\n"
         "sys.path[:0] = %r\n"
@@ -313,7 +314,7 @@ def test_conv_variants_are_bit_identical(tmp_path):
         "from oracle import resnet_oracle as R\n"
         "plan = ssg_b200.EmbedPlan(16); plan.load_model(R.build_model(2, 0))\n"
         "out = plan.forward(R.synth_images(9, 11).cuda(), 2); torch.cuda.synchronize()\n"
-        "np.save(sys.argv[1], out.cpu().numpy())\n" % ([p for p in sys.path if p.endswith(("repo", "_b200"))],))
+        "np.save(sys.argv[1], out.cpu().numpy())\n" % ([os.path.join(root, "self-similarity-grouping_b200"), root],))
     env = dict(os.environ, SSG_STEM_BRES="0", SSG_STEM_POOL="0", SSG_CONV_BN256_RES="0")
     out_file = str(tmp_path / "plain.npy")
     subprocess.run([sys.executable, "-c", script, out_file], check=True, env=env, timeout=300)
