@@ -121,7 +121,7 @@ def _worker(rank, world, init_file, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])      # 4 ranks > 3 banks: some ranks own no bank (the 8-GPU regime)
 def test_sharded_cycle_matches_single_process(world):
     import torch
     import torch.multiprocessing as mp
