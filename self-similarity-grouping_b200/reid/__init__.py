@@ -15,15 +15,21 @@ Put ``self-similarity-grouping_b200/`` ahead of the reference on ``sys.path`` an
 Only the hot path and its "next" rows live here; datasets, samplers, the other trainers/losses and
 checkpoint I/O are the reference's own and out of scope.
 """
-from . import evaluation_metrics  # noqa: F401
-from . import feature_extraction  # noqa: F401
-from . import models  # noqa: F401
-from . import evaluators  # noqa: F401
-from . import rerank  # noqa: F401
-from . import rerank_initial  # noqa: F401
-from . import cluster  # noqa: F401
-from . import eug  # noqa: F401
-from . import loss  # noqa: F401
-from . import trainers  # noqa: F401
+from . import _reference
+
+# everything this package does not define (datasets, dist_metric, metric_learning, utils.data ...) resolves to the
+# reference's own files when the reference is on sys.path behind us / at SSG_REFERENCE_ROOT
+_reference.extend_path(__path__)
+
+from . import evaluation_metrics  # noqa: F401,E402
+from . import feature_extraction  # noqa: F401,E402
+from . import models  # noqa: F401,E402
+from . import evaluators  # noqa: F401,E402
+from . import rerank  # noqa: F401,E402
+from . import rerank_initial  # noqa: F401,E402
+from . import cluster  # noqa: F401,E402
+from . import eug  # noqa: F401,E402
+from . import loss  # noqa: F401,E402
+from . import trainers  # noqa: F401,E402
 
 __version__ = '0.2.0'

