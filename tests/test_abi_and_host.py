@@ -179,7 +179,7 @@ from reid import datasets
 from reid import models
 from reid.dist_metric import DistanceMetric
 from reid.loss import TripletLoss, FocalLoss
-from reid.trainers import Trainer, FinedTrainer, FinedTrainer2
+from reid.trainers import Trainer, FinedTrainer, FinedTrainer2, JointTrainer2, DistillTrainer   # + semitraining.py:19, eug.py:4
 from reid.evaluators import Evaluator, extract_features
 from reid.utils.data import transforms as T
 from reid.utils.data.preprocessor import Preprocessor
