@@ -206,3 +206,32 @@ print("driver imports ok")
        os.path.join(root, "self-similarity-grouping_b200"))
     out = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "driver imports ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/ssg_b200.h is the C ABI: it must compile as C99 (no torch / C++ types), and a C program that only
+    includes it must link against libssg_b200.so and run its no-GPU entry points."""
+    import shutil
+    import subprocess
+    from ssg_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "ssg_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                   check=True)
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "ssg_b200.h"\n'
+                   'int main(void) { int cin, cout, k, s; char a[64], b[64];\n'
+                   '  if (ssg_version() < 100) return 1;\n'
+                   '  if (ssg_embed_layer_info(0, &cin, &cout, &k, &s, a, b, 64) != SSG_OK) return 2;\n'
+                   '  if (ssg_embed_layer_info(-1, 0, 0, 0, 0, 0, 0, 0) != SSG_ERR_INVALID) return 3;\n'
+                   '  printf("%d %d %d %d %s %d %s\\n", cin, cout, k, s, a, ssg_embed_num_layers(), ssg_last_error());\n'
+                   '  return 0; }\n')
+    exe = tmp_path / "probe"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-lssg_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.startswith("3 64 7 2 conv1 53 ")
