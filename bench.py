@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replicas", action="store_true",
                     help="N>1: independent replicas (weak scaling) instead of sharding one cycle over the GPUs")
+    ap.add_argument("--shard-finish", action="store_true",
+                    help="N>1 sharded mode: row-sharded finish (every rank holds only its rows of final_dist; "
+                         "distributed eps and DBSCAN) instead of the bank-parallel finish")
     ap.add_argument("--quick", action="store_true",
                     help="profiling runs (ncu): exactly --warmup warm-up steps, no e2e leg, no CPU baseline")
     return ap.parse_args()
@@ -280,7 +283,8 @@ def main():
             ev[1].record()
         if sharded:
             out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, RHO, backend=backend,
-                                                   comm=comm, features=(tf, sf))
+                                                   comm=comm, features=(tf, sf),
+                                                   shard_finish=True if args.shard_finish else None)
         else:
             out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local)
         if record:
@@ -434,7 +438,9 @@ def main():
                        "value_is": "Mpairs/s of the re-rank+eps+DBSCAN stage inside the full step; embed stage under 'embed'; "
                                    "ms_per_step is the whole cycle",
                        "parallelism": ("one cycle sharded over %d GPUs: image shards, NCCL all-gather of the feature banks, "
-                                       "row-block distance stage, bank-parallel finish" % world) if sharded else
+                                       "row-block distance stage, %s finish"
+                                       % (world, "row-sharded" if (args.shard_finish or sdist._shard_finish_default())
+                                          else "bank-parallel")) if sharded else
                                       "%d independent replicas (one target set per GPU)" % world,
                        "dist_mode": args.dist_mode},
             "embed": embed,

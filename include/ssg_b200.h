@@ -141,6 +141,59 @@ int ssg_dbscan_host(ssg_cluster_plan* plan, const void* h_dist, int dtype, int n
                     int min_samples, int64_t* h_labels, int* h_n_clusters);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row-sharded variants for one process per GPU.  Rank r of `world` holds the rows
+ * [lo_r, hi_r) of final_dist (lo_r = r*(n/world) + min(r, n%world): the first n%world ranks own one row more),
+ * as a [rows, n] block with leading dimension n.  The library launches the kernels; the CALLER runs the collectives
+ * (torch.distributed / NCCL) on the plan's buffers, whose device pointers ssg_cluster_buffers returns:
+ *   hist uint64[4096], state uint64[8], partial double[n_max], list double[2^20], cnt int32[n_max],
+ *   nbr int32[max_neighbors].
+ *
+ * ssg_rerank_finish_rows: ssg_rerank_finish, but only rows [row0, row0+rows) of final_dist are produced, into
+ *   d_final_rows (which points at row row0).  The sparse stages run for all n rows on every rank (they are cheap and
+ *   read other rows' tables); the tables must be complete (all-gathered) as for ssg_rerank_finish.
+ *
+ * eps (selftraining.py:289-293) on a SYMMETRIC matrix; every unordered pair is visited by exactly one rank
+ * (diagonal block: strict upper triangle; off-diagonal block (r,c): taken by rank r iff r<c and r+c odd, or r>c and
+ * r+c even).  Sequence, identical on every rank:
+ *   ssg_eps_shard_begin
+ *   for pass in 0, 1:  ssg_eps_shard_hist(pass); all-reduce(sum) hist; ssg_eps_shard_pick(pass, rho)
+ *   ssg_eps_shard_gather(exact_threshold=0, &count)   -- per-row sums below the threshold's 24-bit bin into
+ *       partial[global row], the bin's entries into list[0, count); count == -1: more than 2^20 such entries
+ *   if every rank's count >= 0 and their sum <= 2^20:
+ *       all-gather the rows of partial in place; concatenate the lists of all ranks (rank order) into list and store
+ *       the total into state[5]; ssg_eps_shard_finish(exact_threshold=0)
+ *   else (massive ties):
+ *       for pass in 2..5: hist, all-reduce, pick;  ssg_eps_shard_gather(exact_threshold=1, NULL);
+ *       all-gather partial; ssg_eps_shard_finish(exact_threshold=1)
+ * The list's entries are summed exactly on their integer mantissas, the per-row partial sums in a fixed order: eps
+ * is bit-reproducible for a given (n, world) and agrees with ssg_eps_estimate to the last few ulps (the order of
+ * the float64 additions differs).
+ *
+ * DBSCAN: ssg_dbscan_shard_count (cnt of the local rows); all-gather cnt rows in place;
+ *   ssg_dbscan_shard_fill (global CSR offsets from cnt, zero nbr[0,total), fill the local rows; SSG_ERR_CAPACITY
+ *   when total exceeds the plan's max_neighbors -- total and the error are the same on every rank);
+ *   all-reduce(sum) nbr[0,total); ssg_dbscan_shard_label (every rank labels all n rows: identical results).
+ * ------------------------------------------------------------------------------------------------ */
+int ssg_rerank_finish_rows(ssg_rerank_plan* plan, const float* d_tgt, int n, int d, int k1, int k2,
+                           double lambda_value, int row0, int rows, double* d_final_rows, void* stream);
+int ssg_cluster_buffers(ssg_cluster_plan* plan, void** d_hist, void** d_state, void** d_partial, void** d_list,
+                        void** d_cnt, void** d_nbr);
+int ssg_eps_shard_begin(ssg_cluster_plan* plan, void* stream);
+int ssg_eps_shard_hist(ssg_cluster_plan* plan, const void* d_rows, int dtype, int n, int world, int rank, int pass,
+                       void* stream);
+int ssg_eps_shard_pick(ssg_cluster_plan* plan, int pass, double rho, void* stream);
+int ssg_eps_shard_gather(ssg_cluster_plan* plan, const void* d_rows, int dtype, int n, int world, int rank,
+                         int exact_threshold, long long* h_list_count, void* stream);
+int ssg_eps_shard_finish(ssg_cluster_plan* plan, int n, int exact_threshold, double* h_eps, long long* h_top_num,
+                         void* stream);
+int ssg_dbscan_shard_count(ssg_cluster_plan* plan, const void* d_rows, int dtype, int n, int row0, int rows,
+                           double eps, void* stream);
+int ssg_dbscan_shard_fill(ssg_cluster_plan* plan, const void* d_rows, int dtype, int n, int row0, int rows,
+                          double eps, long long* h_total, void* stream);
+int ssg_dbscan_shard_label(ssg_cluster_plan* plan, int n, int min_samples, int64_t* d_labels, int* h_n_clusters,
+                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Embedding: reid/evaluators.py:18-60 extract_features + reid/feature_extraction/cnn.py:10-23 +
  * reid/models/resnet.py:86-134 (ResNet-50 trunk, num_classes=0, cluster=False) for 256x128 inputs.
  *   forward: images fp32 NCHW [n,3,256,128] (already mean/std normalised, as the reference's loaders

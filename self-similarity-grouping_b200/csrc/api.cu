@@ -377,10 +377,14 @@ extern "C" int ssg_rerank_tables(ssg_rerank_plan* p, float** d_rowmin, float** d
     return SSG_OK;
 }
 
-extern "C" int ssg_rerank_finish(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2,
-                                 double lambda_value, double* d_final, void* stream) {
+// Everything after the tables are complete: the sparse stages for all n rows (they read other rows' rank lists and V
+// rows, rerank.py:77,97,102), then rows [row0, row0+rows) of final_dist into d_final (which points at row row0).
+static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2, double lambda_value,
+                       int row0, int rows, double* d_final, void* stream) {
     SSG_TRY(check_run_args(p, d_tgt, 1, d_tgt, n, d, k1, k2));
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
+    if (row0 < 0 || rows < 0 || row0 + rows > n)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_finish: rows [%d,%d) outside [0,%d)", row0, row0 + rows, n);
     SSG_CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int k1p = k1 + 1;
@@ -413,10 +417,20 @@ extern "C" int ssg_rerank_finish(ssg_rerank_plan* p, const float* d_tgt, int n, 
     }
     // (vii)-(viii) rerank.py:101-122
     { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
-    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
-                                 d_final, st)); }
+    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, row0, rows, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec,
+                                 lambda_value, d_final, st)); }
     p->last_n = n;
     return SSG_OK;
+}
+
+extern "C" int ssg_rerank_finish(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2,
+                                 double lambda_value, double* d_final, void* stream) {
+    return finish_rows(p, d_tgt, n, d, k1, k2, lambda_value, 0, n, d_final, stream);
+}
+
+extern "C" int ssg_rerank_finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2,
+                                      double lambda_value, int row0, int rows, double* d_final_rows, void* stream) {
+    return finish_rows(p, d_tgt, n, d, k1, k2, lambda_value, row0, rows, d_final_rows, stream);
 }
 
 extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,

@@ -365,6 +365,121 @@ static int eps_run(ssg_cluster_plan* p, const T* D, int n, double rho, cudaStrea
     return SSG_OK;
 }
 
+// ---- row-sharded eps (multi-GPU): rank r of `world` holds the rows [lo_r, hi_r) of a SYMMETRIC
+// matrix (ssg_b200.dist.shard_bounds: the first n % world ranks own one row more).  Every unordered pair {a, b},
+// a != b, is visited by exactly one rank, and the rows of a rank are read in contiguous column runs:
+//   * inside the diagonal block of the rank: the strict upper triangle, i.e. columns (i, hi_r) of row i;
+//   * an off-diagonal block (r, c) is taken by rank r when r < c and r + c is odd, or r > c and r + c is even
+//     (the mirror block (c, r) holds the same values and is skipped by rank c) -- every rank reads about half of its
+//     row block, where the plain upper triangle would leave rank 0 with twice the work of the average.
+// The multiset of visited values equals that of np.triu(D, 1) because D is exactly symmetric (rerank.cu).
+struct ShardGeom {
+    int n, world, rank, base, rem;
+    __host__ __device__ int lo(int r) const { return r * base + (r < rem ? r : rem); }
+    __host__ __device__ bool takes(int c) const {
+        if (c == rank) return true;
+        const bool odd = ((rank + c) & 1) != 0;
+        return rank < c ? odd : !odd;
+    }
+};
+static ShardGeom make_geom(int n, int world, int rank) {
+    ShardGeom g;
+    g.n = n; g.world = world; g.rank = rank; g.base = n / world; g.rem = n % world;
+    return g;
+}
+
+// Calls body(value, valid) for every assigned column of global row i, EPS_NT * 4 columns per step with four
+// independent loads in flight per thread; all threads of the CTA make the same number of calls (body may use
+// warp-synchronous primitives), `valid` is false for the padding slots.
+template <typename T, class Body>
+__device__ __forceinline__ void shard_row_scan(const T* __restrict__ row, int i, const ShardGeom& g, Body body) {
+    for (int c = 0; c < g.world; ++c) {
+        if (!g.takes(c)) continue;
+        const int jb0 = c == g.rank ? i + 1 : g.lo(c);
+        const int je = g.lo(c + 1);
+        for (int jb = jb0; jb < je; jb += EPS_NT * 4) {
+            double vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = jb + u * EPS_NT + (int)threadIdx.x;
+                vv[u] = j < je ? ld_as_double<T>(row, j) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) body(vv[u], jb + u * EPS_NT + (int)threadIdx.x < je);
+        }
+    }
+}
+
+// one CTA per local row (block row blockIdx.x = global row lo_rank + blockIdx.x)
+template <typename T>
+__global__ void __launch_bounds__(EPS_NT)
+eps_hist_rows_kernel(const T* __restrict__ D, ShardGeom g, int pass, const unsigned long long* __restrict__ state,
+                     unsigned long long* __restrict__ ghist) {
+    __shared__ unsigned int hist[EPS_BINS];
+    for (int b = threadIdx.x; b < EPS_BINS; b += EPS_NT) hist[b] = 0u;
+    __syncthreads();
+    const int shift = c_eps_shift[pass], width = c_eps_width[pass];
+    const unsigned long long prefix = state[0];
+    const unsigned mask = (1u << width) - 1u;
+    const int hs = shift + width;
+    const int i = g.lo(g.rank) + (int)blockIdx.x;
+    shard_row_scan<T>(D + (size_t)blockIdx.x * g.n, i, g, [&](double v, bool valid) {
+        bool in = false;
+        unsigned bin = 0;
+        if (valid && v != 0.0) {
+            const unsigned long long k = f64_key(v);
+            in = (pass == 0) || ((k >> hs) == (prefix >> hs));
+            bin = (unsigned)(k >> shift) & mask;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const unsigned peers = __match_any_sync(act, bin);
+            if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[bin], __popc(peers));
+        }
+    });
+    __syncthreads();
+    for (int b = threadIdx.x; b < EPS_BINS; b += EPS_NT) {
+        const unsigned c = hist[b];
+        if (c) atomicAdd(&ghist[b], (unsigned long long)c);
+    }
+}
+
+// mode 0 (3-pass path): sum of the entries below the threshold's 24-bit bin -> partial[global row]; the entries
+//                       inside the bin are appended to `list` (cursor state[5], overflow flag state[6]);
+// mode 1 (6-pass path): sum of the entries whose key is below the exact threshold state[0] -> partial[global row].
+template <typename T>
+__global__ void __launch_bounds__(EPS_NT)
+eps_gather_rows_kernel(const T* __restrict__ D, ShardGeom g, int mode, unsigned long long* __restrict__ state,
+                       double* __restrict__ list, double* __restrict__ partial) {
+    const unsigned long long pre = state[0] >> 40, thr = state[0];
+    const int i = g.lo(g.rank) + (int)blockIdx.x;
+    double acc = 0.0;
+    if (state[2] > 0) {
+        shard_row_scan<T>(D + (size_t)blockIdx.x * g.n, i, g, [&](double v, bool valid) {
+            if (!valid || v == 0.0) return;
+            const unsigned long long k = f64_key(v);
+            if (mode == 1) {
+                if (k < thr) acc += v;
+                return;
+            }
+            const unsigned long long h = k >> 40;
+            if (h < pre) acc += v;
+            else if (h == pre) {
+                const unsigned long long pos = atomicAdd(&state[5], 1ull);
+                if (pos < (unsigned long long)EPS_LIST_CAP) list[pos] = v; else state[6] = 1ull;
+            }
+        });
+    }
+    __shared__ double sh[EPS_NT];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = EPS_NT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[i] = sh[0];
+}
+
 // -------------------------------------------------------------------------------------------- DBSCAN
 constexpr int DB_NT = 256;
 
@@ -477,6 +592,8 @@ db_label_kernel(int n, const int* __restrict__ rowptr, const int* __restrict__ n
     if (lane == 0) labels[i] = best == INT_MAX ? (int64_t)-1 : (int64_t)best;
 }
 
+static int dbscan_label_stage(ssg_cluster_plan* p, int n, int min_samples, int64_t* labels, cudaStream_t st);
+
 template <typename T>
 static int dbscan_run(ssg_cluster_plan* p, const T* D, int n, double eps, int min_samples,
                       int64_t* labels, cudaStream_t st) {
@@ -486,6 +603,12 @@ static int dbscan_run(ssg_cluster_plan* p, const T* D, int n, double eps, int mi
     SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
     { SSG_PROF("dbscan_fill", st); db_fill_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags); }
     SSG_CHECK_LAUNCH();
+    return dbscan_label_stage(p, n, min_samples, labels, st);
+}
+
+// union-find over the core-core edges of the complete neighbour CSR, cluster ids, border points (needs cnt, rowptr
+// and nbr of all n rows)
+static int dbscan_label_stage(ssg_cluster_plan* p, int n, int min_samples, int64_t* labels, cudaStream_t st) {
     db_init_kernel<<<ssg_cdiv(n, 256), 256, 0, st>>>(n, p->cnt, min_samples, p->parent, p->core);
     SSG_CHECK_LAUNCH();
     const int wgrid = ssg_cdiv(n, DB_NT / 32);
@@ -646,4 +769,167 @@ extern "C" int ssg_dbscan_host(ssg_cluster_plan* p, const void* h_dist, int dtyp
     cudaFree(d_labels);
     if (rc == SSG_OK && h_n_clusters) *h_n_clusters = ncl;
     return rc;
+}
+
+// ------------------------------------------------------------------------- row-sharded eps / DBSCAN
+// The caller owns the collectives (torch.distributed / NCCL on the buffers ssg_cluster_buffers exposes); see
+// include/ssg_b200.h for the call sequence and ssg_b200/dist.py for the one this repo uses.
+extern "C" int ssg_cluster_buffers(ssg_cluster_plan* p, void** d_hist, void** d_state, void** d_partial,
+                                   void** d_list, void** d_cnt, void** d_nbr) {
+    if (!p) return ssg_set_error(SSG_ERR_INVALID, "cluster_buffers: null plan");
+    if (d_hist) *d_hist = p->hist;
+    if (d_state) *d_state = p->state;
+    if (d_partial) *d_partial = p->partial;
+    if (d_list) *d_list = p->list;
+    if (d_cnt) *d_cnt = p->cnt;
+    if (d_nbr) *d_nbr = p->nbr;
+    return SSG_OK;
+}
+
+static int check_shard(const ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int world, int rank,
+                       const char* who) {
+    if (!p || n <= 0 || n > p->n_max || world <= 0 || rank < 0 || rank >= world)
+        return ssg_set_error(SSG_ERR_INVALID, "%s: bad arguments (n=%d, world=%d, rank=%d)", who, n, world, rank);
+    if (dtype != SSG_F64 && dtype != SSG_F32) return ssg_set_error(SSG_ERR_INVALID, "%s: dtype %d", who, dtype);
+    const ShardGeom g = make_geom(n, world, rank);
+    if (!d_rows && g.lo(rank + 1) > g.lo(rank)) return ssg_set_error(SSG_ERR_INVALID, "%s: null row block", who);
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_shard_begin(ssg_cluster_plan* p, void* stream) {
+    if (!p) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_begin: null plan");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_shard_hist(ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int world, int rank,
+                                  int pass, void* stream) {
+    SSG_TRY(check_shard(p, d_rows, dtype, n, world, rank, "eps_shard_hist"));
+    if (pass < 0 || pass > 5) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_hist: pass %d", pass);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardGeom g = make_geom(n, world, rank);
+    const int rows = g.lo(rank + 1) - g.lo(rank);
+    if (rows == 0) return SSG_OK;
+    SSG_PROF("eps_hist", st);
+    if (dtype == SSG_F64)
+        eps_hist_rows_kernel<double><<<rows, EPS_NT, 0, st>>>((const double*)d_rows, g, pass, p->state, p->hist);
+    else
+        eps_hist_rows_kernel<float><<<rows, EPS_NT, 0, st>>>((const float*)d_rows, g, pass, p->state, p->hist);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_shard_pick(ssg_cluster_plan* p, int pass, double rho, void* stream) {
+    if (!p || pass < 0 || pass > 5) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_pick: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    eps_pick_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->hist, p->state, pass, rho);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_shard_gather(ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int world, int rank,
+                                    int exact_threshold, long long* h_list_count, void* stream) {
+    SSG_TRY(check_shard(p, d_rows, dtype, n, world, rank, "eps_shard_gather"));
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const ShardGeom g = make_geom(n, world, rank);
+    const int rows = g.lo(rank + 1) - g.lo(rank);
+    const int mode = exact_threshold ? 1 : 0;
+    if (rows > 0) {
+        SSG_PROF(mode ? "eps_sum" : "eps_gather", st);
+        if (dtype == SSG_F64)
+            eps_gather_rows_kernel<double><<<rows, EPS_NT, 0, st>>>((const double*)d_rows, g, mode, p->state, p->list,
+                                                                    p->partial);
+        else
+            eps_gather_rows_kernel<float><<<rows, EPS_NT, 0, st>>>((const float*)d_rows, g, mode, p->state, p->list,
+                                                                   p->partial);
+        SSG_CHECK_LAUNCH();
+    }
+    if (h_list_count) {
+        unsigned long long hs[8];
+        SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+        // more entries than the list holds share the threshold's leading 24 key bits: report the overflow as -1
+        *h_list_count = hs[6] ? -1ll : (long long)hs[5];
+    }
+    return SSG_OK;
+}
+
+extern "C" int ssg_eps_shard_finish(ssg_cluster_plan* p, int n, int exact_threshold, double* h_eps,
+                                    long long* h_top_num, void* stream) {
+    if (!p || n <= 0 || n > p->n_max || !h_eps) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_finish: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (exact_threshold) eps_final_kernel<<<1, 1024, 0, st>>>(p->partial, n, p->state, p->eps_out);
+    else eps_list_finish_kernel<<<1, 1024, 0, st>>>(p->list, p->state, p->partial, n, p->eps_out);
+    SSG_CHECK_LAUNCH();
+    unsigned long long hs[8];
+    SSG_CUDA_TRY(cudaMemcpyAsync(h_eps, p->eps_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_top_num) *h_top_num = (long long)hs[2];
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan_shard_count(ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int row0, int rows,
+                                      double eps, void* stream) {
+    if (!p || n <= 0 || n > p->n_max || row0 < 0 || rows < 0 || row0 + rows > n || (!d_rows && rows > 0) ||
+        (dtype != SSG_F64 && dtype != SSG_F32))
+        return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_count: bad arguments (n=%d, rows [%d,%d))", n, row0,
+                             row0 + rows);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
+    if (rows == 0) return SSG_OK;
+    SSG_PROF("dbscan_count", st);
+    if (dtype == SSG_F64) db_count_kernel<double><<<rows, DB_NT, 0, st>>>((const double*)d_rows, n, eps, p->cnt + row0);
+    else db_count_kernel<float><<<rows, DB_NT, 0, st>>>((const float*)d_rows, n, eps, p->cnt + row0);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan_shard_fill(ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int row0, int rows,
+                                     double eps, long long* h_total, void* stream) {
+    if (!p || n <= 0 || n > p->n_max || row0 < 0 || rows < 0 || row0 + rows > n || (!d_rows && rows > 0) ||
+        (dtype != SSG_F64 && dtype != SSG_F32) || !h_total)
+        return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_fill: bad arguments (n=%d, rows [%d,%d))", n, row0,
+                             row0 + rows);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // cnt holds the counts of ALL rows by now (the caller gathered them): global CSR offsets, the same on every rank
+    SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
+    int total = 0;
+    SSG_CUDA_TRY(cudaMemcpyAsync(&total, p->rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    *h_total = (long long)total;
+    if (total < 0 || (long long)total > p->max_nbr)
+        return ssg_set_error(SSG_ERR_CAPACITY, "dbscan: %d neighbour pairs within eps exceed the plan's %lld; "
+                             "re-create the plan with a larger max_neighbors", total, p->max_nbr);
+    // rows of the other ranks stay zero: the caller completes the list with a sum all-reduce over nbr[0, total)
+    SSG_CUDA_TRY(cudaMemsetAsync(p->nbr, 0, sizeof(int) * (size_t)total, st));
+    if (rows == 0) return SSG_OK;
+    SSG_PROF("dbscan_fill", st);
+    if (dtype == SSG_F64)
+        db_fill_kernel<double><<<rows, DB_NT, 0, st>>>((const double*)d_rows, n, eps, p->rowptr + row0, p->max_nbr, p->nbr, p->flags);
+    else
+        db_fill_kernel<float><<<rows, DB_NT, 0, st>>>((const float*)d_rows, n, eps, p->rowptr + row0, p->max_nbr, p->nbr, p->flags);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan_shard_label(ssg_cluster_plan* p, int n, int min_samples, int64_t* d_labels,
+                                      int* h_n_clusters, void* stream) {
+    if (!p || !d_labels || n <= 0 || n > p->n_max) return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_label: bad arguments");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_TRY(dbscan_label_stage(p, n, min_samples, d_labels, st));
+    if (h_n_clusters) {
+        SSG_CUDA_TRY(cudaMemcpyAsync(h_n_clusters, p->cid + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return SSG_OK;
 }

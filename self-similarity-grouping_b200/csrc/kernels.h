@@ -49,9 +49,10 @@ int launch_query_expand(const int* rank, int n, int k2, const int* v_idx, const 
                         const int* v_cnt, int* q_idx, float* q_val, int* q_cnt, cudaStream_t st);
 int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int* colptr, int* cursor,
                      int* csc_row, cudaStream_t st);
-int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
-                         const int* csc_row, const float* vec, double lambda_value, double* final_dist,
-                         cudaStream_t st);
+// rows [row0, row0+rows) of final_dist; `final_dist` points at the first of those rows (leading dimension n)
+int launch_jaccard_final(int n, int row0, int rows, const int* q_idx, const float* q_val, const int* q_cnt,
+                         const int* colptr, const int* csc_row, const float* vec, double lambda_value,
+                         double* final_dist, cudaStream_t st);
 int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                         const int* csc_row, const float* dmat, const float* rowmax, double lambda_value, float* out,
                         cudaStream_t st);

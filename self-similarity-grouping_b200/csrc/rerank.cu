@@ -512,12 +512,12 @@ __device__ __forceinline__ void jaccard_row(int n, int i, const int* __restrict_
 }
 
 __global__ void __launch_bounds__(JF_NT)
-jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+jaccard_final_kernel(int n, int row0, const int* __restrict__ q_idx, const float* __restrict__ q_val,
                      const int* __restrict__ q_cnt, const int* __restrict__ colptr,
                      const int* __restrict__ csc_row, const float* __restrict__ vec, double lambda_value,
                      float one_minus_lambda, double* __restrict__ final_dist) {
     extern __shared__ unsigned char jf_smem[];
-    const int i = blockIdx.x;
+    const int i = row0 + (int)blockIdx.x;          // final_dist holds rows [row0, row0 + gridDim.x) of the matrix
     // rerank.py:117-118 clamps J < 0 to 0; J = 1 - S/(2-S) with 0 <= S <= 1(+rounding) cannot go below -1e-7,
     // and the clamp is applied inside store through fmaxf
     struct Clamp : OutSourceF64 {
@@ -525,7 +525,7 @@ jaccard_final_kernel(int n, const int* __restrict__ q_idx, const float* __restri
     };
     Clamp o;
     o.vec = vec; o.vi = vec[i]; o.lambda_value = lambda_value; o.oml = one_minus_lambda;
-    o.out = final_dist + (size_t)i * n;
+    o.out = final_dist + (size_t)blockIdx.x * n;
     jaccard_row(n, i, q_idx, q_val, q_cnt, colptr, csc_row, o, jf_smem);
 }
 
@@ -546,17 +546,18 @@ static size_t jaccard_smem(int n) {
            sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
 }
 
-int launch_jaccard_final(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
-                         const int* csc_row, const float* vec, double lambda_value, double* final_dist,
-                         cudaStream_t st) {
+int launch_jaccard_final(int n, int row0, int rows, const int* q_idx, const float* q_val, const int* q_cnt,
+                         const int* colptr, const int* csc_row, const float* vec, double lambda_value,
+                         double* final_dist, cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
     const size_t smem = jaccard_smem(n);
     if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
     SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
     // (1 - lambda_value) is a Python float cast to float32 by numpy when it multiplies the fp32 array
     const float oml = (float)(1.0 - lambda_value);
-    jaccard_final_kernel<<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value,
-                                                 oml, final_dist);
+    jaccard_final_kernel<<<rows, JF_NT, smem, st>>>(n, row0, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value,
+                                                    oml, final_dist);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -13,6 +13,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 DIST_EXACT, DIST_TENSOR = 0, 1
 F32, F64 = 0, 1
 RANK_STRIDE, V_STRIDE, VQ_STRIDE = 32, 256, 1536
+EPS_BINS, EPS_LIST_CAP = 4096, 1 << 20
 (STAGE_VEC, STAGE_ROWMAX, STAGE_RANK, STAGE_RANK_VAL, STAGE_V_CNT, STAGE_V_IDX, STAGE_V_VAL,
  STAGE_VQ_CNT, STAGE_VQ_IDX, STAGE_VQ_VAL, STAGE_FLAGGED) = range(11)
 
@@ -48,6 +49,18 @@ PROTOTYPES = {
     "ssg_dbscan_core_mask": (c_int, [c_void_p, c_void_p, c_int]),
     "ssg_eps_estimate_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, P(c_double), P(c_ll)]),
     "ssg_dbscan_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_int, c_void_p, P(c_int)]),
+    "ssg_rerank_finish_rows": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_int, c_void_p,
+                                       c_void_p]),
+    "ssg_cluster_buffers": (c_int, [c_void_p, P(c_void_p), P(c_void_p), P(c_void_p), P(c_void_p), P(c_void_p),
+                                    P(c_void_p)]),
+    "ssg_eps_shard_begin": (c_int, [c_void_p, c_void_p]),
+    "ssg_eps_shard_hist": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ssg_eps_shard_pick": (c_int, [c_void_p, c_int, c_double, c_void_p]),
+    "ssg_eps_shard_gather": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, P(c_ll), c_void_p]),
+    "ssg_eps_shard_finish": (c_int, [c_void_p, c_int, c_int, P(c_double), P(c_ll), c_void_p]),
+    "ssg_dbscan_shard_count": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p]),
+    "ssg_dbscan_shard_fill": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, P(c_ll), c_void_p]),
+    "ssg_dbscan_shard_label": (c_int, [c_void_p, c_int, c_int, c_void_p, P(c_int), c_void_p]),
     "ssg_embed_num_layers": (c_int, []),
     "ssg_embed_layer_info": (c_int, [c_int, P(c_int), P(c_int), P(c_int), P(c_int), ctypes.c_char_p, ctypes.c_char_p,
                                      c_size_t]),

@@ -50,6 +50,61 @@ class ClusterPlan(object):
         _lib.check(_lib.load().ssg_dbscan_core_mask(self._h, out.ctypes.data, n))
         return out.astype(bool)
 
+    # ---- row-sharded primitives (one process per GPU; the collectives between them are run by ssg_b200.dist)
+    def buffers(self, n, nbr_len=0):
+        """Zero-copy torch views of the plan's exchange buffers: hist int64[4096], state int64[8], partial
+        float64[n], list float64[2^20], cnt int32[n], nbr int32[nbr_len]."""
+        import torch
+        ptrs = [ctypes.c_void_p() for _ in range(6)]
+        _lib.check(_lib.load().ssg_cluster_buffers(self._h, *[ctypes.byref(p) for p in ptrs]))
+        specs = [((_lib.EPS_BINS,), "<i8"), ((8,), "<i8"), ((n,), "<f8"), ((_lib.EPS_LIST_CAP,), "<f8"),
+                 ((n,), "<i4"), ((max(int(nbr_len), 1),), "<i4")]
+        names = ("hist", "state", "partial", "list", "cnt", "nbr")
+        return {k: torch.as_tensor(_DevArray(p.value, shape, ts), device=self.device)
+                for k, p, (shape, ts) in zip(names, ptrs, specs)}
+
+    def eps_shard_begin(self):
+        _lib.check(_lib.load().ssg_eps_shard_begin(self._h, _lib.stream_ptr()))
+
+    def eps_shard_hist(self, rows, n, world, rank, npass):
+        _lib.check(_lib.load().ssg_eps_shard_hist(self._h, _ptr(rows), _rows_dtype(rows, n), n, world, rank,
+                                                  int(npass), _lib.stream_ptr()))
+
+    def eps_shard_pick(self, npass, rho):
+        _lib.check(_lib.load().ssg_eps_shard_pick(self._h, int(npass), float(rho), _lib.stream_ptr()))
+
+    def eps_shard_gather(self, rows, n, world, rank, exact):
+        cnt = ctypes.c_longlong()
+        _lib.check(_lib.load().ssg_eps_shard_gather(self._h, _ptr(rows), _rows_dtype(rows, n), n, world, rank,
+                                                    int(bool(exact)), None if exact else ctypes.byref(cnt),
+                                                    _lib.stream_ptr()))
+        return None if exact else cnt.value
+
+    def eps_shard_finish(self, n, exact):
+        eps, top = ctypes.c_double(), ctypes.c_longlong()
+        _lib.check(_lib.load().ssg_eps_shard_finish(self._h, n, int(bool(exact)), ctypes.byref(eps), ctypes.byref(top),
+                                                    _lib.stream_ptr()))
+        return eps.value, top.value
+
+    def dbscan_shard_count(self, rows, n, row0, eps):
+        _lib.check(_lib.load().ssg_dbscan_shard_count(self._h, _ptr(rows), _rows_dtype(rows, n), n, int(row0),
+                                                      rows.shape[0], float(eps), _lib.stream_ptr()))
+
+    def dbscan_shard_fill(self, rows, n, row0, eps):
+        total = ctypes.c_longlong()
+        _lib.check(_lib.load().ssg_dbscan_shard_fill(self._h, _ptr(rows), _rows_dtype(rows, n), n, int(row0),
+                                                     rows.shape[0], float(eps), ctypes.byref(total),
+                                                     _lib.stream_ptr()))
+        return total.value
+
+    def dbscan_shard_label(self, n, min_samples=4):
+        import torch
+        labels = torch.empty((n,), dtype=torch.int64, device=self.device)
+        ncl = ctypes.c_int()
+        _lib.check(_lib.load().ssg_dbscan_shard_label(self._h, n, int(min_samples), labels.data_ptr(),
+                                                      ctypes.byref(ncl), _lib.stream_ptr()))
+        return labels, ncl.value
+
     # ---- host matrices (numpy)
     def eps_host(self, dist, rho):
         dist, dt = _host_matrix(dist)
@@ -66,6 +121,29 @@ class ClusterPlan(object):
         _lib.check(_lib.load().ssg_dbscan_host(self._h, dist.ctypes.data, dt, n, float(eps), int(min_samples),
                                                labels.ctypes.data, ctypes.byref(ncl)))
         return labels, ncl.value
+
+
+class _DevArray(object):
+    """Minimal __cuda_array_interface__ holder for a raw device pointer owned by a plan."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def _ptr(rows):
+    return rows.data_ptr() if rows.shape[0] else None
+
+
+def _rows_dtype(rows, n):
+    """A [rows, n] contiguous CUDA block of a float64 / float32 matrix -> SSG_F64 / SSG_F32."""
+    import torch
+    assert rows.is_cuda and rows.dim() == 2 and rows.shape[1] == n and rows.is_contiguous()
+    if rows.dtype == torch.float64:
+        return _lib.F64
+    if rows.dtype == torch.float32:
+        return _lib.F32
+    raise ValueError("distance rows must be float64 or float32")
 
 
 def _dtype_code(t):

@@ -10,6 +10,13 @@ Sharding of ONE cycle over `world` ranks:
                of their banks in parallel;
   4. labels  : broadcast from the owners (N int64 per bank).
 
+`shard_finish=True` (opt-in, SSG_SHARD_FINISH=1) replaces phase B and step 4 by a row-sharded finish: every rank runs the
+sparse stages of a bank (cheap, they need all rows' tables anyway) and then only ITS rows of final_dist
+(ssg_rerank_finish_rows); eps is a distributed radix select (histogram all-reduce, list all-gather), DBSCAN a local row
+scan with an all-gather of the neighbour counts and a sum all-reduce that completes the neighbour CSR, after which every
+rank labels all rows identically.  Nothing N x N lives on one GPU, and the N^2-sized stages scale with the ranks
+instead of with min(banks, world).
+
 All collectives go through a small `Comm` wrapper, and all compute through a `backend` object, so that the sharding
 logic itself is exercised on CPU with the gloo backend (tests/test_dist_gloo.py) against a fake backend.
 """
@@ -62,6 +69,33 @@ class Comm(object):
         lo, hi = shard_bounds(n_total, self.world, self.rank)
         full.copy_(self.all_gather_rows(full[lo:hi], n_total, 0))
         return full
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def all_gather_ints(self, value, device):
+        """One Python int per rank -> list of the ints of all ranks (rank order)."""
+        import torch
+        if self.world == 1:
+            return [int(value)]
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        out = torch.empty((self.world,), dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return [int(v) for v in out.tolist()]
+
+    def all_gather_var(self, local, counts):
+        """local: 1-D tensor whose first counts[rank] entries are valid -> concatenation over the ranks (rank order)."""
+        import torch
+        if self.world == 1:
+            return local[: counts[0]]
+        m = max(max(counts), 1)
+        pad = torch.zeros((m,), dtype=local.dtype, device=local.device)
+        pad[: counts[self.rank]] = local[: counts[self.rank]]
+        out = torch.empty((self.world * m,), dtype=local.dtype, device=local.device)
+        self.dist.all_gather_into_tensor(out, pad, group=self.group)
+        return torch.cat([out[r * m: r * m + counts[r]] for r in range(self.world)], 0)
 
     def broadcast(self, t, src):
         if self.world > 1:
@@ -127,6 +161,26 @@ class CudaBackend(object):
         return _with_capacity_retry(n, self.dev.index, lambda p: p.dbscan(final, eps, min_samples)[0])
 
 
+    # ---- row-sharded finish (shard_finish=True)
+    def finish_rows(self, plan, tgt, k1, k2, lambda_value, row0, rows, final_rows):
+        L = self._lib
+        L.check(L.load().ssg_rerank_finish_rows(plan._h, tgt.data_ptr(), tgt.shape[0], tgt.shape[1], int(k1), int(k2),
+                                                float(lambda_value), int(row0), int(rows),
+                                                final_rows.data_ptr() if rows else None, L.stream_ptr()))
+
+    def new_final_rows(self, rows, n):
+        import torch
+        return torch.empty((rows, n), dtype=torch.float64, device=self.dev)
+
+    def cluster_plan(self, n, max_neighbors=0):
+        from .cluster import get_plan
+        return get_plan(n, self.dev.index, max_neighbors)
+
+    def with_capacity_retry(self, n, fn):
+        from .cluster import _with_capacity_retry
+        return _with_capacity_retry(n, self.dev.index, fn)
+
+
 class _DevArray(object):
     """Minimal __cuda_array_interface__ holder for a raw device pointer owned by a plan."""
 
@@ -135,8 +189,59 @@ class _DevArray(object):
                                          "version": 3, "strides": None}
 
 
+def sharded_eps(cplan, comm, rows, n, rho):
+    """selftraining.py:289-293 over a row-sharded symmetric matrix (`rows` = this rank's [hi-lo, n] block): the radix
+    select of ssg_eps_estimate with its histograms all-reduced and its candidate list all-gathered (call sequence:
+    include/ssg_b200.h, "Row-sharded variants").  Returns (eps, top_num), the same on every rank."""
+    from ._lib import EPS_LIST_CAP
+    w, r = comm.world, comm.rank
+    buf = cplan.buffers(n)
+    cplan.eps_shard_begin()
+    for npass in (0, 1):
+        cplan.eps_shard_hist(rows, n, w, r, npass)
+        comm.all_reduce_sum(buf["hist"])
+        cplan.eps_shard_pick(npass, rho)
+    count = cplan.eps_shard_gather(rows, n, w, r, exact=False)
+    counts = comm.all_gather_ints(count, rows.device)
+    if min(counts) >= 0 and sum(counts) <= EPS_LIST_CAP:
+        comm.all_gather_rows_inplace(buf["partial"], n)
+        merged = comm.all_gather_var(buf["list"], counts)
+        buf["list"][: merged.shape[0]] = merged
+        buf["state"][5] = sum(counts)
+        return cplan.eps_shard_finish(n, exact=False)
+    # massive ties: more than 2^20 entries share the threshold's leading 24 key bits -> finish the radix select
+    for npass in (2, 3, 4, 5):
+        cplan.eps_shard_hist(rows, n, w, r, npass)
+        comm.all_reduce_sum(buf["hist"])
+        cplan.eps_shard_pick(npass, rho)
+    cplan.eps_shard_gather(rows, n, w, r, exact=True)
+    comm.all_gather_rows_inplace(buf["partial"], n)
+    return cplan.eps_shard_finish(n, exact=True)
+
+
+def sharded_dbscan(backend, comm, rows, n, row0, eps, min_samples=4):
+    """sklearn DBSCAN(precomputed) over a row-sharded matrix: local region queries, all-gather of the neighbour
+    counts, sum all-reduce completing the neighbour CSR, then every rank labels all n rows (identical results).
+    A neighbour list that outgrows the plan raises on every rank alike (the counts are global), so the retry with a
+    larger plan stays collective."""
+    def attempt(cplan):
+        cplan.dbscan_shard_count(rows, n, row0, eps)
+        comm.all_gather_rows_inplace(cplan.buffers(n)["cnt"], n)
+        total = cplan.dbscan_shard_fill(rows, n, row0, eps)
+        if total > 0:
+            comm.all_reduce_sum(cplan.buffers(n, total)["nbr"])
+        return cplan.dbscan_shard_label(n, min_samples)[0]
+    return backend.with_capacity_retry(n, attempt)
+
+
+def _shard_finish_default():
+    import os
+    return os.environ.get("SSG_SHARD_FINISH", "0") not in ("", "0")
+
+
 def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_split=2, lambda_value=0.1, rho=1.6e-3,
-                               eps_list=None, min_samples=4, k1=20, k2=6, backend=None, comm=None, features=None):
+                               eps_list=None, min_samples=4, k1=20, k2=6, backend=None, comm=None, features=None,
+                               shard_finish=None):
     """Run one pseudo-label cycle sharded over the ranks of `comm`.
 
     tgt_shard / src_shard: this rank's image rows [shard_bounds(n, world, rank)) (host or device tensors).
@@ -157,6 +262,23 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
     src = comm.all_gather_rows(sloc, n_src, dim=1)
     lo, hi = shard_bounds(n_tgt, comm.world, comm.rank)
     plan = backend.plan(n_tgt, n_src, tgt.shape[2])
+    if _shard_finish_default() if shard_finish is None else shard_finish:
+        # row-sharded finish: bank after bank, every rank works on its rows [lo, hi) of every stage
+        final_rows = backend.new_final_rows(hi - lo, n_tgt)
+        labels, eps_vals = [], []
+        for b in range(banks):
+            tb, sb = tgt[b].contiguous(), src[b].contiguous()
+            backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
+            for tab in backend.tables(plan, n_tgt):
+                comm.all_gather_rows_inplace(tab, n_tgt)
+            backend.finish_rows(plan, tb, k1, k2, lambda_value, lo, hi - lo, final_rows)
+            cplan = backend.cluster_plan(n_tgt)
+            eps = sharded_eps(cplan, comm, final_rows, n_tgt, rho)[0] if eps_list is None else float(eps_list[b])
+            lab = sharded_dbscan(backend, comm, final_rows, n_tgt, lo, eps, min_samples)
+            labels.append(lab.cpu().numpy())
+            eps_vals.append(eps)
+        keep = ~(np.stack(labels, 0) == -1).any(0)
+        return labels, eps_vals, keep
     # phase A — all ranks, bank after bank: row-block distance stage, then all-gather of the per-row tables; the owner
     # of a bank keeps a copy of its tables (the plan holds one set).  Phase B — the owners finish their banks in
     # parallel (k-reciprocal encoding ... final distance, eps, DBSCAN); nobody waits for an owner between banks.

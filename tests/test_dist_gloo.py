@@ -85,6 +85,33 @@ class OracleBackend(object):
         import torch
         return torch.empty((n, n), dtype=torch.float64)
 
+    # ---- row-sharded finish (shard_finish=True): rows of final_dist + the numpy stand-in of the sharded primitives
+    def finish_rows(self, plan, tgt, k1, k2, lambda_value, row0, rows, final_rows):
+        import torch
+        full = torch.empty((tgt.shape[0], tgt.shape[0]), dtype=torch.float64)
+        self.finish(plan, tgt, k1, k2, lambda_value, full)
+        final_rows.copy_(full[row0:row0 + rows])
+
+    def new_final_rows(self, rows, n):
+        import torch
+        return torch.empty((rows, n), dtype=torch.float64)
+
+    def cluster_plan(self, n, max_neighbors=0):
+        from shard_fake import FakeClusterPlan
+        if getattr(self, "_cplan", None) is None or self._cplan.max_neighbors < max_neighbors:
+            self._cplan = FakeClusterPlan(n, max_neighbors or self.nbr_cap)
+        return self._cplan
+
+    nbr_cap = 0          # tests set a tiny capacity to drive the collective capacity retry
+
+    def with_capacity_retry(self, n, fn):
+        cap = 0
+        while True:
+            try:
+                return fn(self.cluster_plan(n, cap))
+            except OverflowError:
+                cap = max(self._cplan.max_neighbors * 8, 64)
+
     def eps(self, final, rho):
         return float(O.eps_estimate(final.numpy(), rho))
 
@@ -104,18 +131,22 @@ def _images():
     return t.astype(np.float32), s.astype(np.float32)
 
 
-def _worker(rank, world, init_file, out_dir):
+def _worker(rank, world, init_file, out_dir, shard_finish=False, nbr_cap=0):
+    import sys
     import torch
     import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))      # shard_fake (spawned interpreter)
     from ssg_b200 import dist as sd
     dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
     try:
         t, s = _images()
         tl, th = sd.shard_bounds(N_T, world, rank)
         sl, sh = sd.shard_bounds(N_S, world, rank)
+        be = OracleBackend(BANKS, D_IMG, D)
+        be.nbr_cap = nbr_cap
         labels, eps, keep = sd.sharded_pseudo_label_cycle(
             None, torch.from_numpy(t[tl:th]), torch.from_numpy(s[sl:sh]), N_T, N_S, num_split=BANKS - 1,
-            lambda_value=LAM, rho=RHO, backend=OracleBackend(BANKS, D_IMG, D), comm=sd.Comm())
+            lambda_value=LAM, rho=RHO, backend=be, comm=sd.Comm(), shard_finish=shard_finish)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), labels=np.stack(labels), eps=np.array(eps), keep=keep)
     finally:
         dist.destroy_process_group()
@@ -145,3 +176,82 @@ def test_sharded_cycle_matches_single_process(world):
         np.testing.assert_allclose(o["eps"], want_eps, rtol=0, atol=1e-15)
         assert np.array_equal(o["keep"], O.keep_mask(want_labels))
     assert max(l.max() for l in want_labels) >= 1          # the case is not degenerate
+
+
+def _single_process_reference():
+    import torch
+    t, s = _images()
+    be = OracleBackend(BANKS, D_IMG, D)
+    tf = be.embed(None, torch.from_numpy(t), BANKS - 1).numpy()
+    sf = be.embed(None, torch.from_numpy(s), BANKS - 1).numpy()
+    return [O.re_ranking(sf[b], tf[b], lambda_value=LAM, mode="f32")[1] for b in range(BANKS)]
+
+
+@pytest.mark.parametrize("world,nbr_cap", [(2, 0), (3, 0), (4, 0), (5, 0), (3, 16)])
+def test_row_sharded_finish_matches_single_process(world, nbr_cap):
+    """shard_finish=True: every rank holds only its rows of final_dist; eps by the distributed radix select
+    (histogram all-reduce, list all-gather), DBSCAN through the gathered counts and the all-reduced neighbour CSR.
+    nbr_cap=16 starts from a neighbour list that is too small, so all ranks go through the capacity retry together."""
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as tmp:
+        init_file = os.path.join(tmp, "init")
+        mp.spawn(_worker, args=(world, init_file, tmp, True, nbr_cap), nprocs=world, join=True)
+        outs = [np.load(os.path.join(tmp, "rank%d.npz" % r)) for r in range(world)]
+    finals = _single_process_reference()
+    want_eps = [O.eps_estimate(f, RHO) for f in finals]
+    for o in outs:
+        # eps: same radix-selected order statistic, float64 sums taken in another order
+        np.testing.assert_allclose(o["eps"], want_eps, rtol=1e-13, atol=0)
+        assert np.array_equal(o["eps"], outs[0]["eps"])                      # bit-identical across the ranks
+        want_labels = [O.dbscan_dfs(f, e, 4) for f, e in zip(finals, o["eps"])]
+        assert np.array_equal(o["labels"], np.stack(want_labels))
+        assert np.array_equal(o["keep"], O.keep_mask(want_labels))
+    assert max(l.max() for l in want_labels) >= 1
+
+
+def test_row_sharded_eps_fake_matches_oracle_incl_massive_ties():
+    """The numpy stand-in itself (single rank and 3 simulated ranks without collectives): 3-pass path, the 6-pass
+    fallback, zeros dropped, empty slice -> NaN."""
+    import sys
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from shard_fake import FakeClusterPlan, shard_lo
+    rng = np.random.RandomState(3)
+    n = 57
+    a = rng.rand(n, n)
+    a[a < 0.1] = 0.0                          # exact zeros are dropped (np.nonzero, selftraining.py:290)
+    d = np.round((a + a.T) / 2, 2)            # symmetric, heavy ties
+    for rho in (0.05, 0.5, 1e-6):
+        want = O.eps_estimate(d, rho)
+        for world in (1, 3):
+            for exact in (False, True):
+                plans = [FakeClusterPlan(n) for _ in range(world)]
+                blocks = [torch.from_numpy(d[shard_lo(n, world, r):shard_lo(n, world, r + 1)].copy())
+                          for r in range(world)]
+                for p in plans:
+                    p.eps_shard_begin()
+                for npass in range(6 if exact else 2):
+                    for r, p in enumerate(plans):
+                        p.eps_shard_hist(blocks[r], n, world, r, npass)
+                    tot = sum(p.hist for p in plans)
+                    for p in plans:
+                        p.hist.copy_(tot)
+                        p.eps_shard_pick(npass, rho)
+                lists = []
+                for r, p in enumerate(plans):
+                    c = p.eps_shard_gather(blocks[r], n, world, r, exact)
+                    lists.append(p.list[:c].clone() if not exact else None)
+                part = sum(p.partial for p in plans)
+                got = []
+                for p in plans:
+                    p.partial.copy_(part)     # rows are disjoint: the sum is the all-gather
+                    if not exact:
+                        merged = torch.cat(lists)
+                        p.list[:len(merged)] = merged
+                        p.state[5] = len(merged)
+                    got.append(p.eps_shard_finish(n, exact)[0])
+                assert all(g == got[0] or (np.isnan(g) and np.isnan(got[0])) for g in got)
+                if np.isnan(want):
+                    assert np.isnan(got[0])
+                else:
+                    np.testing.assert_allclose(got[0], want, rtol=1e-13)
