@@ -179,7 +179,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16/f64 (numpy/scipy/sklearn)", "data": "synthetic",
-        "config": {"workload": "pseudo-label cycle (re-rank+eps+DBSCAN), bounded sample: " + sample},
+        "config": {"workload": "configs[1]: N=Ns=%d synthetic, pseudo-label cycle (re-rank k1=20 k2=6 lambda=0.1 -> eps "
+                               "rho=1.6e-3 -> DBSCAN min_samples=4); each step is a bounded sample of it: %s"
+                               % (args.n, sample),
+                   "value_is": "Mpairs/s of re-rank+eps+DBSCAN on the host cores; embedding (torch CPU) under 'embed'"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
                          "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -376,10 +379,14 @@ def main():
                 batches = 2.0 * n * (1.0 / world if sharded else 1.0) / tj["batch_images"]
                 traffic = {"bytes_per_step": tj["dram_bytes_per_batch"] * batches, "source": "profiles/r01_final_conv_traffic.json",
                            "algorithmic_note": "see DESIGN.md 3.1: the convolution path is HBM bound in its 1x1 layers"}
-            roof = {"kernel": "gemm_kernel<StagedEpi> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)"
-                              % sum(prof[c][1] for c in conv_names if c in prof),
+            conv_launches = sum(prof[c][1] for c in conv_names if c in prof)
+            roof = {"kernel": "gemm_kernel<StagedEpi> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)" % conv_launches,
                     "bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["tensor"], "traffic": traffic, "ms_per_step": conv_ms / k,
+                    "frac": ach / peaks["tensor"],
+                    # DRAM bytes per launch, averaged over the template's launches of one step (ncu capture of one batch)
+                    "traffic": (traffic["bytes_per_step"] * k / conv_launches) if traffic and conv_launches else None,
+                    "traffic_detail": traffic, "flops_per_launch": flops / max(conv_launches, 1),
+                    "ms_per_launch": conv_ms / max(conv_launches, 1), "ms_per_step": conv_ms / k,
                     "peak_source": peaks["source"],
                     "note": "algorithmic flops = 2 x 2 669 150 208 conv MACs per image-pass (SURVEY.md 8d), summed over "
                             "all conv launches of the step"}
