@@ -177,6 +177,55 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
     return SSG_OK;
 }
 
+// One bottleneck block (conv1 1x1 -> conv2 3x3 [stride on it] -> conv3 1x1 + shortcut, ReLU) over NB image-passes.
+// x: input [NB,H,W,C], y: the other ping-pong buffer; on return x holds the output and H, W, C, li are advanced.
+// out (chunked mode, last block of a chunk): the output goes there instead of y, and x / y are left alone.
+static int run_block(ssg_embed_plan* p, int L, int b, int NB, int fuse_ds, void*& x, void*& y, int& H, int& W, int& C,
+                     int& li, void* out, cudaStream_t st) {
+    const int mid = 64 << L, outc = mid * 4;
+    const int stride = (b == 0 && L > 0) ? 2 : 1;
+    const int OH = H / stride, OW = W / stride;
+    const int i1 = li, i2 = li + 1, i3 = li + 2, id = li + 3;
+    li += (b == 0) ? 4 : 3;
+    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
+    if (stride == 2 && s2_strided_tma()) {
+        { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+    } else if (stride == 2) {
+        { SSG_PROF("parity_split", st); SSG_TRY(parity_split(p->t1, NB, H, W, mid, 4, p->planes, st)); }
+        { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+    } else {
+        { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, H, W, mid, 1, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+    }
+    if (b == 0 && fuse_ds) {
+        if (out) return ssg_set_error(SSG_ERR_INVALID, "embed: a chunk cannot end on a downsample block");
+        { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv_fused_ds(p->t2, x, NB, OH, OW, mid, C, stride, p->wf[L], p->bf[L], outc, y, st)); }
+        void* t = x; x = y; y = t;
+        H = OH; W = OW; C = outc;
+        return SSG_OK;
+    }
+    const void* res = x;
+    if (b == 0) {
+        if (stride == 2 && s2_strided_tma()) {
+            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1_s2(x, NB, OH, OW, C, p->w[id], p->b[id], outc, 0, p->ds, st)); }
+        } else if (stride == 2) {
+            { SSG_PROF("parity_split", st); SSG_TRY(parity_split(x, NB, H, W, C, 1, p->xs, st)); }
+            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->xs, NB * OH * OW, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
+        } else {
+            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
+        }
+        res = p->ds;
+    }
+    if (out) {
+        { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->t2, NB * OH * OW, mid, p->w[i3], p->b[i3], outc, res, 1, out, st)); }
+        H = OH; W = OW; C = outc;
+        return SSG_OK;
+    }
+    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->t2, NB * OH * OW, mid, p->w[i3], p->b[i3], outc, res, 1, y, st)); }
+    void* t = x; x = y; y = t;
+    H = OH; W = OW; C = outc;
+    return SSG_OK;
+}
+
 // One forward over a batch; the images come either as fp32 NCHW (d_images) or as raw uint8 HWC pixels (d_u8 with the
 // loader's per-channel mean / std).
 static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const uint8_t* d_u8, const float* mean,
@@ -224,6 +273,49 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
     bool pooled = false;       // the max-pool already ran inside the stem kernel
     if (d_u8 && !p->stem_windows)
         return ssg_set_error(SSG_ERR_UNSUPPORTED, "embed_forward_u8 needs the window stem (SSG_STEM_WINDOWS != 0)");
+    // SSG_L2_CHUNK=<image-passes> (default 0 = off): run layers 1-2 -- whose 1x1 convolutions are HBM bound, DESIGN.md
+    // 3.1 -- over chunks of that many image-passes that re-use the head of the ping-pong buffers, so that a chunk's
+    // activations (2.5 MB per image-pass in layer 1: 32 passes = 80 MB) stay in the 126 MB L2 from the kernel that
+    // writes them to the kernel that reads them and are overwritten there by the next chunk instead of being written
+    // back.  The stem (whole images per CTA: it wants >= 148 of them) and layers 3-4 (tensor bound, they want the big
+    // grids) run over the whole batch as before; the pooled stem map and the layer-2 outputs of all passes live in
+    // full-batch buffers that are idle in this configuration (the unpooled-stem and the im2col buffer).  Original and
+    // mirrored images are independent passes until the pooled tail, so a chunk is any contiguous range of passes.
+    // Same kernels on the same per-image tiles: bit-identical features.
+    static int l2_chunk = -1;
+    if (l2_chunk < 0) { const char* e = getenv("SSG_L2_CHUNK"); l2_chunk = e ? atoi(e) : 0; }
+    if (l2_chunk > 0 && NB > l2_chunk && p->stem_windows == 2 && stem_pool_fused() && fuse_ds) {
+        {
+            SSG_PROF("stem_prep", st);
+            if (d_u8) SSG_TRY(stem_prep_u8(d_u8, n, flip, mean, stdv, p->stemP, st));
+            else SSG_TRY(stem_prep(d_images, n, flip, p->stemP, st));
+        }
+        char* pooled_all = (char*)p->stem;                    // [NB][64][32][64] bf16
+        char* l2_all = (char*)p->col;                         // [NB][32][16][512] bf16
+        const size_t E0 = (size_t)64 * 32 * 64 * 2, E2 = (size_t)32 * 16 * 512 * 2;   // bytes per image-pass
+        { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, /* tensor-map placeholder, never written */ p->x, st, pooled_all)); }
+        const int blocks[4] = {3, 4, 6, 3};
+        for (int q0 = 0; q0 < NB; q0 += l2_chunk) {
+            const int NBc = NB - q0 < l2_chunk ? NB - q0 : l2_chunk;
+            int lc = 1, H = 64, W = 32, C = 64;
+            void *x = pooled_all + (size_t)q0 * E0, *y = p->y;
+            for (int L = 0; L < 2; ++L)
+                for (int b = 0; b < blocks[L]; ++b) {
+                    const bool last = L == 1 && b == blocks[1] - 1;
+                    SSG_TRY(run_block(p, L, b, NBc, fuse_ds, x, y, H, W, C, lc, last ? l2_all + (size_t)q0 * E2 : nullptr, st));
+                    if (L == 0 && b == 0) y = p->x;           // the chunk's input slice is read-only: ping-pong on x / y
+                }
+        }
+        int lc = 24, H = 32, W = 16, C = 512;                  // layer 3 starts at layer index 1 + 10 + 13
+        void *x = l2_all, *y = p->y;
+        for (int L = 2; L < 4; ++L)
+            for (int b = 0; b < blocks[L]; ++b) {
+                SSG_TRY(run_block(p, L, b, NB, fuse_ds, x, y, H, W, C, lc, nullptr, st));
+                if (L == 2 && b == 0) y = p->x;               // keep the im2col buffer out of the ping-pong
+            }
+        { SSG_PROF("pooled_tail", st); SSG_TRY(pooled_tail(x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, st)); }
+        return SSG_OK;
+    }
     if (p->stem_windows) {
         {
             SSG_PROF("stem_prep", st);
@@ -244,45 +336,9 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
     int H = 64, W = 32, C = 64;
     void *x = p->x, *y = p->y;
     const int blocks[4] = {3, 4, 6, 3};
-    for (int L = 0; L < 4; ++L) {
-        const int mid = 64 << L, outc = mid * 4;
-        for (int b = 0; b < blocks[L]; ++b) {
-            const int stride = (b == 0 && L > 0) ? 2 : 1;
-            const int OH = H / stride, OW = W / stride;
-            const int i1 = li, i2 = li + 1, i3 = li + 2, id = li + 3;
-            li += (b == 0) ? 4 : 3;
-            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
-            if (stride == 2 && s2_strided_tma()) {
-                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
-            } else if (stride == 2) {
-                { SSG_PROF("parity_split", st); SSG_TRY(parity_split(p->t1, NB, H, W, mid, 4, p->planes, st)); }
-                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
-            } else {
-                { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, H, W, mid, 1, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
-            }
-            if (b == 0 && fuse_ds) {
-                { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv_fused_ds(p->t2, x, NB, OH, OW, mid, C, stride, p->wf[L], p->bf[L], outc, y, st)); }
-                void* t = x; x = y; y = t;
-                H = OH; W = OW; C = outc;
-                continue;
-            }
-            const void* res = x;
-            if (b == 0) {
-                if (stride == 2 && s2_strided_tma()) {
-                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1_s2(x, NB, OH, OW, C, p->w[id], p->b[id], outc, 0, p->ds, st)); }
-                } else if (stride == 2) {
-                    { SSG_PROF("parity_split", st); SSG_TRY(parity_split(x, NB, H, W, C, 1, p->xs, st)); }
-                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->xs, NB * OH * OW, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
-                } else {
-                    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[id], p->b[id], outc, nullptr, 0, p->ds, st)); }
-                }
-                res = p->ds;
-            }
-            { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(p->t2, NB * OH * OW, mid, p->w[i3], p->b[i3], outc, res, 1, y, st)); }
-            void* t = x; x = y; y = t;
-            H = OH; W = OW; C = outc;
-        }
-    }
+    for (int L = 0; L < 4; ++L)
+        for (int b = 0; b < blocks[L]; ++b)
+            SSG_TRY(run_block(p, L, b, NB, fuse_ds, x, y, H, W, C, li, nullptr, st));
     (void)sp;
     { SSG_PROF("pooled_tail", st); SSG_TRY(pooled_tail(x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, st)); }
     return SSG_OK;

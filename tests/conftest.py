@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "gpu_next: needs a CUDA device; opt-in variants that have not had a GPU run yet "
+                                       "(not part of `-m gpu`; run with `-m gpu_next` before switching a default)")
 
 
 def _has_gpu():
@@ -28,7 +30,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
-        if "gpu" in item.keywords:
+        if "gpu" in item.keywords or "gpu_next" in item.keywords:
             item.add_marker(skip)
 
 
