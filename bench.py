@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--shard-finish", action="store_true",
                     help="N>1 sharded mode: row-sharded finish (every rank holds only its rows of final_dist; "
                          "distributed eps and DBSCAN) instead of the bank-parallel finish")
+    ap.add_argument("--sparse-finish", action="store_true",
+                    help="single-GPU / --replicas: never materialise final_dist (CSR over the touched pairs, certified "
+                         "eps + DBSCAN on it; DESIGN.md 3.6) instead of the dense N x N float64 matrix")
     ap.add_argument("--quick", action="store_true",
                     help="profiling runs (ncu): exactly --warmup warm-up steps, no e2e leg, no CPU baseline")
     return ap.parse_args()
@@ -289,7 +292,8 @@ def main():
                                                    comm=comm, features=(tf, sf),
                                                    shard_finish=True if args.shard_finish else None)
         else:
-            out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local)
+            out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local,
+                                              sparse=True if args.sparse_finish else None)
         if record:
             ev[2].record()
             torch.cuda.synchronize()
@@ -449,7 +453,8 @@ def main():
                                        % (world, "row-sharded" if (args.shard_finish or sdist._shard_finish_default())
                                           else "bank-parallel")) if sharded else
                                       "%d independent replicas (one target set per GPU)" % world,
-                       "dist_mode": args.dist_mode},
+                       "dist_mode": args.dist_mode,
+                       "final_dist": "sparse (CSR over the touched pairs)" if args.sparse_finish else "dense float64 N x N"},
             "embed": embed,
             "rerank": {"value": value, "unit": UNIT, "ms_per_step": ms_rerank / k},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / k, "rerank_ms_per_step": ms_e2e_rerank / k,

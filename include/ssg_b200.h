@@ -194,6 +194,31 @@ int ssg_dbscan_shard_label(ssg_cluster_plan* plan, int n, int min_samples, int64
                            void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sparse form of final_dist, for callers that only want eps and the labels (selftraining.py:289-306 is all the driver
+ * uses the matrix for).  A column m that shares no k-reciprocal neighbour with row i has Jaccard distance 1, hence
+ * final_dist[i,m] = fl32(1-lambda) + fl32(v_i+v_m)*lambda >= fl32(1-lambda) =: threshold (rerank.py:115-122, v >= 0).
+ * Only the other ("touched", ~1 %) entries can be smaller:
+ *   ssg_rerank_finish_sparse : ssg_rerank_finish, but the result is a CSR over the touched columns (ascending inside a
+ *                              row, values bit-identical to the dense matrix) kept in the plan; 0 <= lambda < 1.
+ *                              Synchronises the stream (row lengths are data dependent; buffers grow on demand).
+ *   ssg_rerank_sparse_view   : device pointers of that CSR (rowptr int32[n+1], col int32[nnz], val double[nnz]) and the
+ *                              threshold below which an entry is guaranteed to be in it.
+ *   ssg_eps_sparse           : ssg_eps_estimate on the CSR.  *h_certified = 1 iff the rho-slice lies entirely below
+ *                              the threshold (then eps is the value the dense matrix gives, up to the order of the
+ *                              float64 additions); 0: the caller must materialise the matrix (ssg_rerank_finish).
+ *   ssg_dbscan_sparse        : ssg_dbscan on the CSR; the caller guarantees eps < threshold (no entry outside the CSR
+ *                              is a neighbour then).  Labels are identical to the dense ones.
+ * ------------------------------------------------------------------------------------------------ */
+int ssg_rerank_finish_sparse(ssg_rerank_plan* plan, const float* d_tgt, int n, int d, int k1, int k2,
+                             double lambda_value, long long* h_nnz, void* stream);
+int ssg_rerank_sparse_view(ssg_rerank_plan* plan, int** d_rowptr, int** d_col, double** d_val, long long* nnz,
+                           double* threshold);
+int ssg_eps_sparse(ssg_cluster_plan* plan, int n, const int* d_rowptr, const int* d_col, const double* d_val,
+                   double threshold, double rho, double* h_eps, long long* h_top_num, int* h_certified, void* stream);
+int ssg_dbscan_sparse(ssg_cluster_plan* plan, int n, const int* d_rowptr, const int* d_col, const double* d_val,
+                      double eps, int min_samples, int64_t* d_labels, int* h_n_clusters, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Embedding: reid/evaluators.py:18-60 extract_features + reid/feature_extraction/cnn.py:10-23 +
  * reid/models/resnet.py:86-134 (ResNet-50 trunk, num_classes=0, cluster=False) for 256x128 inputs.
  *   forward: images fp32 NCHW [n,3,256,128] (already mean/std normalised, as the reference's loaders

@@ -70,6 +70,8 @@ struct ssg_rerank_plan {
     float *io_src, *io_tgt; size_t io_src_bytes, io_tgt_bytes;
     double* io_final; size_t io_final_bytes;
     float* io_euclid; size_t io_euclid_bytes;
+    // sparse form of final_dist (ssg_rerank_finish_sparse): CSR over the touched columns, grown on demand
+    int *sp_cnt, *sp_rowptr, *sp_col; double* sp_val; size_t sp_cap; long long sp_nnz; double sp_threshold;
     int last_n;
 };
 
@@ -131,14 +133,15 @@ extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
                     p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid, p->split_ta,
                     p->split_tb, p->split_sb, p->norm_t, p->norm_s, p->norm_max, p->cand_idx, p->cand_val,
                     p->cand_exact, p->flag_src, p->flag_tgt, p->fb_rows, p->fb_f32, p->fb_i32, p->mean_partial,
-                    p->mean};
+                    p->mean, p->sp_cnt, p->sp_rowptr, p->sp_col, p->sp_val};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return SSG_OK;
 }
 
 extern "C" size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* p) {
-    return p ? p->bytes + p->io_src_bytes + p->io_tgt_bytes + p->io_final_bytes + p->io_euclid_bytes : 0;
+    return p ? p->bytes + p->io_src_bytes + p->io_tgt_bytes + p->io_final_bytes + p->io_euclid_bytes +
+                   p->sp_cap * (sizeof(int) + sizeof(double)) : 0;
 }
 
 static int check_run_args(ssg_rerank_plan* p, const void* src, int ns, const void* tgt, int n, int d,
@@ -379,6 +382,8 @@ extern "C" int ssg_rerank_tables(ssg_rerank_plan* p, float** d_rowmin, float** d
 
 // Everything after the tables are complete: the sparse stages for all n rows (they read other rows' rank lists and V
 // rows, rerank.py:77,97,102), then rows [row0, row0+rows) of final_dist into d_final (which points at row row0).
+static int finish_sparse_stages(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2, cudaStream_t st);
+
 static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2, double lambda_value,
                        int row0, int rows, double* d_final, void* stream) {
     SSG_TRY(check_run_args(p, d_tgt, 1, d_tgt, n, d, k1, k2));
@@ -387,6 +392,15 @@ static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int
         return ssg_set_error(SSG_ERR_INVALID, "rerank_finish: rows [%d,%d) outside [0,%d)", row0, row0 + rows, n);
     SSG_CUDA_TRY(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
+    SSG_TRY(finish_sparse_stages(p, d_tgt, n, d, k1, k2, st));
+    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, row0, rows, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec,
+                                 lambda_value, d_final, st)); }
+    p->last_n = n;
+    return SSG_OK;
+}
+
+// stages (i, tail) and (v)-(vii, inverted index): source vector, k-reciprocal rows, query expansion, CSC
+static int finish_sparse_stages(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2, cudaStream_t st) {
     const int k1p = k1 + 1;
     const int khp = (int)rint(k1 / 2.0) + 1;   // int(np.around(k1/2)) + 1, rerank.py:83
     // (i, tail) rerank.py:38-40: v = 1 - exp(-rowmin); v /= max(v)
@@ -417,9 +431,6 @@ static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int
     }
     // (vii)-(viii) rerank.py:101-122
     { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
-    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, row0, rows, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec,
-                                 lambda_value, d_final, st)); }
-    p->last_n = n;
     return SSG_OK;
 }
 
@@ -440,6 +451,56 @@ extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, co
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
     SSG_TRY(ssg_rerank_distance_rows(p, d_src, ns, d_tgt, n, d, k1, dist_mode, 0, n, d_euclid, stream));
     return ssg_rerank_finish(p, d_tgt, n, d, k1, k2, lambda_value, d_final, stream);
+}
+
+// final_dist in sparse form (see rerank.cu, jaccard_sparse_kernel).  Synchronises the stream once (the row lengths are
+// data dependent; the CSR buffers grow on demand).
+extern "C" int ssg_rerank_finish_sparse(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2,
+                                        double lambda_value, long long* h_nnz, void* stream) {
+    SSG_TRY(check_run_args(p, d_tgt, 1, d_tgt, n, d, k1, k2));
+    if (!(lambda_value >= 0.0 && lambda_value < 1.0))
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_finish_sparse: lambda_value %g outside [0, 1)", lambda_value);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->sp_cnt) {
+        SSG_TRY(dalloc((void**)&p->sp_cnt, sizeof(int) * (size_t)p->n_max, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->sp_rowptr, sizeof(int) * ((size_t)p->n_max + 1), &p->bytes));
+    }
+    SSG_TRY(finish_sparse_stages(p, d_tgt, n, d, k1, k2, st));
+    { SSG_PROF("jaccard_sparse", st); SSG_TRY(launch_jaccard_sparse(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
+                                   nullptr, p->sp_cnt, nullptr, nullptr, st)); }
+    SSG_TRY(launch_exclusive_scan_i32(p->sp_cnt, p->sp_rowptr, n, st));
+    int total = 0;
+    SSG_CUDA_TRY(cudaMemcpyAsync(&total, p->sp_rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (total < 0) return ssg_set_error(SSG_ERR_CAPACITY, "rerank_finish_sparse: more than 2^31 touched pairs; use the dense form");
+    if ((size_t)total > p->sp_cap) {
+        if (p->sp_col) cudaFree(p->sp_col);
+        if (p->sp_val) cudaFree(p->sp_val);
+        p->sp_col = nullptr; p->sp_val = nullptr; p->sp_cap = 0;
+        const size_t cap = (size_t)total + (size_t)total / 4 + 1024;
+        SSG_CUDA_TRY(cudaMalloc((void**)&p->sp_col, sizeof(int) * cap));
+        SSG_CUDA_TRY(cudaMalloc((void**)&p->sp_val, sizeof(double) * cap));
+        p->sp_cap = cap;
+    }
+    { SSG_PROF("jaccard_sparse", st); SSG_TRY(launch_jaccard_sparse(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value,
+                                   p->sp_rowptr, p->sp_cnt, p->sp_col, p->sp_val, st)); }
+    p->sp_nnz = total;
+    p->sp_threshold = (double)(float)(1.0 - lambda_value);      // every entry NOT in the CSR is >= this
+    p->last_n = n;
+    if (h_nnz) *h_nnz = total;
+    return SSG_OK;
+}
+
+extern "C" int ssg_rerank_sparse_view(ssg_rerank_plan* p, int** d_rowptr, int** d_col, double** d_val, long long* nnz,
+                                      double* threshold) {
+    if (!p || !p->sp_rowptr) return ssg_set_error(SSG_ERR_INVALID, "rerank_sparse_view: no sparse result in this plan");
+    if (d_rowptr) *d_rowptr = p->sp_rowptr;
+    if (d_col) *d_col = p->sp_col;
+    if (d_val) *d_val = p->sp_val;
+    if (nnz) *nnz = p->sp_nnz;
+    if (threshold) *threshold = p->sp_threshold;
+    return SSG_OK;
 }
 
 static int grow(void** ptr, size_t* have, size_t need) {

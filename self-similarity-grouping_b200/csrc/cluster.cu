@@ -105,7 +105,7 @@ eps_hist_kernel(const T* __restrict__ D, int n, int pass, const unsigned long lo
 // single CTA: pick the bin holding the `remaining`-th smallest key, extend the prefix.
 __global__ void __launch_bounds__(1024)
 eps_pick_kernel(unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ state, int pass,
-                double rho) {
+                double rho, long long n_pairs = -1, const unsigned long long* __restrict__ zeros = nullptr) {
     __shared__ unsigned long long cum[EPS_BINS];
     const int tid = threadIdx.x;
     // serial-ish scan: 4096 bins, 1024 threads x 4 bins, then thread 0 stitches 1024 partials
@@ -123,14 +123,19 @@ eps_pick_kernel(unsigned long long* __restrict__ ghist, unsigned long long* __re
     const unsigned long long total = cum[1024];
     if (pass == 0 && tid == 0) {
         // M = number of non-zero upper-triangle entries; top_num = np.round(rho*M) (half to even)
-        double t = rint(rho * (double)total);
+        // sparse form (n_pairs >= 0): the histogram holds only the entries that lie below every entry outside the CSR;
+        // M = all pairs minus the exact zeros, and the selection is valid iff it stays inside the histogram
+        // (state[7] = 1 otherwise: the caller falls back to the dense matrix).
+        const unsigned long long M = n_pairs >= 0 ? (unsigned long long)n_pairs - zeros[0] : total;
+        double t = rint(rho * (double)M);
         if (t < 0.0) t = 0.0;
         unsigned long long top = (unsigned long long)t;
-        if (top > total) top = total;
-        state[3] = total;
+        if (top > M) top = M;
+        state[3] = M;
         state[2] = top;
         state[1] = top;      // remaining
         state[0] = 0ull;     // prefix
+        if (n_pairs >= 0 && top > total) { state[7] = 1ull; state[1] = 0ull; }
     }
     __syncthreads();
     const unsigned long long rem = state[1];
@@ -478,6 +483,119 @@ eps_gather_rows_kernel(const T* __restrict__ D, ShardGeom g, int mode, unsigned 
         __syncthreads();
     }
     if (threadIdx.x == 0) partial[i] = sh[0];
+}
+
+// ---- eps over the sparse form of final_dist (CSR of the touched columns, rerank.cu): one warp per row, only the
+// strict upper triangle (col > row), zeros dropped (and counted: they are missing from M), entries >= thr ignored --
+// they cannot be told apart from the entries outside the CSR, so the selection is certified by eps_pick_kernel.
+constexpr int SP_NT = 256;
+
+__global__ void __launch_bounds__(SP_NT)
+eps_sp_hist_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int n,
+                   double thr, int pass, const unsigned long long* __restrict__ state,
+                   unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ zeros) {
+    __shared__ unsigned int hist[EPS_BINS];
+    for (int b = threadIdx.x; b < EPS_BINS; b += SP_NT) hist[b] = 0u;
+    __syncthreads();
+    const int shift = c_eps_shift[pass], width = c_eps_width[pass];
+    const unsigned long long prefix = state[0];
+    const unsigned mask = (1u << width) - 1u;
+    const int hs = shift + width;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (SP_NT / 32) + (threadIdx.x >> 5);
+    if (i < n && !state[7]) {
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        int nz = 0;
+        for (int base = beg; base < end; base += 32) {
+            const int e = base + lane;
+            const bool up = e < end && col[e] > i;
+            const double v = up ? val[e] : 1.0;
+            nz += (up && v == 0.0);
+            bool in = false;
+            unsigned bin = 0;
+            if (up && v != 0.0 && v < thr) {
+                const unsigned long long k = f64_key(v);
+                in = (pass == 0) || ((k >> hs) == (prefix >> hs));
+                bin = (unsigned)(k >> shift) & mask;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (in) {
+                const unsigned peers = __match_any_sync(act, bin);
+                if ((int)(__ffs(peers) - 1) == lane) atomicAdd(&hist[bin], __popc(peers));
+            }
+        }
+        if (pass == 0) {
+            nz = warp_sum_i(nz);
+            if (lane == 0 && nz) atomicAdd(zeros, (unsigned long long)nz);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < EPS_BINS; b += SP_NT) {
+        const unsigned c = hist[b];
+        if (c) atomicAdd(&ghist[b], (unsigned long long)c);
+    }
+}
+
+__global__ void __launch_bounds__(SP_NT)
+eps_sp_gather_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, int n,
+                     double thr, unsigned long long* __restrict__ state, double* __restrict__ list,
+                     double* __restrict__ partial) {
+    const unsigned long long pre = state[0] >> 40;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (SP_NT / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    double acc = 0.0;
+    if (state[2] > 0 && !state[7]) {
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        for (int e = beg + lane; e < end; e += 32) {
+            if (col[e] <= i) continue;
+            const double v = val[e];
+            if (v == 0.0 || !(v < thr)) continue;
+            const unsigned long long h = f64_key(v) >> 40;
+            if (h < pre) acc += v;
+            else if (h == pre) {
+                const unsigned long long pos = atomicAdd(&state[5], 1ull);
+                if (pos < (unsigned long long)EPS_LIST_CAP) list[pos] = v; else state[6] = 1ull;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);   // fixed butterfly: deterministic
+    if (lane == 0) partial[i] = acc;
+}
+
+// region query on the sparse form: valid while eps is below every entry outside the CSR (checked by the caller)
+__global__ void __launch_bounds__(SP_NT)
+db_sp_count_kernel(const int* __restrict__ rowptr, const double* __restrict__ val, int n, double eps,
+                   int* __restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (SP_NT / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    int c = 0;
+    for (int e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) c += (val[e] <= eps);
+    c = warp_sum_i(c);
+    if (lane == 0) cnt[i] = c;
+}
+
+__global__ void __launch_bounds__(SP_NT)
+db_sp_fill_kernel(const int* __restrict__ sp_rowptr, const int* __restrict__ col, const double* __restrict__ val, int n,
+                  double eps, const int* __restrict__ rowptr, long long max_nbr, int* __restrict__ nbr,
+                  int* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (SP_NT / 32) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int obeg = rowptr[i], oend = rowptr[i + 1];
+    if (oend == obeg) return;
+    if ((long long)oend > max_nbr) { if (lane == 0) flags[0] = 1; return; }
+    int out = obeg;
+    const int beg = sp_rowptr[i], end = sp_rowptr[i + 1];
+    for (int base = beg; base < end; base += 32) {
+        const int e = base + lane;
+        const bool hit = e < end && val[e] <= eps;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (hit) nbr[out + __popc(m & ((1u << lane) - 1u))] = col[e];
+        out += __popc(m);
+    }
 }
 
 // -------------------------------------------------------------------------------------------- DBSCAN
@@ -930,6 +1048,68 @@ extern "C" int ssg_dbscan_shard_label(ssg_cluster_plan* p, int n, int min_sample
     if (h_n_clusters) {
         SSG_CUDA_TRY(cudaMemcpyAsync(h_n_clusters, p->cid + n, sizeof(int), cudaMemcpyDeviceToHost, st));
         SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    return SSG_OK;
+}
+
+// ------------------------------------------------------------- eps / DBSCAN on the sparse form of final_dist
+// (ssg_rerank_finish_sparse: CSR rows = touched columns ascending; every entry outside the CSR is >= threshold)
+extern "C" int ssg_eps_sparse(ssg_cluster_plan* p, int n, const int* d_rowptr, const int* d_col, const double* d_val,
+                              double threshold, double rho, double* h_eps, long long* h_top_num, int* h_certified,
+                              void* stream) {
+    if (!p || !d_rowptr || !d_col || !d_val || n <= 0 || n > p->n_max || !h_eps || !h_certified)
+        return ssg_set_error(SSG_ERR_INVALID, "eps_sparse: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
+    SSG_CUDA_TRY(cudaMemsetAsync(p->eps_out, 0, sizeof(double) * 2, st));
+    unsigned long long* zeros = reinterpret_cast<unsigned long long*>(p->eps_out + 1);   // spare 8-byte slot
+    const int grid = ssg_cdiv(n, SP_NT / 32);
+    const long long n_pairs = (long long)n * (n - 1) / 2;
+    for (int pass = 0; pass < 2; ++pass) {
+        { SSG_PROF("eps_hist", st); eps_sp_hist_kernel<<<grid, SP_NT, 0, st>>>(d_rowptr, d_col, d_val, n, threshold, pass, p->state, p->hist, zeros); }
+        SSG_CHECK_LAUNCH();
+        eps_pick_kernel<<<1, 1024, 0, st>>>(p->hist, p->state, pass, rho, n_pairs, zeros);
+        SSG_CHECK_LAUNCH();
+    }
+    { SSG_PROF("eps_gather", st); eps_sp_gather_kernel<<<grid, SP_NT, 0, st>>>(d_rowptr, d_col, d_val, n, threshold, p->state, p->list, p->partial); }
+    SSG_CHECK_LAUNCH();
+    eps_list_finish_kernel<<<1, 1024, 0, st>>>(p->list, p->state, p->partial, n, p->eps_out);
+    SSG_CHECK_LAUNCH();
+    unsigned long long hs[8];
+    SSG_CUDA_TRY(cudaMemcpyAsync(h_eps, p->eps_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaMemcpyAsync(hs, p->state, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    // not certified: the rho-slice reaches past the entries the CSR can vouch for, or > 2^20 ties around the threshold
+    *h_certified = (hs[7] || hs[6]) ? 0 : 1;
+    if (h_top_num) *h_top_num = (long long)hs[2];
+    return SSG_OK;
+}
+
+extern "C" int ssg_dbscan_sparse(ssg_cluster_plan* p, int n, const int* d_rowptr, const int* d_col, const double* d_val,
+                                 double eps, int min_samples, int64_t* d_labels, int* h_n_clusters, void* stream) {
+    if (!p || !d_rowptr || !d_col || !d_val || !d_labels || n <= 0 || n > p->n_max)
+        return ssg_set_error(SSG_ERR_INVALID, "dbscan_sparse: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
+    const int grid = ssg_cdiv(n, SP_NT / 32);
+    { SSG_PROF("dbscan_count", st); db_sp_count_kernel<<<grid, SP_NT, 0, st>>>(d_rowptr, d_val, n, eps, p->cnt); }
+    SSG_CHECK_LAUNCH();
+    SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
+    { SSG_PROF("dbscan_fill", st); db_sp_fill_kernel<<<grid, SP_NT, 0, st>>>(d_rowptr, d_col, d_val, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags); }
+    SSG_CHECK_LAUNCH();
+    SSG_TRY(dbscan_label_stage(p, n, min_samples, d_labels, st));
+    if (h_n_clusters) {
+        int flags[4], ncl = 0;
+        SSG_CUDA_TRY(cudaMemcpyAsync(flags, p->flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaMemcpyAsync(&ncl, p->cid + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (flags[0])
+            return ssg_set_error(SSG_ERR_CAPACITY, "dbscan: more than %lld neighbour pairs within eps; "
+                                 "re-create the plan with a larger max_neighbors", p->max_nbr);
+        *h_n_clusters = ncl;
     }
     return SSG_OK;
 }

@@ -53,6 +53,11 @@ int launch_csc_build(int n, const int* q_idx, const int* q_cnt, int* colcnt, int
 int launch_jaccard_final(int n, int row0, int rows, const int* q_idx, const float* q_val, const int* q_cnt,
                          const int* colptr, const int* csc_row, const float* vec, double lambda_value,
                          double* final_dist, cudaStream_t st);
+// sparse form of final_dist: sp_rowptr == NULL counts the touched columns per row into sp_cnt, otherwise the rows are
+// written (ascending columns) at sp_rowptr[i]
+int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                          const int* csc_row, const float* vec, double lambda_value, const int* sp_rowptr, int* sp_cnt,
+                          int* sp_col, double* sp_val, cudaStream_t st);
 int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                         const int* csc_row, const float* dmat, const float* rowmax, double lambda_value, float* out,
                         cudaStream_t st);

@@ -575,6 +575,145 @@ int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Sparse form of final_dist (same arithmetic as jaccard_final_kernel).  A column m that shares no non-zero column with
+// row i has J = 1 and final[i,m] = fl32(1 - lambda) + fl32(v_i + v_m) * lambda >= fl32(1 - lambda) (v >= 0): only the
+// TOUCHED columns (~1 % of a row) can be smaller, and those are all eps and DBSCAN ever look at while eps stays below
+// that bound.  Row i of the CSR = its touched columns in ascending order with their final values.
+// One CTA per row, two launches: FILL = false counts the touched columns (bitmap popcount), FILL = true writes them.
+// The position of a column inside its row is the rank of its bit in the bitmap, so the layout is deterministic.
+// ---------------------------------------------------------------------------------------------------
+template <bool FILL>
+__global__ void __launch_bounds__(JF_NT)
+jaccard_sparse_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+                      const int* __restrict__ q_cnt, const int* __restrict__ colptr, const int* __restrict__ csc_row,
+                      const float* __restrict__ vec, double lambda_value, float oml, const int* __restrict__ sp_rowptr,
+                      int* __restrict__ sp_cnt, int* __restrict__ sp_col, double* __restrict__ sp_val) {
+    extern __shared__ unsigned char jf_smem[];
+    int* si = reinterpret_cast<int*>(jf_smem);                       // [VQ_STRIDE]
+    float* sv = reinterpret_cast<float*>(si + SSG_VQ_STRIDE);        // [VQ_STRIDE]
+    int* pref = reinterpret_cast<int*>(sv + SSG_VQ_STRIDE);          // [VQ_STRIDE + 1]
+    const int nwords = (n + 31) >> 5;
+    unsigned* bitmap = reinterpret_cast<unsigned*>(pref + SSG_VQ_STRIDE + 1);  // [nwords + 1]
+    int* wpre = reinterpret_cast<int*>(bitmap + nwords + 1);         // [nwords + 1] exclusive popcount prefix
+    __shared__ int wsum[JF_NT / 32];
+    __shared__ int s_carry;
+
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int ci = q_cnt[i];
+    for (int s = tid; s < ci; s += JF_NT) {
+        si[s] = q_idx[(size_t)i * SSG_VQ_STRIDE + s];
+        sv[s] = q_val[(size_t)i * SSG_VQ_STRIDE + s];
+    }
+    for (int w = tid; w < nwords; w += JF_NT) bitmap[w] = 0u;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ci; base += JF_NT) {                   // prefix sums of the inverted-list lengths
+        const int s = base + tid;
+        int len = 0;
+        if (s < ci) len = colptr[si[s] + 1] - colptr[si[s]];
+        int tot;
+        const int ex = block_exclusive_scan<JF_NT>(len, wsum, tot);
+        const int c = s_carry;
+        if (s < ci) pref[s] = c + ex;
+        __syncthreads();
+        if (tid == 0) s_carry = c + tot;
+        __syncthreads();
+    }
+    const int T = s_carry;
+    if (tid == 0) pref[ci] = T;
+    __syncthreads();
+    for (int f = tid; f < T; f += JF_NT) {
+        int lo = 0, hi = ci - 1;                                     // largest s with pref[s] <= f
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pref[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        const int m = csc_row[colptr[si[lo]] + (f - pref[lo])];
+        atomicOr(&bitmap[m >> 5], 1u << (m & 31));
+    }
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nwords; base += JF_NT) {               // rank of every word's first bit
+        const int w = base + tid;
+        const int pc = w < nwords ? __popc(bitmap[w]) : 0;
+        int tot;
+        const int ex = block_exclusive_scan<JF_NT>(pc, wsum, tot);
+        const int c = s_carry;
+        if (w < nwords) wpre[w] = c + ex;
+        __syncthreads();
+        if (tid == 0) s_carry = c + tot;
+        __syncthreads();
+    }
+    const int cnt = s_carry;
+    if (!FILL) {
+        if (tid == 0) sp_cnt[i] = cnt;
+        return;
+    }
+    const size_t out0 = (size_t)sp_rowptr[i];
+    for (int w = tid; w < nwords; w += JF_NT) {
+        unsigned bits = bitmap[w];
+        int pos = wpre[w];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            sp_col[out0 + pos++] = (w << 5) + b;
+            bits &= bits - 1u;
+        }
+    }
+    __syncthreads();                                                 // the column list of this row is complete
+    const float vi = vec[i];
+    for (int e = tid; e < cnt; e += JF_NT) {
+        const int m = sp_col[out0 + e];
+        const int cm = q_cnt[m];
+        const int* mi = q_idx + (size_t)m * SSG_VQ_STRIDE;
+        const float* mv = q_val + (size_t)m * SSG_VQ_STRIDE;
+        float S = 0.f;
+        int a = 0, b = 0;
+        int ib = cm > 0 ? mi[0] : INT_MAX;
+        while (a < ci && b < cm) {                                   // same merge, same order as jaccard_row
+            const int ia = si[a];
+            if (ia == ib) {
+                S = __fadd_rn(S, fminf(sv[a], mv[b]));
+                ++a; ++b;
+                ib = b < cm ? mi[b] : INT_MAX;
+            } else if (ia < ib) {
+                ++a;
+            } else {
+                ++b;
+                ib = b < cm ? mi[b] : INT_MAX;
+            }
+        }
+        const float J = fmaxf(__fsub_rn(1.0f, __fdiv_rn(S, __fsub_rn(2.0f, S))), 0.f);
+        const float Jm = __fmul_rn(J, oml);
+        sp_val[out0 + e] = __dadd_rn((double)Jm, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+    }
+}
+
+static size_t jaccard_sparse_smem(int n) {
+    return sizeof(int) * SSG_VQ_STRIDE + sizeof(float) * SSG_VQ_STRIDE + sizeof(int) * (SSG_VQ_STRIDE + 1) +
+           2 * sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
+}
+
+// sp_rowptr == NULL: count pass (sp_cnt[i] = touched columns of row i); else fill pass.
+int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                          const int* csc_row, const float* vec, double lambda_value, const int* sp_rowptr, int* sp_cnt,
+                          int* sp_col, double* sp_val, cudaStream_t st) {
+    const size_t smem = jaccard_sparse_smem(n);
+    if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
+    const float oml = (float)(1.0 - lambda_value);
+    if (!sp_rowptr) {
+        SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_sparse_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jaccard_sparse_kernel<false><<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value, oml,
+                                                             nullptr, sp_cnt, nullptr, nullptr);
+    } else {
+        SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_sparse_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jaccard_sparse_kernel<true><<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value, oml,
+                                                            sp_rowptr, sp_cnt, sp_col, sp_val);
+    }
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // re_ranking_init front end (rerank_initial.py:43-48): D'[r,c] = 2 - 2*S[c,r] with S = [[qq, qg],[qg^T, gg]]
 // (the reference normalises by the column max and transposes; D' is that transpose before the division).
 // ---------------------------------------------------------------------------------------------------

@@ -50,6 +50,24 @@ class ClusterPlan(object):
         _lib.check(_lib.load().ssg_dbscan_core_mask(self._h, out.ctypes.data, n))
         return out.astype(bool)
 
+    # ---- sparse form of final_dist (RerankPlan.finish_sparse)
+    def eps_sparse(self, n, rowptr, col, val, threshold, rho):
+        """-> (eps, top_num, certified).  certified False: the caller must use the dense matrix."""
+        eps, top, ok = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_int()
+        _lib.check(_lib.load().ssg_eps_sparse(self._h, int(n), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                              float(threshold), float(rho), ctypes.byref(eps), ctypes.byref(top),
+                                              ctypes.byref(ok), _lib.stream_ptr()))
+        return eps.value, top.value, bool(ok.value)
+
+    def dbscan_sparse(self, n, rowptr, col, val, eps, min_samples=4):
+        import torch
+        labels = torch.empty((n,), dtype=torch.int64, device=self.device)
+        ncl = ctypes.c_int()
+        _lib.check(_lib.load().ssg_dbscan_sparse(self._h, int(n), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                                 float(eps), int(min_samples), labels.data_ptr(), ctypes.byref(ncl),
+                                                 _lib.stream_ptr()))
+        return labels, ncl.value
+
     # ---- row-sharded primitives (one process per GPU; the collectives between them are run by ssg_b200.dist)
     def buffers(self, n, nbr_len=0):
         """Zero-copy torch views of the plan's exchange buffers: hist int64[4096], state int64[8], partial

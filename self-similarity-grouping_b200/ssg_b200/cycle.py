@@ -96,12 +96,22 @@ def generate_keep_mask(labels_list):
     return ~(L == -1).any(0)
 
 
+def _sparse_default():
+    return os.environ.get("SSG_SPARSE_FINISH", "0") not in ("", "0")
+
+
 def pseudo_label_cycle(source_features, target_features, lambda_value=0.1, rho=1.6e-3, eps_list=None,
-                       min_samples=4, k1=20, k2=6, dist_mode=None, device=None, quiet=True):
+                       min_samples=4, k1=20, k2=6, dist_mode=None, device=None, quiet=True, sparse=None):
     """Features (per bank: [Ns,d], [N,d]; host or device) -> (labels_list, eps_list, keep_mask).
 
     One bank at a time: upload, re-rank into a re-used [N,N] float64 device buffer, eps (unless frozen
     values are passed, as in iterations > 0), DBSCAN, download the labels.  Nothing N x N leaves the GPU.
+
+    sparse=True (opt-in, SSG_SPARSE_FINISH=1): final_dist is never materialised.  Every entry outside the ~1 % of
+    "touched" pairs is >= fl32(1 - lambda) (Jaccard distance 1), so eps (a rho-quantile far below that) and DBSCAN's
+    region queries only need the touched entries, which RerankPlan.finish_sparse returns as a CSR.  The shortcut is
+    taken only when it is certified (the rho-slice lies below the bound, eps < bound); otherwise the bank falls back
+    to the dense matrix.  Labels are identical either way; eps agrees up to the order of the float64 additions.
     """
     import torch
     dev = _lib.require_cuda(device)
@@ -114,9 +124,30 @@ def pseudo_label_cycle(source_features, target_features, lambda_value=0.1, rho=1
         s, t = _to_device(s, dev), _to_device(t, dev)
         n = t.shape[0]
         plan = _rerank_plan(n, s.shape[0], t.shape[1], dev.index)
-        if final is None or final.shape[0] != n:
-            final = torch.empty((n, n), dtype=torch.float64, device=dev)
-        plan.run(s, t, k1, k2, lambda_value, mode, want_euclid=False, out=final)
+        if (_sparse_default() if sparse is None else sparse) and 0.0 <= lambda_value < 1.0:
+            plan.distance_rows(s, t, k1, mode)
+            rowptr, col, val, bound = plan.finish_sparse(t, k1, k2, lambda_value)
+            cplan = _cluster_plan(n, dev.index)
+            if eps_list is None:
+                eps, _, ok = cplan.eps_sparse(n, rowptr, col, val, bound, rho)
+            else:
+                eps, ok = float(eps_list[b]), True
+            if ok and eps < bound:
+                labels = _with_capacity_retry(n, dev.index,
+                                              lambda p: p.dbscan_sparse(n, rowptr, col, val, eps, min_samples)[0])
+                eps_out.append(eps)
+                labels_list.append(labels)
+                continue
+            # not certified (the rho-slice or eps reaches the untouched entries): dense matrix for this bank; the tables
+            # are already in the plan, ssg_rerank_finish repeats the cheap sparse stages and adds the N x N fill
+            if final is None or final.shape[0] != n:
+                final = torch.empty((n, n), dtype=torch.float64, device=dev)
+            _lib.check(_lib.load().ssg_rerank_finish(plan._h, t.data_ptr(), n, t.shape[1], int(k1), int(k2),
+                                                     float(lambda_value), final.data_ptr(), _lib.stream_ptr()))
+        else:
+            if final is None or final.shape[0] != n:
+                final = torch.empty((n, n), dtype=torch.float64, device=dev)
+            plan.run(s, t, k1, k2, lambda_value, mode, want_euclid=False, out=final)
         cplan = _cluster_plan(n, dev.index)
         eps = cplan.eps(final, rho)[0] if eps_list is None else float(eps_list[b])
         labels = _with_capacity_retry(n, dev.index, lambda p: p.dbscan(final, eps, min_samples)[0])

@@ -62,6 +62,34 @@ class RerankPlan(object):
             euclid.ctypes.data if euclid is not None else None))
         return euclid, final
 
+    def distance_rows(self, src, tgt, k1=20, dist_mode=_lib.DIST_EXACT, row0=0, rows=None):
+        """Stages (i)-(iv) for target rows [row0, row0+rows) (all rows by default): fills the plan's tables."""
+        src, tgt = src.contiguous(), tgt.contiguous()
+        rows = tgt.shape[0] - row0 if rows is None else rows
+        _lib.check(_lib.load().ssg_rerank_distance_rows(self._h, src.data_ptr(), src.shape[0], tgt.data_ptr(),
+                                                        tgt.shape[0], tgt.shape[1], int(k1), int(dist_mode), int(row0),
+                                                        int(rows), None, _lib.stream_ptr()))
+
+    def finish_sparse(self, tgt, k1=20, k2=6, lambda_value=0.2):
+        """final_dist as a CSR over the touched columns (see include/ssg_b200.h).  Returns (rowptr int32 [n+1],
+        col int32 [nnz], val float64 [nnz], threshold): zero-copy views of plan-owned buffers, valid until the next
+        call on this plan."""
+        import torch
+        tgt = tgt.contiguous()
+        n = tgt.shape[0]
+        nnz = ctypes.c_longlong()
+        _lib.check(_lib.load().ssg_rerank_finish_sparse(self._h, tgt.data_ptr(), n, tgt.shape[1], int(k1), int(k2),
+                                                        float(lambda_value), ctypes.byref(nnz), _lib.stream_ptr()))
+        ptrs = [ctypes.c_void_p() for _ in range(3)]
+        cnt, thr = ctypes.c_longlong(), ctypes.c_double()
+        _lib.check(_lib.load().ssg_rerank_sparse_view(self._h, ctypes.byref(ptrs[0]), ctypes.byref(ptrs[1]),
+                                                      ctypes.byref(ptrs[2]), ctypes.byref(cnt), ctypes.byref(thr)))
+        from .cluster import _DevArray
+        m = max(int(cnt.value), 1)
+        views = [torch.as_tensor(_DevArray(p.value, shape, ts), device=self.device)
+                 for p, (shape, ts) in zip(ptrs, [((n + 1,), "<i4"), ((m,), "<i4"), ((m,), "<f8")])]
+        return views[0], views[1][: cnt.value], views[2][: cnt.value], thr.value
+
     def stage(self, which, n):
         """Copy an intermediate of the last run to the host (stage-isolated parity tests)."""
         shapes = {

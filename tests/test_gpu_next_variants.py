@@ -36,3 +36,42 @@ def test_l2_chunked_layers_are_bit_identical(tmp_path, chunk):
     got = _embed_in_subprocess(tmp_path, "chunk%d" % chunk, {"SSG_L2_CHUNK": str(chunk)})
     assert np.isfinite(want).all()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu_next
+@pytest.mark.parametrize("n,d", [(2000, 64), (3001, 128)])
+def test_c_harness_sparse_final_dist_matches_dense(n, d):
+    """tests/c/sparse_check.c: CSR entries byte-equal to the dense matrix, everything outside >= the bound, eps within
+    1e-13, labels byte-equal, an oversized rho-slice refused."""
+    cdir = os.path.join(ROOT, "tests", "c")
+    subprocess.check_call(["make", "-C", cdir], stdout=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(cdir, "_build", "sparse_check"), str(n), str(d)], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0 and "SPARSE_CHECK PASSED" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu_next
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_sparse_cycle_matches_dense_cycle(mode):
+    """pseudo_label_cycle(sparse=True) against the dense cycle: labels identical, eps to 1e-13; a rho so large that the
+    slice cannot be certified silently takes the dense path and still agrees."""
+    import torch
+    import ssg_b200
+    from ssg_b200 import _lib
+    from oracle import ssg_oracle as O
+    n, ns, d, banks, lam = 1500, 1100, 128, 2, 0.1
+    dm = _lib.DIST_EXACT if mode == "exact" else _lib.DIST_TENSOR
+    tgt = [torch.from_numpy(O.synth_features(n, d, 30 + b)[0]).cuda() for b in range(banks)]
+    src = [torch.from_numpy(O.synth_features(ns, d, 40 + b, noise=0.6)[0]).cuda() for b in range(banks)]
+    for rho in (0.02, 0.6):
+        want_l, want_e, want_k = ssg_b200.pseudo_label_cycle(src, tgt, lam, rho, dist_mode=dm, device=0, sparse=False)
+        got_l, got_e, got_k = ssg_b200.pseudo_label_cycle(src, tgt, lam, rho, dist_mode=dm, device=0, sparse=True)
+        np.testing.assert_allclose(got_e, want_e, rtol=1e-13, atol=0)
+        for a, b in zip(got_l, want_l):
+            assert np.array_equal(a, b)
+        assert np.array_equal(got_k, want_k)
+    # frozen eps (iterations > 0)
+    got_l, _, _ = ssg_b200.pseudo_label_cycle(src, tgt, lam, 0.02, eps_list=want_e, dist_mode=dm, device=0, sparse=True)
+    want_l, _, _ = ssg_b200.pseudo_label_cycle(src, tgt, lam, 0.02, eps_list=want_e, dist_mode=dm, device=0, sparse=False)
+    for a, b in zip(got_l, want_l):
+        assert np.array_equal(a, b)
