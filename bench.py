@@ -52,7 +52,7 @@ def parse():
                     help="N>1 sharded mode: row-sharded finish (every rank holds only its rows of final_dist; "
                          "distributed eps and DBSCAN) instead of the bank-parallel finish")
     ap.add_argument("--sparse-finish", action="store_true",
-                    help="single-GPU / --replicas: never materialise final_dist (CSR over the touched pairs, certified "
+                    help="never materialise final_dist (CSR over the touched pairs, certified "
                          "eps + DBSCAN on it; DESIGN.md 3.6) instead of the dense N x N float64 matrix")
     ap.add_argument("--quick", action="store_true",
                     help="profiling runs (ncu): exactly --warmup warm-up steps, no e2e leg, no CPU baseline")
@@ -290,7 +290,8 @@ def main():
         if sharded:
             out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, RHO, backend=backend,
                                                    comm=comm, features=(tf, sf),
-                                                   shard_finish=True if args.shard_finish else None)
+                                                   shard_finish=True if args.shard_finish else None,
+                                                   sparse=True if args.sparse_finish else None)
         else:
             out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local,
                                               sparse=True if args.sparse_finish else None)

@@ -10,6 +10,10 @@ Sharding of ONE cycle over `world` ranks:
                of their banks in parallel;
   4. labels  : broadcast from the owners (N int64 per bank).
 
+`sparse=True` (opt-in, SSG_SPARSE_FINISH=1): the owners finish their banks on the sparse form of final_dist (DESIGN.md
+3.6) -- no N x N matrix, so phase B costs about a millisecond per bank and the cycle scales with the row-sharded
+distance stage.
+
 `shard_finish=True` (opt-in, SSG_SHARD_FINISH=1) replaces phase B and step 4 by a row-sharded finish: every rank runs the
 sparse stages of a bank (cheap, they need all rows' tables anyway) and then only ITS rows of final_dist
 (ssg_rerank_finish_rows); eps is a distributed radix select (histogram all-reduce, list all-gather), DBSCAN a local row
@@ -161,6 +165,17 @@ class CudaBackend(object):
         return _with_capacity_retry(n, self.dev.index, lambda p: p.dbscan(final, eps, min_samples)[0])
 
 
+    # ---- sparse form of final_dist (sparse=True): no N x N matrix on the owner
+    def finish_sparse(self, plan, tgt, k1, k2, lambda_value):
+        return plan.finish_sparse(tgt, k1, k2, lambda_value)              # rowptr, col, val, bound
+
+    def eps_sparse(self, n, rowptr, col, val, bound, rho):
+        eps, _, ok = self.cluster_plan(n).eps_sparse(n, rowptr, col, val, bound, rho)
+        return eps, ok
+
+    def dbscan_sparse(self, n, rowptr, col, val, eps, min_samples):
+        return self.with_capacity_retry(n, lambda p: p.dbscan_sparse(n, rowptr, col, val, eps, min_samples)[0])
+
     # ---- row-sharded finish (shard_finish=True)
     def finish_rows(self, plan, tgt, k1, k2, lambda_value, row0, rows, final_rows):
         L = self._lib
@@ -241,7 +256,7 @@ def _shard_finish_default():
 
 def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_split=2, lambda_value=0.1, rho=1.6e-3,
                                eps_list=None, min_samples=4, k1=20, k2=6, backend=None, comm=None, features=None,
-                               shard_finish=None):
+                               shard_finish=None, sparse=None):
     """Run one pseudo-label cycle sharded over the ranks of `comm`.
 
     tgt_shard / src_shard: this rank's image rows [shard_bounds(n, world, rank)) (host or device tensors).
@@ -279,6 +294,10 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
             eps_vals.append(eps)
         keep = ~(np.stack(labels, 0) == -1).any(0)
         return labels, eps_vals, keep
+    if sparse is None:
+        from .cycle import _sparse_default
+        sparse = _sparse_default()
+    use_sparse = bool(sparse) and 0.0 <= lambda_value < 1.0
     # phase A — all ranks, bank after bank: row-block distance stage, then all-gather of the per-row tables; the owner
     # of a bank keeps a copy of its tables (the plan holds one set).  Phase B — the owners finish their banks in
     # parallel (k-reciprocal encoding ... final distance, eps, DBSCAN); nobody waits for an owner between banks.
@@ -301,11 +320,24 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
         if comm.rank == b % comm.world:
             for dst, keep in zip(backend.tables(plan, n_tgt), saved[b]):
                 dst.copy_(keep)
-            if final is None:
-                final = backend.new_final(n_tgt)
-            backend.finish(plan, tb, k1, k2, lambda_value, final)
-            eps = backend.eps(final, rho) if eps_list is None else float(eps_list[b])
-            lab.copy_(backend.dbscan(final, eps, min_samples))
+            done = False
+            if use_sparse:
+                # the owner never materialises final_dist (cycle.pseudo_label_cycle) unless the
+                # shortcut cannot be certified for this bank
+                rowptr, col, val, bound = backend.finish_sparse(plan, tb, k1, k2, lambda_value)
+                if eps_list is None:
+                    eps, ok = backend.eps_sparse(n_tgt, rowptr, col, val, bound, rho)
+                else:
+                    eps, ok = float(eps_list[b]), True
+                if ok and eps < bound:
+                    lab.copy_(backend.dbscan_sparse(n_tgt, rowptr, col, val, eps, min_samples))
+                    done = True
+            if not done:
+                if final is None:
+                    final = backend.new_final(n_tgt)
+                backend.finish(plan, tb, k1, k2, lambda_value, final)
+                eps = backend.eps(final, rho) if eps_list is None else float(eps_list[b])
+                lab.copy_(backend.dbscan(final, eps, min_samples))
             eps_t[0] = eps
         labels_dev.append(lab)
         eps_out.append(eps_t)

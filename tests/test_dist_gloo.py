@@ -85,6 +85,39 @@ class OracleBackend(object):
         import torch
         return torch.empty((n, n), dtype=torch.float64)
 
+    # ---- sparse form of final_dist (sparse=True): CSR over the pairs whose expanded rows share a column
+    def finish_sparse(self, plan, tgt, k1, k2, lambda_value):
+        import torch
+        st = {}
+        src = plan.src_by_tgt[tgt.data_ptr()]
+        _, f = O.re_ranking(src.numpy(), tgt.numpy(), k1, k2, lambda_value, mode="f32", stages=st)
+        touched = (st["Vq"] @ st["Vq"].T) != 0
+        rowptr = np.concatenate([[0], np.cumsum(touched.sum(1))]).astype(np.int32)
+        rows, cols = np.nonzero(touched)                               # row-major: ascending columns inside a row
+        return (torch.from_numpy(rowptr), torch.from_numpy(cols.astype(np.int32)), torch.from_numpy(f[rows, cols]),
+                float(np.float32(1.0 - lambda_value)))
+
+    sparse_calls = 0
+
+    def eps_sparse(self, n, rowptr, col, val, bound, rho):
+        rp, c, v = rowptr.numpy(), col.numpy(), val.numpy()
+        row = np.repeat(np.arange(n), np.diff(rp))
+        up = v[c > row]
+        m_total = n * (n - 1) // 2 - int((up == 0).sum())
+        top = int(np.round(rho * m_total))
+        low = np.sort(up[(up != 0) & (up < bound)])
+        if top > low.size:
+            return float("nan"), False
+        return (float(low[:top].mean()) if top else float("nan")), True
+
+    def dbscan_sparse(self, n, rowptr, col, val, eps, min_samples):
+        import torch
+        type(self).sparse_calls += 1
+        rp, c, v = rowptr.numpy(), col.numpy(), val.numpy()
+        dense = np.full((n, n), np.inf)
+        dense[np.repeat(np.arange(n), np.diff(rp)), c] = v
+        return torch.from_numpy(O.dbscan_dfs(dense, eps, min_samples))
+
     # ---- row-sharded finish (shard_finish=True): rows of final_dist + the numpy stand-in of the sharded primitives
     def finish_rows(self, plan, tgt, k1, k2, lambda_value, row0, rows, final_rows):
         import torch
@@ -131,7 +164,7 @@ def _images():
     return t.astype(np.float32), s.astype(np.float32)
 
 
-def _worker(rank, world, init_file, out_dir, shard_finish=False, nbr_cap=0):
+def _worker(rank, world, init_file, out_dir, shard_finish=False, nbr_cap=0, sparse=False, rho=None):
     import sys
     import torch
     import torch.distributed as dist
@@ -146,7 +179,10 @@ def _worker(rank, world, init_file, out_dir, shard_finish=False, nbr_cap=0):
         be.nbr_cap = nbr_cap
         labels, eps, keep = sd.sharded_pseudo_label_cycle(
             None, torch.from_numpy(t[tl:th]), torch.from_numpy(s[sl:sh]), N_T, N_S, num_split=BANKS - 1,
-            lambda_value=LAM, rho=RHO, backend=be, comm=sd.Comm(), shard_finish=shard_finish)
+            lambda_value=LAM, rho=RHO if rho is None else rho, backend=be, comm=sd.Comm(), shard_finish=shard_finish,
+            sparse=sparse)
+        if sparse:
+            np.save(os.path.join(out_dir, "sparse_calls%d.npy" % rank), np.array(OracleBackend.sparse_calls))
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), labels=np.stack(labels), eps=np.array(eps), keep=keep)
     finally:
         dist.destroy_process_group()
@@ -255,3 +291,23 @@ def test_row_sharded_eps_fake_matches_oracle_incl_massive_ties():
                     assert np.isnan(got[0])
                 else:
                     np.testing.assert_allclose(got[0], want, rtol=1e-13)
+
+
+@pytest.mark.parametrize("world,rho,expect_sparse", [(2, RHO, True), (4, RHO, True), (3, 0.9, False)])
+def test_sparse_owner_finish_matches_single_process(world, rho, expect_sparse):
+    """sparse=True: the bank owners finish on the CSR form of final_dist; a rho whose slice cannot be certified
+    (0.9: most pairs) must fall back to the dense matrix on the owner and still give the reference's labels."""
+    import torch.multiprocessing as mp
+    with tempfile.TemporaryDirectory() as tmp:
+        init_file = os.path.join(tmp, "init")
+        mp.spawn(_worker, args=(world, init_file, tmp, False, 0, True, rho), nprocs=world, join=True)
+        outs = [np.load(os.path.join(tmp, "rank%d.npz" % r)) for r in range(world)]
+        calls = sum(int(np.load(os.path.join(tmp, "sparse_calls%d.npy" % r))) for r in range(world))
+    finals = _single_process_reference()
+    want_eps = [O.eps_estimate(f, rho) for f in finals]
+    assert calls == (BANKS if expect_sparse else 0)
+    for o in outs:
+        np.testing.assert_allclose(o["eps"], want_eps, rtol=1e-13, atol=0)
+        want_labels = [O.dbscan_dfs(f, e, 4) for f, e in zip(finals, o["eps"])]
+        assert np.array_equal(o["labels"], np.stack(want_labels))
+        assert np.array_equal(o["keep"], O.keep_mask(want_labels))

@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of the next round: everything that was written after round 1's GPU budget was spent.
+#   gpurun --timeout 900 -- 'bash tools/gpu_next.sh'            (one GPU, ~6 min)
+# 1. plain-C harnesses on the C ABI (seconds each, no Python start-up)   2. pytest -m gpu_next
+# 3. A/B timings of the opt-in variants against the defaults (bench.py --quick: CUDA-event timers, no CPU legs)
+# Each step has its own time limit; results land in gpurun_out/next_*.
+mkdir -p gpurun_out
+make -C tests/c > gpurun_out/next_make.log 2>&1
+timeout 60 tests/c/_build/shard_check 4000 8 > gpurun_out/next_shard_check.log 2>&1; echo "rc=$?" >> gpurun_out/next_shard_check.log
+timeout 60 tests/c/_build/sparse_check 4000 128 > gpurun_out/next_sparse_check.log 2>&1; echo "rc=$?" >> gpurun_out/next_sparse_check.log
+timeout 600 python -m pytest tests -m gpu_next -q -x > gpurun_out/next_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/next_pytest.log
+Q="--quick --steps 2 --warmup 1"
+timeout 200 python bench.py $Q > gpurun_out/next_ab_default.json 2> gpurun_out/next_ab_default.err
+timeout 200 python bench.py $Q --sparse-finish > gpurun_out/next_ab_sparse.json 2> gpurun_out/next_ab_sparse.err
+for c in 16 32 48; do
+  SSG_L2_CHUNK=$c timeout 200 python bench.py $Q > gpurun_out/next_ab_l2chunk$c.json 2> gpurun_out/next_ab_l2chunk$c.err
+done
+tail -n 3 gpurun_out/next_*.log; cat gpurun_out/next_ab_*.json
+# multi-GPU (separate call, gpurun --gpus 2/8):
+#   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
+#       bench.py --gpus 8 --steps 3 --warmup 3 [--sparse-finish | --shard-finish]
