@@ -235,3 +235,18 @@ def test_header_is_plain_c_and_links_against_the_library(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert out.returncode == 0, out.stderr
     assert out.stdout.startswith("3 64 7 2 conv1 53 ")
+
+
+def test_no_unbound_names_in_python_sources():
+    """No pyflakes in this image: tools/lint_names.py flags names that are read but never bound anywhere in a file --
+    the only static net under the code paths that need a GPU to execute (bench.py's GPU arm, the ctypes wrappers)."""
+    import glob
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for pat in ("self-similarity-grouping_b200/ssg_b200/*.py", "self-similarity-grouping_b200/reid/*.py",
+                "self-similarity-grouping_b200/reid/*/*.py", "tests/*.py", "oracle/*.py", "tools/*.py"):
+        files += sorted(glob.glob(os.path.join(root, pat)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")] + files, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
