@@ -214,6 +214,7 @@ struct EpiDist {
     const float* nb;   // [N]
     float* out;        // [M, ldc]
     size_t ldc;
+    static constexpr bool kSkippable = false;
     __device__ __forceinline__ void operator()(int row, int col0, int ncols, const uint32_t (&acc)[32]) const {
         const float a = na[row];
         float* o = out + (size_t)row * ldc + col0;
@@ -234,9 +235,60 @@ struct EpiDist {
     }
 };
 
+// Symmetric form (opt-in, SSG_DIST_SYM=1): A and B are the two splits of the SAME rows, M == N, and `out` holds the
+// whole square matrix.  Tiles that lie entirely below the diagonal are not computed; element (i, j) with i <= j is
+// stored by the tile that computes it, element (j, i) as its mirror -- every element is written exactly once, so the
+// matrix is deterministic.  The mirrored value is A_i.B_j where a direct computation would give A_j.B_i: both are
+// within the certified error of the true distance (api.cu, tensor_eps_rel), which is all the candidate selection
+// relies on.
+struct EpiDistSym {
+    const float* na;   // [M] (== nb: the same rows)
+    const float* nb;
+    float* out;        // [M, ldc]
+    size_t ldc;
+    static constexpr bool kSkippable = true;
+    __device__ __forceinline__ bool skip_tile(int m_blk, int n_blk, int bn) const {
+        return (n_blk + 1) * bn <= m_blk * tc::BM;             // last column < first row
+    }
+    __device__ __forceinline__ void operator()(int row, int col0, int ncols, const uint32_t (&acc)[32]) const {
+        const float a = na[row];
+        float* o = out + (size_t)row * ldc + col0;
+        const int r0 = row & ~31;                     // rows of this warp: [r0, r0 + 32); col0 is a multiple of 32
+        if (col0 < r0) return;                        // below the diagonal: arrives as a mirror
+        if (col0 > r0 && ncols == 32) {               // strictly above: direct row + mirrored column, unmasked
+            float r[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = fmaf(-2.0f, __uint_as_float(acc[q]), a + nb[col0 + q]);
+            if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(o + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) o[q] = r[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 32; ++q) out[(size_t)(col0 + q) * ldc + row] = r[q];   // lanes = consecutive rows
+            return;
+        }
+        for (int q = 0; q < ncols; ++q) {             // the diagonal chunk (or a ragged last chunk)
+            const int j = col0 + q;
+            const float r = fmaf(-2.0f, __uint_as_float(acc[q]), a + nb[j]);
+            if (j >= row) o[q] = r;
+            if (j > row) out[(size_t)j * ldc + row] = r;
+        }
+    }
+};
+
 // C = dist(A', B') with pre-split operands.  M x N output, K = 3d.
 int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_split, const float* nb, int n,
-                     int k, float* out, size_t ldc, cudaStream_t st) {
+                     int k, float* out, size_t ldc, cudaStream_t st, int sym) {
+    if (sym) {
+        if (m != n) return ssg_set_error(SSG_ERR_INVALID, "gemm_dist: the symmetric form needs M == N (%d, %d)", m, n);
+        EpiDistSym es{na, nb, out, ldc};
+        if (n < 256) return tc::launch_gemm<128, EpiDistSym>(a_split, m, b_split, n, k, es, st);
+        return tc::launch_gemm<256, EpiDistSym>(a_split, m, b_split, n, k, es, st);
+    }
     EpiDist epi{na, nb, out, ldc};
     // 128x256 tiles halve the shared-memory operand traffic per MMA (128x128 is smem-bandwidth bound); the
     // environment switch exists for A/B measurements only

@@ -50,6 +50,7 @@ struct StagedEpi {
     int relu;
     int has_res;
     void* pool_out;        // VAR_BRES only: != NULL fuses the 3x3/2 max-pool behind the stem (the conv map is not stored)
+    static constexpr bool kSkippable = false;   // every tile is computed
 };
 
 // BN <= 128 (staged): one output sub-buffer per 64-column sub-tile + two residual tile buffers, 3-5 operand stages.
@@ -192,6 +193,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             for (int t = t_begin; t < t_end; t += t_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
+                if constexpr (Epi::kSkippable) { if (epi.skip_tile(m_blk, n_blk, BN)) continue; }
                 int b0 = 0, h0 = 0;
                 if (A.mode == 1 || (A.kb_split > 0 && A.mode1 == 1)) {
                     if (A.bb > 1) { b0 = m_blk * A.bb; }
@@ -261,6 +263,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             tc_fence_after();
         }
         for (int t = t_begin; t < t_end; t += t_step) {
+            if constexpr (Epi::kSkippable) {
+                int m_blk, n_blk;
+                tile_coords(t, m_blk, n_blk);
+                if (epi.skip_tile(m_blk, n_blk, BN)) continue;    // the same tiles in all three roles
+            }
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -333,6 +340,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             for (int t = t_begin; t < t_end; t += t_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
+                if constexpr (Epi::kSkippable) { if (epi.skip_tile(m_blk, n_blk, BN)) continue; }
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 const int row = m_blk * BM + q * 32 + lane;

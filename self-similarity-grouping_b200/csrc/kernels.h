@@ -33,8 +33,10 @@ int launch_sqdist_tensor(const float* X, int nx, const float* Y, int ny, int d, 
 int launch_split_bf16x3(const float* x, int n, int d, int which, const float* centre, void* out_bf16, float* norm2,
                         cudaStream_t st);
 int launch_col_mean(const float* x, int n, int d, double* partial, float* mean, cudaStream_t st);
+// sym != 0: A and B are the two splits of the same rows and `out` is the whole square matrix -- only the tiles that
+// touch the upper triangle are computed, the rest is mirrored (half the tensor work)
 int launch_gemm_dist(const void* a_split, const float* na, int m, const void* b_split, const float* nb, int n,
-                     int k, float* out, size_t ldc, cudaStream_t st);
+                     int k, float* out, size_t ldc, cudaStream_t st, int sym = 0);
 
 // rerank.cu
 int launch_source_vector(const float* rowmin, int n, float* vec, float* scratch, cudaStream_t st);

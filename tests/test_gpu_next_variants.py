@@ -75,3 +75,32 @@ def test_sparse_cycle_matches_dense_cycle(mode):
     want_l, _, _ = ssg_b200.pseudo_label_cycle(src, tgt, lam, 0.02, eps_list=want_e, dist_mode=dm, device=0, sparse=False)
     for a, b in zip(got_l, want_l):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu_next
+def test_symmetric_distance_gemm_gives_the_exact_mode_results(tmp_path):
+    """SSG_DIST_SYM=1: only the tiles touching the upper triangle of the target x target distance GEMM are computed and
+    mirrored.  The approximate matrix differs slightly below the diagonal, the OUTPUTS must not: rank tables and
+    final_dist equal to the exact mode bit for bit (candidates are re-scored exactly and certified)."""
+    script = (
+        "import sys, numpy as np, torch\n"
+        "sys.path[:0] = %r\n"
+        "import ssg_b200\n"
+        "from ssg_b200 import _lib\n"
+        "from oracle import ssg_oracle as O\n"
+        "n, ns, d = 3000, 2100, 128\n"
+        "t = torch.from_numpy(O.synth_features(n, d, 3)[0]).cuda(); s = torch.from_numpy(O.synth_features(ns, d, 4, noise=0.6)[0]).cuda()\n"
+        "plan = ssg_b200.rerank.get_plan(n, ns, d, 0)\n"
+        "out = {}\n"
+        "for name, mode in (('exact', _lib.DIST_EXACT), ('tensor', _lib.DIST_TENSOR)):\n"
+        "    _, f = plan.run(s, t, 20, 6, 0.1, mode); torch.cuda.synchronize()\n"
+        "    out[name + '_final'] = f.cpu().numpy(); out[name + '_rank'] = plan.stage(_lib.STAGE_RANK, n)[:, :21]\n"
+        "    out[name + '_flagged'] = plan.stage(_lib.STAGE_FLAGGED, n)\n"
+        "np.savez(sys.argv[1], **out)\n" % ([os.path.join(ROOT, "self-similarity-grouping_b200"), ROOT],))
+    out_file = str(tmp_path / "sym.npz")
+    subprocess.run([sys.executable, "-c", script, out_file], check=True, env=dict(os.environ, SSG_DIST_SYM="1"),
+                   timeout=600)
+    o = np.load(out_file)
+    assert np.array_equal(o["tensor_rank"], o["exact_rank"])
+    assert np.array_equal(o["tensor_final"], o["exact_final"])
+    assert int(o["tensor_flagged"][0]) < 30          # the mirrored values certify as well as the direct ones
