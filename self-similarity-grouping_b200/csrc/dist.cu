@@ -6,6 +6,8 @@
 //   * pair_exact        : exact distance for sparse (row, column) pairs      (rerank.py:91 gathers)
 #include <limits.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -443,7 +445,11 @@ int launch_row_select(const float* M, size_t ld, int rows, int cols, const float
 // independent accumulator chains (pair slots slot, slot+KP, ...): the float64 add chain of one pair is strictly
 // sequential (k = 0..d-1, cdist order), so instruction-level parallelism has to come from different pairs.  The row
 // block is staged through shared memory in CHUNK-wide float64 chunks shared by all the pairs of a row.
-template <int KP, int PPT, int ROWS, int CHUNK>
+// VEC8 (opt-in, SSG_PAIR_VEC8=1): every chain loads 32 contiguous bytes (two float4 = one whole 32-byte sector) of its
+// partner row per step instead of 16.  With 16-byte steps each sector is requested twice, a step apart, and the
+// shared-memory carve-out leaves almost no L1 to catch the second request: the kernel ran at the L2 bandwidth of twice
+// the useful bytes (profiles/r01g_rerank_full.md).  Same subtraction / product / sum per element in the same k order.
+template <int KP, int PPT, int ROWS, int CHUNK, bool VEC8 = false>
 __global__ void __launch_bounds__(KP * ROWS)
 pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict__ B, int d,
                   const int* __restrict__ idx, int idx_stride, const int* __restrict__ cnt,
@@ -483,7 +489,31 @@ pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict
             __syncthreads();
             const int kend = min(CHUNK, d - k0);
             const double* ar = sa[r_in];
-            if (vec_ok) {
+            if (VEC8 && (d & 7) == 0) {
+                for (int k = 0; k < kend; k += 8) {
+                    float4 t[PPT], t2[PPT];
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        const bool on = act[u] && m[u] >= 0;
+                        t[u] = on ? *reinterpret_cast<const float4*>(b[u] + k0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        t2[u] = on ? *reinterpret_cast<const float4*>(b[u] + k0 + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const double a0 = ar[k], a1 = ar[k + 1], a2 = ar[k + 2], a3 = ar[k + 3];
+                    const double a4 = ar[k + 4], a5 = ar[k + 5], a6 = ar[k + 6], a7 = ar[k + 7];
+#pragma unroll
+                    for (int u = 0; u < PPT; ++u) {
+                        double df;
+                        df = __dsub_rn(a0, (double)t[u].x); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a1, (double)t[u].y); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a2, (double)t[u].z); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a3, (double)t[u].w); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a4, (double)t2[u].x); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a5, (double)t2[u].y); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a6, (double)t2[u].z); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                        df = __dsub_rn(a7, (double)t2[u].w); acc[u] = __dadd_rn(acc[u], __dmul_rn(df, df));
+                    }
+                }
+            } else if (vec_ok) {
                 for (int k = 0; k < kend; k += 4) {
                     float4 t[PPT];
 #pragma unroll
@@ -520,6 +550,18 @@ pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict
 int launch_pair_exact(const float* A, int rows, const float* B, int d, const int* idx, int idx_stride,
                       const int* cnt, int fixed_cnt, float* out, int out_stride, cudaStream_t st) {
     if (rows <= 0) return SSG_OK;
+    static int vec8 = -1;
+    if (vec8 < 0) { const char* e = getenv("SSG_PAIR_VEC8"); vec8 = e ? atoi(e) : 0; }
+    if (vec8 && (d & 7) == 0 && (reinterpret_cast<uintptr_t>(B) & 31) == 0) {
+        if (!cnt && fixed_cnt <= 8)
+            pair_exact_kernel<2, 4, 128, 32, true><<<ssg_cdiv(rows, 128), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt,
+                                                                                     fixed_cnt, out, out_stride);
+        else
+            pair_exact_kernel<8, 4, 32, 128, true><<<ssg_cdiv(rows, 32), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt,
+                                                                                    fixed_cnt, out, out_stride);
+        SSG_CHECK_LAUNCH();
+        return SSG_OK;
+    }
     if (!cnt && fixed_cnt <= 8) {
         // few pairs per row (row min / max candidates): 2 threads x 4 chains per row, 128 rows per CTA
         pair_exact_kernel<2, 4, 128, 32><<<ssg_cdiv(rows, 128), 256, 0, st>>>(A, rows, B, d, idx, idx_stride, cnt, fixed_cnt,

@@ -78,10 +78,12 @@ def test_sparse_cycle_matches_dense_cycle(mode):
 
 
 @pytest.mark.gpu_next
-def test_symmetric_distance_gemm_gives_the_exact_mode_results(tmp_path):
+@pytest.mark.parametrize("switch", ["SSG_DIST_SYM", "SSG_PAIR_VEC8"])
+def test_distance_stage_variants_give_the_exact_mode_results(tmp_path, switch):
     """SSG_DIST_SYM=1: only the tiles touching the upper triangle of the target x target distance GEMM are computed and
     mirrored.  The approximate matrix differs slightly below the diagonal, the OUTPUTS must not: rank tables and
-    final_dist equal to the exact mode bit for bit (candidates are re-scored exactly and certified)."""
+    final_dist equal to the exact mode bit for bit (candidates are re-scored exactly and certified).
+    SSG_PAIR_VEC8=1: the exact re-scoring reads whole 32-byte sectors per step -- same arithmetic, same bits."""
     script = (
         "import sys, numpy as np, torch\n"
         "sys.path[:0] = %r\n"
@@ -98,7 +100,7 @@ def test_symmetric_distance_gemm_gives_the_exact_mode_results(tmp_path):
         "    out[name + '_flagged'] = plan.stage(_lib.STAGE_FLAGGED, n)\n"
         "np.savez(sys.argv[1], **out)\n" % ([os.path.join(ROOT, "self-similarity-grouping_b200"), ROOT],))
     out_file = str(tmp_path / "sym.npz")
-    subprocess.run([sys.executable, "-c", script, out_file], check=True, env=dict(os.environ, SSG_DIST_SYM="1"),
+    subprocess.run([sys.executable, "-c", script, out_file], check=True, env=dict(os.environ, **{switch: "1"}),
                    timeout=600)
     o = np.load(out_file)
     assert np.array_equal(o["tensor_rank"], o["exact_rank"])
