@@ -447,8 +447,10 @@ int launch_row_select(const float* M, size_t ld, int rows, int cols, const float
 // block is staged through shared memory in CHUNK-wide float64 chunks shared by all the pairs of a row.
 // VEC8 (opt-in, SSG_PAIR_VEC8=1): every chain loads 32 contiguous bytes (two float4 = one whole 32-byte sector) of its
 // partner row per step instead of 16.  With 16-byte steps each sector is requested twice, a step apart, and the
-// shared-memory carve-out leaves almost no L1 to catch the second request: the kernel ran at the L2 bandwidth of twice
-// the useful bytes (profiles/r01g_rerank_full.md).  Same subtraction / product / sum per element in the same k order.
+// shared-memory carve-out leaves almost no L1 to catch the second request.  Working hypothesis for why the kernel sits
+// at ~3 TB/s of useful bytes with DRAM and the FP64 pipe both far from busy (profiles/r01g_rerank_full.md: 0.55 GB of
+// DRAM reads, 12 % SM throughput): to be confirmed by the A/B run.  Same subtraction / product / sum per element in
+// the same k order, hence the same bits.
 template <int KP, int PPT, int ROWS, int CHUNK, bool VEC8 = false>
 __global__ void __launch_bounds__(KP * ROWS)
 pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict__ B, int d,
