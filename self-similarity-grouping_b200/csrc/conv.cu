@@ -40,6 +40,18 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     epi.pool_out = pool_out;
     SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
     SSG_TRY(make_tmap_2d_bf16(&epi.mapR, residual ? residual : y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    // SSG_CONV_EPI2=1 (opt-in): the one-barrier, pipelined-load epilogue of gemm_tc.cuh for the generic kernels
+    static int epi2 = -1;
+    if (epi2 < 0) { const char* e = getenv("SSG_CONV_EPI2"); epi2 = e ? atoi(e) : 0; }
+    const bool stem_kernel = stem_variant() && A.mode == 3 && cout == 64 && k == tc::BRES_K;
+    if (epi2 && !stem_kernel && !pool_out) {
+        if (!residual && cout % 256 == 0 && k >= 256)
+            return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
+        if (residual && cout % 256 == 0 && k >= 256)
+            return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_RRING, true>(A, m, w, cout, k, epi, st);
+        if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
+        return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
+    }
     // 128x256 tiles for the K-heavy convolutions without a residual (SSG_CONV_BN256=0 disables, for A/B runs)
     static int bn256 = -1;
     if (bn256 < 0) { const char* e = getenv("SSG_CONV_BN256"); bn256 = e ? atoi(e) : 1; }

@@ -77,7 +77,12 @@ constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3;
 constexpr int STEM_ROW_BYTES = 64 * 64;     // one input row of a stem tile in shared memory: 64 windows x 64 B
 constexpr int BRES_K = 256;
 
-template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
+// EPI2 (opt-in, SSG_CONV_EPI2=1; generic staged epilogue only): ONE named barrier per 64-column sub-tile instead of
+// two (the leader waits for the previous TMA store to leave the other staging buffer BEFORE the barrier that publishes
+// the current sub-tile, so that barrier also frees the next buffer), software-pipelined tcgen05.ld (the load of
+// sub-tile j+1 is in flight while j is converted), the accumulator released as soon as its last columns are in
+// registers, bias rows double-buffered per tile, residual ring refilled a full ring ahead.  Always two staging buffers.
+template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE, bool EPI2 = false>
 struct SmemLayout {
     static constexpr bool PLANES = VAR == VAR_BRESP;
     static constexpr bool BRES = VAR == VAR_BRES || PLANES, RRING = VAR == VAR_RRING;
@@ -88,7 +93,7 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
-    static constexpr int NBUF = NSUB > 2 ? 2 : NSUB;             // output sub-buffers
+    static constexpr int NBUF = EPI2 ? 2 : (NSUB > 2 ? 2 : NSUB);   // output sub-buffers
     static constexpr bool HAS_R = BN <= 128 || RRING;            // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
@@ -102,6 +107,7 @@ struct SmemLayout {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
     static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
+    static_assert(!(EPI2 && (BRES || !STAGED)), "EPI2 is a variant of the generic staged epilogue");
     static_assert(TOTAL <= 232448, "shared-memory layout exceeds 227 KB");
 };
 
@@ -116,11 +122,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
 
-template <int BN, class Epi, bool STAGED, bool KHS = false, int VAR = VAR_NONE>
+template <int BN, class Epi, bool STAGED, bool KHS = false, int VAR = VAR_NONE, bool EPI2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N,
             int num_k_blocks, const __grid_constant__ Epi epi) {
-    using L = SmemLayout<BN, STAGED, KHS, VAR>;
+    using L = SmemLayout<BN, STAGED, KHS, VAR, EPI2>;
     constexpr int STAGES = L::STAGES;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
     extern __shared__ unsigned char smem_raw[];
@@ -166,7 +172,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     // tile sequence of this CTA: round-robin, except for the stem with the fused max-pool, where a CTA owns whole
     // images and walks their 64 two-row tiles in order (the pool needs the previous tile's last row)
     int t_begin = blockIdx.x, t_end = num_tiles, t_step = gridDim.x;
-    if constexpr (SmemLayout<BN, STAGED, KHS, VAR>::BRES) {
+    if constexpr (L::BRES) {
         if (epi.pool_out != nullptr) {
             const long long images = m_blocks / 64;
             t_begin = (int)(images * blockIdx.x / gridDim.x) * 64;
@@ -369,7 +375,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             const int r_in = q * 32 + lane;                           // row inside the tile
             const uint32_t row_off = (uint32_t)r_in * 128u;
             const uint32_t sw = (uint32_t)(r_in & 7);
-            __shared__ float s_bias[BN];
+            __shared__ float s_bias[EPI2 ? 2 * BN : BN];
             const int epi_tid = threadIdx.x - 64;
             auto load_residual = [&](int tile, int buf) {
                 int mb, nb;
@@ -461,12 +467,117 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 mbar_arrive_expect_tx(&res_bar[slot], L::SUB_BYTES);
                 tma_load_2d(r_s + slot * L::SUB_BYTES, &epi.mapR, &res_bar[slot], nb * BN + (s % NSUB) * 64, mb * BM);
             };
+            if constexpr (EPI2) {
+                // ---- one barrier per sub-tile, pipelined TMEM loads (see SmemLayout).  g = it * NSUB + j counts this
+                // CTA's sub-tiles: sub-tile g is staged in buffer g % 2, its residual (RRING) sits in ring slot g % RS.
+                if constexpr (L::RRING) {
+                    if (leader && has_res) {
+                        for (int s0 = 0; s0 < RS; ++s0) load_residual_sub(s0);      // the whole ring
+                    }
+                } else {
+                    if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+                }
+                if (t_begin < t_end) {
+                    int mb0, nb0;
+                    tile_coords(t_begin, mb0, nb0);
+                    if (epi_tid < BN) s_bias[epi_tid] = epi.bias[nb0 * BN + epi_tid];
+                }
+                epi_bar_sync();                                           // bias row of the first tile visible
+                int it2 = 0;
+                for (int t = t_begin; t < t_end; t += t_step, ++it2) {
+                    int m_blk, n_blk;
+                    tile_coords(t, m_blk, n_blk);
+                    const int rb = it2 & 1;
+                    if constexpr (!L::RRING) {
+                        // the other residual buffer was last read by tile it2-1, whose last barrier every thread has passed
+                        if (leader && has_res && t + (int)gridDim.x < num_tiles) load_residual(t + gridDim.x, rb ^ 1);
+                    }
+                    if (t + t_step < t_end) {
+                        // bias row of the NEXT tile into the other half (last read by tile it2-1); it becomes visible
+                        // through the barriers of this tile
+                        int mb2, nb2;
+                        tile_coords(t + t_step, mb2, nb2);
+                        if (epi_tid < BN) s_bias[((it2 + 1) & 1) * BN + epi_tid] = epi.bias[nb2 * BN + epi_tid];
+                    }
+                    const float* sb = s_bias + (it2 & 1) * BN;
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    if constexpr (!L::RRING) {
+                        if (has_res) mbar_wait(&res_bar[rb], (uint32_t)((it2 >> 1) & 1));
+                    }
+                    const unsigned char* rbuf = r_s + rb * L::R_BYTES;
+                    const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + grp * 32);
+                    uint32_t v[2][32];
+                    tmem_ld_32x32(t_addr, v[0]);
+#pragma unroll
+                    for (int j = 0; j < NSUB; ++j) {
+                        tmem_ld_wait();                                   // columns of sub-tile j are in v[j & 1]
+                        if (j + 1 < NSUB) tmem_ld_32x32(t_addr + (uint32_t)((j + 1) * 64), v[(j + 1) & 1]);
+                        if (j == NSUB - 1) {                              // accumulator drained: MMAs may reuse it
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                        }
+                        const int g = it2 * NSUB + j;
+                        unsigned char* csub = c_s + (g & 1) * L::SUB_BYTES + row_off;
+                        const unsigned char* rsub = rbuf + j * L::SUB_BYTES + row_off;
+                        if constexpr (L::RRING) {
+                            if (has_res) mbar_wait(&res_bar[g % RS], (uint32_t)((g / RS) & 1));
+                            rsub = r_s + (g % RS) * L::SUB_BYTES + row_off;
+                        }
+                        const int c = 2 * j + grp;
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {                  // 8 columns = one 16-byte chunk
+                            const uint32_t chunk = ((uint32_t)(grp * 4 + gq) ^ sw) << 4;
+                            float f[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * gq);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * gq + 4);
+                            f[0] = __uint_as_float(v[j & 1][8 * gq + 0]) + b0.x; f[1] = __uint_as_float(v[j & 1][8 * gq + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[j & 1][8 * gq + 2]) + b0.z; f[3] = __uint_as_float(v[j & 1][8 * gq + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[j & 1][8 * gq + 4]) + b1.x; f[5] = __uint_as_float(v[j & 1][8 * gq + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[j & 1][8 * gq + 6]) + b1.z; f[7] = __uint_as_float(v[j & 1][8 * gq + 7]) + b1.w;
+                            if (has_res) {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(rsub + chunk);
+                                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 ff = __bfloat1622float2(rp[e]);
+                                    f[2 * e] += ff.x;
+                                    f[2 * e + 1] += ff.y;
+                                }
+                            }
+                            if (epi.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                            }
+                            uint4 pk;
+                            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            *reinterpret_cast<uint4*>(csub + chunk) = pk;
+                        }
+                        fence_proxy_async();                              // smem writes -> visible to the TMA engine
+                        if (leader) tma_store_wait_read<0>();             // store g-1 has left buffer (g+1) & 1
+                        epi_bar_sync();                                   // sub-tile g complete; next buffer free
+                        if (leader) {
+                            tma_store_2d(&epi.mapC, c_s + (g & 1) * L::SUB_BYTES, n_blk * BN + j * 64, m_blk * BM);
+                            tma_store_commit();
+                            if constexpr (L::RRING) {
+                                if (has_res) load_residual_sub(g + RS);   // slot g % RS was read before the barrier
+                            }
+                        }
+                    }
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                if (leader) tma_store_wait_all();
+                t_begin = t_end;                                          // nothing left for the loop below
+            }
             if constexpr (L::RRING) {
-                if (leader && has_res) {
+                if (leader && has_res && !EPI2) {
                     for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
                 }
             } else {
-                if (leader && has_res && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
+                if (leader && has_res && !EPI2 && (int)blockIdx.x < num_tiles) load_residual(blockIdx.x, 0);
             }
             int it = 0;
             for (int t = t_begin; t < t_end; t += t_step, ++it) {
@@ -559,9 +670,9 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 }
 
 // Launch with a fully prepared A operand.
-template <int BN, class Epi, bool STAGED = false, bool KHS = false, int VAR = VAR_NONE>
+template <int BN, class Epi, bool STAGED = false, bool KHS = false, int VAR = VAR_NONE, bool EPI2 = false>
 int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGED, KHS, VAR>;
+    using L = SmemLayout<BN, STAGED, KHS, VAR, EPI2>;
     if ((VAR == VAR_BRES || VAR == VAR_BRESP) && (A.mode != 3 || n != BN || k != BRES_K))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
@@ -580,7 +691,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
             grid = images < sms ? images : sms;
         }
     }
-    auto kern = gemm_kernel<BN, Epi, STAGED, KHS, VAR>;
+    auto kern = gemm_kernel<BN, Epi, STAGED, KHS, VAR, EPI2>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks
     // VAR_BRESP: the whole K range of a tile rides in one stage

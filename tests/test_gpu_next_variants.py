@@ -106,3 +106,13 @@ def test_distance_stage_variants_give_the_exact_mode_results(tmp_path, switch):
     assert np.array_equal(o["tensor_rank"], o["exact_rank"])
     assert np.array_equal(o["tensor_final"], o["exact_final"])
     assert int(o["tensor_flagged"][0]) < 30          # the mirrored values certify as well as the direct ones
+
+
+@pytest.mark.gpu_next
+def test_one_barrier_epilogue_is_bit_identical(tmp_path):
+    """SSG_CONV_EPI2=1: the generic staged epilogue with one named barrier per sub-tile, pipelined tcgen05.ld and a
+    full-ring residual prefetch -- same bias / residual / ReLU arithmetic per element, so the same features."""
+    want = _embed_in_subprocess(tmp_path, "epi1", {"SSG_CONV_EPI2": "0"})
+    got = _embed_in_subprocess(tmp_path, "epi2", {"SSG_CONV_EPI2": "1"})
+    assert np.isfinite(want).all()
+    assert np.array_equal(got, want)
