@@ -34,6 +34,7 @@ struct ProfScope {
     cudaStream_t st_;
     void* e0_;
 };
+void prof_suspend(bool on);   // no timers while a stream capture records launches
 }  // namespace ssg
 #define SSG_PROF(name, st) ssg::ProfScope prof_scope__(name, st)
 

@@ -71,6 +71,11 @@ struct ssg_embed_plan {
     void* stemP;                 // padded 4-channel bf16 input [2*batch][256][144][4]
     int stem_windows;            // 1: window GEMM (no im2col), 0: im2col + GEMM, -1: undecided
     void *col, *stem, *x, *y, *ds, *t1, *t2, *planes, *xs;
+    // SSG_L2_CHUNK: the chunk loop over layers 1-2 as a CUDA graph on a side stream (one graph per batch size)
+    cudaStream_t side;
+    cudaEvent_t ev_in, ev_out;
+    cudaGraphExec_t l2_graph;
+    int l2_graph_nb, l2_graph_chunk;
 };
 
 static int ealloc(void** p, size_t bytes, size_t* total) {
@@ -103,6 +108,10 @@ extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
     void* bufs[] = {p->col, p->stem, p->x, p->y, p->ds, p->t1, p->t2, p->planes, p->xs, p->w_stem448, p->w_stem256, p->b_stem448,
                     p->stemP};
     for (void* q : bufs) if (q) cudaFree(q);
+    if (p->l2_graph) cudaGraphExecDestroy(p->l2_graph);
+    if (p->ev_in) cudaEventDestroy(p->ev_in);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
+    if (p->side) cudaStreamDestroy(p->side);
     delete p;
     return SSG_OK;
 }
@@ -115,6 +124,7 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     ssg_embed_plan* p = new ssg_embed_plan();
     p->device = device; p->batch_max = batch_max; p->bytes = 0;
     p->col = p->stem = p->x = p->y = p->ds = p->t1 = p->t2 = p->planes = p->xs = nullptr;
+    p->side = nullptr; p->ev_in = nullptr; p->ev_out = nullptr; p->l2_graph = nullptr; p->l2_graph_nb = 0; p->l2_graph_chunk = 0;
     const auto& sp = specs();
     p->w.assign(sp.size(), nullptr);
     p->b.assign(sp.size(), nullptr);
@@ -295,16 +305,55 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
         const size_t E0 = (size_t)64 * 32 * 64 * 2, E2 = (size_t)32 * 16 * 512 * 2;   // bytes per image-pass
         { SSG_PROF("conv_stem_tc", st); SSG_TRY(conv_stem_windows64(p->stemP, NB, p->w_stem256, p->b_stem448, /* tensor-map placeholder, never written */ p->x, st, pooled_all)); }
         const int blocks[4] = {3, 4, 6, 3};
-        for (int q0 = 0; q0 < NB; q0 += l2_chunk) {
-            const int NBc = NB - q0 < l2_chunk ? NB - q0 : l2_chunk;
-            int lc = 1, H = 64, W = 32, C = 64;
-            void *x = pooled_all + (size_t)q0 * E0, *y = p->y;
-            for (int L = 0; L < 2; ++L)
-                for (int b = 0; b < blocks[L]; ++b) {
-                    const bool last = L == 1 && b == blocks[1] - 1;
-                    SSG_TRY(run_block(p, L, b, NBc, fuse_ds, x, y, H, W, C, lc, last ? l2_all + (size_t)q0 * E2 : nullptr, st));
-                    if (L == 0 && b == 0) y = p->x;           // the chunk's input slice is read-only: ping-pong on x / y
-                }
+        auto chunk_loop = [&](cudaStream_t cs) -> int {
+            for (int q0 = 0; q0 < NB; q0 += l2_chunk) {
+                const int NBc = NB - q0 < l2_chunk ? NB - q0 : l2_chunk;
+                int lc = 1, H = 64, W = 32, C = 64;
+                void *x = pooled_all + (size_t)q0 * E0, *y = p->y;
+                for (int L = 0; L < 2; ++L)
+                    for (int b = 0; b < blocks[L]; ++b) {
+                        const bool last = L == 1 && b == blocks[1] - 1;
+                        SSG_TRY(run_block(p, L, b, NBc, fuse_ds, x, y, H, W, C, lc, last ? l2_all + (size_t)q0 * E2 : nullptr, cs));
+                        if (L == 0 && b == 0) y = p->x;       // the chunk's input slice is read-only: ping-pong on x / y
+                    }
+            }
+            return SSG_OK;
+        };
+        // The loop issues (NB / chunk) x 21 launches whose host cost (tensor-map encodes + launch, ~8 us each) would
+        // exceed their GPU time: record it ONCE per batch size as a CUDA graph on a side stream (every pointer in it is
+        // plan-owned, so the graph is valid for every later batch of that size) and replay it.  SSG_L2_GRAPH=0: direct.
+        static int l2_graph = -1;
+        if (l2_graph < 0) { const char* e = getenv("SSG_L2_GRAPH"); l2_graph = e ? atoi(e) : 1; }
+        if (l2_graph) {
+            if (!p->side) {
+                SSG_CUDA_TRY(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+                SSG_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+                SSG_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+            }
+            if (!p->l2_graph || p->l2_graph_nb != NB || p->l2_graph_chunk != l2_chunk) {
+                if (p->l2_graph) { cudaGraphExecDestroy(p->l2_graph); p->l2_graph = nullptr; }
+                cudaGraph_t graph = nullptr;
+                prof_suspend(true);
+                cudaError_t ce = cudaStreamBeginCapture(p->side, cudaStreamCaptureModeThreadLocal);
+                int rc = ce == cudaSuccess ? chunk_loop(p->side) : SSG_OK;
+                if (ce == cudaSuccess) ce = cudaStreamEndCapture(p->side, &graph);
+                prof_suspend(false);
+                if (rc != SSG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess || !graph)
+                    return ssg_set_error(SSG_ERR_CUDA, "embed: capturing the chunk loop failed: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(&p->l2_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess)
+                    return ssg_set_error(SSG_ERR_CUDA, "embed: cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+                p->l2_graph_nb = NB; p->l2_graph_chunk = l2_chunk;
+            }
+            SSG_CUDA_TRY(cudaEventRecord(p->ev_in, st));
+            SSG_CUDA_TRY(cudaStreamWaitEvent(p->side, p->ev_in, 0));
+            { SSG_PROF("conv_l2_graph", p->side); SSG_CUDA_TRY(cudaGraphLaunch(p->l2_graph, p->side)); }
+            SSG_CUDA_TRY(cudaEventRecord(p->ev_out, p->side));
+            SSG_CUDA_TRY(cudaStreamWaitEvent(st, p->ev_out, 0));
+        } else {
+            SSG_TRY(chunk_loop(st));
         }
         int lc = 24, H = 32, W = 16, C = 512;                  // layer 3 starts at layer index 1 + 10 + 13
         void *x = l2_all, *y = p->y;

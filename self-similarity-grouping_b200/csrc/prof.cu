@@ -13,6 +13,7 @@ struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 struct ProfAgg { double ms = 0.0; long long launches = 0; };
 
 static bool g_on = false;
+static int g_suspend = 0;      // > 0 while a stream capture is recording launches (events recorded there cannot be timed)
 static std::vector<ProfRec> g_open;
 static std::vector<cudaEvent_t> g_pool;
 static std::map<std::string, ProfAgg> g_agg;
@@ -26,7 +27,7 @@ static cudaEvent_t get_event() {
 }
 
 ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), e0_(nullptr) {
-    if (!g_on) return;
+    if (!g_on || g_suspend) return;
     e0_ = get_event();
     cudaEventRecord((cudaEvent_t)e0_, st);
 }
@@ -36,6 +37,8 @@ ProfScope::~ProfScope() {
     cudaEventRecord(e1, st_);
     g_open.push_back(ProfRec{name_, (cudaEvent_t)e0_, e1});
 }
+
+void prof_suspend(bool on) { g_suspend += on ? 1 : -1; }
 
 }  // namespace ssg
 

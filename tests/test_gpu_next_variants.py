@@ -18,7 +18,9 @@ def _embed_in_subprocess(tmp_path, name, env, n_img=21, batch=32):
         "import ssg_b200\n"
         "from oracle import resnet_oracle as R\n"
         "plan = ssg_b200.EmbedPlan(%d); plan.load_model(R.build_model(2, 0))\n"
-        "out = plan.forward(R.synth_images(%d, 11).cuda(), 2); torch.cuda.synchronize()\n"
+        "x = R.synth_images(%d, 11).cuda()\n"
+        "first = plan.forward(x, 2).clone(); out = plan.forward(x, 2); torch.cuda.synchronize()\n"
+        "assert torch.equal(first, out)\n"
         "np.save(sys.argv[1], out.cpu().numpy())\n"
         % ([os.path.join(ROOT, "self-similarity-grouping_b200"), ROOT], batch, n_img))
     out_file = str(tmp_path / (name + ".npy"))
@@ -27,13 +29,16 @@ def _embed_in_subprocess(tmp_path, name, env, n_img=21, batch=32):
 
 
 @pytest.mark.gpu_next
-@pytest.mark.parametrize("chunk", [8, 10, 32])
-def test_l2_chunked_layers_are_bit_identical(tmp_path, chunk):
+@pytest.mark.parametrize("chunk,graph", [(8, 1), (10, 1), (32, 1), (10, 0)])
+def test_l2_chunked_layers_are_bit_identical(tmp_path, chunk, graph):
     """SSG_L2_CHUNK: layers 1-2 over chunks of image-passes that stay in L2 (embed.cu) -- same kernels on the same
     per-image tiles, so the features must equal the unchunked forward bit for bit (21 images = 42 passes: chunk 8 and
     10 leave a ragged last chunk, 32 a short one)."""
     want = _embed_in_subprocess(tmp_path, "plain", {"SSG_L2_CHUNK": "0"})
-    got = _embed_in_subprocess(tmp_path, "chunk%d" % chunk, {"SSG_L2_CHUNK": str(chunk)})
+    # graph = 1: the chunk loop is recorded once as a CUDA graph on a side stream and replayed (two forwards in the
+    # subprocess would replay it; one forward records + launches), graph = 0: direct launches
+    got = _embed_in_subprocess(tmp_path, "chunk%d_%d" % (chunk, graph),
+                               {"SSG_L2_CHUNK": str(chunk), "SSG_L2_GRAPH": str(graph)})
     assert np.isfinite(want).all()
     assert np.array_equal(got, want)
 
