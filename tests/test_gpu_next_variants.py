@@ -121,3 +121,22 @@ def test_one_barrier_epilogue_is_bit_identical(tmp_path):
     got = _embed_in_subprocess(tmp_path, "epi2", {"SSG_CONV_EPI2": "1"})
     assert np.isfinite(want).all()
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu_next
+@pytest.mark.parametrize("n,ns", [(2, 1), (3, 5), (10, 7), (21, 30), (22, 22)])
+def test_tiny_target_sets_against_oracle(n, ns):
+    """Fewer targets than k1 + 1 = 21 rank columns (reid/rerank.py:76 slices whatever is there): an edge the
+    reference handles implicitly and the GPU suite had not covered -- final_dist within 1e-4 of the float32-mode
+    oracle, exact mode."""
+    import torch
+    import ssg_b200
+    from ssg_b200 import _lib
+    from oracle import ssg_oracle as O
+    rng = np.random.RandomState(n * 31 + ns)
+    tgt = rng.randn(n, 64).astype(np.float32)
+    src = rng.randn(ns, 64).astype(np.float32)
+    _, want = O.re_ranking(src, tgt, lambda_value=0.1, mode="f32")
+    _, got = ssg_b200.re_ranking_device(torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda(), lambda_value=0.1,
+                                        dist_mode=_lib.DIST_EXACT)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-4)

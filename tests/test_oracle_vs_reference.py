@@ -17,6 +17,17 @@ def test_re_ranking_bit_exact(mode, n, ns, d, seed):
     assert np.array_equal(e0, e1) and np.array_equal(f0, f1)
 
 
+@pytest.mark.parametrize("n,ns", [(2, 1), (3, 5), (10, 7), (21, 30), (22, 22)])
+def test_re_ranking_bit_exact_below_k1_targets(n, ns):
+    """Fewer targets than the k1 + 1 = 21 rank columns reid/rerank.py:76 slices: the reference just works with the
+    shorter rows; pin that edge (the CUDA parity case for it is tests/test_gpu_next_variants.py)."""
+    rng = np.random.RandomState(n * 31 + ns)
+    tgt, src = rng.randn(n, 64).astype(np.float32), rng.randn(ns, 64).astype(np.float32)
+    _, f0 = refshim.ref_re_ranking(src, tgt, mode="f32", lambda_value=0.1)
+    _, f1 = O.re_ranking(src, tgt, lambda_value=0.1, mode="f32")
+    assert np.array_equal(f0, f1)
+
+
 def test_no_rerank_returns_none():
     tgt, _ = O.synth_features(40, 32, 0)
     e0, f0 = refshim.ref_re_ranking(tgt, tgt, mode="f32", no_rerank=True)
