@@ -338,7 +338,10 @@ query_expand_kernel(const int* __restrict__ rank, int n, int k2, const int* __re
     }
     if (tid == 0) s_base = 0;
     __syncthreads();
-    const float kf = (float)k2;
+    // np.mean over the rows rank[i, :k2] that exist (rerank.py:97): k2 of them unless the whole set is smaller than k2
+    int nvalid = 0;
+    for (int j = 0; j < k2; ++j) nvalid += rows[j] >= 0;
+    const float kf = (float)nvalid;
     for (int base = 0; base < total; base += QE_NT) {
         const int e = base + tid;
         bool head = false;
