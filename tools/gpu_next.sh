@@ -8,6 +8,14 @@ mkdir -p gpurun_out
 make -C tests/c > gpurun_out/next_make.log 2>&1
 timeout 60 tests/c/_build/shard_check 4000 8 > gpurun_out/next_shard_check.log 2>&1; echo "rc=$?" >> gpurun_out/next_shard_check.log
 timeout 60 tests/c/_build/sparse_check 4000 128 > gpurun_out/next_sparse_check.log 2>&1; echo "rc=$?" >> gpurun_out/next_sparse_check.log
+# embedding variants, byte-compared against the default through the plain-C harness (seconds each)
+D=tests/c/_build/embed_dump
+timeout 120 $D /tmp/emb_default.bin > gpurun_out/next_embed_dump.log 2>&1
+for v in "SSG_CONV_EPI2=1" "SSG_L2_CHUNK=8" "SSG_L2_CHUNK=10 SSG_L2_GRAPH=0" "SSG_L2_CHUNK=32" "SSG_CONV_EPI2=1 SSG_L2_CHUNK=16"; do
+  env $v timeout 120 $D /tmp/emb_variant.bin >> gpurun_out/next_embed_dump.log 2>&1
+  if cmp -s /tmp/emb_default.bin /tmp/emb_variant.bin; then echo "$v: identical to the default" >> gpurun_out/next_embed_dump.log
+  else echo "$v: DIFFERS from the default" >> gpurun_out/next_embed_dump.log; fi
+done
 timeout 600 python -m pytest tests -m gpu_next -q -x > gpurun_out/next_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/next_pytest.log
 Q="--quick --steps 2 --warmup 1"
 timeout 200 python bench.py $Q > gpurun_out/next_ab_default.json 2> gpurun_out/next_ab_default.err
