@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Builds the CPU-emulated variant of the library's plain-CUDA translation units (TEST INFRASTRUCTURE).
+
+api.cu, rerank.cu, cluster.cu, dist.cu and prof.cu are copied with two mechanical rewrites --
+    kernel<<<grid, block, smem, stream>>>(args)   ->  emu::launch([&]() { kernel(args); }, grid, block, smem, stream)
+    extern __shared__ T name[];                   ->  T* name = (T*)emu::dyn_smem;
+-- and compiled by g++ against tests/cpu_cuda/stub/cuda_runtime.h + emu.cpp (fibers, one host thread; see the stub's
+header comment) into tests/cpu_cuda/_build/libssg_emu.so.  The tensor-core translation units (gemm_tc.cu, conv.cu,
+embed.cu: tcgen05 / TMA, nothing to emulate) are left out; the four launch wrappers api.cu calls from them report
+SSG_ERR_UNSUPPORTED, so only dist_mode = SSG_DIST_EXACT works.  The plain-C harnesses of tests/c are then built against
+it (same sources, `*_emu` binaries), which runs the real kernel source of the exact-mode re-ranking, eps and DBSCAN --
+dense, row-sharded and sparse -- on the CPU.
+
+    python tests/cpu_cuda/build_emu.py        # -> prints the paths of the binaries
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "self-similarity-grouping_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu"]
+
+STUBS = r'''// launch wrappers of the tensor-core translation units that api.cu references: not available under emulation
+#include "common.cuh"
+#include "kernels.h"
+namespace ssg {
+int launch_sqdist_tensor(const float*, int, const float*, int, int, float*, size_t, cudaStream_t) {
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: the tcgen05 distance GEMM is not emulated (use SSG_DIST_EXACT)");
+}
+int launch_split_bf16x3(const float*, int, int, int, const float*, void*, float*, cudaStream_t) {
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
+}
+int launch_col_mean(const float*, int, int, double*, float*, cudaStream_t) {
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
+}
+int launch_gemm_dist(const void*, const float*, int, const void*, const float*, int, int, float*, size_t, cudaStream_t, int) {
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
+}
+}  // namespace ssg
+'''
+
+
+def _match_forward(s, i, open_ch, close_ch):
+    """s[i] == open_ch -> index just past the matching close_ch."""
+    depth = 0
+    while True:
+        c = s[i]
+        if c == open_ch:
+            depth += 1
+        elif c == close_ch:
+            depth -= 1
+            if depth == 0:
+                return i + 1
+        i += 1
+
+
+def rewrite(src):
+    src = re.sub(r"extern\s+__shared__\s+([A-Za-z_][\w ]*?)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = (\1*)emu::dyn_smem;", src)
+    out, pos = [], 0
+    while True:
+        k = src.find("<<<", pos)
+        if k < 0:
+            out.append(src[pos:])
+            return "".join(out)
+        # kernel expression: identifier (with ::) optionally followed by a template argument list, just before <<<
+        j = k
+        while src[j - 1].isspace():
+            j -= 1
+        if src[j - 1] == ">":                          # template arguments: walk back to the matching <
+            depth, j = 0, j - 1
+            while True:
+                if src[j] == ">":
+                    depth += 1
+                elif src[j] == "<":
+                    depth -= 1
+                    if depth == 0:
+                        break
+                j -= 1
+        while j > 0 and (src[j - 1].isalnum() or src[j - 1] in "_:"):
+            j -= 1
+        kern = src[j:k].strip()
+        e = src.index(">>>", k)
+        cfg = src[k + 3:e]
+        a = e + 3
+        while src[a].isspace():
+            a += 1
+        assert src[a] == "(", "launch without an argument list near: " + src[k - 40:k + 40]
+        b = _match_forward(src, a, "(", ")")
+        args = src[a + 1:b - 1]
+        out.append(src[pos:j])
+        out.append("emu::launch([&]() { %s(%s); }, %s)" % (kern, args, cfg))
+        pos = b
+
+
+def build(verbose=False):
+    os.makedirs(os.path.join(OUT, "src"), exist_ok=True)
+    srcs = []
+    for u in UNITS:
+        with open(os.path.join(CSRC, u)) as f:
+            text = rewrite(f.read())
+        assert "<<<" not in text
+        dst = os.path.join(OUT, "src", u.replace(".cu", "_emu.cpp"))
+        with open(dst, "w") as f:
+            f.write(text)
+        srcs.append(dst)
+    stub = os.path.join(OUT, "src", "tc_stubs_emu.cpp")
+    with open(stub, "w") as f:
+        f.write(STUBS)
+    srcs += [stub, os.path.join(HERE, "emu.cpp")]
+    lib = os.path.join(OUT, "libssg_emu.so")
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-D__CUDACC__", "-w",
+             "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
+    # -Bsymbolic: the library's cudaMalloc / cudaSetDevice / ... must bind to ITS stand-ins even inside a process that has
+    # the real libcudart loaded (pytest imports torch)
+    cmd = ["g++"] + flags + ["-shared", "-Wl,-Bsymbolic", "-o", lib] + srcs
+    subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
+    bins = []
+    for h in ("shard_check", "sparse_check"):
+        exe = os.path.join(OUT, h + "_emu")
+        subprocess.run(["gcc", "-std=c99", "-O1", "-I" + os.path.join(HERE, "stub"), "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", h + ".c"), "-o", exe, "-L" + OUT, "-lssg_emu", "-lm",
+                        "-Wl,-rpath," + OUT], check=True)
+        bins.append(exe)
+    return lib, bins
+
+
+if __name__ == "__main__":
+    lib, bins = build(verbose=True)
+    print(lib)
+    for b in bins:
+        print(b)

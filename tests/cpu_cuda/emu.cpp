@@ -1,0 +1,168 @@
+// CPU execution model for the library's plain-CUDA kernels: cooperative fibers (ucontext), one host thread.
+// See stub/cuda_runtime.h.  TEST INFRASTRUCTURE.
+#include <ucontext.h>
+#include <sys/mman.h>
+#include <vector>
+
+#include "cuda_runtime.h"
+
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
+namespace emu {
+
+unsigned char* dyn_smem = nullptr;
+static const size_t STACK = 256 * 1024;
+
+struct Coll { unsigned mask = 0, arrived = 0; unsigned long gen = 0; uint64_t vals[32], snap[2][32]; };
+struct Fiber { ucontext_t ctx; bool done = false; };
+
+static ucontext_t g_main;
+static std::vector<Fiber> g_fib;
+static std::vector<char*> g_stacks;
+static std::vector<std::vector<Coll>> g_coll;        // per warp
+static const std::function<void()>* g_body = nullptr;
+static int g_cur = 0, g_n = 0, g_alive = 0, g_arrived = 0, g_or_acc = 0, g_or_res[2];
+static unsigned long g_bar_gen = 0, g_events = 0;
+
+static void set_thread_idx(int t) {
+    threadIdx.x = t % blockDim.x;
+    threadIdx.y = (t / blockDim.x) % blockDim.y;
+    threadIdx.z = t / (blockDim.x * blockDim.y);
+}
+static void yield_() { swapcontext(&g_fib[g_cur].ctx, &g_main); }
+int lane_id() { return g_cur & 31; }
+
+static void release_barrier_if_complete() {
+    if (g_alive > 0 && g_arrived >= g_alive) {
+        g_or_res[g_bar_gen & 1] = g_or_acc;
+        g_or_acc = 0;
+        g_arrived = 0;
+        ++g_bar_gen;
+        ++g_events;
+    }
+}
+int syncthreads_or(int pred) {
+    const unsigned long g = g_bar_gen;
+    g_or_acc |= pred != 0;
+    ++g_arrived;
+    release_barrier_if_complete();
+    while (g_bar_gen == g) yield_();
+    return g_or_res[g & 1];
+}
+void syncthreads() { (void)syncthreads_or(0); }
+
+const uint64_t* exchange(unsigned mask, uint64_t v) {
+    std::vector<Coll>& wc = g_coll[g_cur >> 5];
+    Coll* c = nullptr;
+    for (Coll& e : wc) if (e.mask == mask) { c = &e; break; }
+    if (!c) { wc.emplace_back(); c = &wc.back(); c->mask = mask; }
+    const int lane = g_cur & 31;
+    if (!((mask >> lane) & 1u)) { fprintf(stderr, "emu: lane %d calls a collective whose mask %08x excludes it\n", lane, mask); abort(); }
+    const unsigned long g = c->gen;
+    c->vals[lane] = v;
+    c->arrived |= 1u << lane;
+    // lanes beyond the block's last thread do not exist: a full mask means "every lane there is"
+    unsigned need = mask;
+    const int warp_first = (g_cur >> 5) << 5;
+    if (warp_first + 32 > g_n) need &= (g_n - warp_first >= 32) ? 0xffffffffu : ((1u << (g_n - warp_first)) - 1u);
+    if ((c->arrived & need) == need) {
+        memcpy(c->snap[g & 1], c->vals, sizeof(c->vals));
+        c->arrived = 0;
+        ++c->gen;
+        ++g_events;
+    } else {
+        // vector may grow (emplace_back by another lane with a new mask): re-find after every yield
+        while (true) {
+            yield_();
+            std::vector<Coll>& w2 = g_coll[g_cur >> 5];
+            c = nullptr;
+            for (Coll& e : w2) if (e.mask == mask) { c = &e; break; }
+            if (c->gen != g) break;
+        }
+    }
+    return c->snap[g & 1];
+}
+
+static void trampoline() {
+    (*g_body)();
+    g_fib[g_cur].done = true;
+    --g_alive;
+    ++g_events;
+    release_barrier_if_complete();          // threads that have exited count as arrived
+    swapcontext(&g_fib[g_cur].ctx, &g_main);
+}
+
+static void run_block(int n) {
+    g_n = n; g_alive = n; g_arrived = 0; g_or_acc = 0;
+    if ((int)g_fib.size() < n) g_fib.resize(n);
+    while ((int)g_stacks.size() < n) {
+        void* s = mmap(nullptr, STACK, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+        if (s == MAP_FAILED) { perror("emu: mmap"); abort(); }
+        g_stacks.push_back((char*)s);
+    }
+    g_coll.assign((n + 31) / 32, std::vector<Coll>());
+    for (auto& w : g_coll) w.reserve(8);
+    for (int t = 0; t < n; ++t) {
+        g_fib[t].done = false;
+        getcontext(&g_fib[t].ctx);
+        g_fib[t].ctx.uc_stack.ss_sp = g_stacks[t];
+        g_fib[t].ctx.uc_stack.ss_size = STACK;
+        g_fib[t].ctx.uc_link = &g_main;
+        makecontext(&g_fib[t].ctx, trampoline, 0);
+    }
+    while (g_alive > 0) {
+        const unsigned long before = g_events;
+        for (int t = 0; t < n; ++t) {
+            if (g_fib[t].done) continue;
+            g_cur = t;
+            set_thread_idx(t);
+            swapcontext(&g_main, &g_fib[t].ctx);
+        }
+        if (g_events == before && g_alive > 0) {
+            fprintf(stderr, "emu: DEADLOCK in block (%u,%u,%u): %d threads alive, %d at the block barrier -- a barrier or warp "
+                    "collective is not reached by all of its participants\n", blockIdx.x, blockIdx.y, blockIdx.z, g_alive, g_arrived);
+            abort();
+        }
+    }
+}
+
+void launch(const std::function<void()>& fn, dim3 grid, dim3 block, size_t smem, cudaStream_t) {
+    if (!dyn_smem) dyn_smem = (unsigned char*)aligned_alloc(1024, 256 * 1024);
+    if (smem > 256 * 1024) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
+    gridDim = grid; blockDim = block;
+    g_body = &fn;
+    const int n = (int)(block.x * block.y * block.z);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+            for (unsigned bx = 0; bx < grid.x; ++bx) {
+                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                run_block(n);
+            }
+}
+
+}  // namespace emu
+
+// ---- "device memory" is host memory
+extern "C" {
+cudaError_t cudaMalloc(void** p, size_t bytes) { *p = aligned_alloc(256, (bytes + 255) / 256 * 256 + 256); return *p ? cudaSuccess : 2; }
+cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, enum cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t) {
+    for (size_t r = 0; r < h; ++r) memmove((char*)d + r * dp, (const char*)s + r * sp, w);
+    return cudaSuccess;
+}
+cudaError_t cudaMemset(void* p, int v, size_t n) { memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(struct cudaDeviceProp* p, int) { memset(p, 0, sizeof(*p)); p->major = 10; p->minor = 0; strcpy(p->name, "cpu-emulation"); return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "emulation error"; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+}
