@@ -141,3 +141,139 @@ def test_eps_and_dbscan_kernels_against_numpy_and_sklearn(emu, n, rho, dtype):
     want = DBSCAN(eps=e_cmp, min_samples=4, metric="precomputed").fit_predict(d)
     _, got = emu.eps_and_labels(d, eps=e_cmp)
     assert np.array_equal(got, want)
+
+
+def test_python_prototypes_of_the_sharded_and_sparse_entry_points(emu):
+    """ssg_b200._lib.PROTOTYPES (the ctypes signatures the GPU wrappers use) applied to the emulated library, with the
+    argument order of ssg_b200.cluster / rerank / dist: a swapped or mistyped argument would show as garbage here
+    rather than on the GPU box.  Two ranks simulated one after another, collectives done by hand."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    names = ["ssg_rerank_plan_create", "ssg_rerank_plan_destroy", "ssg_rerank_run", "ssg_rerank_distance_rows",
+             "ssg_rerank_finish_rows", "ssg_rerank_finish_sparse", "ssg_rerank_sparse_view", "ssg_cluster_plan_create",
+             "ssg_cluster_plan_destroy", "ssg_cluster_buffers", "ssg_eps_estimate", "ssg_dbscan", "ssg_eps_shard_begin",
+             "ssg_eps_shard_hist", "ssg_eps_shard_pick", "ssg_eps_shard_gather", "ssg_eps_shard_finish",
+             "ssg_dbscan_shard_count", "ssg_dbscan_shard_fill", "ssg_dbscan_shard_label", "ssg_eps_sparse",
+             "ssg_dbscan_sparse", "ssg_last_error"]
+    for nm in names:
+        fn = getattr(lib, nm)
+        fn.restype, fn.argtypes = L.PROTOTYPES[nm]
+
+    def ok(rc):
+        assert rc == 0, lib.ssg_last_error().decode()
+    ptr = lambda a: a.ctypes.data                                                       # noqa: E731
+    n, ns, d, lam, rho, world = 90, 50, 16, 0.1, 0.03, 2
+    tgt, _ = O.synth_features(n, d, 1, per_cluster=10, noise=0.3)
+    src, _ = O.synth_features(ns, d, 2, per_cluster=10, noise=0.4)
+    rp, cp = ctypes.c_void_p(), ctypes.c_void_p()
+    ok(lib.ssg_rerank_plan_create(ctypes.byref(rp), 0, n, ns, d))
+    ok(lib.ssg_cluster_plan_create(ctypes.byref(cp), 0, n, 0))
+    final = np.empty((n, n), np.float64)
+    ok(lib.ssg_rerank_run(rp, ptr(src), ns, ptr(tgt), n, d, 20, 6, lam, L.DIST_EXACT, ptr(final), None, None))
+    eps0, top0, ncl0 = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_int()
+    ok(lib.ssg_eps_estimate(cp, ptr(final), L.F64, n, rho, ctypes.byref(eps0), ctypes.byref(top0), None))
+    lab0 = np.empty(n, np.int64)
+    ok(lib.ssg_dbscan(cp, ptr(final), L.F64, n, eps0.value, 4, ptr(lab0), ctypes.byref(ncl0), None))
+    assert ncl0.value >= 2
+
+    # ---- rows of final_dist (dist.CudaBackend.finish_rows)
+    from ssg_b200.dist import shard_bounds
+    blocks = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        blk = np.empty((hi - lo, n), np.float64)
+        ok(lib.ssg_rerank_distance_rows(rp, ptr(src), ns, ptr(tgt), n, d, 20, L.DIST_EXACT, lo, hi - lo, None, None))
+        blocks.append(blk)
+    for r in range(world):            # tables complete (one plan holds all rows here): finish every block
+        lo, hi = shard_bounds(n, world, r)
+        ok(lib.ssg_rerank_finish_rows(rp, ptr(tgt), n, d, 20, 6, lam, lo, hi - lo, ptr(blocks[r]), None))
+    assert np.array_equal(np.concatenate(blocks), final)
+
+    # ---- sharded eps (dist.sharded_eps / cluster.ClusterPlan.eps_shard_*), two plans = two ranks
+    def buffers(plan):
+        p = [ctypes.c_void_p() for _ in range(6)]
+        ok(lib.ssg_cluster_buffers(plan, *[ctypes.byref(x) for x in p]))
+        mk = lambda v, ct, cnt: np.ctypeslib.as_array(ctypes.cast(v.value, ctypes.POINTER(ct)), shape=(cnt,))   # noqa: E731
+        return dict(hist=mk(p[0], ctypes.c_int64, L.EPS_BINS), state=mk(p[1], ctypes.c_int64, 8),
+                    partial=mk(p[2], ctypes.c_double, n), list=mk(p[3], ctypes.c_double, L.EPS_LIST_CAP),
+                    cnt=mk(p[4], ctypes.c_int32, n), nbr_ptr=p[5])
+    plans = []
+    for r in range(world):
+        h = ctypes.c_void_p()
+        ok(lib.ssg_cluster_plan_create(ctypes.byref(h), 0, n, 0))
+        plans.append((h, buffers(h)))
+        ok(lib.ssg_eps_shard_begin(h, None))
+    for npass in (0, 1):
+        for r, (h, b) in enumerate(plans):
+            ok(lib.ssg_eps_shard_hist(h, ptr(blocks[r]), L.F64, n, world, r, npass, None))
+        tot = sum(b["hist"].copy() for _, b in plans)
+        for h, b in plans:
+            b["hist"][:] = tot
+            ok(lib.ssg_eps_shard_pick(h, npass, rho, None))
+    counts, lists = [], []
+    for r, (h, b) in enumerate(plans):
+        c = ctypes.c_longlong()
+        ok(lib.ssg_eps_shard_gather(h, ptr(blocks[r]), L.F64, n, world, r, 0, ctypes.byref(c), None))
+        counts.append(c.value)
+        lists.append(b["list"][:c.value].copy())
+    assert min(counts) >= 0
+    part = np.zeros(n)
+    for r, (h, b) in enumerate(plans):
+        lo, hi = shard_bounds(n, world, r)
+        part[lo:hi] = b["partial"][lo:hi]
+    merged = np.concatenate(lists)
+    got = []
+    for h, b in plans:
+        b["partial"][:] = part
+        b["list"][:len(merged)] = merged
+        b["state"][5] = len(merged)
+        e, t = ctypes.c_double(), ctypes.c_longlong()
+        ok(lib.ssg_eps_shard_finish(h, n, 0, ctypes.byref(e), ctypes.byref(t), None))
+        got.append((e.value, t.value))
+    assert got[0] == got[1] and got[0][1] == top0.value
+    np.testing.assert_allclose(got[0][0], eps0.value, rtol=1e-13)
+
+    # ---- sharded DBSCAN (dist.sharded_dbscan)
+    for r, (h, b) in enumerate(plans):
+        lo, hi = shard_bounds(n, world, r)
+        ok(lib.ssg_dbscan_shard_count(h, ptr(blocks[r]), L.F64, n, lo, hi - lo, eps0.value, None))
+    cnt = np.zeros(n, np.int32)
+    for r, (h, b) in enumerate(plans):
+        lo, hi = shard_bounds(n, world, r)
+        cnt[lo:hi] = b["cnt"][lo:hi]
+    nbr_sum = None
+    for r, (h, b) in enumerate(plans):
+        lo, hi = shard_bounds(n, world, r)
+        b["cnt"][:] = cnt
+        total = ctypes.c_longlong()
+        ok(lib.ssg_dbscan_shard_fill(h, ptr(blocks[r]), L.F64, n, lo, hi - lo, eps0.value, ctypes.byref(total), None))
+        nb = np.ctypeslib.as_array(ctypes.cast(b["nbr_ptr"].value, ctypes.POINTER(ctypes.c_int32)), shape=(total.value,))
+        nbr_sum = nb.copy() if nbr_sum is None else nbr_sum + nb
+    for h, b in plans:
+        nb = np.ctypeslib.as_array(ctypes.cast(b["nbr_ptr"].value, ctypes.POINTER(ctypes.c_int32)), shape=(len(nbr_sum),))
+        nb[:] = nbr_sum
+        lab, ncl = np.empty(n, np.int64), ctypes.c_int()
+        ok(lib.ssg_dbscan_shard_label(h, n, 4, ptr(lab), ctypes.byref(ncl), None))
+        assert np.array_equal(lab, lab0) and ncl.value == ncl0.value
+
+    # ---- sparse form (rerank.RerankPlan.finish_sparse, cluster.ClusterPlan.eps_sparse / dbscan_sparse)
+    nnz = ctypes.c_longlong()
+    ok(lib.ssg_rerank_distance_rows(rp, ptr(src), ns, ptr(tgt), n, d, 20, L.DIST_EXACT, 0, n, None, None))
+    ok(lib.ssg_rerank_finish_sparse(rp, ptr(tgt), n, d, 20, 6, lam, ctypes.byref(nnz), None))
+    v = [ctypes.c_void_p() for _ in range(3)]
+    cnt2, thr = ctypes.c_longlong(), ctypes.c_double()
+    ok(lib.ssg_rerank_sparse_view(rp, ctypes.byref(v[0]), ctypes.byref(v[1]), ctypes.byref(v[2]), ctypes.byref(cnt2),
+                                  ctypes.byref(thr)))
+    assert cnt2.value == nnz.value and thr.value == float(np.float32(1 - lam))
+    e, t, certified = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_int()
+    ok(lib.ssg_eps_sparse(cp, n, v[0], v[1], v[2], thr.value, rho, ctypes.byref(e), ctypes.byref(t), ctypes.byref(certified), None))
+    assert certified.value == 1 and t.value == top0.value
+    np.testing.assert_allclose(e.value, eps0.value, rtol=1e-13)
+    lab, ncl = np.empty(n, np.int64), ctypes.c_int()
+    ok(lib.ssg_dbscan_sparse(cp, n, v[0], v[1], v[2], eps0.value, 4, ptr(lab), ctypes.byref(ncl), None))
+    assert np.array_equal(lab, lab0) and ncl.value == ncl0.value
+    for h, _ in plans:
+        lib.ssg_cluster_plan_destroy(h)
+    lib.ssg_cluster_plan_destroy(cp)
+    lib.ssg_rerank_plan_destroy(rp)
