@@ -125,6 +125,12 @@ def build(verbose=False):
                         os.path.join(ROOT, "tests", "c", h + ".c"), "-o", exe, "-L" + OUT, "-lssg_emu", "-lm",
                         "-Wl,-rpath," + OUT], check=True)
         bins.append(exe)
+    # C++ driver on the library's internal launch wrappers: sparse vs dense Jaccard at n > 8192 (slow: opt-in test)
+    exe = os.path.join(OUT, "jaccard_big")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-w", "-I" + os.path.join(HERE, "stub"), "-I" + CSRC,
+                    "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "jaccard_big.cpp"), "-o", exe, "-L" + OUT,
+                    "-lssg_emu", "-Wl,-rpath," + OUT], check=True)
+    bins.append(exe)
     return lib, bins
 
 

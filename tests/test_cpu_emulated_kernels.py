@@ -277,3 +277,11 @@ def test_python_prototypes_of_the_sharded_and_sparse_entry_points(emu):
         lib.ssg_cluster_plan_destroy(h)
     lib.ssg_cluster_plan_destroy(cp)
     lib.ssg_rerank_plan_destroy(rp)
+
+
+@pytest.mark.skipif(not os.environ.get("SSG_SLOW"), reason="about two minutes: set SSG_SLOW=1")
+def test_sparse_jaccard_beyond_256_bitmap_words(emu):
+    """n = 9000 -> 282 bitmap words: the word-rank scan of jaccard_sparse_kernel takes two passes of its block-wide loop,
+    as at the production size.  Last run: profiles/r01_emulated_checks.log."""
+    r = subprocess.run([emu.bins["jaccard_big"], "9000"], capture_output=True, text=True, timeout=3000)
+    assert r.returncode == 0 and "JACCARD_BIG PASSED" in r.stdout, r.stdout + r.stderr
