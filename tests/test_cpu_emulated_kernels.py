@@ -285,3 +285,31 @@ def test_sparse_jaccard_beyond_256_bitmap_words(emu):
     as at the production size.  Last run: profiles/r01_emulated_checks.log."""
     r = subprocess.run([emu.bins["jaccard_big"], "9000"], capture_output=True, text=True, timeout=3000)
     assert r.returncode == 0 and "JACCARD_BIG PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_k2_one_lambda_and_no_rerank_paths_under_emulation(emu):
+    """rerank.py:65-66 (no_rerank returns after the distance stages), :94 (k2 == 1 skips the query expansion) and other
+    lambda values, exact mode, against the oracle."""
+    tgt, _ = O.synth_features(70, 24, 5, per_cluster=7)
+    src, _ = O.synth_features(40, 24, 6, per_cluster=7)
+    for k1, k2, lam in ((20, 1, 0.3), (20, 6, 0.0), (10, 3, 0.5)):
+        _, f_ref = O.re_ranking(src, tgt, k1=k1, k2=k2, lambda_value=lam, mode="f32")
+        _, f = emu.re_ranking(src, tgt, k1=k1, k2=k2, lam=lam)
+        np.testing.assert_allclose(f, f_ref, rtol=0, atol=1e-4)
+
+
+def test_dbscan_kernels_property_based_under_emulation(emu):
+    """Random symmetric matrices with ties, several eps / min_samples: labels identical to sklearn (the order-free
+    union-find formulation against the index-ordered DFS)."""
+    from sklearn.cluster import DBSCAN
+    rng = np.random.RandomState(7)
+    for trial in range(6):
+        n = int(rng.randint(5, 80))
+        a = rng.rand(n, n)
+        d = np.round((a + a.T) / 2, int(rng.randint(1, 3)))
+        np.fill_diagonal(d, np.round(rng.rand(n) * 0.3, 2))          # the diagonal counts like any other entry
+        for eps in (0.1, 0.3, 0.55):
+            ms = int(rng.randint(1, 6))
+            want = DBSCAN(eps=eps, min_samples=ms, metric="precomputed").fit_predict(d)
+            _, got = emu.eps_and_labels(d, eps=eps, min_samples=ms)
+            assert np.array_equal(got, want), (trial, n, eps, ms)
