@@ -95,6 +95,15 @@ int ssg_rerank_host(ssg_rerank_plan* plan, const float* h_src, int ns, const flo
 int ssg_rerank_init(ssg_rerank_plan* plan, const float* d_qg, const float* d_qq, const float* d_gg, int q, int g,
                     int k1, int k2, double lambda_value, float* d_out, void* stream);
 
+/* reid/rerank_plain.py:125-178 re_ranking(input_feature_source, input_feature, k=20, lambda_value=0.1) -- the plain
+ * kNN-set variant both drivers carry as a commented-out import (selftraining.py:29):
+ *   S_i = { j != i : d2[i,j] <= k-th smallest entry of row i (diagonal included) },
+ *   J = scipy cdist(S, S, 'jaccard'),  final = J*(1-lambda) + (v_i+v_j)*lambda with v as in reid/rerank.py:36-40.
+ * d_final: [n,n] float64 (the reference returns it twice).  1 <= k <= 31, n >= k.  float16 -> float32 as for
+ * ssg_rerank_run.  Synchronises the stream. */
+int ssg_rerank_plain(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d, int k,
+                     double lambda_value, int dist_mode, double* d_final, void* stream);
+
 /* Intermediate results of the last ssg_rerank_run, copied to the host (stage-isolated parity tests). */
 #define SSG_STAGE_VEC 0       /* float  [n]        normalised source vector v (rerank.py:36-40)     */
 #define SSG_STAGE_ROWMAX 1    /* float  [n]        row maximum of the squared distance (rerank.py:68) */

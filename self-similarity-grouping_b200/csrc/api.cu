@@ -73,6 +73,8 @@ struct ssg_rerank_plan {
     float* io_euclid; size_t io_euclid_bytes;
     // sparse form of final_dist (ssg_rerank_finish_sparse): CSR over the touched columns, grown on demand
     int *sp_cnt, *sp_rowptr, *sp_col; double* sp_val; size_t sp_cap; long long sp_nnz; double sp_threshold;
+    // plain kNN-set re-ranking (ssg_rerank_plain): rows with a tied k-th neighbour and their exact fallback
+    int *pl_flag_rows, *pl_flags, *pl_sel_idx; float *pl_sel_val, *pl_rows;
     int last_n;
 };
 
@@ -134,7 +136,8 @@ extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
                     p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid, p->split_ta,
                     p->split_tb, p->split_sb, p->norm_t, p->norm_s, p->norm_max, p->cand_idx, p->cand_val,
                     p->cand_exact, p->flag_src, p->flag_tgt, p->fb_rows, p->fb_f32, p->fb_i32, p->mean_partial,
-                    p->mean, p->sp_cnt, p->sp_rowptr, p->sp_col, p->sp_val};
+                    p->mean, p->sp_cnt, p->sp_rowptr, p->sp_col, p->sp_val, p->pl_flag_rows, p->pl_flags, p->pl_sel_idx,
+                    p->pl_sel_val, p->pl_rows};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return SSG_OK;
@@ -506,6 +509,56 @@ extern "C" int ssg_rerank_sparse_view(ssg_rerank_plan* p, int** d_rowptr, int** 
     if (d_val) *d_val = p->sp_val;
     if (nnz) *nnz = p->sp_nnz;
     if (threshold) *threshold = p->sp_threshold;
+    return SSG_OK;
+}
+
+// reid/rerank_plain.py:125-178 re_ranking(input_feature_source, input_feature, k=20, lambda_value=0.1): kNN-set Jaccard
+// distance + the source term of reid/rerank.py.  d_final: [n,n] float64.  Synchronises the stream (flag counts).
+extern "C" int ssg_rerank_plain(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d, int k,
+                                double lambda_value, int dist_mode, double* d_final, void* stream) {
+    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k, 1));
+    if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_plain: d_final is null");
+    if (n < k) return ssg_set_error(SSG_ERR_INVALID, "rerank_plain: k=%d exceeds the %d targets (np.partition raises, "
+                                    "rerank_plain.py:167)", k, n);
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int PL_ROWS = 256;                 // rows per exact-fallback batch
+    if (!p->pl_flags) {
+        SSG_TRY(dalloc((void**)&p->pl_flag_rows, sizeof(int) * (size_t)p->n_max, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->pl_flags, sizeof(int) * 4, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->pl_sel_idx, sizeof(int) * PL_ROWS * SSG_RANK_STRIDE, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->pl_sel_val, sizeof(float) * PL_ROWS * SSG_RANK_STRIDE, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->pl_rows, sizeof(float) * (size_t)PL_ROWS * p->d, &p->bytes));
+    }
+    // distance stages with k1 = k: source row minimum, row maximum, k+1 leading rank columns
+    SSG_TRY(distance_stages(p, d_src, ns, d_tgt, n, d, k, dist_mode, nullptr, true, 0, n, st));
+    { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vector(p->rowmin, n, p->vec, p->scratch, st)); }
+    SSG_CUDA_TRY(cudaMemsetAsync(p->pl_flags, 0, sizeof(int) * 4, st));
+    { SSG_PROF("knn_sets", st); SSG_TRY(launch_knn_sets(p->rank, p->rank_val, n, k, p->q_idx, p->q_cnt, p->pl_flag_rows, p->pl_flags, st)); }
+    int h_flags[4];
+    SSG_CUDA_TRY(cudaMemcpyAsync(h_flags, p->pl_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+    SSG_CUDA_TRY(cudaStreamSynchronize(st));
+    const int nflag = h_flags[0];
+    const int cap_rows = (int)(p->dmat_elems / (size_t)n < (size_t)PL_ROWS ? p->dmat_elems / (size_t)n : (size_t)PL_ROWS);
+    for (int f0 = 0; f0 < nflag; f0 += cap_rows) {
+        const int cnt = nflag - f0 < cap_rows ? nflag - f0 : cap_rows;
+        SSG_TRY(launch_gather_rows(d_tgt, d, p->pl_flag_rows + f0, cnt, p->pl_rows, st));
+        { SSG_PROF("sqdist_exact", st); SSG_TRY(launch_sqdist_exact(p->pl_rows, cnt, d_tgt, n, d, p->dmat, (size_t)n, st)); }
+        { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, cnt, n, nullptr, k, false, p->pl_sel_idx, p->pl_sel_val,
+                                  SSG_RANK_STRIDE, p->cursor, st)); }
+        { SSG_PROF("knn_sets", st); SSG_TRY(launch_knn_scan(p->dmat, (size_t)n, cnt, n, p->pl_sel_val, SSG_RANK_STRIDE, k, p->pl_flag_rows + f0,
+                                p->q_idx, p->q_cnt, p->pl_flags + 1, st)); }
+    }
+    if (nflag > 0) {
+        SSG_CUDA_TRY(cudaMemcpyAsync(h_flags, p->pl_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+        SSG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_flags[1])
+            return ssg_set_error(SSG_ERR_CAPACITY, "rerank_plain: a neighbour set exceeds %d entries (massive ties at the "
+                                 "k-th distance)", SSG_VQ_STRIDE);
+    }
+    { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
+    { SSG_PROF("jaccard_plain", st); SSG_TRY(launch_jaccard_plain(n, p->q_idx, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value, d_final, st)); }
+    p->last_n = n;
     return SSG_OK;
 }
 

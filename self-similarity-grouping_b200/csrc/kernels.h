@@ -60,6 +60,13 @@ int launch_jaccard_final(int n, int row0, int rows, const int* q_idx, const floa
 int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                           const int* csc_row, const float* vec, double lambda_value, const int* sp_rowptr, int* sp_cnt,
                           int* sp_col, double* sp_val, cudaStream_t st);
+// plain kNN-set re-ranking (reid/rerank_plain.py:125-178)
+int launch_knn_sets(const int* rank, const float* rank_val, int n, int k, int* set_idx, int* set_cnt, int* flag_rows,
+                    int* flag_cnt, cudaStream_t st);
+int launch_knn_scan(const float* M, size_t ld, int rows, int cols, const float* sel_val, int sel_stride, int k,
+                    const int* rows_list, int* set_idx, int* set_cnt, int* overflow, cudaStream_t st);
+int launch_jaccard_plain(int n, const int* s_idx, const int* s_cnt, const int* colptr, const int* csc_row,
+                         const float* vec, double lambda_value, double* final_dist, cudaStream_t st);
 int launch_jaccard_init(int n, int q, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                         const int* csc_row, const float* dmat, const float* rowmax, double lambda_value, float* out,
                         cudaStream_t st);

@@ -717,6 +717,158 @@ int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Plain kNN-set re-ranking: reid/rerank_plain.py:125-178 re_ranking(source, target, k, lambda).
+//   S_i    = { j != i : od[i,j] <= k-th smallest entry of row i of od }   (od = squared distances, diagonal included)
+//   J[i,j] = scipy cdist(S, S, 'jaccard') = (|S_i u S_j| - |S_i n S_j|) / |S_i u S_j|   (0 when both are empty)
+//   final  = fl(J * fl(1 - lambda)) + fl(v_i + v_j) * lambda, v as in reid/rerank.py:36-40.
+// The sets come from the rank table of the distance stages (sorted by (od / rowmax, index); the division is
+// monotone, so while the k-th and (k+1)-th normalised values differ strictly the first k columns ARE the k smallest
+// raw distances); rows whose boundary is tied are handed to the exact fallback (knn_scan_kernel on recomputed rows).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+knn_sets_kernel(const int* __restrict__ rank, const float* __restrict__ rank_val, int n, int k,
+                int* __restrict__ set_idx, int* __restrict__ set_cnt, int* __restrict__ flag_rows,
+                int* __restrict__ flag_cnt) {
+    const int i = blockIdx.x, lane = threadIdx.x;
+    constexpr int RS = SSG_RANK_STRIDE;
+    const bool tied = n > k && !(rank_val[(size_t)i * RS + k - 1] < rank_val[(size_t)i * RS + k]);
+    if (tied) {
+        if (lane == 0) { flag_rows[atomicAdd(flag_cnt, 1)] = i; set_cnt[i] = 0; }
+        return;
+    }
+    int c = lane < k ? rank[(size_t)i * RS + lane] : INT_MAX;
+    if (c == i || c < 0) c = INT_MAX;                    // knn_bool[i, i] = False
+    int pos = 0;                                          // ascending index order (the Jaccard kernel merges sorted lists)
+    for (int l = 0; l < 32; ++l) {
+        const int o = __shfl_sync(0xffffffffu, c, l);
+        pos += (o < c) || (o == c && l < lane);
+    }
+    if (c != INT_MAX) set_idx[(size_t)i * SSG_VQ_STRIDE + pos] = c;
+    const unsigned have = __ballot_sync(0xffffffffu, c != INT_MAX);
+    if (lane == 0) set_cnt[i] = __popc(have);
+}
+
+// exact fallback: block b = flagged row rows_list[b], whose raw squared distances are row b of M and whose k smallest
+// raw values (sorted) are sel_val[b, 0..k): S = { j != i : M[b, j] <= sel_val[b, k-1] } in ascending j.
+__global__ void __launch_bounds__(256)
+knn_scan_kernel(const float* __restrict__ M, size_t ld, int cols, const float* __restrict__ sel_val, int sel_stride,
+                int k, const int* __restrict__ rows_list, int* __restrict__ set_idx, int* __restrict__ set_cnt,
+                int* __restrict__ overflow) {
+    __shared__ int wsum[8];
+    __shared__ int s_carry;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int i = rows_list[b];
+    const float thr = sel_val[(size_t)b * sel_stride + k - 1];
+    const float* row = M + (size_t)b * ld;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int j0 = 0; j0 < cols; j0 += 256) {
+        const int j = j0 + tid;
+        const int hit = (j < cols && j != i && row[j] <= thr) ? 1 : 0;
+        int tot;
+        const int ex = block_exclusive_scan<256>(hit, wsum, tot);
+        const int base = s_carry;
+        if (hit) {
+            if (base + ex < SSG_VQ_STRIDE) set_idx[(size_t)i * SSG_VQ_STRIDE + base + ex] = j;
+            else *overflow = 1;
+        }
+        __syncthreads();
+        if (tid == 0) s_carry = base + tot;
+        __syncthreads();
+    }
+    if (tid == 0) set_cnt[i] = s_carry < SSG_VQ_STRIDE ? s_carry : SSG_VQ_STRIDE;
+}
+
+__global__ void __launch_bounds__(JF_NT)
+jaccard_plain_kernel(int n, const int* __restrict__ s_idx, const int* __restrict__ s_cnt,
+                     const int* __restrict__ colptr, const int* __restrict__ csc_row, const float* __restrict__ vec,
+                     double lambda_value, float oml, double* __restrict__ final_dist) {
+    extern __shared__ unsigned char jf_smem[];
+    int* si = reinterpret_cast<int*>(jf_smem);                       // [VQ_STRIDE]
+    int* pref = si + SSG_VQ_STRIDE;                                  // [VQ_STRIDE + 1]
+    unsigned* bitmap = reinterpret_cast<unsigned*>(pref + SSG_VQ_STRIDE + 1);
+    __shared__ int wsum[JF_NT / 32];
+    __shared__ int s_carry;
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int ci = s_cnt[i];
+    const int nwords = (n + 31) >> 5;
+    const float vi = vec[i];
+    double* out = final_dist + (size_t)i * n;
+    auto store = [&](int m, float J) {
+        const float Jm = __fmul_rn(J, oml);
+        out[m] = __dadd_rn((double)Jm, __dmul_rn((double)__fadd_rn(vec[m], vi), lambda_value));
+    };
+    for (int s = tid; s < ci; s += JF_NT) si[s] = s_idx[(size_t)i * SSG_VQ_STRIDE + s];
+    for (int w = tid; w < nwords; w += JF_NT) bitmap[w] = 0u;
+    // no common neighbour: J = 1 (0 when both sets are empty, as scipy defines the distance of two all-False rows)
+    for (int m = tid; m < n; m += JF_NT) store(m, (ci + s_cnt[m]) > 0 ? 1.0f : 0.0f);
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ci; base += JF_NT) {
+        const int s = base + tid;
+        int len = 0;
+        if (s < ci) len = colptr[si[s] + 1] - colptr[si[s]];
+        int tot;
+        const int ex = block_exclusive_scan<JF_NT>(len, wsum, tot);
+        const int c = s_carry;
+        if (s < ci) pref[s] = c + ex;
+        __syncthreads();
+        if (tid == 0) s_carry = c + tot;
+        __syncthreads();
+    }
+    const int T = s_carry;
+    if (tid == 0) pref[ci] = T;
+    __syncthreads();
+    for (int f = tid; f < T; f += JF_NT) {
+        int lo = 0, hi = ci - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (pref[mid] <= f) lo = mid; else hi = mid - 1;
+        }
+        const int m = csc_row[colptr[si[lo]] + (f - pref[lo])];
+        const unsigned bit = 1u << (m & 31);
+        if (atomicOr(&bitmap[m >> 5], bit) & bit) continue;          // another thread owns column m
+        const int cm = s_cnt[m];
+        const int* mi = s_idx + (size_t)m * SSG_VQ_STRIDE;
+        int inter = 0, a = 0, b = 0;
+        while (a < ci && b < cm) {
+            const int ia = si[a], ib = mi[b];
+            if (ia == ib) { ++inter; ++a; ++b; }
+            else if (ia < ib) ++a;
+            else ++b;
+        }
+        const int uni = ci + cm - inter;
+        // scipy: (number of positions where exactly one is set) / (number where at least one is set), in double
+        store(m, uni > 0 ? (float)((double)(uni - inter) / (double)uni) : 0.0f);
+    }
+}
+
+int launch_knn_sets(const int* rank, const float* rank_val, int n, int k, int* set_idx, int* set_cnt, int* flag_rows,
+                    int* flag_cnt, cudaStream_t st) {
+    if (k < 1 || k > 31) return ssg_set_error(SSG_ERR_INVALID, "rerank_plain: k=%d out of range (1..31)", k);
+    knn_sets_kernel<<<n, 32, 0, st>>>(rank, rank_val, n, k, set_idx, set_cnt, flag_rows, flag_cnt);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int launch_knn_scan(const float* M, size_t ld, int rows, int cols, const float* sel_val, int sel_stride, int k,
+                    const int* rows_list, int* set_idx, int* set_cnt, int* overflow, cudaStream_t st) {
+    if (rows <= 0) return SSG_OK;
+    knn_scan_kernel<<<rows, 256, 0, st>>>(M, ld, cols, sel_val, sel_stride, k, rows_list, set_idx, set_cnt, overflow);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int launch_jaccard_plain(int n, const int* s_idx, const int* s_cnt, const int* colptr, const int* csc_row,
+                         const float* vec, double lambda_value, double* final_dist, cudaStream_t st) {
+    const size_t smem = sizeof(int) * (2 * SSG_VQ_STRIDE + 1) + sizeof(unsigned) * (size_t)((n + 31) / 32 + 1);
+    if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
+    SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_plain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jaccard_plain_kernel<<<n, JF_NT, smem, st>>>(n, s_idx, s_cnt, colptr, csc_row, vec, lambda_value,
+                                                 (float)(1.0 - lambda_value), final_dist);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // re_ranking_init front end (rerank_initial.py:43-48): D'[r,c] = 2 - 2*S[c,r] with S = [[qq, qg],[qg^T, gg]]
 // (the reference normalises by the column max and transposes; D' is that transpose before the division).
 // ---------------------------------------------------------------------------------------------------

@@ -154,6 +154,29 @@ def re_ranking(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.
     return plan.run_host(src, tgt, k1, k2, lambda_value, dist_mode, no_rerank, want_euclid=True)
 
 
+def re_ranking_plain(input_feature_source, input_feature, k=20, lambda_value=0.1, MemorySave=False, Minibatch=2000,
+                     dist_mode=None):
+    """Drop-in for reid/rerank_plain.py:125 re_ranking (the kNN-set Jaccard variant): same
+    positional order and defaults, returns ``(final_dist, final_dist)`` as the reference does (float64 [N,N]).
+    MemorySave / Minibatch only chunk the reference's cdist and are ignored."""
+    import os
+    import torch
+    dev = _lib.require_cuda()
+    if dist_mode is None:
+        dist_mode = int(os.environ.get("SSG_DIST_MODE", _lib.DIST_EXACT))
+    src = torch.from_numpy(np.ascontiguousarray(input_feature_source, dtype=np.float32)).to(dev)
+    tgt = torch.from_numpy(np.ascontiguousarray(input_feature, dtype=np.float32)).to(dev)
+    n, d = tgt.shape
+    plan = get_plan(n, src.shape[0], d, dev.index)
+    print('computing source distance...')
+    print('computing original distance...')
+    final = torch.empty((n, n), dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().ssg_rerank_plain(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), n, d, int(k),
+                                            float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr()))
+    out = final.cpu().numpy()
+    return out, out
+
+
 def re_ranking_init_blocks(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
     """reid/rerank_initial.py:40 re_ranking_init on similarity blocks (numpy or CUDA tensors).
     Returns a numpy float32 [q,g] array for numpy inputs, a CUDA tensor for CUDA inputs."""

@@ -250,3 +250,21 @@ def test_no_unbound_names_in_python_sources():
         files += sorted(glob.glob(os.path.join(root, pat)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "lint_names.py")] + files, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_rerank_plain_drop_in_surface():
+    """Row f4: reid.rerank_plain keeps the reference's names and signatures (rerank_plain.py:27,125); without a GPU the
+    CUDA-backed function raises loudly instead of falling back."""
+    import inspect
+    import numpy as np
+    import pytest as _pt
+    import torch
+    from reid import rerank_plain
+    sig = inspect.signature(rerank_plain.re_ranking)
+    assert list(sig.parameters)[:6] == ["input_feature_source", "input_feature", "k", "lambda_value", "MemorySave", "Minibatch"]
+    assert sig.parameters["k"].default == 20 and sig.parameters["lambda_value"].default == 0.1
+    assert list(inspect.signature(rerank_plain.re_ranking_lh).parameters)[:5] == [
+        "input_feature_source", "input_feature", "k1", "k2", "lambda_value"]
+    if not torch.cuda.is_available():
+        with _pt.raises(RuntimeError):
+            rerank_plain.re_ranking(np.zeros((4, 8), np.float32), np.zeros((30, 8), np.float32))

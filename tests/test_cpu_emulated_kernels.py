@@ -313,3 +313,31 @@ def test_dbscan_kernels_property_based_under_emulation(emu):
             want = DBSCAN(eps=eps, min_samples=ms, metric="precomputed").fit_predict(d)
             _, got = emu.eps_and_labels(d, eps=eps, min_samples=ms)
             assert np.array_equal(got, want), (trial, n, eps, ms)
+
+
+@pytest.mark.parametrize("n,ns,k,quant", [(60, 40, 20, None), (25, 10, 20, None), (20, 30, 20, None), (48, 48, 5, None),
+                                          (70, 30, 20, 1), (40, 20, 3, 0)])
+def test_plain_knn_set_reranker_against_oracle(emu, n, ns, k, quant):
+    """ssg_rerank_plain (reid/rerank_plain.py:125-178) under emulation, exact mode, against the
+    restatement that is pinned bit for bit to the reference (oracle/rerank_plain_oracle.py).  quant rounds the features so
+    that many distances tie at the k-th neighbour: those rows go through the exact fallback scan and their sets grow
+    beyond k, as `tem_vec <= kThreshold` does in the reference."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    from oracle import rerank_plain_oracle as P
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    for nm in ("ssg_rerank_plan_create", "ssg_rerank_plan_destroy", "ssg_rerank_plain", "ssg_last_error"):
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+    rng = np.random.RandomState(n + k)
+    tgt, src = rng.randn(n, 12).astype(np.float32), rng.randn(ns, 12).astype(np.float32)
+    if quant is not None:
+        tgt, src = np.round(tgt, quant), np.round(src, quant)
+    want = P.re_ranking_plain(src, tgt, k=k, lambda_value=0.1, mode="f32")
+    plan = ctypes.c_void_p()
+    assert lib.ssg_rerank_plan_create(ctypes.byref(plan), 0, n, ns, 12) == 0
+    got = np.empty((n, n), np.float64)
+    rc = lib.ssg_rerank_plain(plan, src.ctypes.data, ns, tgt.ctypes.data, n, 12, k, 0.1, L.DIST_EXACT, got.ctypes.data, None)
+    assert rc == 0, lib.ssg_last_error().decode()
+    lib.ssg_rerank_plan_destroy(plan)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)          # the Jaccard part is exact; exp() of the source term
+    assert np.array_equal(got, got.T)

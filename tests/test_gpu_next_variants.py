@@ -140,3 +140,24 @@ def test_tiny_target_sets_against_oracle(n, ns):
     _, got = ssg_b200.re_ranking_device(torch.from_numpy(src).cuda(), torch.from_numpy(tgt).cuda(), lambda_value=0.1,
                                         dist_mode=_lib.DIST_EXACT)
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu_next
+@pytest.mark.parametrize("mode", ["exact", "tensor"])
+def test_plain_knn_set_reranker_on_the_device(mode):
+    """reid.rerank_plain.re_ranking (row f4) on the GPU against the pinned restatement: the Jaccard part is exact, the
+    source term carries exp() -- 2e-6.  Quantised features force ties at the k-th neighbour (exact fallback scan)."""
+    import ssg_b200
+    from ssg_b200 import _lib
+    from ssg_b200.rerank import re_ranking_plain
+    from oracle import ssg_oracle as O, rerank_plain_oracle as P
+    dm = _lib.DIST_EXACT if mode == "exact" else _lib.DIST_TENSOR
+    for n, ns, d, k, quant in ((300, 200, 64, 20, None), (257, 100, 128, 20, 1), (64, 64, 32, 5, None)):
+        tgt, _ = O.synth_features(n, d, 3)
+        src, _ = O.synth_features(ns, d, 4, noise=0.6)
+        if quant is not None:
+            tgt, src = np.round(tgt, quant), np.round(src, quant)
+        want = P.re_ranking_plain(src, tgt, k=k, lambda_value=0.1, mode="f32")
+        got, again = re_ranking_plain(src, tgt, k, 0.1, dist_mode=dm)
+        assert got is again and got.dtype == np.float64
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
