@@ -65,7 +65,8 @@ size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* plan);
 
 /* Device in / device out.  d_final: [n,n] float64 (row-major) = final_dist of the reference;
  * d_euclid: optional [n,n] float32 = euclidean_dist of the reference (pre-normalisation squared
- * distances), may be NULL.  k1 <= 31, k2 <= 8. */
+ * distances), may be NULL.  k1 <= 20 (the k-reciprocal row capacity: (k1+1) * (round(k1/2) + 2) <= SSG_V_STRIDE;
+ * larger values return SSG_ERR_INVALID), k2 <= 8; k2 > k1 + 1 is allowed, as in the reference. */
 int ssg_rerank_run(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d,
                    int k1, int k2, double lambda_value, int dist_mode, double* d_final,
                    float* d_euclid, void* stream);

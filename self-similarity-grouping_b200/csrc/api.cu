@@ -75,6 +75,7 @@ struct ssg_rerank_plan {
     int *sp_cnt, *sp_rowptr, *sp_col; double* sp_val; size_t sp_cap; long long sp_nnz; double sp_threshold;
     // plain kNN-set re-ranking (ssg_rerank_plain): rows with a tied k-th neighbour and their exact fallback
     int *pl_flag_rows, *pl_flags, *pl_sel_idx; float *pl_sel_val, *pl_rows;
+    int rank_cols;               // leading rank columns the last distance stage produced (k1 + 1 of that call)
     int last_n;
 };
 
@@ -359,6 +360,7 @@ static int distance_stages_exact(ssg_rerank_plan* p, const float* d_src, int ns,
 static int distance_stages(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d,
                            int k1, int dist_mode, float* d_euclid, bool want_rank, int row_begin, int row_end,
                            cudaStream_t st) {
+    if (want_rank) p->rank_cols = k1 + 1;
     if (dist_mode == SSG_DIST_EXACT)
         return distance_stages_exact(p, d_src, ns, d_tgt, n, d, k1, dist_mode, d_euclid, want_rank, row_begin, row_end, st);
     if (dist_mode == SSG_DIST_TENSOR)
@@ -410,6 +412,10 @@ static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int
 
 // stages (i, tail) and (v)-(vii, inverted index): source vector, k-reciprocal rows, query expansion, CSC
 static int finish_sparse_stages(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int k1, int k2, cudaStream_t st) {
+    // rerank.py:77,97 slice initial_rank[:, :k1+1] and [:, :k2]; the table holds the columns of the last distance stage
+    if (k1 + 1 > p->rank_cols || k2 > p->rank_cols)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank_finish: k1=%d / k2=%d need %d rank columns, the distance stage produced "
+                             "%d (run it with k1 >= max(k1, k2 - 1))", k1, k2, (k1 + 1 > k2 ? k1 + 1 : k2), p->rank_cols);
     const int k1p = k1 + 1;
     const int khp = (int)rint(k1 / 2.0) + 1;   // int(np.around(k1/2)) + 1, rerank.py:83
     // (i, tail) rerank.py:38-40: v = 1 - exp(-rowmin); v /= max(v)
@@ -458,7 +464,9 @@ extern "C" int ssg_rerank_run(ssg_rerank_plan* p, const float* d_src, int ns, co
                               float* d_euclid, void* stream) {
     SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
-    SSG_TRY(ssg_rerank_distance_rows(p, d_src, ns, d_tgt, n, d, k1, dist_mode, 0, n, d_euclid, stream));
+    // k2 > k1 + 1 (legal in the reference, whose argsort keeps every column): make the table wide enough for both
+    const int k1d = k1 > k2 - 1 ? k1 : k2 - 1;
+    SSG_TRY(ssg_rerank_distance_rows(p, d_src, ns, d_tgt, n, d, k1d, dist_mode, 0, n, d_euclid, stream));
     return ssg_rerank_finish(p, d_tgt, n, d, k1, k2, lambda_value, d_final, stream);
 }
 

@@ -341,3 +341,29 @@ def test_plain_knn_set_reranker_against_oracle(emu, n, ns, k, quant):
     lib.ssg_rerank_plan_destroy(plan)
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)          # the Jaccard part is exact; exp() of the source term
     assert np.array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("n,ns,d,k1,k2,lam,kind", [(40, 33, 3, 1, 8, 0.1, "quant"), (4, 33, 3, 2, 8, 0.7, "gauss"),
+                                                   (7, 2, 8, 2, 6, 0.7, "dups"), (65, 9, 17, 1, 6, 0.1, "dups"),
+                                                   (32, 9, 8, 20, 6, 0.7, "dups"), (33, 9, 3, 1, 8, 1.0, "quant"),
+                                                   (31, 1, 8, 20, 1, 0.0, "gauss")])
+def test_re_ranking_kernels_edge_parameters(emu, n, ns, d, k1, k2, lam, kind):
+    """Cases a fuzz run over the emulated library turned up or passed through: k2 > k1 + 1 (the reference slices its
+    full argsort; the rank table must then be wider than k1 + 1 columns -- it used to read stale columns), duplicate
+    and quantised targets, a single source, lambda 0 and 1."""
+    rng = np.random.RandomState(n * 7 + ns)
+    tgt, src = rng.randn(n, d).astype(np.float32), rng.randn(ns, d).astype(np.float32)
+    if kind == "quant":
+        tgt, src = np.round(tgt), np.round(src)
+    if kind == "dups":
+        tgt[n // 2:] = tgt[: n - n // 2]
+    _, want = O.re_ranking(src, tgt, k1=k1, k2=k2, lambda_value=lam, mode="f32")
+    _, got = emu.re_ranking(src, tgt, k1=k1, k2=k2, lam=lam)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-4, equal_nan=True)
+
+
+def test_k1_beyond_the_row_capacity_is_refused(emu):
+    rng = np.random.RandomState(0)
+    tgt, src = rng.randn(40, 8).astype(np.float32), rng.randn(9, 8).astype(np.float32)
+    with pytest.raises(AssertionError, match="capacity"):
+        emu.re_ranking(src, tgt, k1=21, k2=6, lam=0.1)
