@@ -623,8 +623,12 @@ extern "C" int ssg_rerank_init(ssg_rerank_plan* p, const float* d_qg, const floa
     const int k1p = k1 + 1, khp = (int)rint(k1 / 2.0) + 1;
     { SSG_PROF("init_assemble", st); SSG_TRY(launch_init_assemble(d_qg, d_qq, d_gg, q, g, p->dmat, st)); }
     { SSG_PROF("row_minmax", st); SSG_TRY(launch_row_minmax(p->dmat, (size_t)n, n, n, nullptr, p->rowmax, st)); }
-    { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, n, n, p->rowmax, k1p, false, p->rank, p->rank_val,
+    // the query expansion reads rank[:, :k2]: the table must hold max(k1 + 1, k2) sorted columns (k2 > k1 + 1 lies
+    // outside the prefix np.argpartition sorts in the reference, rerank_initial.py:52 -- sorted order is what we define)
+    const int kcols = k1p > k2 ? k1p : k2;
+    { SSG_PROF("row_select", st); SSG_TRY(launch_row_select(p->dmat, (size_t)n, n, n, p->rowmax, kcols, false, p->rank, p->rank_val,
                                       SSG_RANK_STRIDE, p->cursor, st)); }
+    p->rank_cols = kcols;
     { SSG_PROF("krecip_build", st); SSG_TRY(launch_krecip_build(p->rank, n, k1p, khp, p->v_idx, p->v_cnt, st)); }
     SSG_TRY(launch_gather_row_vals(p->dmat, (size_t)n, n, p->v_idx, p->v_cnt, SSG_V_STRIDE, p->v_val, st));
     { SSG_PROF("krecip_weights", st); SSG_TRY(launch_krecip_weights(p->rowmax, n, p->v_cnt, p->v_val, 0, st)); }

@@ -367,3 +367,30 @@ def test_k1_beyond_the_row_capacity_is_refused(emu):
     tgt, src = rng.randn(40, 8).astype(np.float32), rng.randn(9, 8).astype(np.float32)
     with pytest.raises(AssertionError, match="capacity"):
         emu.re_ranking(src, tgt, k1=21, k2=6, lam=0.1)
+
+
+@pytest.mark.parametrize("q,g,k1,k2,lam,quant", [(1, 22, 2, 6, 0.0, False), (30, 40, 5, 6, 1.0, True), (3, 22, 20, 1, 0.3, False),
+                                                  (12, 5, 2, 3, 0.3, True)])
+def test_re_ranking_init_kernels_against_oracle(emu, q, g, k1, k2, lam, quant):
+    """reid/rerank_initial.py:40-99 (cosine k-reciprocal re-ranking on similarity blocks) under emulation, including
+    k2 > k1 + 1 (the table must hold max(k1 + 1, k2) sorted columns) and quantised similarities."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    for nm in ("ssg_rerank_plan_create", "ssg_rerank_plan_destroy", "ssg_rerank_init", "ssg_last_error"):
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+    rng = np.random.RandomState(q * 100 + g)
+    f = rng.randn(q + g, 16).astype(np.float32)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    if quant:
+        f = np.round(f, 1)
+    Q, G = f[:q], f[q:]
+    qg, qq, gg = [np.ascontiguousarray(x, np.float32) for x in (Q @ G.T, Q @ Q.T, G @ G.T)]
+    want = O.re_ranking_init(qg, qq, gg, k1=k1, k2=k2, lambda_value=lam)
+    plan = ctypes.c_void_p()
+    assert lib.ssg_rerank_plan_create(ctypes.byref(plan), 0, q + g, 1, 64) == 0
+    out = np.empty((q, g), np.float32)
+    rc = lib.ssg_rerank_init(plan, qg.ctypes.data, qq.ctypes.data, gg.ctypes.data, q, g, k1, k2, lam, out.ctypes.data, None)
+    assert rc == 0, lib.ssg_last_error().decode()
+    lib.ssg_rerank_plan_destroy(plan)
+    np.testing.assert_allclose(out, want, rtol=0, atol=1e-5)
