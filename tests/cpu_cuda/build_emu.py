@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Builds the CPU-emulated variant of the library's plain-CUDA translation units (TEST INFRASTRUCTURE).
 
-api.cu, rerank.cu, cluster.cu, dist.cu and prof.cu are copied with two mechanical rewrites --
+api.cu, rerank.cu, cluster.cu, dist.cu, prof.cu and triplet.cu are copied with two mechanical rewrites --
     kernel<<<grid, block, smem, stream>>>(args)   ->  emu::launch([&]() { kernel(args); }, grid, block, smem, stream)
     extern __shared__ T name[];                   ->  T* name = (T*)emu::dyn_smem;
 -- and compiled by g++ against tests/cpu_cuda/stub/cuda_runtime.h + emu.cpp (fibers, one host thread; see the stub's
@@ -22,7 +22,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "self-similarity-grouping_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu"]
+UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu", "triplet.cu"]
 
 STUBS = r'''// launch wrappers of the tensor-core translation units that api.cu references: not available under emulation
 #include "common.cuh"

@@ -130,6 +130,8 @@ static inline long long __double_as_longlong(double d) { long long r; memcpy(&r,
 static inline double __longlong_as_double(long long l) { double r; memcpy(&r, &l, 8); return r; }
 static inline unsigned __float_as_uint(float f) { unsigned r; memcpy(&r, &f, 4); return r; }
 static inline float __uint_as_float(unsigned u) { float r; memcpy(&r, &u, 4); return r; }
+static inline float __int_as_float(int i) { float r; memcpy(&r, &i, 4); return r; }
+static inline int __float_as_int(float f) { int r; memcpy(&r, &f, 4); return r; }
 template <class A, class B> static inline auto min(A a, B b) -> decltype(a + b) { return a < b ? a : b; }
 template <class A, class B> static inline auto max(A a, B b) -> decltype(a + b) { return a > b ? a : b; }
 #endif

@@ -394,3 +394,35 @@ def test_re_ranking_init_kernels_against_oracle(emu, q, g, k1, k2, lam, quant):
     assert rc == 0, lib.ssg_last_error().decode()
     lib.ssg_rerank_plan_destroy(plan)
     np.testing.assert_allclose(out, want, rtol=0, atol=1e-5)
+
+
+def test_triplet_loss_kernels_against_reference_goldens(emu, golden_dir):
+    """Row f1: ssg_triplet_forward / backward (csrc/triplet.cu) under emulation against the golden vectors made by the
+    reference's TripletLoss module (loss, precision, gradient; 1e-5 relative, the tolerance of that row)."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    for nm in ("ssg_triplet_forward", "ssg_triplet_backward", "ssg_last_error"):
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+    g = np.load(os.path.join(golden_dir, "triplet_cases.npz"))
+    done = 0
+    for ci, row in enumerate(g["cases"]):
+        x, t = np.ascontiguousarray(g["x_%d" % ci], np.float32), np.ascontiguousarray(g["t_%d" % ci], np.int64)
+        n, d = x.shape
+        if n * n * d > 3e7:
+            continue                                    # keep the emulated tier quick
+        K, margin, semi = int(row[1]), float(row[4]), int(bool(row[5]))
+        dist, coef = np.empty((n, n), np.float32), np.empty((n, n), np.float32)
+        lp, status, grad = np.empty(2, np.float32), np.zeros(2, np.int32), np.empty((n, d), np.float32)
+        rc = lib.ssg_triplet_forward(x.ctypes.data, t.ctypes.data, n, d, K, margin, semi, dist.ctypes.data, coef.ctypes.data,
+                                     lp.ctypes.data, status.ctypes.data, None)
+        assert rc == 0, lib.ssg_last_error().decode()
+        assert status[0] == 0
+        rc = lib.ssg_triplet_backward(x.ctypes.data, n, d, coef.ctypes.data, None, grad.ctypes.data, None)
+        assert rc == 0, lib.ssg_last_error().decode()
+        loss, ref = float(g["loss_%d" % ci]), g["grad_%d" % ci]
+        assert abs(float(lp[0]) - loss) <= 1e-5 * max(1.0, abs(loss)), ci
+        assert abs(float(lp[1]) - float(g["prec_%d" % ci])) < 1e-6, ci
+        assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max(), ci
+        done += 1
+    assert done >= 2
