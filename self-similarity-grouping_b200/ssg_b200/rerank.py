@@ -36,7 +36,10 @@ class RerankPlan(object):
         """src [ns,d], tgt [n,d]: float32 CUDA tensors.  Returns (euclid or None, final) CUDA tensors
         (float32 [n,n], float64 [n,n]); asynchronous on the current stream."""
         import torch
-        assert src.is_cuda and tgt.is_cuda and src.dtype == torch.float32 and tgt.dtype == torch.float32
+        if src.device.type != self.device.type or tgt.device.type != self.device.type:
+            raise ValueError("ssg_b200: features must live on the plan's device (%s), got %s / %s"
+                             % (self.device, src.device, tgt.device))
+        assert src.dtype == torch.float32 and tgt.dtype == torch.float32
         src, tgt = src.contiguous(), tgt.contiguous()
         n, d = tgt.shape
         ns = src.shape[0]

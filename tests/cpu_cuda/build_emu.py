@@ -96,7 +96,21 @@ def rewrite(src):
         pos = b
 
 
-def build(verbose=False):
+def _up_to_date(outputs):
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "emu.cpp"), os.path.abspath(__file__),
+            os.path.join(HERE, "stub", "cuda_runtime.h"), os.path.join(HERE, "jaccard_big.cpp"),
+            os.path.join(ROOT, "include", "ssg_b200.h"), os.path.join(ROOT, "tests", "c", "shard_check.c"),
+            os.path.join(ROOT, "tests", "c", "sparse_check.c")]
+    if not all(os.path.isfile(o) for o in outputs):
+        return False
+    return min(os.path.getmtime(o) for o in outputs) > max(os.path.getmtime(d) for d in deps)
+
+
+def build(verbose=False, force=False):
+    outputs = [os.path.join(OUT, "libssg_emu.so")] + [os.path.join(OUT, b) for b in
+                                                      ("shard_check_emu", "sparse_check_emu", "jaccard_big")]
+    if not force and _up_to_date(outputs):
+        return outputs[0], outputs[1:]
     os.makedirs(os.path.join(OUT, "src"), exist_ok=True)
     srcs = []
     for u in UNITS:

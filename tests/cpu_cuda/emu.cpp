@@ -15,9 +15,25 @@ unsigned char* dyn_smem = nullptr;
 static const size_t STACK = 256 * 1024;
 
 struct Coll { unsigned mask = 0, arrived = 0; unsigned long gen = 0; uint64_t vals[32], snap[2][32]; };
-struct Fiber { ucontext_t ctx; bool done = false; };
+// Context switch: on x86-64 a dozen instructions (callee-saved registers + stack pointer) instead of swapcontext, whose
+// two sigprocmask system calls per switch dominated the run time (a block barrier is blockDim switches).
+#if defined(__x86_64__)
+#define EMU_FAST_SWITCH 1
+struct Ctx { void* sp; };
+extern "C" void emu_switch(Ctx* from, Ctx* to);
+asm(".text\n.globl emu_switch\n.type emu_switch,@function\nemu_switch:\n"
+    "pushq %rbp\npushq %rbx\npushq %r12\npushq %r13\npushq %r14\npushq %r15\n"
+    "movq %rsp, (%rdi)\nmovq (%rsi), %rsp\n"
+    "popq %r15\npopq %r14\npopq %r13\npopq %r12\npopq %rbx\npopq %rbp\nret\n"
+    ".size emu_switch,.-emu_switch\n");
+#else
+#define EMU_FAST_SWITCH 0
+struct Ctx { ucontext_t uc; };
+static void emu_switch(Ctx* from, Ctx* to) { swapcontext(&from->uc, &to->uc); }
+#endif
+struct Fiber { Ctx ctx; bool done = false; };
 
-static ucontext_t g_main;
+static Ctx g_main;
 static std::vector<Fiber> g_fib;
 static std::vector<char*> g_stacks;
 static std::vector<std::vector<Coll>> g_coll;        // per warp
@@ -30,7 +46,7 @@ static void set_thread_idx(int t) {
     threadIdx.y = (t / blockDim.x) % blockDim.y;
     threadIdx.z = t / (blockDim.x * blockDim.y);
 }
-static void yield_() { swapcontext(&g_fib[g_cur].ctx, &g_main); }
+static void yield_() { emu_switch(&g_fib[g_cur].ctx, &g_main); }
 int lane_id() { return g_cur & 31; }
 
 static void release_barrier_if_complete() {
@@ -90,7 +106,8 @@ static void trampoline() {
     --g_alive;
     ++g_events;
     release_barrier_if_complete();          // threads that have exited count as arrived
-    swapcontext(&g_fib[g_cur].ctx, &g_main);
+    emu_switch(&g_fib[g_cur].ctx, &g_main);
+    abort();                                // a finished fiber is never resumed
 }
 
 static void run_block(int n) {
@@ -105,11 +122,22 @@ static void run_block(int n) {
     for (auto& w : g_coll) w.reserve(8);
     for (int t = 0; t < n; ++t) {
         g_fib[t].done = false;
-        getcontext(&g_fib[t].ctx);
-        g_fib[t].ctx.uc_stack.ss_sp = g_stacks[t];
-        g_fib[t].ctx.uc_stack.ss_size = STACK;
-        g_fib[t].ctx.uc_link = &g_main;
-        makecontext(&g_fib[t].ctx, trampoline, 0);
+#if EMU_FAST_SWITCH
+        // initial frame: six zeroed callee-saved registers, then the entry point emu_switch's `ret` jumps to, then a
+        // null return address -- so that the entry sees rsp % 16 == 8 as after a call
+        uintptr_t top = ((uintptr_t)g_stacks[t] + STACK) & ~(uintptr_t)15;
+        void** sp = (void**)top;
+        *--sp = nullptr;
+        *--sp = (void*)trampoline;
+        for (int r = 0; r < 6; ++r) *--sp = nullptr;
+        g_fib[t].ctx.sp = sp;
+#else
+        getcontext(&g_fib[t].ctx.uc);
+        g_fib[t].ctx.uc.uc_stack.ss_sp = g_stacks[t];
+        g_fib[t].ctx.uc.uc_stack.ss_size = STACK;
+        g_fib[t].ctx.uc.uc_link = &g_main.uc;
+        makecontext(&g_fib[t].ctx.uc, trampoline, 0);
+#endif
     }
     while (g_alive > 0) {
         const unsigned long before = g_events;
@@ -117,7 +145,7 @@ static void run_block(int n) {
             if (g_fib[t].done) continue;
             g_cur = t;
             set_thread_idx(t);
-            swapcontext(&g_main, &g_fib[t].ctx);
+            emu_switch(&g_main, &g_fib[t].ctx);
         }
         if (g_events == before && g_alive > 0) {
             fprintf(stderr, "emu: DEADLOCK in block (%u,%u,%u): %d threads alive, %d at the block barrier -- a barrier or warp "

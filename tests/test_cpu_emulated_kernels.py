@@ -77,8 +77,8 @@ def emu():
     return Emu()
 
 
-@pytest.mark.parametrize("name,args", [("shard_check_emu", ["150", "3"]), ("shard_check_emu", ["97", "5"]),
-                                       ("sparse_check_emu", ["160", "32"])])
+@pytest.mark.parametrize("name,args", [("shard_check_emu", ["300", "3"]), ("shard_check_emu", ["97", "5"]),
+                                       ("shard_check_emu", ["64", "8"]), ("sparse_check_emu", ["400", "32"])])
 def test_c_harnesses_pass_under_emulation(emu, name, args):
     """tests/c/shard_check.c and sparse_check.c (the programs the GPU box runs) against the emulated library: rows of
     final_dist, sharded eps / DBSCAN, CSR form of final_dist, certified sparse eps, sparse DBSCAN -- all equal to the
@@ -90,7 +90,7 @@ def test_c_harnesses_pass_under_emulation(emu, name, args):
 def test_pair_exact_vec8_variant_is_byte_identical_under_emulation(emu):
     outs = []
     for v in ("0", "1"):
-        r = subprocess.run([emu.bins["sparse_check_emu"], "120", "32"], capture_output=True, text=True, timeout=900,
+        r = subprocess.run([emu.bins["sparse_check_emu"], "200", "32"], capture_output=True, text=True, timeout=900,
                            env=dict(os.environ, SSG_PAIR_VEC8=v))
         assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout + r.stderr
         outs.append([l for l in r.stdout.splitlines() if l.startswith(("CSR", "eps", "dbscan"))])
@@ -279,7 +279,6 @@ def test_python_prototypes_of_the_sharded_and_sparse_entry_points(emu):
     lib.ssg_rerank_plan_destroy(rp)
 
 
-@pytest.mark.skipif(not os.environ.get("SSG_SLOW"), reason="about two minutes: set SSG_SLOW=1")
 def test_sparse_jaccard_beyond_256_bitmap_words(emu):
     """n = 9000 -> 282 bitmap words: the word-rank scan of jaccard_sparse_kernel takes two passes of its block-wide loop,
     as at the production size.  Last run: profiles/r01_emulated_checks.log."""
