@@ -105,6 +105,12 @@ int ssg_rerank_init(ssg_rerank_plan* plan, const float* d_qg, const float* d_qq,
 int ssg_rerank_plain(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d, int k,
                      double lambda_value, int dist_mode, double* d_final, void* stream);
 
+/* reid/rerank_plain.py:27-123 re_ranking_lh(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.2): the
+ * k-reciprocal / Jaccard re-ranking of ssg_rerank_run with that function's source term -- v_i = min_j cdist(t_i, s_j) on
+ * the un-squared float64 distances, v /= max(v), source_dist = v_i + v_j, all in float64.  d_final: [n,n] float64. */
+int ssg_rerank_lh(ssg_rerank_plan* plan, const float* d_src, int ns, const float* d_tgt, int n, int d, int k1, int k2,
+                  double lambda_value, int dist_mode, double* d_final, void* stream);
+
 /* Intermediate results of the last ssg_rerank_run, copied to the host (stage-isolated parity tests). */
 #define SSG_STAGE_VEC 0       /* float  [n]        normalised source vector v (rerank.py:36-40)     */
 #define SSG_STAGE_ROWMAX 1    /* float  [n]        row maximum of the squared distance (rerank.py:68) */

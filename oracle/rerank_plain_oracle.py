@@ -56,3 +56,19 @@ def re_ranking_plain(src, tgt, k=20, lambda_value=0.1, mode="f32"):
     n = od.shape[0]
     jac = jaccard_sets(knn_sets(od, k), n, dt)
     return O.final_distance(jac, vec, lambda_value)              # :139-146,174 (v_i + v_j summed in the storage dtype)
+
+
+def re_ranking_lh(src, tgt, k1=20, k2=6, lambda_value=0.2, mode="f32"):
+    """reid/rerank_plain.py:27-123 re_ranking_lh: reid/rerank.py:27 re_ranking with another source term --
+    v = min_j cdist(t_i, s_j) taken on the UN-squared float64 distances, no 1 - exp(), v /= max(v) in float64
+    (:36-40), source_dist = v_i + v_j in float64 (:41-43); the Jaccard part (:46-113) is the same code.
+    final = J * (1 - lambda) [storage dtype] + source_dist * lambda [float64] (:120)."""
+    st = {}
+    O.re_ranking(src, tgt, k1=k1, k2=k2, lambda_value=lambda_value, mode=mode, stages=st)
+    v = cdist(tgt, src).min(axis=1)
+    v = v / v.max()
+    n = v.shape[0]
+    source_dist = np.zeros([n, n])
+    for i in range(n):
+        source_dist[i, :] = v + v[i]
+    return st["J"] * (1 - lambda_value) + source_dist * lambda_value

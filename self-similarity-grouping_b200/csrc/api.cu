@@ -75,6 +75,7 @@ struct ssg_rerank_plan {
     int *sp_cnt, *sp_rowptr, *sp_col; double* sp_val; size_t sp_cap; long long sp_nnz; double sp_threshold;
     // plain kNN-set re-ranking (ssg_rerank_plain): rows with a tied k-th neighbour and their exact fallback
     int *pl_flag_rows, *pl_flags, *pl_sel_idx; float *pl_sel_val, *pl_rows;
+    double *lh_minsum, *lh_vec;  // re_ranking_lh: float64 source term
     int rank_cols;               // leading rank columns the last distance stage produced (k1 + 1 of that call)
     int last_n;
 };
@@ -138,7 +139,7 @@ extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
                     p->split_tb, p->split_sb, p->norm_t, p->norm_s, p->norm_max, p->cand_idx, p->cand_val,
                     p->cand_exact, p->flag_src, p->flag_tgt, p->fb_rows, p->fb_f32, p->fb_i32, p->mean_partial,
                     p->mean, p->sp_cnt, p->sp_rowptr, p->sp_col, p->sp_val, p->pl_flag_rows, p->pl_flags, p->pl_sel_idx,
-                    p->pl_sel_val, p->pl_rows};
+                    p->pl_sel_val, p->pl_rows, p->lh_minsum, p->lh_vec};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete p;
     return SSG_OK;
@@ -566,6 +567,28 @@ extern "C" int ssg_rerank_plain(ssg_rerank_plan* p, const float* d_src, int ns, 
     }
     { SSG_PROF("csc_build", st); SSG_TRY(launch_csc_build(n, p->q_idx, p->q_cnt, p->colcnt, p->colptr, p->cursor, p->csc_row, st)); }
     { SSG_PROF("jaccard_plain", st); SSG_TRY(launch_jaccard_plain(n, p->q_idx, p->q_cnt, p->colptr, p->csc_row, p->vec, lambda_value, d_final, st)); }
+    p->last_n = n;
+    return SSG_OK;
+}
+
+// reid/rerank_plain.py:27-123 re_ranking_lh(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.2): the
+// k-reciprocal / Jaccard part of ssg_rerank_run with the float64 source term of that function.
+extern "C" int ssg_rerank_lh(ssg_rerank_plan* p, const float* d_src, int ns, const float* d_tgt, int n, int d, int k1,
+                             int k2, double lambda_value, int dist_mode, double* d_final, void* stream) {
+    SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
+    if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_lh: d_final is null");
+    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p->lh_vec) {
+        SSG_TRY(dalloc((void**)&p->lh_minsum, sizeof(double) * (size_t)p->n_max, &p->bytes));
+        SSG_TRY(dalloc((void**)&p->lh_vec, sizeof(double) * (size_t)p->n_max, &p->bytes));
+    }
+    const int k1d = k1 > k2 - 1 ? k1 : k2 - 1;
+    SSG_TRY(ssg_rerank_distance_rows(p, d_src, ns, d_tgt, n, d, k1d, dist_mode, 0, n, nullptr, stream));
+    SSG_TRY(finish_sparse_stages(p, d_tgt, n, d, k1, k2, st));
+    { SSG_PROF("source_vector", st); SSG_TRY(launch_source_vec_f64(d_tgt, n, d_src, ns, d, p->lh_minsum, p->lh_vec, st)); }
+    { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final_lh(n, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->lh_vec, lambda_value,
+                                    d_final, st)); }
     p->last_n = n;
     return SSG_OK;
 }

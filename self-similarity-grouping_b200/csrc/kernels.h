@@ -60,6 +60,12 @@ int launch_jaccard_final(int n, int row0, int rows, const int* q_idx, const floa
 int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
                           const int* csc_row, const float* vec, double lambda_value, const int* sp_rowptr, int* sp_cnt,
                           int* sp_col, double* sp_val, cudaStream_t st);
+// re_ranking_lh (reid/rerank_plain.py:27-123): float64 source term on the un-squared distances
+int launch_source_vec_f64(const float* tgt, int n, const float* src, int ns, int d, double* minsum, double* vec,
+                          cudaStream_t st);
+int launch_jaccard_final_lh(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                            const int* csc_row, const double* vec, double lambda_value, double* final_dist,
+                            cudaStream_t st);
 // plain kNN-set re-ranking (reid/rerank_plain.py:125-178)
 int launch_knn_sets(const int* rank, const float* rank_val, int n, int k, int* set_idx, int* set_cnt, int* flag_rows,
                     int* flag_cnt, cudaStream_t st);

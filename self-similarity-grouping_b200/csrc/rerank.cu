@@ -717,6 +717,104 @@ int launch_jaccard_sparse(int n, const int* q_idx, const float* q_val, const int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// re_ranking_lh (reid/rerank_plain.py:27-123): reid/rerank.py's re_ranking with a float64 source term built on the
+// UN-squared distances: v_i = min_j cdist(t_i, s_j) (float64, sequential sum as cdist), v /= max(v), source_dist =
+// v_i + v_j in float64; final = fl32(J * fl32(1 - lambda)) + (v_m + v_i) * lambda.  sqrt is monotone and correctly
+// rounded, so min_j sqrt(sum_j) = sqrt(min_j sum_j): the kernel keeps the smallest float64 sum per target row.
+// ---------------------------------------------------------------------------------------------------
+constexpr int LH_NT = 128;
+__global__ void __launch_bounds__(LH_NT)
+source_min_f64_kernel(const float* __restrict__ tgt, const float* __restrict__ src, int ns, int d,
+                      double* __restrict__ out_minsum) {
+    extern __shared__ unsigned char jf_smem[];
+    double* a = reinterpret_cast<double*>(jf_smem);          // [d] target row as float64
+    __shared__ double red[LH_NT];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    for (int k = tid; k < d; k += LH_NT) a[k] = (double)tgt[(size_t)i * d + k];
+    __syncthreads();
+    double best = __longlong_as_double(0x7ff0000000000000ll);        // +inf
+    for (int j = tid; j < ns; j += LH_NT) {
+        const float* b = src + (size_t)j * d;
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) {
+            const double df = __dsub_rn(a[k], (double)b[k]);
+            acc = __dadd_rn(acc, __dmul_rn(df, df));
+        }
+        best = acc < best ? acc : best;
+    }
+    red[tid] = best;
+    __syncthreads();
+    for (int o = LH_NT / 2; o > 0; o >>= 1) {
+        if (tid < o) red[tid] = red[tid + o] < red[tid] ? red[tid + o] : red[tid];
+        __syncthreads();
+    }
+    if (tid == 0) out_minsum[i] = red[0];
+}
+
+// v = sqrt(minsum); v /= max(v)   (one CTA; float64 throughout, rerank_plain.py:37-38)
+__global__ void __launch_bounds__(1024)
+source_vec_f64_kernel(const double* __restrict__ minsum, int n, double* __restrict__ vec) {
+    __shared__ double red[1024];
+    const int tid = threadIdx.x;
+    double mx = 0.0;
+    for (int i = tid; i < n; i += 1024) {
+        const double v = sqrt(minsum[i]);
+        vec[i] = v;
+        mx = v > mx ? v : mx;
+    }
+    red[tid] = mx;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (tid < o) red[tid] = red[tid + o] > red[tid] ? red[tid + o] : red[tid];
+        __syncthreads();
+    }
+    const double m = red[0];
+    for (int i = tid; i < n; i += 1024) vec[i] = vec[i] / m;
+}
+
+struct OutSourceLH {         // rerank_plain.py:41-43,120: final = J*(1-lambda) + (v_m + v_i)*lambda with float64 v
+    const double* vec; double vi; double lambda_value; float oml; double* out;
+    __device__ __forceinline__ bool wants(int m) const { return true; }
+    __device__ __forceinline__ void store(int m, float J) const {
+        const float Jm = __fmul_rn(fmaxf(J, 0.f), oml);
+        out[m] = __dadd_rn((double)Jm, __dmul_rn(__dadd_rn(vec[m], vi), lambda_value));
+    }
+};
+
+__global__ void __launch_bounds__(JF_NT)
+jaccard_final_lh_kernel(int n, const int* __restrict__ q_idx, const float* __restrict__ q_val,
+                        const int* __restrict__ q_cnt, const int* __restrict__ colptr, const int* __restrict__ csc_row,
+                        const double* __restrict__ vec, double lambda_value, float oml, double* __restrict__ final_dist) {
+    extern __shared__ unsigned char jf_smem[];
+    const int i = blockIdx.x;
+    OutSourceLH o{vec, vec[i], lambda_value, oml, final_dist + (size_t)i * n};
+    jaccard_row(n, i, q_idx, q_val, q_cnt, colptr, csc_row, o, jf_smem);
+}
+
+int launch_source_vec_f64(const float* tgt, int n, const float* src, int ns, int d, double* minsum, double* vec,
+                          cudaStream_t st) {
+    const size_t smem = sizeof(double) * (size_t)d;
+    if (smem > 200 * 1024) return ssg_set_error(SSG_ERR_INVALID, "rerank_lh: d=%d too large", d);
+    SSG_CUDA_TRY(cudaFuncSetAttribute(source_min_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    source_min_f64_kernel<<<n, LH_NT, smem, st>>>(tgt, src, ns, d, minsum);
+    SSG_CHECK_LAUNCH();
+    source_vec_f64_kernel<<<1, 1024, 0, st>>>(minsum, n, vec);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int launch_jaccard_final_lh(int n, const int* q_idx, const float* q_val, const int* q_cnt, const int* colptr,
+                            const int* csc_row, const double* vec, double lambda_value, double* final_dist,
+                            cudaStream_t st) {
+    const size_t smem = jaccard_smem(n);
+    if (smem > 220 * 1024) return ssg_set_error(SSG_ERR_INVALID, "jaccard: n=%d too large for the bitmap", n);
+    SSG_CUDA_TRY(cudaFuncSetAttribute(jaccard_final_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jaccard_final_lh_kernel<<<n, JF_NT, smem, st>>>(n, q_idx, q_val, q_cnt, colptr, csc_row, vec, lambda_value,
+                                                    (float)(1.0 - lambda_value), final_dist);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Plain kNN-set re-ranking: reid/rerank_plain.py:125-178 re_ranking(source, target, k, lambda).
 //   S_i    = { j != i : od[i,j] <= k-th smallest entry of row i of od }   (od = squared distances, diagonal included)
 //   J[i,j] = scipy cdist(S, S, 'jaccard') = (|S_i u S_j| - |S_i n S_j|) / |S_i u S_j|   (0 when both are empty)

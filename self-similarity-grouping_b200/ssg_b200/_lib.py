@@ -63,6 +63,8 @@ PROTOTYPES = {
     "ssg_dbscan_shard_label": (c_int, [c_void_p, c_int, c_int, c_void_p, P(c_int), c_void_p]),
     "ssg_rerank_plain": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_int, c_void_p,
                                  c_void_p]),
+    "ssg_rerank_lh": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_double, c_int, c_void_p,
+                              c_void_p]),
     "ssg_rerank_finish_sparse": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, P(c_ll), c_void_p]),
     "ssg_rerank_sparse_view": (c_int, [c_void_p, P(c_void_p), P(c_void_p), P(c_void_p), P(c_ll), P(c_double)]),
     "ssg_eps_sparse": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_double, c_double, P(c_double), P(c_ll),

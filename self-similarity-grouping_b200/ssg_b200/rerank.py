@@ -180,6 +180,28 @@ def re_ranking_plain(input_feature_source, input_feature, k=20, lambda_value=0.1
     return out, out
 
 
+def re_ranking_lh(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.2, MemorySave=False, Minibatch=2000,
+                  dist_mode=None):
+    """Drop-in for reid/rerank_plain.py:27 re_ranking_lh: returns (euclidean_dist float32, final_dist float64)."""
+    import os
+    import torch
+    dev = _lib.require_cuda()
+    if dist_mode is None:
+        dist_mode = int(os.environ.get("SSG_DIST_MODE", _lib.DIST_EXACT))
+    src = torch.from_numpy(np.ascontiguousarray(input_feature_source, dtype=np.float32)).to(dev)
+    tgt = torch.from_numpy(np.ascontiguousarray(input_feature, dtype=np.float32)).to(dev)
+    n, d = tgt.shape
+    plan = get_plan(n, src.shape[0], d, dev.index)
+    print('computing source distance...')
+    print('computing original distance...')
+    print('starting re_ranking...')
+    final = torch.empty((n, n), dtype=torch.float64, device=dev)
+    _lib.check(_lib.load().ssg_rerank_lh(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), n, d, int(k1), int(k2),
+                                         float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr()))
+    euclid = sqdist(tgt, tgt, _lib.DIST_EXACT)
+    return euclid.cpu().numpy(), final.cpu().numpy()
+
+
 def re_ranking_init_blocks(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3):
     """reid/rerank_initial.py:40 re_ranking_init on similarity blocks (numpy or CUDA tensors).
     Returns a numpy float32 [q,g] array for numpy inputs, a CUDA tensor for CUDA inputs."""

@@ -425,3 +425,26 @@ def test_triplet_loss_kernels_against_reference_goldens(emu, golden_dir):
         assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max(), ci
         done += 1
     assert done >= 2
+
+
+@pytest.mark.parametrize("n,ns,k1,k2,lam", [(60, 40, 20, 6, 0.2), (25, 1, 5, 8, 0.5), (40, 33, 10, 1, 0.0)])
+def test_re_ranking_lh_kernels_against_oracle(emu, n, ns, k1, k2, lam):
+    """Row f4, re_ranking_lh (reid/rerank_plain.py:27-123): the float64 source term on un-squared distances, under
+    emulation against the restatement pinned to the reference (tests/test_oracle_vs_reference.py)."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    from oracle import rerank_plain_oracle as P
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    for nm in ("ssg_rerank_plan_create", "ssg_rerank_plan_destroy", "ssg_rerank_lh", "ssg_last_error"):
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+    rng = np.random.RandomState(n + ns)
+    tgt, src = rng.randn(n, 12).astype(np.float32), rng.randn(ns, 12).astype(np.float32)
+    want = P.re_ranking_lh(src, tgt, k1, k2, lam, "f32")
+    plan = ctypes.c_void_p()
+    assert lib.ssg_rerank_plan_create(ctypes.byref(plan), 0, n, ns, 12) == 0
+    got = np.empty((n, n), np.float64)
+    rc = lib.ssg_rerank_lh(plan, src.ctypes.data, ns, tgt.ctypes.data, n, 12, k1, k2, lam, L.DIST_EXACT, got.ctypes.data, None)
+    assert rc == 0, lib.ssg_last_error().decode()
+    lib.ssg_rerank_plan_destroy(plan)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)     # J to float32 rounding (exp in the weights), v exact
+    assert np.array_equal(got, got.T)

@@ -161,3 +161,15 @@ def test_plain_knn_set_reranker_on_the_device(mode):
         got, again = re_ranking_plain(src, tgt, k, 0.1, dist_mode=dm)
         assert got is again and got.dtype == np.float64
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+
+
+@pytest.mark.gpu_next
+def test_re_ranking_lh_on_the_device():
+    """reid.rerank_plain.re_ranking_lh (row f4) on the GPU against the pinned restatement."""
+    from ssg_b200.rerank import re_ranking_lh
+    from oracle import ssg_oracle as O, rerank_plain_oracle as P
+    tgt, _ = O.synth_features(300, 128, 3)
+    src, _ = O.synth_features(200, 128, 4, noise=0.6)
+    e, f = re_ranking_lh(src, tgt, 20, 6, 0.2)
+    assert np.array_equal(e, O.original_distance(tgt))
+    np.testing.assert_allclose(f, P.re_ranking_lh(src, tgt, 20, 6, 0.2, "f32"), rtol=0, atol=1e-4)

@@ -98,3 +98,23 @@ def test_rerank_plain_restatement_bit_exact(mode, n, ns, d, seed, noise):
     assert want is again
     got = P.re_ranking_plain(src, tgt, 20, 0.1, mode)
     assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["f32", "ref"])
+@pytest.mark.parametrize("n,ns,d,seed", [(90, 70, 64, 0), (64, 40, 32, 2)])
+def test_rerank_lh_restatement_bit_exact(mode, n, ns, d, seed):
+    """Row f4, second function: reid/rerank_plain.py:27-123 re_ranking_lh against the unmodified reference."""
+    import contextlib
+    import os
+    from oracle import rerank_plain_oracle as P
+    refshim.load_reference()
+    with refshim._reference_on_path():
+        import reid.rerank_plain as RP
+    tgt, _ = O.synth_features(n, d, seed)
+    src, _ = O.synth_features(ns, d, seed + 9)
+    ctx = refshim.f32_stable(RP) if mode == "f32" else contextlib.nullcontext()
+    with ctx, contextlib.redirect_stdout(open(os.devnull, "w")):
+        want = RP.re_ranking_lh(src, tgt, k1=20, k2=6, lambda_value=0.2)
+    want = want[-1] if isinstance(want, tuple) else want
+    got = P.re_ranking_lh(src, tgt, 20, 6, 0.2, mode)
+    assert got.dtype == want.dtype and np.array_equal(got, want)
