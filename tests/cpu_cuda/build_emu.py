@@ -6,8 +6,9 @@ api.cu, rerank.cu, cluster.cu, dist.cu, prof.cu and triplet.cu are copied with t
     extern __shared__ T name[];                   ->  T* name = (T*)emu::dyn_smem;
 -- and compiled by g++ against tests/cpu_cuda/stub/cuda_runtime.h + emu.cpp (fibers, one host thread; see the stub's
 header comment) into tests/cpu_cuda/_build/libssg_emu.so.  The tensor-core translation units (gemm_tc.cu, conv.cu,
-embed.cu: tcgen05 / TMA, nothing to emulate) are left out; the four launch wrappers api.cu calls from them report
-SSG_ERR_UNSUPPORTED, so only dist_mode = SSG_DIST_EXACT works.  The plain-C harnesses of tests/c are then built against
+embed.cu: tcgen05 / TMA, nothing to emulate) are left out, except the plain-CUDA operand split / centring kernels of
+gemm_tc.cu; the approximate distance GEMM itself is a float stand-in (optionally perturbed within the certified error
+bound), so that the tensor distance MODE -- candidate selection, exact re-scoring, certification, fallback -- runs too.  The plain-C harnesses of tests/c are then built against
 it (same sources, `*_emu` binaries), which runs the real kernel source of the exact-mode re-ranking, eps and DBSCAN --
 dense, row-sharded and sparse -- on the CPU.
 
@@ -24,21 +25,44 @@ CSRC = os.path.join(ROOT, "self-similarity-grouping_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu", "triplet.cu"]
 
-STUBS = r'''// launch wrappers of the tensor-core translation units that api.cu references: not available under emulation
+STUBS = r'''// Stand-ins for the tensor-core distance GEMM (gemm_tc.cu: tcgen05 / TMA, not emulated).  The operand split, the
+// centring and everything downstream of the GEMM (candidate selection, exact re-scoring, certification, fallback) are the
+// library's real kernels; only the approximate d2 matrix itself is computed here, in plain float arithmetic on the
+// same bf16x3 operands, optionally perturbed: SSG_EMU_GEMM_NOISE=f adds a deterministic pseudo-random error of up to
+// f * E per entry, E = tensor_eps_rel(d) * (|x_i|^2 + max|y|^2) being the bound the certification assumes -- results
+// must not depend on WHICH approximation within the bound the hardware produces.
+#include <cuda_bf16.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 namespace ssg {
+static inline float bf(const void* p, size_t i) { return __bfloat162float(((const __nv_bfloat16*)p)[i]); }
+int launch_gemm_dist(const void* a, const float* na, int m, const void* b, const float* nb, int n, int k, float* out,
+                     size_t ldc, cudaStream_t, int sym) {
+    const char* e = getenv("SSG_EMU_GEMM_NOISE");
+    const double noise = e ? atof(e) : 0.0;
+    const int d = k / 3;
+    const double eps_rel = 1.18e-5 + 2.24e-8 * d;                 // api.cu tensor_eps_rel
+    float nbmax = 0.f;
+    for (int j = 0; j < n; ++j) nbmax = nb[j] > nbmax ? nb[j] : nbmax;
+    unsigned long long s = 88172645463325252ull;
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (sym && j < i) { out[(size_t)i * ldc + j] = out[(size_t)j * ldc + i]; continue; }
+            float dot = 0.f;
+            for (int q = 0; q < k; ++q) dot += bf(a, (size_t)i * k + q) * bf(b, (size_t)j * k + q);
+            float v = fmaf(-2.0f, dot, na[i] + nb[j]);
+            if (noise != 0.0) {
+                s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+                const double u = (double)(s >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+                v += (float)(u * noise * eps_rel * ((double)na[i] + (double)nbmax));
+            }
+            out[(size_t)i * ldc + j] = v;
+        }
+    return SSG_OK;
+}
 int launch_sqdist_tensor(const float*, int, const float*, int, int, float*, size_t, cudaStream_t) {
-    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: the tcgen05 distance GEMM is not emulated (use SSG_DIST_EXACT)");
-}
-int launch_split_bf16x3(const float*, int, int, int, const float*, void*, float*, cudaStream_t) {
-    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
-}
-int launch_col_mean(const float*, int, int, double*, float*, cudaStream_t) {
-    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
-}
-int launch_gemm_dist(const void*, const float*, int, const void*, const float*, int, int, float*, size_t, cudaStream_t, int) {
-    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: tensor distance mode is not emulated");
+    return ssg_set_error(SSG_ERR_UNSUPPORTED, "CPU emulation: ssg_sqdist(mode = TENSOR) is not emulated");
 }
 }  // namespace ssg
 '''
@@ -124,7 +148,16 @@ def build(verbose=False, force=False):
     stub = os.path.join(OUT, "src", "tc_stubs_emu.cpp")
     with open(stub, "w") as f:
         f.write(STUBS)
-    srcs += [stub, os.path.join(HERE, "emu.cpp")]
+    # the plain-CUDA front end of the tensor distance mode (column mean, bf16x3 operand split) lives in gemm_tc.cu next
+    # to the tcgen05 code: take just that region
+    with open(os.path.join(CSRC, "gemm_tc.cu")) as f:
+        g = f.read()
+    region = g[g.index("constexpr int MEAN_GROUPS"):g.index("struct EpiDist {")]
+    prep = os.path.join(OUT, "src", "dist_prep_emu.cpp")
+    with open(prep, "w") as f:
+        f.write('#include <cuda_bf16.h>\n#include "common.cuh"\n#include "kernels.h"\nnamespace ssg {\n'
+                + rewrite(region) + "\n}  // namespace ssg\n")
+    srcs += [stub, prep, os.path.join(HERE, "emu.cpp")]
     lib = os.path.join(OUT, "libssg_emu.so")
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-D__CUDACC__", "-w",
              "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]

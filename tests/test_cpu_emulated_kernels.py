@@ -448,3 +448,79 @@ def test_re_ranking_lh_kernels_against_oracle(emu, n, ns, k1, k2, lam):
     lib.ssg_rerank_plan_destroy(plan)
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-4)     # J to float32 rounding (exp in the weights), v exact
     assert np.array_equal(got, got.T)
+
+
+def _tensor_vs_exact(lib, L, src, tgt):
+    def run(mode):
+        n, d = tgt.shape
+        plan = ctypes.c_void_p()
+        assert lib.ssg_rerank_plan_create(ctypes.byref(plan), 0, n, src.shape[0], d) == 0
+        f = np.empty((n, n))
+        rc = lib.ssg_rerank_run(plan, src.ctypes.data, src.shape[0], tgt.ctypes.data, n, d, 20, 6, 0.1, mode, f.ctypes.data, None, None)
+        assert rc == 0, lib.ssg_last_error().decode()
+        rank, fl = np.empty((n, 32), np.int32), np.empty(1, np.int32)
+        assert lib.ssg_rerank_get_stage(plan, L.STAGE_RANK, rank.ctypes.data, rank.nbytes) == 0
+        assert lib.ssg_rerank_get_stage(plan, L.STAGE_FLAGGED, fl.ctypes.data, 4) == 0
+        lib.ssg_rerank_plan_destroy(plan)
+        return f, rank[:, :21], int(fl[0])
+    fe, re_, _ = run(L.DIST_EXACT)
+    ft, rt, flagged = run(L.DIST_TENSOR)
+    return np.array_equal(re_, rt) and np.array_equal(fe, ft), flagged
+
+
+def test_tensor_distance_mode_is_exact_for_any_approximation_within_the_bound(emu):
+    """DESIGN.md §4 under emulation: the operand split, candidate selection, exact re-scoring, certification and
+    fallback are the library's kernels; the approximate d2 matrix comes from a float stand-in that can be perturbed by
+    up to f * E per entry (E = the certified bound).  For f < 1 the outputs must equal the exact mode bit for bit --
+    tie-heavy integer features (rows that cannot be certified take the exact fallback) and clustered data alike; f = 30
+    violates the error model and must be able to break it (the test has teeth)."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    lib = ctypes.CDLL(os.path.join(build_emu.OUT, "libssg_emu.so"))
+    for nm in ("ssg_rerank_plan_create", "ssg_rerank_plan_destroy", "ssg_rerank_run", "ssg_rerank_get_stage", "ssg_last_error"):
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+    rng = np.random.RandomState(0)
+    ti = rng.randint(0, 3, (150, 8)).astype(np.float32)
+    si = rng.randint(0, 3, (40, 8)).astype(np.float32)
+    tc, _ = O.synth_features(130, 32, 3, per_cluster=12)
+    sc, _ = O.synth_features(70, 32, 4, noise=0.6)
+    saved = os.environ.get("SSG_EMU_GEMM_NOISE")
+    try:
+        for f in ("0", "0.5", "0.95"):
+            os.environ["SSG_EMU_GEMM_NOISE"] = f
+            same, flagged = _tensor_vs_exact(lib, L, si, ti)
+            assert same and flagged > 0, (f, flagged)          # ties: some rows must take the exact fallback
+            same, flagged = _tensor_vs_exact(lib, L, sc, tc)
+            assert same, f
+        os.environ["SSG_EMU_GEMM_NOISE"] = "30"
+        same, _ = _tensor_vs_exact(lib, L, si, ti)
+        assert not same                                         # an error 30x the bound is NOT covered, and shows
+    finally:
+        if saved is None:
+            os.environ.pop("SSG_EMU_GEMM_NOISE", None)
+        else:
+            os.environ["SSG_EMU_GEMM_NOISE"] = saved
+
+
+def test_symmetric_distance_matrix_leaves_the_outputs_unchanged_under_emulation(emu):
+    """SSG_DIST_SYM=1 (read once per process -> subprocess): the mirrored approximate matrix (stand-in GEMM with the same
+    upper-triangle-and-mirror semantics) feeds the same pipeline; outputs equal to the exact mode."""
+    script = (
+        "import sys, os, ctypes, numpy as np\n"
+        "sys.path[:0] = %r\n"
+        "import build_emu\n"
+        "from ssg_b200 import _lib as L\n"
+        "sys.path.insert(0, %r)\n"
+        "import test_cpu_emulated_kernels as T\n"
+        "from oracle import ssg_oracle as O\n"
+        "lib = ctypes.CDLL(os.path.join(build_emu.OUT, 'libssg_emu.so'))\n"
+        "for nm in ('ssg_rerank_plan_create', 'ssg_rerank_plan_destroy', 'ssg_rerank_run', 'ssg_rerank_get_stage', 'ssg_last_error'):\n"
+        "    getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]\n"
+        "t, _ = O.synth_features(120, 32, 3, per_cluster=12); s, _ = O.synth_features(60, 32, 4, noise=0.6)\n"
+        "same, flagged = T._tensor_vs_exact(lib, L, s, t)\n"
+        "print('SAME' if same else 'DIFFERENT', flagged)\n"
+        % ([ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda")],
+           os.path.join(ROOT, "tests")))
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, SSG_DIST_SYM="1", SSG_EMU_GEMM_NOISE="0.9"))
+    assert r.returncode == 0 and "SAME" in r.stdout, r.stdout + r.stderr
