@@ -70,6 +70,12 @@ def test_pseudo_label_cycle_dense_and_sparse_single_process(emulated):
         for a, b in zip(labels, want_l):
             assert np.array_equal(a, b), name
         assert np.array_equal(keep, O.keep_mask(want_l)), name
+    # tensor distance mode (the cycle's default on the GPU; stand-in GEMM, real certification): same results
+    for sparse in (False, True):
+        labels, eps, _ = ssg_b200.pseudo_label_cycle(sl, tl, LAM, RHO, dist_mode=_lib.DIST_TENSOR, sparse=sparse)
+        np.testing.assert_allclose(eps, runs["dense"][1], rtol=1e-12, atol=0)
+        for a, b in zip(labels, want_l):
+            assert np.array_equal(a, b)
     # frozen eps (iterations > 0) through the sparse form
     labels, _, _ = ssg_b200.pseudo_label_cycle(sl, tl, LAM, RHO, eps_list=want_e, dist_mode=_lib.DIST_EXACT, sparse=True)
     for a, b in zip(labels, want_l):
