@@ -1,0 +1,123 @@
+// Call-trace stand-in for conv.cu + the CUDA runtime, used to check the HOST orchestration of embed.cu (which has no
+// kernels of its own) without a GPU: every launcher embed.cu calls is replaced by a function that appends one line to
+// a log -- name, dimensions, and every pointer as an offset into ONE arena that backs all cudaMalloc calls, so two
+// builds of embed.cu that issue the same work produce byte-identical logs.  TEST INFRASTRUCTURE (tests/cpu_cuda).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "cuda_runtime.h"
+#include "common.cuh"
+#include "conv.h"
+
+static std::string g_log;
+static char* g_arena = nullptr;
+static size_t g_used = 0;
+static const size_t ARENA = (size_t)64 << 30;         // virtual: never touched
+
+static long long off(const void* p) {
+    if (!p) return -1;
+    const char* c = (const char*)p;
+    return (c >= g_arena && c < g_arena + ARENA) ? (long long)(c - g_arena) : -2;
+}
+static void logf(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_log += buf;
+    g_log += "\n";
+}
+
+static thread_local char g_err[512];
+int ssg_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+extern "C" const char* ssg_last_error(void) { return g_err; }
+extern "C" const char* trace_dump(void) { return g_log.c_str(); }
+extern "C" void trace_reset(void) { g_log.clear(); }
+extern "C" void* trace_alloc(size_t bytes) { void* p; cudaMalloc(&p, bytes); return p; }
+
+struct CUtensorMap;
+namespace ssg {
+int make_tmap_stem_windows(CUtensorMap*, const void*, uint64_t) { return 0; }
+ProfScope::ProfScope(const char*, cudaStream_t) : name_(nullptr), st_(nullptr), e0_(nullptr) {}
+ProfScope::~ProfScope() {}
+void prof_suspend(bool) {}
+bool s2_strided_tma() { return true; }
+bool stem_pool_fused() { return true; }
+int conv1x1(const void* x, int m, int cin, const void* w, const float* bias, int cout, const void* res, int relu, void* y, cudaStream_t) {
+    logf("conv1x1 x=%lld m=%d cin=%d w=%lld b=%lld cout=%d res=%lld relu=%d y=%lld", off(x), m, cin, off(w), off(bias), cout, off(res), relu, off(y));
+    return 0;
+}
+int conv1x1_s2(const void* x, int B, int H, int W, int cin, const void* w, const float* bias, int cout, int relu, void* y, cudaStream_t) {
+    logf("conv1x1_s2 x=%lld B=%d H=%d W=%d cin=%d w=%lld b=%lld cout=%d relu=%d y=%lld", off(x), B, H, W, cin, off(w), off(bias), cout, relu, off(y));
+    return 0;
+}
+int conv_fused_ds(const void* t2, const void* x, int B, int H, int W, int mid, int cin, int stride, const void* w, const float* bias, int cout, void* y, cudaStream_t) {
+    logf("conv_fused_ds t2=%lld x=%lld B=%d H=%d W=%d mid=%d cin=%d stride=%d w=%lld b=%lld cout=%d y=%lld", off(t2), off(x), B, H, W, mid, cin, stride, off(w), off(bias), cout, off(y));
+    return 0;
+}
+int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout, int relu, void* y, cudaStream_t) {
+    logf("conv3x3 x=%lld B=%d H=%d W=%d cin=%d stride=%d w=%lld b=%lld cout=%d relu=%d y=%lld", off(x), B, H, W, cin, stride, off(w), off(bias), cout, relu, off(y));
+    return 0;
+}
+int vec_add_f32(const float* a, const float* b, int n, float* out, cudaStream_t) { logf("vec_add a=%lld b=%lld n=%d out=%lld", off(a), off(b), n, off(out)); return 0; }
+int fold_bn(const float*, int cout, int cin, int kh, int kw, const float*, const float*, const float*, const float*, float, int kpad, void* wout, float* bout, cudaStream_t) {
+    logf("fold_bn cout=%d cin=%d k=%dx%d kpad=%d w=%lld b=%lld", cout, cin, kh, kw, kpad, off(wout), off(bout));
+    return 0;
+}
+int fold_bn_stem(const float*, const float*, const float*, const float*, const float*, float, void* wout, float* bout, void* wout64, cudaStream_t) {
+    logf("fold_bn_stem w=%lld b=%lld w64=%lld", off(wout), off(bout), off(wout64));
+    return 0;
+}
+int stem_prep(const float* img, int n, int flip, void* P, cudaStream_t) { logf("stem_prep img=%lld n=%d flip=%d P=%lld", off(img), n, flip, off(P)); return 0; }
+int stem_prep_u8(const uint8_t* img, int n, int flip, const float*, const float*, void* P, cudaStream_t) { logf("stem_prep_u8 img=%lld n=%d flip=%d P=%lld", off(img), n, flip, off(P)); return 0; }
+int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t, void* pool_out) {
+    logf("stem64 P=%lld images=%d w=%lld b=%lld y=%lld pool=%lld", off(P), images, off(w256), off(bias), off(y), off(pool_out));
+    return 0;
+}
+int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t) { logf("stem128 P=%lld images=%d w=%lld b=%lld y=%lld", off(P), images, off(w448), off(bias), off(y)); return 0; }
+int stem_im2col(const float* img, int n, int flip, void* out, cudaStream_t) { logf("im2col img=%lld n=%d flip=%d out=%lld", off(img), n, flip, off(out)); return 0; }
+int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t) { logf("maxpool x=%lld B=%d H=%d W=%d C=%d y=%lld", off(x), B, H, W, C, off(y)); return 0; }
+int parity_split(const void* x, int B, int H, int W, int C, int np, void* y, cudaStream_t) { logf("parity_split x=%lld B=%d H=%d W=%d C=%d np=%d y=%lld", off(x), B, H, W, C, np, off(y)); return 0; }
+int pooled_tail(const void* x, int n, int num_split, int eval_mode, int flip, float* feat, size_t bank_stride, int row0, cudaStream_t) {
+    logf("pooled_tail x=%lld n=%d split=%d eval=%d flip=%d feat=%lld stride=%zu row0=%d", off(x), n, num_split, eval_mode, flip, off(feat), bank_stride, row0);
+    return 0;
+}
+}  // namespace ssg
+
+extern "C" {
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+    if (!g_arena) g_arena = (char*)0x100000000000ull;       // address space only: the trace never touches device memory
+    *p = g_arena + g_used;
+    g_used += (bytes + 255) / 256 * 256;
+    return g_used <= ARENA ? cudaSuccess : 2;
+}
+cudaError_t cudaFree(void*) { return cudaSuccess; }
+cudaError_t cudaMemcpy(void*, const void*, size_t, enum cudaMemcpyKind) { return cudaSuccess; }
+cudaError_t cudaMemcpyAsync(void*, const void*, size_t, enum cudaMemcpyKind, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, enum cudaMemcpyKind, cudaStream_t) {
+    logf("memcpy2d d=%lld dp=%zu s=%lld sp=%zu w=%zu h=%zu", off(d), dp, off(s), sp, w, h);
+    return cudaSuccess;
+}
+cudaError_t cudaMemset(void*, int, size_t) { return cudaSuccess; }
+cudaError_t cudaMemsetAsync(void*, int, size_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+cudaError_t cudaGetDeviceProperties(struct cudaDeviceProp* p, int) { memset(p, 0, sizeof(*p)); p->major = 10; return cudaSuccess; }
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "trace"; }
+cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
+}
