@@ -159,7 +159,7 @@ def build(verbose=False, force=False):
                 + rewrite(region) + "\n}  // namespace ssg\n")
     srcs += [stub, prep, os.path.join(HERE, "emu.cpp")]
     lib = os.path.join(OUT, "libssg_emu.so")
-    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-D__CUDACC__", "-w",
+    flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-D__CUDACC__", "-w",
              "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
     # -Bsymbolic: the library's cudaMalloc / cudaSetDevice / ... must bind to ITS stand-ins even inside a process that has
     # the real libcudart loaded (pytest imports torch)
@@ -181,8 +181,52 @@ def build(verbose=False, force=False):
     return lib, bins
 
 
+def build_tc(verbose=False, force=False):
+    """The whole library, tensor-core kernels included, against the FUNCTIONAL emulation of tcgen05 / TMA / mbarrier
+    (stub_tc/tc_common.cuh): gemm_tc.cuh compiles unchanged except for the five helpers it defines with inline PTX
+    (TMA store, named barrier), which are cut from its text.  -> _build/libssg_emu_tc.so (same C ABI, every entry point)."""
+    out = os.path.join(OUT, "libssg_emu_tc.so")
+    src_dir = os.path.join(OUT, "src_tc")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.abspath(__file__), os.path.join(HERE, "emu.cpp"),
+            os.path.join(HERE, "emu_tc.cpp")] + [os.path.join(HERE, d, f) for d in ("stub", "stub_tc")
+                                                   for f in os.listdir(os.path.join(HERE, d))]
+    if not force and os.path.isfile(out) and os.path.getmtime(out) > max(os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(src_dir, exist_ok=True)
+    srcs = []
+    for u in [f for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]:
+        with open(os.path.join(CSRC, u)) as f:
+            text = rewrite(f.read())
+        dst = os.path.join(src_dir, u.replace(".cu", "_emu.cpp"))
+        with open(dst, "w") as f:
+            f.write(text)
+        srcs.append(dst)
+    with open(os.path.join(CSRC, "gemm_tc.cuh")) as f:
+        h = f.read()
+    a = h.index("__device__ __forceinline__ void tma_store_2d(")
+    b = h.index("template <int BN, class Epi, bool STAGED, bool KHS = false, int VAR = VAR_NONE, bool EPI2 = false>\n__global__")
+    h = (h[:a] + "// (TMA store helpers: stub_tc/tc_common.cuh)\n"
+         "__device__ __forceinline__ void epi_bar_sync() { emu::named_barrier(1, 32 * EPI_WARPS); }\n\n" + h[b:])
+    assert "asm volatile" not in h
+    with open(os.path.join(src_dir, "gemm_tc.cuh"), "w") as f:
+        f.write(rewrite(h))
+    for hname, hdir in (("tc_common.cuh", os.path.join(HERE, "stub_tc")), ("conv.h", CSRC), ("kernels.h", CSRC)):
+        with open(os.path.join(hdir, hname)) as f, open(os.path.join(src_dir, hname), "w") as g:
+            g.write(f.read())
+    with open(os.path.join(CSRC, "common.cuh")) as f, open(os.path.join(src_dir, "common.cuh"), "w") as g:
+        g.write(f.read().replace('"../../include/ssg_b200.h"', '"ssg_b200.h"'))
+    flags = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-D__CUDACC__", "-w",
+             "-I" + src_dir, "-I" + os.path.join(HERE, "stub_tc"), "-I" + os.path.join(HERE, "stub"),
+             "-I" + os.path.join(ROOT, "include")]
+    cmd = ["g++"] + flags + ["-shared", "-Wl,-Bsymbolic", "-o", out] + srcs + [os.path.join(HERE, "emu.cpp"),
+                                                                             os.path.join(HERE, "emu_tc.cpp")]
+    subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return out
+
+
 if __name__ == "__main__":
     lib, bins = build(verbose=True)
     print(lib)
     for b in bins:
         print(b)
+    print(build_tc(verbose=True))

@@ -2,9 +2,12 @@
 // See stub/cuda_runtime.h.  TEST INFRASTRUCTURE.
 #include <ucontext.h>
 #include <sys/mman.h>
+#include <map>
 #include <vector>
 
 #include "cuda_runtime.h"
+
+namespace emu { struct MBar { int count = 0, pending = 0; long long tx = 0; unsigned phase = 0; }; }
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -12,6 +15,7 @@ dim3 blockDim, gridDim;
 namespace emu {
 
 unsigned char* dyn_smem = nullptr;
+static unsigned long g_named_calls = 0, g_block_barriers = 0, g_launches = 0;
 static const size_t STACK = 256 * 1024;
 
 struct Coll { unsigned mask = 0, arrived = 0; unsigned long gen = 0; uint64_t vals[32], snap[2][32]; };
@@ -59,6 +63,7 @@ static void release_barrier_if_complete() {
     }
 }
 int syncthreads_or(int pred) {
+    ++g_block_barriers;
     const unsigned long g = g_bar_gen;
     g_or_acc |= pred != 0;
     ++g_arrived;
@@ -100,6 +105,28 @@ const uint64_t* exchange(unsigned mask, uint64_t v) {
     return c->snap[g & 1];
 }
 
+void yield_now() { yield_(); }
+
+// bar.sync id, count: a barrier among `count` threads of the block
+struct NamedBar { int arrived = 0; unsigned long gen = 0; };
+static NamedBar g_named[16];
+static void print_stats() {
+    if (getenv("SSG_EMU_STATS"))
+        fprintf(stderr, "emu stats: %lu launches, %lu block-barrier arrivals, %lu named-barrier arrivals\n", g_launches,
+                g_block_barriers, g_named_calls);
+}
+void named_barrier(int id, int count) {
+    ++g_named_calls;
+    NamedBar& b = g_named[id & 15];
+    const unsigned long g = b.gen;
+    if (++b.arrived >= count) { b.arrived = 0; ++b.gen; ++g_events; }
+    else while (b.gen == g) yield_();
+}
+
+float tmem[128][512];
+std::map<const void*, MBar>& mbars() { static std::map<const void*, MBar> m; return m; }
+void note_event() { ++g_events; }          // asynchronous-unit progress (mbarrier arrivals, TMA, MMA) counts as progress
+
 static void trampoline() {
     (*g_body)();
     g_fib[g_cur].done = true;
@@ -118,6 +145,8 @@ static void run_block(int n) {
         if (s == MAP_FAILED) { perror("emu: mmap"); abort(); }
         g_stacks.push_back((char*)s);
     }
+    mbars().clear();
+    for (NamedBar& b : g_named) b = NamedBar();
     g_coll.assign((n + 31) / 32, std::vector<Coll>());
     for (auto& w : g_coll) w.reserve(8);
     for (int t = 0; t < n; ++t) {
@@ -156,7 +185,8 @@ static void run_block(int n) {
 }
 
 void launch(const std::function<void()>& fn, dim3 grid, dim3 block, size_t smem, cudaStream_t) {
-    if (!dyn_smem) dyn_smem = (unsigned char*)aligned_alloc(1024, 256 * 1024);
+    if (!dyn_smem) { dyn_smem = (unsigned char*)aligned_alloc(1024, 256 * 1024); atexit(print_stats); }
+    ++g_launches;
     if (smem > 256 * 1024) { fprintf(stderr, "emu: %zu bytes of dynamic shared memory\n", smem); abort(); }
     gridDim = grid; blockDim = block;
     g_body = &fn;

@@ -19,3 +19,17 @@ static inline float __bfloat162float(__nv_bfloat16 h) {
     memcpy(&f, &u, 4);
     return f;
 }
+
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+struct emu_float2 { float x, y; };
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { __nv_bfloat162 r; r.x = __float2bfloat16_rn(a); r.y = __float2bfloat16_rn(b); return r; }
+#ifdef __cplusplus
+#include <cuda_runtime.h>
+static inline float2 __bfloat1622float2(__nv_bfloat162 v) { return make_float2(__bfloat162float(v.x), __bfloat162float(v.y)); }
+static inline __nv_bfloat162 __hmax2(__nv_bfloat162 a, __nv_bfloat162 b) {
+    __nv_bfloat162 r;
+    r.x = __bfloat162float(a.x) >= __bfloat162float(b.x) ? a.x : b.x;
+    r.y = __bfloat162float(a.y) >= __bfloat162float(b.y) ? a.y : b.y;
+    return r;
+}
+#endif

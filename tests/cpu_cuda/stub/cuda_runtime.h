@@ -24,6 +24,8 @@ struct dim3 {
 struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r = {x, y}; return r; }
 static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
 static inline float2 make_float2(float x, float y) { float2 r = {x, y}; return r; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
@@ -73,6 +75,14 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 }
 
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// driver entry point (tensor-map encoder), device attributes, stream-ordered allocation
+enum cudaDriverEntryPointQueryResult { cudaDriverEntryPointSuccess = 0 };
+enum { cudaEnableDefault = 0, cudaDevAttrMultiProcessorCount = 16 };
+cudaError_t cudaGetDriverEntryPoint(const char* name, void** fn, unsigned long long flags, cudaDriverEntryPointQueryResult* res);
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 3; return cudaSuccess; }     // 3 "SMs": persistent CTAs walk several tiles
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { return cudaFree(p); }
 // streams / events / graphs as embed.cu uses them: a "capture" simply executes, a graph launch does nothing more
 typedef void* cudaGraph_t;
 typedef void* cudaGraphExec_t;
