@@ -181,12 +181,21 @@ def build(verbose=False, force=False):
     return lib, bins
 
 
-def build_tc(verbose=False, force=False):
+FAULTS = {
+    # name -> (text in gemm_tc.cuh, replacement): deliberate protocol violations, to show that the late completion model
+    # of emu_tc.cpp notices them (tests/test_cpu_emulated_tensor_kernels.py)
+    "epi2_no_store_wait": ("if (leader) tma_store_wait_read<0>();             // store g-1 has left buffer (g+1) & 1", ""),
+    "stage_freed_early": ("umma_commit(&empty_bar[stage]);                        // smem slot free once the MMAs retire",
+                          "mbar_arrive(&empty_bar[stage]);"),
+}
+
+
+def build_tc(verbose=False, force=False, fault=None):
     """The whole library, tensor-core kernels included, against the FUNCTIONAL emulation of tcgen05 / TMA / mbarrier
     (stub_tc/tc_common.cuh): gemm_tc.cuh compiles unchanged except for the five helpers it defines with inline PTX
     (TMA store, named barrier), which are cut from its text.  -> _build/libssg_emu_tc.so (same C ABI, every entry point)."""
-    out = os.path.join(OUT, "libssg_emu_tc.so")
-    src_dir = os.path.join(OUT, "src_tc")
+    out = os.path.join(OUT, "libssg_emu_tc%s.so" % ("_" + fault if fault else ""))
+    src_dir = os.path.join(OUT, "src_tc" + ("_" + fault if fault else ""))
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.abspath(__file__), os.path.join(HERE, "emu.cpp"),
             os.path.join(HERE, "emu_tc.cpp")] + [os.path.join(HERE, d, f) for d in ("stub", "stub_tc")
                                                    for f in os.listdir(os.path.join(HERE, d))]
@@ -208,6 +217,10 @@ def build_tc(verbose=False, force=False):
     h = (h[:a] + "// (TMA store helpers: stub_tc/tc_common.cuh)\n"
          "__device__ __forceinline__ void epi_bar_sync() { emu::named_barrier(1, 32 * EPI_WARPS); }\n\n" + h[b:])
     assert "asm volatile" not in h
+    if fault:
+        good, bad = FAULTS[fault]
+        assert h.count(good) == 1, "fault anchor not found: " + fault
+        h = h.replace(good, bad)
     with open(os.path.join(src_dir, "gemm_tc.cuh"), "w") as f:
         f.write(rewrite(h))
     for hname, hdir in (("tc_common.cuh", os.path.join(HERE, "stub_tc")), ("conv.h", CSRC), ("kernels.h", CSRC)):

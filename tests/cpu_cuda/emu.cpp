@@ -124,6 +124,9 @@ void named_barrier(int id, int count) {
 }
 
 float tmem[128][512];
+static void (*g_tc_reset)() = nullptr;
+void set_tc_reset(void (*f)()) { g_tc_reset = f; }
+static void tc_reset_hook() { if (g_tc_reset) g_tc_reset(); }
 std::map<const void*, MBar>& mbars() { static std::map<const void*, MBar> m; return m; }
 void note_event() { ++g_events; }          // asynchronous-unit progress (mbarrier arrivals, TMA, MMA) counts as progress
 
@@ -146,6 +149,7 @@ static void run_block(int n) {
         g_stacks.push_back((char*)s);
     }
     mbars().clear();
+    tc_reset_hook();
     for (NamedBar& b : g_named) b = NamedBar();
     g_coll.assign((n + 31) / 32, std::vector<Coll>());
     for (auto& w : g_coll) w.reserve(8);

@@ -6,7 +6,13 @@ gemm_tc.cuh (the warp-specialised persistent GEMM with all its variants), conv.c
 unchanged on cooperative fibers.  What it establishes: operand staging, descriptor arithmetic, pipeline protocol (a
 missed arrival is a detected deadlock), epilogues and the host orchestration compute the right function; what it cannot:
 timing, data races, the tensor core's internal accumulation order (results are compared with float references to a
-tolerance, and BETWEEN variants bit for bit)."""
+tolerance, and BETWEEN variants bit for bit).
+
+The asynchronous units have two completion models (tests/cpu_cuda/emu_tc.cpp): "eager" -- a TMA load / store or an MMA
+takes effect when it is issued -- and "late" -- it takes effect at the last moment the protocol allows (when the
+mbarrier it signals is polled, when cp.async.bulk.wait_group stops tolerating it).  A correct kernel computes the same
+bytes under both; the fault-injection test at the end shows that the late model catches a stage released before its
+MMAs retired and a staging buffer rewritten under an in-flight TMA store, which the eager model cannot see."""
 import ctypes
 import os
 import shutil
@@ -56,6 +62,7 @@ def tc_lib():
     return lib
 
 
+@pytest.mark.parametrize("late", [0, 1], ids=["eager", "late"])
 @pytest.mark.parametrize("B,H,W,cin,cout,k,stride,use_res,relu", [
     (2, 8, 16, 64, 64, 1, 1, True, True),        # 128x64 tiles, whole-tile residual double buffer
     (2, 8, 16, 64, 128, 1, 1, True, False),      # 128x128 tiles
@@ -66,7 +73,8 @@ def tc_lib():
     (2, 16, 32, 128, 128, 3, 2, False, True),    # stride 2 through element-strided TMA boxes
     (2, 16, 16, 256, 512, 1, 2, False, False),   # 1x1 stride 2 (downsample branch)
 ])
-def test_convolution_kernels_against_float_reference(tc_lib, B, H, W, cin, cout, k, stride, use_res, relu):
+def test_convolution_kernels_against_float_reference(tc_lib, B, H, W, cin, cout, k, stride, use_res, relu, late):
+    tc_lib.ssg_emu_set_async(late)
     rng = np.random.RandomState(B * 1000 + cin + cout + k)
     x = from_bf16(to_bf16(rng.randn(B, H, W, cin)))
     w = from_bf16(to_bf16(rng.randn(cout, k, k, cin) / np.sqrt(cin * k * k)))
@@ -79,6 +87,7 @@ def test_convolution_kernels_against_float_reference(tc_lib, B, H, W, cin, cout,
     scratch = np.zeros(x.size + 64, np.uint16)
     rc = tc_lib.ssg_op_conv(xb.ctypes.data, B, H, W, cin, k, stride, wb.ctypes.data, bias.ctypes.data, cout,
                             rb.ctypes.data if use_res else None, int(relu), y.ctypes.data, scratch.ctypes.data, None)
+    tc_lib.ssg_emu_set_async(0)
     assert rc == 0, tc_lib.ssg_last_error().decode()
     want = conv_ref(x, w, bias, k, stride, res, relu)
     assert np.abs(from_bf16(y) - want).max() <= 0.01 * np.abs(want).max() + 0.02      # bf16 output rounding
@@ -98,13 +107,15 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
     max-pool; kernel-row sharing; element-strided stride-2 boxes; K-concatenated downsample; residual ring; pooled tail)
     on the reference's golden image and weights: features within the GPU smoke tolerance of the reference's, and the
     opt-in variants -- one-barrier epilogue, L2-resident chunking (direct and through graph capture), plain stem --
-    bit-identical to the default."""
+    bit-identical to the default.  The variants run under the LATE completion model (module docstring), the default under
+    the eager one: the same bytes under both is the protocol check."""
     base, rel = _embed(tmp_path, "default", {})
     assert rel < 3e-2 and np.isfinite(base).all()
-    for name, env in (("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
+    for name, env in (("default_late", {}),
+                      ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
                       ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
                       ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"})):
-        got, _ = _embed(tmp_path, name, env)
+        got, _ = _embed(tmp_path, name, dict(env, SSG_EMU_ASYNC="late"))
         assert np.array_equal(got, base), name
 
 
@@ -132,7 +143,55 @@ def test_distance_gemm_kernel_and_its_symmetric_variant(tmp_path):
         "    lib.ssg_rerank_plan_destroy(plan)\n"
         "print('SAME' if np.array_equal(out[0], out[1]) else 'DIFFERENT')\n"
         % ([ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda")],))
-    for sym in ("0", "1"):
+    for sym, model in (("0", "eager"), ("1", "eager"), ("0", "late"), ("1", "late")):
         r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=1200,
-                           env=dict(os.environ, SSG_DIST_SYM=sym))
-        assert r.returncode == 0 and "SAME" in r.stdout, (sym, r.stdout + r.stderr)
+                           env=dict(os.environ, SSG_DIST_SYM=sym, SSG_EMU_ASYNC=model))
+        assert r.returncode == 0 and "SAME" in r.stdout, (sym, model, r.stdout + r.stderr)
+
+
+FAULT_SCRIPT = r"""
+import sys, os, ctypes, numpy as np
+sys.path[:0] = %r
+import build_emu
+from ssg_b200 import _lib as L
+from test_cpu_emulated_tensor_kernels import to_bf16, from_bf16, conv_ref
+lib = ctypes.CDLL(build_emu.build_tc(fault=sys.argv[1] if sys.argv[1] != "none" else None))
+lib.ssg_op_conv.restype, lib.ssg_op_conv.argtypes = L.PROTOTYPES["ssg_op_conv"]
+B, H, W, cin, cout = 3, 8, 16, 512, 256                 # 128x256 tiles, 8 K blocks (> stages) and 4 sub-tiles per tile
+rng = np.random.RandomState(7)
+x = from_bf16(to_bf16(rng.randn(B, H, W, cin))); w = from_bf16(to_bf16(rng.randn(cout, 1, 1, cin) / 22))
+bias = (rng.randn(cout) * 0.1).astype(np.float32)
+res = from_bf16(to_bf16(rng.randn(B, H, W, cout))); rb = to_bf16(res)
+want = conv_ref(x, w, bias, 1, 1, res, True)
+for late in (0, 1):
+    lib.ssg_emu_set_async(late)
+    y = np.zeros((B, H, W, cout), np.uint16); scratch = np.zeros(x.size + 64, np.uint16)
+    xb, wb = to_bf16(x), to_bf16(w)
+    rc = lib.ssg_op_conv(xb.ctypes.data, B, H, W, cin, 1, 1, wb.ctypes.data, bias.ctypes.data, cout, rb.ctypes.data, 1,
+                         y.ctypes.data, scratch.ctypes.data, None)
+    ok = rc == 0 and np.abs(from_bf16(y) - want).max() <= 0.01 * np.abs(want).max() + 0.02
+    print("late" if late else "eager", "RIGHT" if ok else "WRONG")
+"""
+
+
+@pytest.mark.parametrize("fault,epi2,expect", [
+    ("none", "0", {"eager": "RIGHT", "late": "RIGHT"}),
+    ("none", "1", {"eager": "RIGHT", "late": "RIGHT"}),
+    # the operand stage handed back to the TMA producer by a plain arrive instead of tcgen05.commit: the refill lands
+    # before the MMAs that read the stage have executed
+    ("stage_freed_early", "0", {"eager": "RIGHT", "late": "WRONG"}),
+    # one-barrier epilogue without the wait on the previous TMA store: the staging buffer is rewritten under it
+    ("epi2_no_store_wait", "1", {"eager": "RIGHT", "late": "WRONG"}),
+    ("epi2_no_store_wait", "0", {"eager": "RIGHT", "late": "RIGHT"}),      # the fault sits in code EPI2 = 0 never runs
+])
+def test_late_completion_model_catches_injected_protocol_faults(fault, epi2, expect):
+    """gemm_tc.cuh rebuilt with ONE deliberate protocol violation (build_emu.FAULTS): invisible when asynchronous work
+    completes at issue, a wrong result when it completes as late as the protocol allows -- which is what makes "same
+    bytes under both models" (tests above) evidence about the real kernels' synchronisation."""
+    paths = [ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda"),
+             os.path.join(ROOT, "tests")]
+    r = subprocess.run([sys.executable, "-c", FAULT_SCRIPT % (paths,), fault], capture_output=True, text=True,
+                       timeout=1200, env=dict(os.environ, SSG_CONV_EPI2=epi2))
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = dict(l.split() for l in r.stdout.splitlines() if l.startswith(("eager", "late")))
+    assert got == expect, r.stdout + r.stderr
