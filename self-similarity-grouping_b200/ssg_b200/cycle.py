@@ -125,7 +125,7 @@ def pseudo_label_cycle(source_features, target_features, lambda_value=0.1, rho=1
         n = t.shape[0]
         plan = _rerank_plan(n, s.shape[0], t.shape[1], dev.index)
         if (_sparse_default() if sparse is None else sparse) and 0.0 <= lambda_value < 1.0:
-            plan.distance_rows(s, t, k1, mode)
+            plan.distance_rows(s, t, max(k1, k2 - 1), mode)      # rerank.py:97 reads k2 rank columns (as ssg_rerank_run)
             rowptr, col, val, bound = plan.finish_sparse(t, k1, k2, lambda_value)
             cplan = _cluster_plan(n, dev.index)
             if eps_list is None:

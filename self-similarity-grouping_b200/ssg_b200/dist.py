@@ -277,13 +277,14 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
     src = comm.all_gather_rows(sloc, n_src, dim=1)
     lo, hi = shard_bounds(n_tgt, comm.world, comm.rank)
     plan = backend.plan(n_tgt, n_src, tgt.shape[2])
+    k1d = max(k1, k2 - 1)        # the rank table must hold k2 columns too (rerank.py:97), as in ssg_rerank_run
     if _shard_finish_default() if shard_finish is None else shard_finish:
         # row-sharded finish: bank after bank, every rank works on its rows [lo, hi) of every stage
         final_rows = backend.new_final_rows(hi - lo, n_tgt)
         labels, eps_vals = [], []
         for b in range(banks):
             tb, sb = tgt[b].contiguous(), src[b].contiguous()
-            backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
+            backend.distance_rows(plan, sb, tb, k1d, lo, hi - lo)
             for tab in backend.tables(plan, n_tgt):
                 comm.all_gather_rows_inplace(tab, n_tgt)
             backend.finish_rows(plan, tb, k1, k2, lambda_value, lo, hi - lo, final_rows)
@@ -306,7 +307,7 @@ def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_sp
     for b in range(banks):
         tb, sb = tgt[b].contiguous(), src[b].contiguous()
         bank_t.append(tb)
-        backend.distance_rows(plan, sb, tb, k1, lo, hi - lo)
+        backend.distance_rows(plan, sb, tb, k1d, lo, hi - lo)
         tabs = backend.tables(plan, n_tgt)
         for tab in tabs:
             comm.all_gather_rows_inplace(tab, n_tgt)

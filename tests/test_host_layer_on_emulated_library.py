@@ -88,6 +88,35 @@ def test_pseudo_label_cycle_dense_and_sparse_single_process(emulated):
         assert np.array_equal(a, b)
 
 
+def test_k2_beyond_k1_plus_one_through_every_host_path(emulated):
+    """rerank.py:97 reads k2 rank columns; for k2 > k1 + 1 the distance stage must be run wide enough.  ssg_rerank_run
+    does that itself; the host paths that call the distance stage on their own (sparse cycle, sharded cycle) must too --
+    the finish refuses a table that is too narrow instead of reading stale columns."""
+    import ssg_b200
+    from ssg_b200 import _lib, dist as sd
+    k1, k2 = 3, 7
+    tgt, src = _features()
+    want = []
+    for b in range(BANKS):
+        _, f = O.re_ranking(src[b].numpy(), tgt[b].numpy(), k1=k1, k2=k2, lambda_value=LAM, mode="f32")
+        want.append(O.dbscan_dfs(f, O.eps_estimate(f, RHO), 4))
+    tl, sl = [tgt[b] for b in range(BANKS)], [src[b] for b in range(BANKS)]
+    runs = {name: ssg_b200.pseudo_label_cycle(sl, tl, LAM, RHO, k1=k1, k2=k2, dist_mode=_lib.DIST_EXACT, sparse=sp)
+            for name, sp in (("dense", False), ("sparse", True))}
+    for name, kw in (("sharded", {}), ("row-sharded finish", {"shard_finish": True}), ("sparse owners", {"sparse": True})):
+        runs[name] = sd.sharded_pseudo_label_cycle(None, None, None, N, NS, num_split=BANKS - 1, lambda_value=LAM, rho=RHO,
+                                                   k1=k1, k2=k2, backend=sd.CudaBackend(0, _lib.DIST_EXACT),
+                                                   comm=sd.Comm(), features=(tgt, src), **kw)
+    for name, (labels, _, _) in runs.items():
+        for a, b in zip(labels, want):
+            assert np.array_equal(a, b), name
+    # and the refusal itself: a table of k1 + 1 columns is not enough for this k2
+    plan = ssg_b200.RerankPlan(N, NS, D, 0)
+    plan.distance_rows(src[0], tgt[0], k1, _lib.DIST_EXACT)
+    with pytest.raises(Exception, match="rank columns"):
+        plan.finish_sparse(tgt[0], k1, k2, LAM)
+
+
 def test_drop_in_functions_on_the_emulated_library(emulated):
     """reid.rerank.re_ranking / DBSCAN and reid.rerank_plain.re_ranking (numpy in, numpy out) against the oracle."""
     from reid.rerank import re_ranking, DBSCAN
