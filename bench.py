@@ -174,14 +174,19 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s = args.cpu_sample
-    for _ in range(min(args.warmup, 1)):
-        cpu_cycle_sample(256)
+    # every step is a bounded sample; the samples are sized so that the whole run stays within ~4 minutes whatever
+    # --steps is: a 512-row probe (also the warm-up) gives the cost of the O(n^2) stage, the sample is the largest
+    # multiple of 64 rows (<= --cpu-sample) whose projected time fits the per-step budget
+    per_step = min(30.0, 240.0 / max(args.steps, 1))
+    embed_budget = min(10.0, per_step / 3.0)
+    t_probe, _ = cpu_cycle_sample(512)
+    n_s = int(512.0 * ((per_step - embed_budget) / max(t_probe, 1e-3)) ** 0.5) // 64 * 64
+    n_s = max(512, min(args.cpu_sample, n_s))
     times, etimes, eimgs_all = [], [], []
     kind = "port"
     for _ in range(args.steps):
         t, kind = cpu_cycle_sample(n_s)
-        esec, eimgs = cpu_embed_sample(args.cpu_embed_sample)
+        esec, eimgs = cpu_embed_sample(args.cpu_embed_sample, budget_s=embed_budget)
         times.append(t)
         etimes.append(esec)
         eimgs_all.append(eimgs)

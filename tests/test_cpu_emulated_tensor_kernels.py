@@ -109,14 +109,20 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
     opt-in variants -- one-barrier epilogue, L2-resident chunking (direct and through graph capture), plain stem --
     bit-identical to the default.  The variants run under the LATE completion model (module docstring), the default under
     the eager one: the same bytes under both is the protocol check."""
-    base, rel = _embed(tmp_path, "default", {})
-    assert rel < 3e-2 and np.isfinite(base).all()
-    for name, env in (("default_late", {}),
-                      ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
-                      ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
-                      ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"})):
-        got, _ = _embed(tmp_path, name, dict(env, SSG_EMU_ASYNC="late"))
-        assert np.array_equal(got, base), name
+    import build_emu
+    from concurrent.futures import ThreadPoolExecutor
+    build_emu.build_tc()                                     # once, before the runs start side by side
+    variants = (("default_late", {}),
+                ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
+                ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
+                ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"}))
+    with ThreadPoolExecutor(max_workers=min(5, os.cpu_count() or 1)) as pool:      # one subprocess each
+        first = pool.submit(_embed, tmp_path, "default", {})
+        rest = [(name, pool.submit(_embed, tmp_path, name, dict(env, SSG_EMU_ASYNC="late"))) for name, env in variants]
+        base, rel = first.result()
+        assert rel < 3e-2 and np.isfinite(base).all()
+        for name, fut in rest:
+            assert np.array_equal(fut.result()[0], base), name
 
 
 def test_distance_gemm_kernel_and_its_symmetric_variant(tmp_path):
@@ -143,10 +149,16 @@ def test_distance_gemm_kernel_and_its_symmetric_variant(tmp_path):
         "    lib.ssg_rerank_plan_destroy(plan)\n"
         "print('SAME' if np.array_equal(out[0], out[1]) else 'DIFFERENT')\n"
         % ([ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda")],))
-    for sym, model in (("0", "eager"), ("1", "eager"), ("0", "late"), ("1", "late")):
-        r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=1200,
-                           env=dict(os.environ, SSG_DIST_SYM=sym, SSG_EMU_ASYNC=model))
-        assert r.returncode == 0 and "SAME" in r.stdout, (sym, model, r.stdout + r.stderr)
+    import build_emu
+    from concurrent.futures import ThreadPoolExecutor
+    build_emu.build_tc()
+    cases = (("0", "eager"), ("1", "eager"), ("0", "late"), ("1", "late"))
+    with ThreadPoolExecutor(max_workers=min(4, os.cpu_count() or 1)) as pool:
+        runs = [pool.submit(subprocess.run, [sys.executable, "-c", script], capture_output=True, text=True, timeout=1200,
+                            env=dict(os.environ, SSG_DIST_SYM=sym, SSG_EMU_ASYNC=model)) for sym, model in cases]
+        for (sym, model), fut in zip(cases, runs):
+            r = fut.result()
+            assert r.returncode == 0 and "SAME" in r.stdout, (sym, model, r.stdout + r.stderr)
 
 
 FAULT_SCRIPT = r"""
