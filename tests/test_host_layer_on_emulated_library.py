@@ -18,17 +18,17 @@ pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
 N, NS, D, BANKS, RHO, LAM = 120, 70, 16, 3, 0.03, 0.1
 
 
-def _features():
+def _features(banks=BANKS):
     import torch
-    tgt = np.stack([O.synth_features(N, D, 10 + b, per_cluster=12, noise=0.3)[0] for b in range(BANKS)])
-    src = np.stack([O.synth_features(NS, D, 20 + b, per_cluster=12, noise=0.4)[0] for b in range(BANKS)])
+    tgt = np.stack([O.synth_features(N, D, 10 + b, per_cluster=12, noise=0.3)[0] for b in range(banks)])
+    src = np.stack([O.synth_features(NS, D, 20 + b, per_cluster=12, noise=0.4)[0] for b in range(banks)])
     return torch.from_numpy(tgt), torch.from_numpy(src)
 
 
-def _oracle_cycle():
-    tgt, src = _features()
+def _oracle_cycle(banks=BANKS):
+    tgt, src = _features(banks)
     labels, eps = [], []
-    for b in range(BANKS):
+    for b in range(banks):
         _, f = O.re_ranking(src[b].numpy(), tgt[b].numpy(), lambda_value=LAM, mode="f32")
         e = O.eps_estimate(f, RHO)
         eps.append(e)
@@ -145,18 +145,21 @@ def _worker(rank, world, init_file, out_dir, kw):
     from ssg_b200 import _lib, dist as sd
     dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
     try:
-        tgt, src = _features()
+        kw = dict(kw)
+        banks = kw.pop("banks", BANKS)
+        tgt, src = _features(banks)
         tl, th = sd.shard_bounds(N, world, rank)
         sl, sh = sd.shard_bounds(NS, world, rank)
         labels, eps, keep = sd.sharded_pseudo_label_cycle(
-            None, None, None, N, NS, num_split=BANKS - 1, lambda_value=LAM, rho=RHO, backend=sd.CudaBackend(0, _lib.DIST_EXACT),
+            None, None, None, N, NS, num_split=banks - 1, lambda_value=LAM, rho=RHO, backend=sd.CudaBackend(0, _lib.DIST_EXACT),
             comm=sd.Comm(), features=(tgt[:, tl:th].contiguous(), src[:, sl:sh].contiguous()), **kw)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), labels=np.stack(labels), eps=np.array(eps), keep=keep)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kw", [(2, {}), (3, {"shard_finish": True}), (2, {"sparse": True}), (4, {"shard_finish": True})])
+@pytest.mark.parametrize("world,kw", [(2, {}), (3, {"shard_finish": True}), (2, {"sparse": True}), (4, {"shard_finish": True}),
+                                      (2, {"banks": 4})])      # BASELINE configs[2]: num_split = 3 -> 4 banks on 2 ranks
 def test_sharded_cycle_with_the_real_backend_over_gloo(world, kw):
     """One process per rank, gloo collectives, ssg_b200.dist.CudaBackend driving the emulated library: feature
     all-gather, row-block distance stage, table gather, then the bank-parallel / row-sharded / sparse-owner finish."""
@@ -167,7 +170,7 @@ def test_sharded_cycle_with_the_real_backend_over_gloo(world, kw):
     with tempfile.TemporaryDirectory() as tmp:
         mp.spawn(_worker, args=(world, os.path.join(tmp, "init"), tmp, kw), nprocs=world, join=True)
         outs = [np.load(os.path.join(tmp, "rank%d.npz" % r)) for r in range(world)]
-    want_l, want_e = _oracle_cycle()
+    want_l, want_e = _oracle_cycle(kw.get("banks", BANKS))
     for o in outs:
         np.testing.assert_allclose(o["eps"], want_e, rtol=1e-6, atol=0)
         assert np.array_equal(o["labels"], np.stack(want_l))
