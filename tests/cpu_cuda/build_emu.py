@@ -130,22 +130,38 @@ def _up_to_date(outputs):
     return min(os.path.getmtime(o) for o in outputs) > max(os.path.getmtime(d) for d in deps)
 
 
-def build(verbose=False, force=False):
-    outputs = [os.path.join(OUT, "libssg_emu.so")] + [os.path.join(OUT, b) for b in
-                                                      ("shard_check_emu", "sparse_check_emu", "jaccard_big")]
+PLAIN_FAULTS = {
+    # name -> (translation unit, text, replacement): deliberate races, to show that running the kernels under different
+    # thread schedules (emu.cpp: SSG_EMU_SCHED / ssg_emu_set_sched) notices them (tests/test_cpu_emulated_kernels.py)
+    # thread 0 publishes the selection state, everybody reads it: without the barrier only "thread 0 first" works
+    "eps_pick_no_barrier": ("cluster.cu",
+                            "        if (n_pairs >= 0 && top > total) { state[7] = 1ull; state[1] = 0ull; }\n    }\n    __syncthreads();\n",
+                            "        if (n_pairs >= 0 && top > total) { state[7] = 1ull; state[1] = 0ull; }\n    }\n"),
+}
+
+
+def build(verbose=False, force=False, fault=None):
+    """fault: a key of PLAIN_FAULTS -> only the library, as _build/libssg_emu_<fault>.so"""
+    tag = "_" + fault if fault else ""
+    outputs = [os.path.join(OUT, "libssg_emu%s.so" % tag)] + ([] if fault else [os.path.join(OUT, b) for b in
+                                                      ("shard_check_emu", "sparse_check_emu", "jaccard_big")])
     if not force and _up_to_date(outputs):
         return outputs[0], outputs[1:]
-    os.makedirs(os.path.join(OUT, "src"), exist_ok=True)
+    os.makedirs(os.path.join(OUT, "src" + tag), exist_ok=True)
     srcs = []
     for u in UNITS:
         with open(os.path.join(CSRC, u)) as f:
-            text = rewrite(f.read())
+            text = f.read()
+        if fault and PLAIN_FAULTS[fault][0] == u:
+            assert text.count(PLAIN_FAULTS[fault][1]) == 1, "fault anchor not found: " + fault
+            text = text.replace(PLAIN_FAULTS[fault][1], PLAIN_FAULTS[fault][2])
+        text = rewrite(text)
         assert "<<<" not in text
-        dst = os.path.join(OUT, "src", u.replace(".cu", "_emu.cpp"))
+        dst = os.path.join(OUT, "src" + tag, u.replace(".cu", "_emu.cpp"))
         with open(dst, "w") as f:
             f.write(text)
         srcs.append(dst)
-    stub = os.path.join(OUT, "src", "tc_stubs_emu.cpp")
+    stub = os.path.join(OUT, "src" + tag, "tc_stubs_emu.cpp")
     with open(stub, "w") as f:
         f.write(STUBS)
     # the plain-CUDA front end of the tensor distance mode (column mean, bf16x3 operand split) lives in gemm_tc.cu next
@@ -153,12 +169,12 @@ def build(verbose=False, force=False):
     with open(os.path.join(CSRC, "gemm_tc.cu")) as f:
         g = f.read()
     region = g[g.index("constexpr int MEAN_GROUPS"):g.index("struct EpiDist {")]
-    prep = os.path.join(OUT, "src", "dist_prep_emu.cpp")
+    prep = os.path.join(OUT, "src" + tag, "dist_prep_emu.cpp")
     with open(prep, "w") as f:
         f.write('#include <cuda_bf16.h>\n#include "common.cuh"\n#include "kernels.h"\nnamespace ssg {\n'
                 + rewrite(region) + "\n}  // namespace ssg\n")
     srcs += [stub, prep, os.path.join(HERE, "emu.cpp")]
-    lib = os.path.join(OUT, "libssg_emu.so")
+    lib = outputs[0]
     flags = ["-std=c++17", "-O1", "-g", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-fno-strict-aliasing", "-D__CUDACC__", "-w",
              "-I" + os.path.join(HERE, "stub"), "-I" + CSRC, "-I" + os.path.join(ROOT, "include")]
     # -Bsymbolic: the library's cudaMalloc / cudaSetDevice / ... must bind to ITS stand-ins even inside a process that has
@@ -166,6 +182,8 @@ def build(verbose=False, force=False):
     cmd = ["g++"] + flags + ["-shared", "-Wl,-Bsymbolic", "-o", lib] + srcs
     subprocess.run(cmd, check=True, stdout=None if verbose else subprocess.DEVNULL)
     bins = []
+    if fault:
+        return lib, bins
     for h in ("shard_check", "sparse_check"):
         exe = os.path.join(OUT, h + "_emu")
         subprocess.run(["gcc", "-std=c99", "-O1", "-I" + os.path.join(HERE, "stub"), "-I" + os.path.join(ROOT, "include"),

@@ -3,6 +3,7 @@
 #include <ucontext.h>
 #include <sys/mman.h>
 #include <map>
+#include <utility>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -45,6 +46,40 @@ static const std::function<void()>* g_body = nullptr;
 static int g_cur = 0, g_n = 0, g_alive = 0, g_arrived = 0, g_or_acc = 0, g_or_res[2];
 static unsigned long g_bar_gen = 0, g_events = 0;
 
+// Thread and block schedules.  A kernel that is free of races between its barriers, and whose outputs do not depend on
+// the order in which blocks run or atomics land, computes the same bytes under every schedule: 0 = forward (threads
+// 0..n-1 inside a sweep, blocks in grid order), 1 = reverse, 2 = a fresh pseudo-random permutation for every sweep and
+// every grid, 3 = the same at warp granularity (warps permuted, the lanes of a warp back to back in lane order: a
+// converged warp polls an mbarrier as ONE instruction, so its lanes cannot observe different phases -- the
+// "all lanes wait, one elected lane acts, __syncwarp" idiom of the tcgen05 kernels relies on that, and mode 2, which
+// lets another warp run between two lanes' polls, deadlocks it by construction).
+// SSG_EMU_SCHED=forward|reverse|random[:seed]|warps[:seed], or ssg_emu_set_sched() between launches.
+static int g_sched = -1;
+static unsigned g_rng = 1u;
+static void sched_init() {
+    if (g_sched >= 0) return;
+    const char* e = getenv("SSG_EMU_SCHED");
+    g_sched = 0;
+    if (e && !strncmp(e, "reverse", 7)) g_sched = 1;
+    if (e && !strncmp(e, "random", 6)) { g_sched = 2; g_rng = e[6] == ':' ? (unsigned)atoi(e + 7) * 2654435761u + 1u : 1u; }
+    if (e && !strncmp(e, "warps", 5)) { g_sched = 3; g_rng = e[5] == ':' ? (unsigned)atoi(e + 6) * 2654435761u + 1u : 1u; }
+}
+static unsigned next_rand() { g_rng = g_rng * 1664525u + 1013904223u; return g_rng >> 8; }
+static void make_order(std::vector<int>& o, int n) {
+    o.resize(n);
+    for (int i = 0; i < n; ++i) o[i] = g_sched == 1 ? n - 1 - i : i;
+    if (g_sched >= 2) for (int i = n - 1; i > 0; --i) { const int j = (int)(next_rand() % (unsigned)(i + 1)); std::swap(o[i], o[j]); }
+}
+static void make_thread_order(std::vector<int>& o, int n) {
+    if (g_sched != 3) { make_order(o, n); return; }
+    const int nw = (n + 31) / 32;
+    std::vector<int> w(nw);
+    for (int i = 0; i < nw; ++i) w[i] = i;
+    for (int i = nw - 1; i > 0; --i) { const int j = (int)(next_rand() % (unsigned)(i + 1)); std::swap(w[i], w[j]); }
+    o.clear();
+    for (int i = 0; i < nw; ++i) for (int t = w[i] * 32; t < n && t < w[i] * 32 + 32; ++t) o.push_back(t);
+}
+
 static void set_thread_idx(int t) {
     threadIdx.x = t % blockDim.x;
     threadIdx.y = (t / blockDim.x) % blockDim.y;
@@ -68,7 +103,11 @@ int syncthreads_or(int pred) {
     g_or_acc |= pred != 0;
     ++g_arrived;
     release_barrier_if_complete();
+    // non-forward schedules: the thread that completes the barrier does not get a head start -- who runs first after a
+    // barrier is decided by the sweep order alone
+    if (g_sched > 0 && g_bar_gen != g) yield_();
     while (g_bar_gen == g) yield_();
+    ++g_events;                             // a thread leaving a wait is progress (deadlock = nobody leaves one)
     return g_or_res[g & 1];
 }
 void syncthreads() { (void)syncthreads_or(0); }
@@ -92,6 +131,11 @@ const uint64_t* exchange(unsigned mask, uint64_t v) {
         c->arrived = 0;
         ++c->gen;
         ++g_events;
+        if (g_sched > 0) {                  // no head start for the lane that completes the collective (see syncthreads_or)
+            yield_();
+            std::vector<Coll>& w2 = g_coll[g_cur >> 5];
+            for (Coll& e : w2) if (e.mask == mask) { c = &e; break; }
+        }
     } else {
         // vector may grow (emplace_back by another lane with a new mask): re-find after every yield
         while (true) {
@@ -102,6 +146,7 @@ const uint64_t* exchange(unsigned mask, uint64_t v) {
             if (c->gen != g) break;
         }
     }
+    ++g_events;
     return c->snap[g & 1];
 }
 
@@ -119,8 +164,9 @@ void named_barrier(int id, int count) {
     ++g_named_calls;
     NamedBar& b = g_named[id & 15];
     const unsigned long g = b.gen;
-    if (++b.arrived >= count) { b.arrived = 0; ++b.gen; ++g_events; }
+    if (++b.arrived >= count) { b.arrived = 0; ++b.gen; ++g_events; if (g_sched > 0) yield_(); }
     else while (b.gen == g) yield_();
+    ++g_events;
 }
 
 float tmem[128][512];
@@ -172,9 +218,13 @@ static void run_block(int n) {
         makecontext(&g_fib[t].ctx.uc, trampoline, 0);
 #endif
     }
+    static std::vector<int> order;
+    make_thread_order(order, n);
     while (g_alive > 0) {
         const unsigned long before = g_events;
-        for (int t = 0; t < n; ++t) {
+        if (g_sched >= 2) make_thread_order(order, n);
+        for (int i = 0; i < n; ++i) {
+            const int t = order[i];
             if (g_fib[t].done) continue;
             g_cur = t;
             set_thread_idx(t);
@@ -195,15 +245,27 @@ void launch(const std::function<void()>& fn, dim3 grid, dim3 block, size_t smem,
     gridDim = grid; blockDim = block;
     g_body = &fn;
     const int n = (int)(block.x * block.y * block.z);
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-            for (unsigned bx = 0; bx < grid.x; ++bx) {
-                blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-                run_block(n);
-            }
+    sched_init();
+    if (g_sched == 0) {
+        for (unsigned bz = 0; bz < grid.z; ++bz)
+            for (unsigned by = 0; by < grid.y; ++by)
+                for (unsigned bx = 0; bx < grid.x; ++bx) {
+                    blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+                    run_block(n);
+                }
+        return;
+    }
+    std::vector<int> blocks;                          // not the static one of run_block: that is rebuilt per sweep
+    make_order(blocks, (int)(grid.x * grid.y * grid.z));
+    for (int b : blocks) {
+        blockIdx.x = (unsigned)b % grid.x; blockIdx.y = ((unsigned)b / grid.x) % grid.y; blockIdx.z = (unsigned)b / (grid.x * grid.y);
+        run_block(n);
+    }
 }
 
 }  // namespace emu
+
+extern "C" void ssg_emu_set_sched(int mode, unsigned seed) { emu::g_sched = mode; emu::g_rng = seed * 2654435761u + 1u; }
 
 // ---- "device memory" is host memory
 extern "C" {

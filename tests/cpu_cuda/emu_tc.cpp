@@ -122,7 +122,9 @@ bool tc_mbar_poll(const void* bar, uint32_t parity) {
             if (q.is_commit) arrive(q.bar); else mma_now(q);
         }
     }
-    return mbars()[bar].phase != parity;
+    const bool done = mbars()[bar].phase != parity;
+    if (done) note_event();                 // a thread leaving a wait is progress (emu.cpp's deadlock detection)
+    return done;
 }
 void tc_tma_load(void* smem_dst, const CUtensorMap* m, const void* bar, const int* c) {
     const uint32_t dst = (uint32_t)((unsigned char*)smem_dst - dyn_smem);

@@ -5,7 +5,9 @@ execution model is cooperative fibers), checked against the oracle, the referenc
 This is not the product (which needs an sm_100 GPU and has no CPU fallback): it is a second line of evidence for the
 kernels' LOGIC -- index arithmetic, barrier and warp-collective protocols (a missed participant is reported as a
 deadlock), tie handling, the certified sparse path -- that runs where no GPU is.  The tensor-core kernels (tcgen05 /
-TMA) are not emulated, and neither are data races."""
+TMA) run in tests/test_cpu_emulated_tensor_kernels.py.  Data races are not detected as such, but their usual symptom is:
+the tests at the end of this file run the kernels under reverse and pseudo-random thread / block schedules and demand
+the same bytes (an injected missing barrier passes the default schedule and fails the others)."""
 import ctypes
 import os
 import shutil
@@ -524,3 +526,115 @@ def test_symmetric_distance_matrix_leaves_the_outputs_unchanged_under_emulation(
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, SSG_DIST_SYM="1", SSG_EMU_GEMM_NOISE="0.9"))
     assert r.returncode == 0 and "SAME" in r.stdout, r.stdout + r.stderr
+
+
+# ---------------------------------------------------------------------------------------------------
+# Thread / block schedules (tests/cpu_cuda/emu.cpp: SSG_EMU_SCHED, ssg_emu_set_sched).  The default schedule runs the
+# threads of a block in index order between barriers and the blocks in grid order -- one of many orders the hardware
+# may produce.  A kernel without races between its barriers, and whose outputs do not depend on the order in which
+# blocks run or atomics land, computes the same bytes under every schedule.
+# ---------------------------------------------------------------------------------------------------
+SCHEDULES = {"forward": (0, 0), "reverse": (1, 0), "random-1": (2, 1), "random-2": (2, 2)}
+
+
+def test_outputs_are_byte_identical_under_every_thread_and_block_schedule(emu):
+    """Re-ranking in the exact and in the tensor distance mode, eps and DBSCAN on its result, the kNN-set re-ranker and
+    re_ranking_lh: forward, reverse and two pseudo-random schedules (fresh permutation per sweep and per grid, the
+    thread that completes a barrier or a warp collective gets no head start) give the same bytes."""
+    import build_emu
+    from ssg_b200 import _lib as L
+    lib = ctypes.CDLL(build_emu.build()[0])
+    for name, (res, args) in L.PROTOTYPES.items():
+        if hasattr(lib, name):
+            getattr(lib, name).restype, getattr(lib, name).argtypes = res, args
+    n, ns, d = 150, 70, 32
+    tgt, _ = O.synth_features(n, d, 3, per_cluster=12)
+    src, _ = O.synth_features(ns, d, 4, noise=0.6)
+    tgt[5] = tgt[6]                                         # duplicate rows: exact ties in the rank tables
+    runs = {}
+    try:
+        for name, (mode, seed) in SCHEDULES.items():
+            lib.ssg_emu_set_sched(mode, seed)
+            out = []
+            plan = ctypes.c_void_p()
+            assert lib.ssg_rerank_plan_create(ctypes.byref(plan), 0, n, ns, d) == 0
+            for dist_mode in (L.DIST_EXACT, L.DIST_TENSOR):
+                f = np.empty((n, n))
+                rc = lib.ssg_rerank_run(plan, src.ctypes.data, ns, tgt.ctypes.data, n, d, 20, 6, 0.1, dist_mode,
+                                        f.ctypes.data, None, None)
+                assert rc == 0, lib.ssg_last_error().decode()
+                out.append(f)
+            for fn, args in ((lib.ssg_rerank_plain, (20, 0.1)), (lib.ssg_rerank_lh, (20, 6, 0.1))):
+                g = np.empty((n, n))
+                rc = fn(plan, src.ctypes.data, ns, tgt.ctypes.data, n, d, *args, L.DIST_EXACT, g.ctypes.data, None)
+                assert rc == 0, lib.ssg_last_error().decode()
+                out.append(g)
+            lib.ssg_rerank_plan_destroy(plan)
+            eps, labels = emu.eps_and_labels(out[0], rho=0.06)
+            out += [np.array([eps]), labels]
+            runs[name] = out
+    finally:
+        lib.ssg_emu_set_sched(0, 0)
+    assert runs["forward"][5].max() >= 1                    # there are clusters to get wrong
+    for name, out in runs.items():
+        for a, b in zip(out, runs["forward"]):
+            assert a.tobytes() == b.tobytes(), name
+
+
+def test_this_module_passes_under_other_schedules():
+    """Everything above (oracle, golden-vector and sklearn comparisons; the C harnesses inherit the environment) once
+    more under a reverse and under a pseudo-random schedule.  The slowest cases are left out."""
+    if os.environ.get("SSG_EMU_SCHED"):
+        pytest.skip("already inside a scheduled run")
+    import build_emu
+    from concurrent.futures import ThreadPoolExecutor
+    build_emu.build()
+    keep = "not (beyond_256 or property_based or schedule or within_the_bound or python_prototypes)"
+    cmd = [sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider", "-k", keep]
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        runs = {s: pool.submit(subprocess.run, cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT,
+                               env=dict(os.environ, SSG_EMU_SCHED=s)) for s in ("reverse", "random:7")}
+        for s, fut in runs.items():
+            r = fut.result()
+            assert r.returncode == 0 and " passed" in r.stdout, (s, r.stdout[-3000:] + r.stderr[-2000:])
+
+
+SCHED_FAULT_SCRIPT = r"""
+import sys, ctypes, numpy as np
+sys.path[:0] = %r
+import build_emu
+from ssg_b200 import _lib as L
+from oracle import ssg_oracle as O
+lib = ctypes.CDLL(build_emu.build(fault=sys.argv[1] if sys.argv[1] != "none" else None)[0])
+for nm in ("ssg_cluster_plan_create", "ssg_cluster_plan_destroy", "ssg_eps_estimate_host"):
+    getattr(lib, nm).restype, getattr(lib, nm).argtypes = L.PROTOTYPES[nm]
+rng = np.random.RandomState(0)
+n = 200
+a = rng.rand(n, n)
+dmat = (a + a.T) / 2
+np.fill_diagonal(dmat, 0)
+want = O.eps_estimate(dmat, 0.05)
+for name, mode in (("forward", 0), ("reverse", 1), ("random", 2)):
+    lib.ssg_emu_set_sched(mode, 1)
+    plan = ctypes.c_void_p()
+    assert lib.ssg_cluster_plan_create(ctypes.byref(plan), 0, n, 0) == 0
+    e, top = ctypes.c_double(), ctypes.c_longlong()
+    rc = lib.ssg_eps_estimate_host(plan, dmat.ctypes.data, 1, n, 0.05, ctypes.byref(e), ctypes.byref(top))
+    lib.ssg_cluster_plan_destroy(plan)
+    print(name, "RIGHT" if rc == 0 and abs(e.value - want) <= 1e-12 * want else "WRONG")
+"""
+
+
+@pytest.mark.parametrize("fault,expect", [
+    ("none", {"forward": "RIGHT", "reverse": "RIGHT", "random": "RIGHT"}),
+    # eps_pick_kernel without the barrier between thread 0 publishing the selection state and everybody reading it:
+    # right whenever thread 0 happens to run first, as it does in the forward schedule
+    ("eps_pick_no_barrier", {"forward": "RIGHT", "reverse": "WRONG", "random": "WRONG"}),
+])
+def test_schedules_catch_an_injected_race(fault, expect):
+    paths = [ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda")]
+    r = subprocess.run([sys.executable, "-c", SCHED_FAULT_SCRIPT % (paths,), fault], capture_output=True, text=True,
+                       timeout=900, env={k: v for k, v in os.environ.items() if k != "SSG_EMU_SCHED"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = dict(l.split() for l in r.stdout.splitlines() if l.split() and l.split()[0] in expect)
+    assert got == expect, r.stdout + r.stderr

@@ -93,6 +93,45 @@ def test_convolution_kernels_against_float_reference(tc_lib, B, H, W, cin, cout,
     assert np.abs(from_bf16(y) - want).max() <= 0.01 * np.abs(want).max() + 0.02      # bf16 output rounding
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout,k,stride,use_res", [
+    (3, 8, 16, 256, 256, 1, 1, True),            # residual sub-tile ring, 4 K blocks over 3 stages
+    (1, 8, 32, 64, 64, 3, 1, False),             # kernel-row sharing
+    (2, 16, 32, 128, 128, 3, 2, False),          # stride-2 boxes, 18 K blocks
+])
+def test_convolution_kernels_are_byte_identical_under_every_schedule_and_completion_model(tc_lib, B, H, W, cin, cout, k,
+                                                                                        stride, use_res):
+    """The warp-specialised GEMM under the thread schedules of tests/cpu_cuda/emu.cpp (who of producer, MMA issuer and the
+    eight epilogue warps runs first after every yield) crossed with the two completion models: same bytes.  The random
+    schedule is warp-granular here: the lanes of a warp poll an mbarrier as one instruction on the hardware, and the
+    "all lanes wait, lane 0 issues and commits, __syncwarp" idiom of the MMA warp depends on it -- a lane-granular random
+    order, which lets the producer refill a stage between lane 0's poll and lane 1's, deadlocks by construction (the
+    emulator reports it)."""
+    rng = np.random.RandomState(11)
+    xb = to_bf16(rng.randn(B, H, W, cin))
+    wb = to_bf16(rng.randn(cout, k, k, cin) / np.sqrt(cin * k * k))
+    bias = (rng.randn(cout) * 0.1).astype(np.float32)
+    OH, OW = H // stride, W // stride
+    rb = to_bf16(rng.randn(B, OH, OW, cout)) if use_res else None
+    outs = {}
+    try:
+        for sched, (mode, seed) in {"forward": (0, 0), "reverse": (1, 0), "random warps": (3, 5)}.items():
+            for late in (0, 1):
+                tc_lib.ssg_emu_set_sched(mode, seed)
+                tc_lib.ssg_emu_set_async(late)
+                y = np.zeros((B, OH, OW, cout), np.uint16)
+                scratch = np.zeros(xb.size + 64, np.uint16)
+                rc = tc_lib.ssg_op_conv(xb.ctypes.data, B, H, W, cin, k, stride, wb.ctypes.data, bias.ctypes.data, cout,
+                                        rb.ctypes.data if use_res else None, 1, y.ctypes.data, scratch.ctypes.data, None)
+                assert rc == 0, tc_lib.ssg_last_error().decode()
+                outs[(sched, late)] = y
+    finally:
+        tc_lib.ssg_emu_set_sched(0, 0)
+        tc_lib.ssg_emu_set_async(0)
+    assert outs[("forward", 0)].any()
+    for key, y in outs.items():
+        assert np.array_equal(y, outs[("forward", 0)]), key
+
+
 def _embed(tmp_path, name, env, n=1):
     out = str(tmp_path / (name + ".npy"))
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cpu_cuda", "run_embed_emu.py"), str(n), out],
