@@ -152,10 +152,12 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
     from concurrent.futures import ThreadPoolExecutor
     build_emu.build_tc()                                     # once, before the runs start side by side
     variants = (("default_late", {}),
+                ("default_reverse_order", {"SSG_EMU_SCHED": "reverse"}),          # thread / block schedules of emu.cpp
+                ("default_random_warps", {"SSG_EMU_SCHED": "warps:3"}),
                 ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
                 ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
                 ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"}))
-    with ThreadPoolExecutor(max_workers=min(5, os.cpu_count() or 1)) as pool:      # one subprocess each
+    with ThreadPoolExecutor(max_workers=min(7, os.cpu_count() or 1)) as pool:      # one subprocess each
         first = pool.submit(_embed, tmp_path, "default", {})
         rest = [(name, pool.submit(_embed, tmp_path, name, dict(env, SSG_EMU_ASYNC="late"))) for name, env in variants]
         base, rel = first.result()
