@@ -173,3 +173,52 @@ def test_re_ranking_lh_on_the_device():
     e, f = re_ranking_lh(src, tgt, 20, 6, 0.2)
     assert np.array_equal(e, O.original_distance(tgt))
     np.testing.assert_allclose(f, P.re_ranking_lh(src, tgt, 20, 6, 0.2, "f32"), rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu_next
+def test_matrix_beyond_2_31_elements():
+    """N = 47 000: N^2 = 2.209e9 > 2^31 elements (17.7 GB of float64 final_dist), the first size at which a 32-bit row
+    offset anywhere in the distance / Jaccard / eps / DBSCAN kernels would read the wrong rows.  Size-independent
+    properties: sampled rows of the rank table against cdist (rows beyond offset 2^31 included), symmetry on sampled
+    blocks that straddle the 2^31 boundary, dense vs sparse finish (identical labels), clusters found among the LAST
+    rows.  CPU counterpart for the eps / DBSCAN kernels: tools/emu_large_index_check.py (profiles/r01_emulated_large_index.log)."""
+    import torch
+    import ssg_b200
+    from scipy.spatial.distance import cdist
+    from ssg_b200 import _lib
+    n, ns, d, lam, rho = 47000, 4000, 64, 0.1, 1.6e-3
+    g = torch.Generator(device="cuda").manual_seed(5)
+    c = n // 20
+    centres = torch.randn(c, d, generator=g, device="cuda")
+    lab = torch.arange(n, device="cuda") % c                     # every centre has 20 members, spread over all rows
+    t = centres[lab] + 0.15 * torch.randn(n, d, generator=g, device="cuda")
+    t = (t / t.norm(dim=1, keepdim=True)).contiguous()
+    s = centres[torch.randint(0, c, (ns,), generator=g, device="cuda")] + 0.6 * torch.randn(ns, d, generator=g, device="cuda")
+    s = (s / s.norm(dim=1, keepdim=True)).contiguous()
+    plan = ssg_b200.RerankPlan(n, ns, d)
+    _, f = plan.run(s, t, lambda_value=lam, dist_mode=_lib.DIST_TENSOR)
+    torch.cuda.synchronize()
+    rank = plan.stage(_lib.STAGE_RANK, n)
+    assert np.array_equal(rank[:, 0], np.arange(n))
+    first_beyond = 2 ** 31 // n + 1
+    rows = np.concatenate([np.arange(0, n, n // 24)[:24], np.arange(first_beyond - 2, first_beyond + 3), [n - 2, n - 1]])
+    th = t.cpu().numpy()
+    od = np.power(cdist(th[rows], th).astype(np.float32), 2).astype(np.float32)
+    odn = od / od.max(axis=1, keepdims=True)
+    assert np.array_equal(np.argsort(odn, kind="stable")[:, :21], rank[rows, :21])
+    blk = torch.cat([torch.arange(0, n, 97, device="cuda"), torch.arange(first_beyond - 8, first_beyond + 8, device="cuda"),
+                     torch.arange(n - 16, n, device="cuda")])
+    sub = f.index_select(0, blk).index_select(1, blk)
+    assert torch.equal(sub, sub.t())
+    cplan = ssg_b200.ClusterPlan(n)
+    eps, top = cplan.eps(f, rho)
+    assert top == int(np.round(rho * (n * (n - 1) // 2)))        # no exact zeros off the diagonal
+    labels, ncl = cplan.dbscan(f, eps, 4)
+    labels = labels.cpu().numpy()
+    assert ncl > 500 and (labels[first_beyond:] >= 0).sum() > (n - first_beyond) // 2
+    del f, plan, cplan, sub
+    torch.cuda.empty_cache()
+    # the sparse finish never builds the matrix: same labels, eps to the order of the additions
+    l_s, e_s, _ = ssg_b200.pseudo_label_cycle([s], [t], lam, rho, dist_mode=_lib.DIST_TENSOR, device=0, sparse=True)
+    assert np.array_equal(l_s[0], labels)
+    np.testing.assert_allclose(e_s[0], eps, rtol=1e-12)
