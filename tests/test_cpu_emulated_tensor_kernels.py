@@ -168,7 +168,8 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
 
 def test_distance_gemm_kernel_and_its_symmetric_variant(tmp_path):
     """The real distance GEMM kernel (EpiDist / EpiDistSym epilogues) under emulation inside the tensor distance mode:
-    outputs bit-equal to the exact mode, with and without SSG_DIST_SYM (read once per process -> subprocesses)."""
+    outputs bit-equal to the exact mode, with and without SSG_DIST_SYM (read once per process -> subprocesses), under
+    eager completion in thread order and under late completion with randomly ordered warps."""
     script = (
         "import sys, os, ctypes, numpy as np\n"
         "sys.path[:0] = %r\n"
@@ -196,7 +197,8 @@ def test_distance_gemm_kernel_and_its_symmetric_variant(tmp_path):
     cases = (("0", "eager"), ("1", "eager"), ("0", "late"), ("1", "late"))
     with ThreadPoolExecutor(max_workers=min(4, os.cpu_count() or 1)) as pool:
         runs = [pool.submit(subprocess.run, [sys.executable, "-c", script], capture_output=True, text=True, timeout=1200,
-                            env=dict(os.environ, SSG_DIST_SYM=sym, SSG_EMU_ASYNC=model)) for sym, model in cases]
+                            env=dict(os.environ, SSG_DIST_SYM=sym, SSG_EMU_ASYNC=model,
+                                     SSG_EMU_SCHED="warps:2" if model == "late" else "forward")) for sym, model in cases]
         for (sym, model), fut in zip(cases, runs):
             r = fut.result()
             assert r.returncode == 0 and "SAME" in r.stdout, (sym, model, r.stdout + r.stderr)
