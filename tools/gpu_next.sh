@@ -24,7 +24,7 @@ SSG_DIST_SYM=1 timeout 200 python bench.py $Q > gpurun_out/next_ab_distsym.json 
 SSG_DIST_SYM=1 timeout 200 python bench.py $Q --sparse-finish > gpurun_out/next_ab_distsym_sparse.json 2> gpurun_out/next_ab_distsym_sparse.err
 SSG_PAIR_VEC8=1 timeout 200 python bench.py $Q > gpurun_out/next_ab_pairvec8.json 2> gpurun_out/next_ab_pairvec8.err
 SSG_CONV_EPI2=1 timeout 200 python bench.py $Q > gpurun_out/next_ab_epi2.json 2> gpurun_out/next_ab_epi2.err
-for c in 16 32 48; do
+for c in 8 16 32 48; do
   SSG_L2_CHUNK=$c timeout 200 python bench.py $Q > gpurun_out/next_ab_l2chunk$c.json 2> gpurun_out/next_ab_l2chunk$c.err
 done
 tail -n 3 gpurun_out/next_*.log; cat gpurun_out/next_ab_*.json
