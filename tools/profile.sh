@@ -3,6 +3,7 @@
 #   launches : every launch of one full step with its device time (cold-cache, serialised: compare SHARES)
 #   full     : ncu --set full of the distance GEMM, stem + layer 1, layer 4 and the re-rank side kernels
 #   traffic  : DRAM bytes + time of every convolution GEMM launch of one embedding batch
+#   traffic_warm : the same without cache flushes between launches, default schedule vs SSG_L2_CHUNK (SSG_CHUNK=32)
 # Reports are 1.4-3 MB per launch and gpurun_out/ is capped at 64 MiB IN TOTAL per call (everything is dropped beyond
 # that), hence the small launch counts: 2 + 8 + 5 + 8 launches ~ 45 MB.
 set -u
@@ -31,6 +32,22 @@ traffic)
   timeout ${LIM:-600} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
       -k regex:gemm_kernel -s 49 -c 49 --csv --log-file gpurun_out/${TAG}_conv_traffic.csv \
       python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_conv_traffic.out 2>&1 ;;
+traffic_warm)
+  # the same with the caches NOT flushed between launches (--cache-control none), once for the default schedule and once
+  # for L2-resident chunks of layers 1-2 (direct launches: the chunk loop as a CUDA graph is one opaque launch to ncu):
+  # what tools/l2_traffic_model.py predicts in its warm mode (profiles/r01_l2_chunk_model.md: 29.7 -> 9.7 GB per batch).
+  # Three metrics fit one pass, so nothing is replayed and the cache state is the program's own.
+  # launches per batch of 512 images (1024 image-passes): stem 1 + layers 1-2 21 per chunk + layers 3-4 27; the first
+  # batch (target set) is skipped, the second (source set) is captured
+  C=${SSG_CHUNK:-32}
+  for v in "SSG_L2_CHUNK=0" "SSG_L2_CHUNK=$C SSG_L2_GRAPH=0"; do
+    name=$(echo "$v" | tr -c 'A-Za-z0-9\n' '_')
+    case "$v" in "SSG_L2_CHUNK=0") S=49 ;; *) S=$((1 + (1024 + C - 1) / C * 21 + 27)) ;; esac
+    env $v timeout ${LIM:-600} ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+        --clock-control none --cache-control none -k regex:gemm_kernel -s $S -c $S --csv \
+        --log-file gpurun_out/${TAG}_conv_traffic_warm_${name}.csv \
+        python bench.py --quick --steps 1 --warmup 0 --n 512 > gpurun_out/${TAG}_conv_traffic_warm_${name}.out 2>&1
+  done ;;
 esac
 done
 ls -la gpurun_out/ | grep "${TAG}_" | tail -12
