@@ -31,3 +31,5 @@ tail -n 3 gpurun_out/next_*.log; cat gpurun_out/next_ab_*.json
 # multi-GPU (separate call, gpurun --gpus 2/8):
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
 #       bench.py --gpus 8 --steps 3 --warmup 3 [--sparse-finish | --shard-finish]
+# L2-chunk traffic against the LRU model (profiles/r01_l2_chunk_model.md), ~2 min more:
+#   bash tools/profile.sh r02a traffic_warm        (SSG_CHUNK=32 by default; DRAM bytes per launch, caches not flushed)
