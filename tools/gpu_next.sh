@@ -27,6 +27,9 @@ SSG_CONV_EPI2=1 timeout 200 python bench.py $Q > gpurun_out/next_ab_epi2.json 2>
 for c in 8 16 32 48; do
   SSG_L2_CHUNK=$c timeout 200 python bench.py $Q > gpurun_out/next_ab_l2chunk$c.json 2> gpurun_out/next_ab_l2chunk$c.err
 done
+# chunks and the one-barrier epilogue together: once the HBM bytes are gone the epilogue is the next limit
+# (profiles/r01_l2_chunk_model.md section 3)
+SSG_L2_CHUNK=32 SSG_CONV_EPI2=1 timeout 200 python bench.py $Q > gpurun_out/next_ab_l2chunk32_epi2.json 2> gpurun_out/next_ab_l2chunk32_epi2.err
 tail -n 3 gpurun_out/next_*.log; cat gpurun_out/next_ab_*.json
 # multi-GPU (separate call, gpurun --gpus 2/8):
 #   python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
