@@ -625,16 +625,26 @@ for name, mode in (("forward", 0), ("reverse", 1), ("random", 2)):
 """
 
 
-@pytest.mark.parametrize("fault,expect", [
+SCHED_FAULT_CASES = [
     ("none", {"forward": "RIGHT", "reverse": "RIGHT", "random": "RIGHT"}),
     # eps_pick_kernel without the barrier between thread 0 publishing the selection state and everybody reading it:
     # right whenever thread 0 happens to run first, as it does in the forward schedule
     ("eps_pick_no_barrier", {"forward": "RIGHT", "reverse": "WRONG", "random": "WRONG"}),
-])
-def test_schedules_catch_an_injected_race(fault, expect):
+]
+
+
+def test_schedules_catch_an_injected_race():
+    import build_emu
+    from concurrent.futures import ThreadPoolExecutor
+    for fault, _ in SCHED_FAULT_CASES:
+        build_emu.build(fault=None if fault == "none" else fault)
     paths = [ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda")]
-    r = subprocess.run([sys.executable, "-c", SCHED_FAULT_SCRIPT % (paths,), fault], capture_output=True, text=True,
-                       timeout=900, env={k: v for k, v in os.environ.items() if k != "SSG_EMU_SCHED"})
-    assert r.returncode == 0, r.stdout + r.stderr
-    got = dict(l.split() for l in r.stdout.splitlines() if l.split() and l.split()[0] in expect)
-    assert got == expect, r.stdout + r.stderr
+    env = {k: v for k, v in os.environ.items() if k != "SSG_EMU_SCHED"}
+    with ThreadPoolExecutor(max_workers=2) as pool:
+        runs = [pool.submit(subprocess.run, [sys.executable, "-c", SCHED_FAULT_SCRIPT % (paths,), fault],
+                            capture_output=True, text=True, timeout=900, env=env) for fault, _ in SCHED_FAULT_CASES]
+        for (fault, expect), fut in zip(SCHED_FAULT_CASES, runs):
+            r = fut.result()
+            assert r.returncode == 0, (fault, r.stdout + r.stderr)
+            got = dict(l.split() for l in r.stdout.splitlines() if l.split() and l.split()[0] in expect)
+            assert got == expect, (fault, r.stdout + r.stderr)

@@ -229,7 +229,7 @@ for late in (0, 1):
 """
 
 
-@pytest.mark.parametrize("fault,epi2,expect", [
+LATE_FAULT_CASES = [
     ("none", "0", {"eager": "RIGHT", "late": "RIGHT"}),
     ("none", "1", {"eager": "RIGHT", "late": "RIGHT"}),
     # the operand stage handed back to the TMA producer by a plain arrive instead of tcgen05.commit: the refill lands
@@ -238,15 +238,25 @@ for late in (0, 1):
     # one-barrier epilogue without the wait on the previous TMA store: the staging buffer is rewritten under it
     ("epi2_no_store_wait", "1", {"eager": "RIGHT", "late": "WRONG"}),
     ("epi2_no_store_wait", "0", {"eager": "RIGHT", "late": "RIGHT"}),      # the fault sits in code EPI2 = 0 never runs
-])
-def test_late_completion_model_catches_injected_protocol_faults(fault, epi2, expect):
+]
+
+
+def test_late_completion_model_catches_injected_protocol_faults():
     """gemm_tc.cuh rebuilt with ONE deliberate protocol violation (build_emu.FAULTS): invisible when asynchronous work
     completes at issue, a wrong result when it completes as late as the protocol allows -- which is what makes "same
     bytes under both models" (tests above) evidence about the real kernels' synchronisation."""
+    import build_emu
+    from concurrent.futures import ThreadPoolExecutor
+    for fault in sorted({c[0] for c in LATE_FAULT_CASES}):
+        build_emu.build_tc(fault=None if fault == "none" else fault)          # before the subprocesses race for it
     paths = [ROOT, os.path.join(ROOT, "self-similarity-grouping_b200"), os.path.join(ROOT, "tests", "cpu_cuda"),
              os.path.join(ROOT, "tests")]
-    r = subprocess.run([sys.executable, "-c", FAULT_SCRIPT % (paths,), fault], capture_output=True, text=True,
-                       timeout=1200, env=dict(os.environ, SSG_CONV_EPI2=epi2))
-    assert r.returncode == 0, r.stdout + r.stderr
-    got = dict(l.split() for l in r.stdout.splitlines() if l.startswith(("eager", "late")))
-    assert got == expect, r.stdout + r.stderr
+    with ThreadPoolExecutor(max_workers=min(5, os.cpu_count() or 1)) as pool:
+        runs = [pool.submit(subprocess.run, [sys.executable, "-c", FAULT_SCRIPT % (paths,), fault], capture_output=True,
+                            text=True, timeout=1200, env=dict(os.environ, SSG_CONV_EPI2=epi2))
+                for fault, epi2, _ in LATE_FAULT_CASES]
+        for (fault, epi2, expect), fut in zip(LATE_FAULT_CASES, runs):
+            r = fut.result()
+            assert r.returncode == 0, (fault, epi2, r.stdout + r.stderr)
+            got = dict(l.split() for l in r.stdout.splitlines() if l.startswith(("eager", "late")))
+            assert got == expect, (fault, epi2, r.stdout + r.stderr)
