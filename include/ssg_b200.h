@@ -10,7 +10,9 @@
  *   - `d_*` pointers are DEVICE pointers on the plan's device, `h_*` pointers are HOST pointers.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All device entry
  *     points are stream-ordered and asynchronous unless they return a host scalar.
- *   - plans own their workspace (allocated once at creation); nothing is allocated per call.
+ *   - plans own their workspace, allocated at creation; nothing is allocated per call, except that the opt-in
+ *     entry points (sparse form, rerank_plain, rerank_lh) add their buffers on first use and the CSR of the sparse
+ *     form grows when a result needs more room.
  *   - plans are bound to one device and are not thread-safe.
  */
 #ifndef SSG_B200_H
