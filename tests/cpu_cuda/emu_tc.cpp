@@ -6,7 +6,8 @@
 //                    bytes) only when somebody polls the mbarrier it signals; an MMA executes, and its tcgen05.commit
 //                    arrives, only when the committed mbarrier is polled; a TMA store reads shared memory only when
 //                    cp.async.bulk.wait_group(.read) stops allowing it to be pending.
-// A kernel whose protocol is right computes the same bytes under both; one that refills an operand stage before the MMA
+//   mixed           : every operation draws (seeded) whether it behaves eagerly or late -- see defer_now().
+// A kernel whose protocol is right computes the same bytes under all of them; one that refills an operand stage before the MMA
 // consumed it, rewrites a staging buffer under an in-flight store, or reads a tile without waiting for its barrier does
 // not.
 #include <stdlib.h>
@@ -26,7 +27,23 @@ void note_event();
 extern float tmem[128][512];
 
 static int g_late = -1;                                        // -1: take it from SSG_EMU_ASYNC on first use
-static int late_mode() { if (g_late < 0) { const char* e = getenv("SSG_EMU_ASYNC"); g_late = (e && !strcmp(e, "late")) ? 1 : 0; } return g_late; }
+static unsigned g_arng = 12345u;
+static int late_mode() {
+    if (g_late < 0) {
+        const char* e = getenv("SSG_EMU_ASYNC");
+        g_late = (e && !strcmp(e, "late")) ? 1 : (e && !strncmp(e, "mixed", 5)) ? 2 : 0;
+        if (g_late == 2 && e[5] == ':') g_arng = (unsigned)atoi(e + 6) * 2654435761u + 1u;
+    }
+    return g_late;
+}
+// mixed (SSG_EMU_ASYNC=mixed[:seed], mode 2): every operation draws whether it completes at issue or as late as allowed
+// (an MMA or commit behind a deferred one is deferred too: the tensor pipe is in order) -- interleavings between the
+// two extremes, e.g. the A tile of a stage landing at once and its B tile at the last moment.
+static bool defer_now() {
+    if (late_mode() != 2) return late_mode() == 1;
+    g_arng = g_arng * 1664525u + 1013904223u;
+    return (g_arng >> 16) & 1u;
+}
 
 static inline uint32_t swz(uint32_t off, uint32_t mode) {
     const uint32_t bits = mode == CU_TENSOR_MAP_SWIZZLE_128B ? 3 : mode == CU_TENSOR_MAP_SWIZZLE_64B ? 2 : mode == CU_TENSOR_MAP_SWIZZLE_32B ? 1 : 0;
@@ -128,13 +145,13 @@ bool tc_mbar_poll(const void* bar, uint32_t parity) {
 }
 void tc_tma_load(void* smem_dst, const CUtensorMap* m, const void* bar, const int* c) {
     const uint32_t dst = (uint32_t)((unsigned char*)smem_dst - dyn_smem);
-    if (late_mode()) { Load l; l.map = *m; l.dst = dst; memcpy(l.c, c, sizeof(l.c)); l.bar = bar; g_loads.push_back(l); note_event(); return; }
+    if (defer_now()) { Load l; l.map = *m; l.dst = dst; memcpy(l.c, c, sizeof(l.c)); l.bar = bar; g_loads.push_back(l); note_event(); return; }
     box_copy(m, dst, c, false);
     MBar& b = mbars()[bar]; b.tx -= box_bytes(m); flip_if_complete(b);
 }
 void tc_tma_store(const CUtensorMap* m, const void* smem_src, const int* c) {
     const uint32_t src = (uint32_t)((const unsigned char*)smem_src - dyn_smem);
-    if (late_mode()) { Store s; s.map = *m; s.src = src; memcpy(s.c, c, sizeof(s.c)); g_open_group.push_back(s); return; }
+    if (defer_now()) { Store s; s.map = *m; s.src = src; memcpy(s.c, c, sizeof(s.c)); g_open_group.push_back(s); return; }
     box_copy(m, src, c, true);
 }
 void tc_store_commit() { if (late_mode()) { g_groups.push_back(g_open_group); g_open_group.clear(); } }
@@ -147,10 +164,10 @@ void tc_store_wait(int allowed_pending) {
 }
 void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     Mma q; q.is_commit = false; q.bar = nullptr; q.tmem_d = tmem_d; q.idesc = idesc; q.accumulate = accumulate; q.da = da; q.db = db;
-    if (late_mode()) { g_mmas.push_back(q); note_event(); } else mma_now(q);
+    if (!g_mmas.empty() || defer_now()) { g_mmas.push_back(q); note_event(); } else mma_now(q);
 }
 void tc_mma_commit(const void* bar) {
-    if (late_mode()) { Mma q; memset(&q, 0, sizeof(q)); q.is_commit = true; q.bar = bar; g_mmas.push_back(q); note_event(); }
+    if (!g_mmas.empty() || defer_now()) { Mma q; memset(&q, 0, sizeof(q)); q.is_commit = true; q.bar = bar; g_mmas.push_back(q); note_event(); }
     else arrive(bar);
 }
 void set_tc_reset(void (*f)());
@@ -158,7 +175,8 @@ static int g_registered = (set_tc_reset(tc_reset), 0);       // emu.cpp clears t
 }  // namespace emu
 
 // switch the completion model between launches (tests run both models in one process)
-extern "C" void ssg_emu_set_async(int late) { emu::g_late = late ? 1 : 0; }
+extern "C" void ssg_emu_set_async(int mode) { emu::g_late = mode < 0 || mode > 2 ? 0 : mode; }    // 0 eager, 1 late, 2 mixed
+extern "C" void ssg_emu_seed_async(unsigned seed) { emu::g_arng = seed * 2654435761u + 1u; }
 
 static CUresult emu_encode_tiled(CUtensorMap* m, CUtensorMapDataType, cuuint32_t rank, void* base, const cuuint64_t* dims,
                                  const cuuint64_t* strides, const cuuint32_t* box, const cuuint32_t* estr,

@@ -10,7 +10,8 @@ tolerance, and BETWEEN variants bit for bit).
 
 The asynchronous units have two completion models (tests/cpu_cuda/emu_tc.cpp): "eager" -- a TMA load / store or an MMA
 takes effect when it is issued -- and "late" -- it takes effect at the last moment the protocol allows (when the
-mbarrier it signals is polled, when cp.async.bulk.wait_group stops tolerating it).  A correct kernel computes the same
+mbarrier it signals is polled, when cp.async.bulk.wait_group stops tolerating it) -- plus "mixed", a seeded draw between
+the two per operation.  A correct kernel computes the same
 bytes under both; the fault-injection test at the end shows that the late model catches a stage released before its
 MMAs retired and a staging buffer rewritten under an in-flight TMA store, which the eager model cannot see."""
 import ctypes
@@ -115,9 +116,10 @@ def test_convolution_kernels_are_byte_identical_under_every_schedule_and_complet
     outs = {}
     try:
         for sched, (mode, seed) in {"forward": (0, 0), "reverse": (1, 0), "random warps": (3, 5)}.items():
-            for late in (0, 1):
+            for late in (0, 1, 2):                           # eager, late, mixed (seeded draw per operation)
                 tc_lib.ssg_emu_set_sched(mode, seed)
                 tc_lib.ssg_emu_set_async(late)
+                tc_lib.ssg_emu_seed_async(7 + seed)
                 y = np.zeros((B, OH, OW, cout), np.uint16)
                 scratch = np.zeros(xb.size + 64, np.uint16)
                 rc = tc_lib.ssg_op_conv(xb.ctypes.data, B, H, W, cin, k, stride, wb.ctypes.data, bias.ctypes.data, cout,
@@ -154,12 +156,13 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
     variants = (("default_late", {}),
                 ("default_reverse_order", {"SSG_EMU_SCHED": "reverse"}),          # thread / block schedules of emu.cpp
                 ("default_random_warps", {"SSG_EMU_SCHED": "warps:3"}),
+                ("default_mixed_completion", {"SSG_EMU_ASYNC": "mixed:3", "SSG_EMU_SCHED": "warps:4"}),
                 ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
                 ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
                 ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"}))
-    with ThreadPoolExecutor(max_workers=min(7, os.cpu_count() or 1)) as pool:      # one subprocess each
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # one subprocess each
         first = pool.submit(_embed, tmp_path, "default", {})
-        rest = [(name, pool.submit(_embed, tmp_path, name, dict(env, SSG_EMU_ASYNC="late"))) for name, env in variants]
+        rest = [(name, pool.submit(_embed, tmp_path, name, dict({"SSG_EMU_ASYNC": "late"}, **env))) for name, env in variants]
         base, rel = first.result()
         assert rel < 3e-2 and np.isfinite(base).all()
         for name, fut in rest:
