@@ -382,6 +382,8 @@ def main():
 
     labels, eps_list, keep = out
     k = args.steps
+    # whole job: a sharded cycle copies every image once (the ranks' shards add up to the set), replicas copy one set each
+    h2d_job = (2 * n * 3 * 256 * 128 * 4 if sharded else h2d * world) if with_embed else h2d * world
     units = 1 if sharded else world          # sharded: all ranks together process ONE data set
     value = pairs_per_step * units * k / (ms_dev / 1e3) / 1e6             # whole cycle (== stage alone with --features-only)
     e2e_value = pairs_per_step * units * k / (ms_e2e / 1e3) / 1e6
@@ -492,7 +494,8 @@ def main():
             "rerank": {"value": stage_value, "unit": UNIT_STAGE, "ms_per_step": ms_rerank / k,
                        "e2e_value": e2e_stage_value},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / k, "rerank_ms_per_step": ms_e2e_rerank / k,
-                    "embed_ms_per_step": ms_e2e_embed / k, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": banks * n * 8,
+                    "embed_ms_per_step": ms_e2e_embed / k, "h2d_bytes_per_step": h2d_job, "d2h_bytes_per_step": banks * n * 8 * world,
+                    "h2d_bytes_per_step_rank0": h2d,
                     "api": "ssg_b200.embed_images(pinned host images) + ssg_b200.pseudo_label_cycle -> host labels"},
             "gpu_launches": int(launches),
             "kernels_ms_per_step": {kk: round(v[0] / k, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
