@@ -50,6 +50,11 @@ int ssg_device_info(int device, int* n_devices, int* sm);
 int ssg_sqdist(const float* d_x, int nx, const float* d_y, int ny, int d, int mode, float* d_out,
                size_t ldo, void* stream);
 
+/* Dot-product block  out[i*ldo + j] = fl32( sum_k x_ik * y_jk )  (products exact, summed sequentially in float64):
+ * the similarity blocks of the cosine re-ranking -- np.dot at reid/rerank.py:174-176 (re_ranking_init from features)
+ * and reid/eug.py:223-225 (EUG label estimation) -- which then go to ssg_rerank_init. */
+int ssg_dot(const float* d_x, int nx, const float* d_y, int ny, int d, float* d_out, size_t ldo, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Source-aware k-reciprocal / Jaccard re-ranking: reid/rerank.py:27-127 re_ranking(
  *   input_feature_source, input_feature, k1=20, k2=6, lambda_value, ...), O-f32 arithmetic
@@ -146,7 +151,8 @@ size_t ssg_cluster_plan_bytes(const ssg_cluster_plan* plan);
 int ssg_eps_estimate(ssg_cluster_plan* plan, const void* d_dist, int dtype, int n, double rho,
                      double* h_eps, long long* h_top_num, void* stream);
 /* labels: int64 [n] on the device, -1 = noise, cluster ids as sklearn assigns them.
- * h_n_clusters (optional) forces a stream synchronisation. */
+ * The call synchronises the stream once to read the neighbour-capacity flag (SSG_ERR_CAPACITY on overflow: the labels
+ * are then undefined); h_n_clusters is optional. */
 int ssg_dbscan(ssg_cluster_plan* plan, const void* d_dist, int dtype, int n, double eps, int min_samples,
                int64_t* d_labels, int* h_n_clusters, void* stream);
 /* core-sample mask of the last ssg_dbscan (uint8 [n], host). */

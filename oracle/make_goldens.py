@@ -82,6 +82,75 @@ def embed_case(name, n_img, seed_img):
     print(name, {k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def cycle_case(name, n, ns, num_split=2, lam=0.1, rhos=(1.6e-3, 1.6e-2, 5e-2), per_identity=8, noise=0.5, keep_rows=16):
+    """The WHOLE path of selftraining.py:196-218, 255-313 through the unmodified reference, from IMAGES to labels:
+    extract_features (fp32 torch CPU, list mode) on seeded identity images -> bank re-stacking -> compute_dist
+    (re_ranking per bank: O-f32 and the as-is fp16 arithmetic) -> generate_selflabel (eps at rho, sklearn DBSCAN).
+    compute_dist / generate_selflabel are the driver's OWN functions, imported from the reference's selftraining.py.
+    Stored: labels, eps, rank tables, final_dist (float32-rounded upper triangle incl. diagonal; the rounding error
+    6e-8 is far below the 1e-4 tolerance) for both arithmetic variants, and the features of the first rows."""
+    import contextlib
+    import io
+    import types
+    import torch
+    from sklearn.metrics import adjusted_rand_score
+    ref = refshim.load_reference()
+    with refshim._reference_on_path(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import importlib
+        drv = importlib.import_module("selftraining")          # /root/reference/selftraining.py, unmodified
+    torch.set_num_threads(os.cpu_count() or 1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = ref.models.create("resnet50", num_classes=0, num_split=num_split, pretrained=False)
+    m.base.load_state_dict(R.make_state_dict(0), strict=False)
+    m.eval()
+    banks = num_split + 1 if num_split > 1 else 1
+    feats = {}
+    ident = {}
+    for tag, cnt, seed in (("tgt", n, 1234), ("src", ns, 4321)):
+        imgs, lab = R.synth_identity_images(cnt, seed, per_identity, noise)
+        names = ["%s%05d" % (tag, i) for i in range(cnt)]
+        batches = [(imgs[i:i + 64], names[i:i + 64], [0] * len(names[i:i + 64]), [0] * len(names[i:i + 64]))
+                   for i in range(0, cnt, 64)]
+        f, _ = ref.evaluators.extract_features(m, batches, print_freq=10 ** 9, for_eval=False)
+        # selftraining.py:197-209 bank re-stacking, in data-set order
+        feats[tag] = [torch.cat([f[k][i].unsqueeze(0) for k in names], 0) for i in range(banks)]
+        ident[tag] = lab.numpy()
+    out = dict(n=n, ns=ns, num_split=num_split, lam=lam, rhos=np.array(rhos), per_identity=per_identity, noise=noise,
+               seed_tgt=1234, seed_src=4321, weight_seed=0, identity=ident["tgt"], versions=versions(),
+               feat_tgt_head=np.stack([b[:keep_rows].numpy() for b in feats["tgt"]]),
+               feat_src_head=np.stack([b[:keep_rows].numpy() for b in feats["src"]]))
+    iu = np.triu_indices(n)
+    for mode in ("f32", "ref"):
+        # the driver's `from reid.rerank import *` bound re_ranking when selftraining.py was imported: patch the `np` of
+        # THAT function's module (its globals), which is a fresh import of the same unmodified file
+        ctx = refshim.f32_stable_globals(drv.re_ranking) if mode == "f32" else contextlib.nullcontext()
+        with ctx, contextlib.redirect_stdout(io.StringIO()):
+            _, r_dist = drv.compute_dist(feats["src"], feats["tgt"], lambda_value=lam, no_rerank=False,
+                                         num_split=num_split)
+        for b in range(banks):
+            out["final_%s_b%d" % (mode, b)] = r_dist[b][iu].astype(np.float32)
+            if mode == "f32":
+                st = {}
+                O.re_ranking(feats["src"][b].numpy(), feats["tgt"][b].numpy(), lambda_value=lam, mode="f32", stages=st)
+                _, f_o = O.re_ranking(feats["src"][b].numpy(), feats["tgt"][b].numpy(), lambda_value=lam, mode="f32")
+                assert np.array_equal(f_o, r_dist[b]), "oracle restatement != reference (O-f32) on bank %d" % b
+                out["rank21_b%d" % b] = st["rank"][:, :21].astype(np.int16)
+        for ri, rho in enumerate(rhos):
+            args = types.SimpleNamespace(no_rerank=False, rho=rho)
+            with contextlib.redirect_stdout(io.StringIO()):
+                labels, clusters = drv.generate_selflabel([[]] * banks, r_dist, 0, args, [])
+            for b in range(banks):
+                out["labels_%s_r%d_b%d" % (mode, ri, b)] = labels[b].astype(np.int32)
+                out["eps_%s_r%d_b%d" % (mode, ri, b)] = np.float64(clusters[b].eps)
+            print(name, mode, "rho", rho, "clusters", [int(l.max()) + 1 for l in labels],
+                  "noise", [int((l < 0).sum()) for l in labels],
+                  "ARI vs identity", [round(adjusted_rand_score(ident["tgt"], l), 3) for l in labels])
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, "bytes", os.path.getsize(os.path.join(OUT, name)))
+
+
 def triplet_cases(name):
     """reid/loss/triplet.py TripletLoss of the unmodified reference on CPU (forward + autograd backward)."""
     import torch
@@ -110,6 +179,9 @@ def triplet_cases(name):
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "cycle":        # only the whole-path golden (minutes of CPU time)
+        cycle_case("cycle_n512_S2.npz", 512, 384)
+        sys.exit(0)
     rerank_case("rerank_n160_d256.npz", 160, 150, 256, seed=3, lam=0.1, rhos=[1.6e-3, 1.6e-2, 5e-2])
     rerank_case("rerank_n257_d2048.npz", 257, 200, 2048, seed=7, lam=0.1, rhos=[1.6e-2, 4e-2])
     rerank_case("rerank_n96_d64_ties.npz", 96, 64, 64, seed=11, lam=0.3, rhos=[2e-2], per_cluster=8,
@@ -117,3 +189,4 @@ if __name__ == "__main__":
     rerank_init_case("rerank_init_q40_g90.npz", 40, 90, 512, seed=5)
     embed_case("embed_4img.npz", 4, 1234)
     triplet_cases("triplet_cases.npz")
+    cycle_case("cycle_n512_S2.npz", 512, 384)

@@ -111,6 +111,19 @@ def f32_stable(module):
         module.np = saved
 
 
+@contextlib.contextmanager
+def f32_stable_globals(func):
+    """The same substitution for whichever module object `func` was defined in (patches func.__globals__['np'])."""
+    import numpy
+    g = func.__globals__
+    saved = g["np"]
+    g["np"] = _NpF32Stable(numpy)
+    try:
+        yield
+    finally:
+        g["np"] = saved
+
+
 def ref_re_ranking(src, tgt, mode="f32", quiet=True, **kw):
     """reid/rerank.py:27 re_ranking of the unmodified reference.  mode: 'ref' (fp16) | 'f32' (O-f32)."""
     ref = load_reference()

@@ -109,3 +109,19 @@ def synth_images(n, seed=1234, h=256, w=128):
     """torch.randn(N,3,256,128) with a seeded CPU generator."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn(n, 3, h, w, generator=g)
+
+
+def synth_identity_images(n, seed=1234, per_identity=8, noise=0.5, h=256, w=128):
+    """[n,3,h,w] float32 on the CPU with identity structure (one random pattern per identity + per-image Gaussian
+    noise) so that the embedded features cluster: random images alone embed to nearly identical features
+    (SURVEY.md 8d).  Seeded CPU generator: the same bits in the build container and on the GPU box.
+    -> (images, identity of every image)."""
+    g = torch.Generator().manual_seed(seed)
+    ids = max(n // per_identity, 1)
+    pat = torch.randn(ids, 3, h, w, generator=g)
+    lab = torch.randint(0, ids, (n,), generator=g)
+    out = torch.empty(n, 3, h, w)
+    for r0 in range(0, n, 64):
+        r1 = min(n, r0 + 64)
+        out[r0:r1] = pat[lab[r0:r1]] + noise * torch.randn(r1 - r0, 3, h, w, generator=g)
+    return out, lab

@@ -46,6 +46,13 @@ extern "C" int ssg_sqdist(const float* d_x, int nx, const float* d_y, int ny, in
     return ssg_set_error(SSG_ERR_INVALID, "sqdist: unknown mode %d", mode);
 }
 
+extern "C" int ssg_dot(const float* d_x, int nx, const float* d_y, int ny, int d, float* d_out, size_t ldo,
+                       void* stream) {
+    if (!d_x || !d_y || !d_out || nx < 0 || ny < 0 || d <= 0 || ldo < (size_t)ny)
+        return ssg_set_error(SSG_ERR_INVALID, "dot: bad arguments");
+    return launch_dot_exact(d_x, nx, d_y, ny, d, d_out, ldo, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------- rerank plan
 struct ssg_rerank_plan {
     int device, n_max, ns_max, d;
@@ -89,7 +96,7 @@ static int dalloc(void** p, size_t bytes, size_t* total) {
 extern "C" int ssg_rerank_plan_create(ssg_rerank_plan** out, int device, int n_max, int ns_max, int d) {
     if (!out || n_max <= 0 || ns_max <= 0 || d <= 0)
         return ssg_set_error(SSG_ERR_INVALID, "rerank_plan_create: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(device));
+    SSG_ON_DEVICE(device);
     ssg_rerank_plan* p = new ssg_rerank_plan();
     memset(p, 0, sizeof(*p));
     p->device = device; p->n_max = n_max; p->ns_max = ns_max; p->d = d;
@@ -132,7 +139,7 @@ extern "C" int ssg_rerank_plan_create(ssg_rerank_plan** out, int device, int n_m
 
 extern "C" int ssg_rerank_plan_destroy(ssg_rerank_plan* p) {
     if (!p) return SSG_OK;
-    cudaSetDevice(p->device);
+    SsgDeviceGuard device_guard__(p->device);
     void* ptrs[] = {p->dmat, p->rowmin, p->rowmax, p->vec, p->scratch, p->rank, p->rank_val, p->v_idx,
                     p->v_val, p->v_cnt, p->q_idx, p->q_val, p->q_cnt, p->colcnt, p->colptr, p->cursor,
                     p->csc_row, p->flagged, p->io_src, p->io_tgt, p->io_final, p->io_euclid, p->split_ta,
@@ -150,6 +157,18 @@ extern "C" size_t ssg_rerank_plan_bytes(const ssg_rerank_plan* p) {
                    p->sp_cap * (sizeof(int) + sizeof(double)) : 0;
 }
 
+// capacity of an expanded row (rerank.py:94-98): the union of k2 k-reciprocal rows, each at most
+// (k1+1) + (k1+1) * (round(k1/2)+1) columns (rerank.py:76-90) -- it must fit the SSG_VQ_STRIDE slot that query_expand
+// writes and jaccard_row stages in shared memory (k2 <= 6 at k1 = 20; larger k2 only with smaller k1)
+static int expanded_row_fits(int k1, int k2) {
+    const int k1p = k1 + 1, khp = (int)rint(k1 / 2.0) + 1;
+    const long long bound = (long long)k2 * (k1p + (long long)k1p * khp);
+    if (bound > SSG_VQ_STRIDE)
+        return ssg_set_error(SSG_ERR_INVALID, "rerank: k1=%d k2=%d may expand a row to %lld columns, the plan holds %d",
+                             k1, k2, bound, SSG_VQ_STRIDE);
+    return SSG_OK;
+}
+
 static int check_run_args(ssg_rerank_plan* p, const void* src, int ns, const void* tgt, int n, int d,
                           int k1, int k2) {
     if (!p || !src || !tgt) return ssg_set_error(SSG_ERR_INVALID, "rerank: null argument");
@@ -158,6 +177,7 @@ static int check_run_args(ssg_rerank_plan* p, const void* src, int ns, const voi
                              n, ns, d, p->n_max, p->ns_max, p->d);
     if (k1 < 1 || k1 > 31 || k2 < 1 || k2 > 8)
         return ssg_set_error(SSG_ERR_INVALID, "rerank: k1=%d k2=%d out of range", k1, k2);
+    SSG_TRY(expanded_row_fits(k1, k2));
     return SSG_OK;
 }
 
@@ -375,7 +395,7 @@ extern "C" int ssg_rerank_distance_rows(ssg_rerank_plan* p, const float* d_src, 
     SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, 1));
     if (row0 < 0 || rows < 0 || row0 + rows > n)
         return ssg_set_error(SSG_ERR_INVALID, "rerank_distance_rows: rows [%d,%d) outside [0,%d)", row0, row0 + rows, n);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_CUDA_TRY(cudaMemsetAsync(p->flagged, 0, sizeof(int) * 4, st));
     if (rows == 0) return SSG_OK;
@@ -402,7 +422,7 @@ static int finish_rows(ssg_rerank_plan* p, const float* d_tgt, int n, int d, int
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank: d_final is null");
     if (row0 < 0 || rows < 0 || row0 + rows > n)
         return ssg_set_error(SSG_ERR_INVALID, "rerank_finish: rows [%d,%d) outside [0,%d)", row0, row0 + rows, n);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_TRY(finish_sparse_stages(p, d_tgt, n, d, k1, k2, st));
     { SSG_PROF("jaccard_final", st); SSG_TRY(launch_jaccard_final(n, row0, rows, p->q_idx, p->q_val, p->q_cnt, p->colptr, p->csc_row, p->vec,
@@ -478,7 +498,7 @@ extern "C" int ssg_rerank_finish_sparse(ssg_rerank_plan* p, const float* d_tgt, 
     SSG_TRY(check_run_args(p, d_tgt, 1, d_tgt, n, d, k1, k2));
     if (!(lambda_value >= 0.0 && lambda_value < 1.0))
         return ssg_set_error(SSG_ERR_INVALID, "rerank_finish_sparse: lambda_value %g outside [0, 1)", lambda_value);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (!p->sp_cnt) {
         SSG_TRY(dalloc((void**)&p->sp_cnt, sizeof(int) * (size_t)p->n_max, &p->bytes));
@@ -529,7 +549,7 @@ extern "C" int ssg_rerank_plain(ssg_rerank_plan* p, const float* d_src, int ns, 
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_plain: d_final is null");
     if (n < k) return ssg_set_error(SSG_ERR_INVALID, "rerank_plain: k=%d exceeds the %d targets (np.partition raises, "
                                     "rerank_plain.py:167)", k, n);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int PL_ROWS = 256;                 // rows per exact-fallback batch
     if (!p->pl_flags) {
@@ -577,7 +597,7 @@ extern "C" int ssg_rerank_lh(ssg_rerank_plan* p, const float* d_src, int ns, con
                              int k2, double lambda_value, int dist_mode, double* d_final, void* stream) {
     SSG_TRY(check_run_args(p, d_src, ns, d_tgt, n, d, k1, k2));
     if (!d_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_lh: d_final is null");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (!p->lh_vec) {
         SSG_TRY(dalloc((void**)&p->lh_minsum, sizeof(double) * (size_t)p->n_max, &p->bytes));
@@ -607,7 +627,7 @@ extern "C" int ssg_rerank_host(ssg_rerank_plan* p, const float* h_src, int ns, c
                                double* h_final, float* h_euclid) {
     SSG_TRY(check_run_args(p, h_src, ns, h_tgt, n, d, k1, k2));
     if (!no_rerank && !h_final) return ssg_set_error(SSG_ERR_INVALID, "rerank_host: h_final is null");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     const size_t nn = (size_t)n * n;
     SSG_TRY(grow((void**)&p->io_src, &p->io_src_bytes, sizeof(float) * (size_t)ns * d));
     SSG_TRY(grow((void**)&p->io_tgt, &p->io_tgt_bytes, sizeof(float) * (size_t)n * d));
@@ -641,7 +661,8 @@ extern "C" int ssg_rerank_init(ssg_rerank_plan* p, const float* d_qg, const floa
     if (n > p->n_max || (size_t)n * n > p->dmat_elems)
         return ssg_set_error(SSG_ERR_INVALID, "rerank_init: q+g=%d exceeds the plan (n_max=%d)", n, p->n_max);
     if (k1 < 1 || k1 > 31 || k2 < 1 || k2 > 8) return ssg_set_error(SSG_ERR_INVALID, "rerank_init: k1/k2 out of range");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_TRY(expanded_row_fits(k1, k2));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int k1p = k1 + 1, khp = (int)rint(k1 / 2.0) + 1;
     { SSG_PROF("init_assemble", st); SSG_TRY(launch_init_assemble(d_qg, d_qq, d_gg, q, g, p->dmat, st)); }
@@ -691,7 +712,7 @@ extern "C" int ssg_rerank_get_stage(ssg_rerank_plan* p, int stage, void* h_dst, 
         default: return ssg_set_error(SSG_ERR_INVALID, "get_stage: unknown stage %d", stage);
     }
     if (bytes < need) return ssg_set_error(SSG_ERR_INVALID, "get_stage: buffer too small (%zu < %zu)", bytes, need);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     SSG_CUDA_TRY(cudaDeviceSynchronize());
     SSG_CUDA_TRY(cudaMemcpy(h_dst, src, need, cudaMemcpyDeviceToHost));
     return SSG_OK;

@@ -626,6 +626,7 @@ __global__ void __launch_bounds__(DB_NT)
 db_fill_kernel(const T* __restrict__ D, int n, double eps, const int* __restrict__ rowptr,
                long long max_nbr, int* __restrict__ nbr, int* __restrict__ flags) {
     const int i = blockIdx.x;
+    if (flags[0]) return;                         // the 64-bit total already exceeds the plan (db_total_check_kernel)
     const int beg = rowptr[i], end = rowptr[i + 1];
     if (end == beg) return;
     if ((long long)end > max_nbr) { if (threadIdx.x == 0) flags[0] = 1; return; }
@@ -644,6 +645,22 @@ db_fill_kernel(const T* __restrict__ D, int n, double eps, const int* __restrict
             if (hit) nbr[beg + base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = j;
         }
     }
+}
+
+// 64-bit total of the per-row counts: the int32 CSR offsets wrap once the neighbour pairs exceed INT_MAX (possible for
+// n > 46 340), so the capacity test cannot be left to the offsets alone.  One CTA; sets flags[0] on overflow.
+__global__ void __launch_bounds__(1024)
+db_total_check_kernel(int n, const int* __restrict__ cnt, long long max_nbr, int* __restrict__ flags) {
+    __shared__ unsigned long long sh[1024];
+    unsigned long long acc = 0;
+    for (int i = threadIdx.x; i < n; i += 1024) acc += (unsigned long long)cnt[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && sh[0] > (unsigned long long)max_nbr) flags[0] = 1;
 }
 
 __global__ void db_init_kernel(int n, const int* __restrict__ cnt, int min_samples, int* __restrict__ parent,
@@ -718,6 +735,8 @@ static int dbscan_run(ssg_cluster_plan* p, const T* D, int n, double eps, int mi
     SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
     { SSG_PROF("dbscan_count", st); db_count_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->cnt); }
     SSG_CHECK_LAUNCH();
+    db_total_check_kernel<<<1, 1024, 0, st>>>(n, p->cnt, p->max_nbr, p->flags);
+    SSG_CHECK_LAUNCH();
     SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
     { SSG_PROF("dbscan_fill", st); db_fill_kernel<T><<<n, DB_NT, 0, st>>>(D, n, eps, p->rowptr, p->max_nbr, p->nbr, p->flags); }
     SSG_CHECK_LAUNCH();
@@ -757,7 +776,7 @@ extern "C" int ssg_cluster_plan_create(ssg_cluster_plan** out, int device, int n
     if (!out || n_max <= 0) return ssg_set_error(SSG_ERR_INVALID, "cluster_plan_create: bad arguments");
     if (max_neighbors <= 0) max_neighbors = 64ll * n_max + (1 << 20);
     if (max_neighbors > 0x7fffffffll) max_neighbors = 0x7fffffffll;
-    SSG_CUDA_TRY(cudaSetDevice(device));
+    SSG_ON_DEVICE(device);
     ssg_cluster_plan* p = new ssg_cluster_plan();
     p->device = device; p->n_max = n_max; p->max_nbr = max_neighbors; p->bytes = 0;
     p->staging = nullptr; p->staging_bytes = 0; p->last_n = 0;
@@ -785,7 +804,7 @@ extern "C" int ssg_cluster_plan_create(ssg_cluster_plan** out, int device, int n
 
 extern "C" int ssg_cluster_plan_destroy(ssg_cluster_plan* p) {
     if (!p) return SSG_OK;
-    cudaSetDevice(p->device);
+    SsgDeviceGuard device_guard__(p->device);
     void* ptrs[] = {p->hist, p->state, p->partial, p->eps_out, p->list, p->cnt, p->rowptr, p->nbr, p->parent,
                     p->isroot, p->cid, p->core, p->flags, p->staging};
     for (void* q : ptrs) if (q) cudaFree(q);
@@ -799,7 +818,7 @@ extern "C" int ssg_eps_estimate(ssg_cluster_plan* p, const void* d_dist, int dty
                                 double* h_eps, long long* h_top_num, void* stream) {
     if (!p || !d_dist || n <= 0 || n > p->n_max || !h_eps)
         return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype != SSG_F64 && dtype != SSG_F32) return ssg_set_error(SSG_ERR_INVALID, "eps_estimate: dtype %d", dtype);
     if (dtype == SSG_F64) SSG_TRY(eps_run3<double>(p, (const double*)d_dist, n, rho, st));
@@ -824,12 +843,14 @@ extern "C" int ssg_dbscan(ssg_cluster_plan* p, const void* d_dist, int dtype, in
                           int min_samples, int64_t* d_labels, int* h_n_clusters, void* stream) {
     if (!p || !d_dist || !d_labels || n <= 0 || n > p->n_max)
         return ssg_set_error(SSG_ERR_INVALID, "dbscan: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SSG_F64) SSG_TRY(dbscan_run<double>(p, (const double*)d_dist, n, eps, min_samples, d_labels, st));
     else if (dtype == SSG_F32) SSG_TRY(dbscan_run<float>(p, (const float*)d_dist, n, eps, min_samples, d_labels, st));
     else return ssg_set_error(SSG_ERR_INVALID, "dbscan: dtype %d", dtype);
-    if (h_n_clusters) {
+    {
+        // the overflow flag is ALWAYS read back (one stream synchronisation): on overflow the neighbour lists are
+        // incomplete and the labels meaningless, which must never pass silently
         int flags[4], ncl = 0;
         SSG_CUDA_TRY(cudaMemcpyAsync(flags, p->flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
         SSG_CUDA_TRY(cudaMemcpyAsync(&ncl, p->cid + n, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -837,14 +858,14 @@ extern "C" int ssg_dbscan(ssg_cluster_plan* p, const void* d_dist, int dtype, in
         if (flags[0])
             return ssg_set_error(SSG_ERR_CAPACITY, "dbscan: more than %lld neighbour pairs within eps; "
                                  "re-create the plan with a larger max_neighbors", p->max_nbr);
-        *h_n_clusters = ncl;
+        if (h_n_clusters) *h_n_clusters = ncl;
     }
     return SSG_OK;
 }
 
 extern "C" int ssg_dbscan_core_mask(ssg_cluster_plan* p, uint8_t* h_core, int n) {
     if (!p || !h_core || n <= 0 || n > p->n_max) return ssg_set_error(SSG_ERR_INVALID, "core_mask: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     SSG_CUDA_TRY(cudaMemcpy(h_core, p->core, (size_t)n, cudaMemcpyDeviceToHost));
     return SSG_OK;
 }
@@ -865,7 +886,7 @@ extern "C" int ssg_eps_estimate_host(ssg_cluster_plan* p, const void* h_dist, in
                                      double* h_eps, long long* h_top_num) {
     if (!p || !h_dist || n <= 0 || n > p->n_max || (dtype != SSG_F32 && dtype != SSG_F64))
         return ssg_set_error(SSG_ERR_INVALID, "eps_estimate_host: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     SSG_TRY(stage_host_matrix(p, h_dist, dtype, n));
     return ssg_eps_estimate(p, p->staging, dtype, n, rho, h_eps, h_top_num, nullptr);
 }
@@ -874,7 +895,7 @@ extern "C" int ssg_dbscan_host(ssg_cluster_plan* p, const void* h_dist, int dtyp
                                int min_samples, int64_t* h_labels, int* h_n_clusters) {
     if (!p || !h_dist || !h_labels || n <= 0 || n > p->n_max || (dtype != SSG_F32 && dtype != SSG_F64))
         return ssg_set_error(SSG_ERR_INVALID, "dbscan_host: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     SSG_TRY(stage_host_matrix(p, h_dist, dtype, n));
     int64_t* d_labels = nullptr;
     SSG_CUDA_TRY(cudaMalloc(&d_labels, sizeof(int64_t) * (size_t)n));
@@ -916,7 +937,7 @@ static int check_shard(const ssg_cluster_plan* p, const void* d_rows, int dtype,
 
 extern "C" int ssg_eps_shard_begin(ssg_cluster_plan* p, void* stream) {
     if (!p) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_begin: null plan");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
     SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
@@ -927,7 +948,7 @@ extern "C" int ssg_eps_shard_hist(ssg_cluster_plan* p, const void* d_rows, int d
                                   int pass, void* stream) {
     SSG_TRY(check_shard(p, d_rows, dtype, n, world, rank, "eps_shard_hist"));
     if (pass < 0 || pass > 5) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_hist: pass %d", pass);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const ShardGeom g = make_geom(n, world, rank);
     const int rows = g.lo(rank + 1) - g.lo(rank);
@@ -943,7 +964,7 @@ extern "C" int ssg_eps_shard_hist(ssg_cluster_plan* p, const void* d_rows, int d
 
 extern "C" int ssg_eps_shard_pick(ssg_cluster_plan* p, int pass, double rho, void* stream) {
     if (!p || pass < 0 || pass > 5) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_pick: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     eps_pick_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(p->hist, p->state, pass, rho);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
@@ -952,7 +973,7 @@ extern "C" int ssg_eps_shard_pick(ssg_cluster_plan* p, int pass, double rho, voi
 extern "C" int ssg_eps_shard_gather(ssg_cluster_plan* p, const void* d_rows, int dtype, int n, int world, int rank,
                                     int exact_threshold, long long* h_list_count, void* stream) {
     SSG_TRY(check_shard(p, d_rows, dtype, n, world, rank, "eps_shard_gather"));
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const ShardGeom g = make_geom(n, world, rank);
     const int rows = g.lo(rank + 1) - g.lo(rank);
@@ -980,7 +1001,7 @@ extern "C" int ssg_eps_shard_gather(ssg_cluster_plan* p, const void* d_rows, int
 extern "C" int ssg_eps_shard_finish(ssg_cluster_plan* p, int n, int exact_threshold, double* h_eps,
                                     long long* h_top_num, void* stream) {
     if (!p || n <= 0 || n > p->n_max || !h_eps) return ssg_set_error(SSG_ERR_INVALID, "eps_shard_finish: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (exact_threshold) eps_final_kernel<<<1, 1024, 0, st>>>(p->partial, n, p->state, p->eps_out);
     else eps_list_finish_kernel<<<1, 1024, 0, st>>>(p->list, p->state, p->partial, n, p->eps_out);
@@ -999,7 +1020,7 @@ extern "C" int ssg_dbscan_shard_count(ssg_cluster_plan* p, const void* d_rows, i
         (dtype != SSG_F64 && dtype != SSG_F32))
         return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_count: bad arguments (n=%d, rows [%d,%d))", n, row0,
                              row0 + rows);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
     if (rows == 0) return SSG_OK;
@@ -1016,7 +1037,7 @@ extern "C" int ssg_dbscan_shard_fill(ssg_cluster_plan* p, const void* d_rows, in
         (dtype != SSG_F64 && dtype != SSG_F32) || !h_total)
         return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_fill: bad arguments (n=%d, rows [%d,%d))", n, row0,
                              row0 + rows);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     // cnt holds the counts of ALL rows by now (the caller gathered them): global CSR offsets, the same on every rank
     SSG_TRY(launch_exclusive_scan_i32(p->cnt, p->rowptr, n, st));
@@ -1042,7 +1063,7 @@ extern "C" int ssg_dbscan_shard_fill(ssg_cluster_plan* p, const void* d_rows, in
 extern "C" int ssg_dbscan_shard_label(ssg_cluster_plan* p, int n, int min_samples, int64_t* d_labels,
                                       int* h_n_clusters, void* stream) {
     if (!p || !d_labels || n <= 0 || n > p->n_max) return ssg_set_error(SSG_ERR_INVALID, "dbscan_shard_label: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_TRY(dbscan_label_stage(p, n, min_samples, d_labels, st));
     if (h_n_clusters) {
@@ -1059,7 +1080,7 @@ extern "C" int ssg_eps_sparse(ssg_cluster_plan* p, int n, const int* d_rowptr, c
                               void* stream) {
     if (!p || !d_rowptr || !d_col || !d_val || n <= 0 || n > p->n_max || !h_eps || !h_certified)
         return ssg_set_error(SSG_ERR_INVALID, "eps_sparse: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_CUDA_TRY(cudaMemsetAsync(p->hist, 0, sizeof(unsigned long long) * EPS_BINS, st));
     SSG_CUDA_TRY(cudaMemsetAsync(p->state, 0, sizeof(unsigned long long) * 8, st));
@@ -1091,7 +1112,7 @@ extern "C" int ssg_dbscan_sparse(ssg_cluster_plan* p, int n, const int* d_rowptr
                                  double eps, int min_samples, int64_t* d_labels, int* h_n_clusters, void* stream) {
     if (!p || !d_rowptr || !d_col || !d_val || !d_labels || n <= 0 || n > p->n_max)
         return ssg_set_error(SSG_ERR_INVALID, "dbscan_sparse: bad arguments (n=%d, n_max=%d)", n, p ? p->n_max : -1);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     SSG_CUDA_TRY(cudaMemsetAsync(p->flags, 0, sizeof(int) * 4, st));
     const int grid = ssg_cdiv(n, SP_NT / 32);

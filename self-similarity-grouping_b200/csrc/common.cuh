@@ -25,6 +25,20 @@ int ssg_set_error(int code, const char* fmt, ...);
 
 #define SSG_CHECK_LAUNCH() SSG_CUDA_TRY(cudaGetLastError())
 
+// Entry points run on the plan's device and hand the caller's current device back on every return path.
+struct SsgDeviceGuard {
+    int prev_;
+    cudaError_t err;
+    explicit SsgDeviceGuard(int dev) : prev_(-1), err(cudaSuccess) {
+        err = cudaGetDevice(&prev_);
+        if (err == cudaSuccess && prev_ != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev_ = -1;
+    }
+    ~SsgDeviceGuard() { if (prev_ >= 0) cudaSetDevice(prev_); }
+};
+#define SSG_ON_DEVICE(dev)            \
+    SsgDeviceGuard device_guard__(dev); \
+    SSG_CUDA_TRY(device_guard__.err)
+
 namespace ssg {
 // RAII CUDA-event timer around a group of launches on one stream (no-op unless ssg_profile_enable(1)).
 struct ProfScope {

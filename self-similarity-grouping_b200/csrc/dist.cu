@@ -27,6 +27,10 @@ __device__ __forceinline__ float finish_sqdist(double s) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int TM = 64, TN = 64, TK = 16;
 
+// DOT = true: out = fl32( sum_k x_ik * y_jk ) instead, the products exact in float64 and summed sequentially in
+// float64 (the dot-product blocks of the cosine re-ranking, np.dot at reid/rerank.py:174-176, reid/eug.py:223-225; at
+// least as accurate as the reference's float32 GEMM).
+template <bool DOT>
 __global__ void __launch_bounds__(256)
 sqdist_exact_kernel(const float* __restrict__ X, int nx, const float* __restrict__ Y, int ny, int d,
                     float* __restrict__ out, size_t ldo) {
@@ -80,8 +84,12 @@ sqdist_exact_kernel(const float* __restrict__ X, int nx, const float* __restrict
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double df = __dsub_rn(a[i], b[j]);
-                    acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(df, df));
+                    if (DOT) {
+                        acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(a[i], b[j]));
+                    } else {
+                        const double df = __dsub_rn(a[i], b[j]);
+                        acc[i][j] = __dadd_rn(acc[i][j], __dmul_rn(df, df));
+                    }
                 }
         }
         __syncthreads();
@@ -93,7 +101,7 @@ sqdist_exact_kernel(const float* __restrict__ X, int nx, const float* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = col0 + tx + 16 * j;
-            if (c < ny) out[(size_t)r * ldo + c] = finish_sqdist(acc[i][j]);
+            if (c < ny) out[(size_t)r * ldo + c] = DOT ? (float)acc[i][j] : finish_sqdist(acc[i][j]);
         }
     }
 }
@@ -102,7 +110,16 @@ int launch_sqdist_exact(const float* X, int nx, const float* Y, int ny, int d, f
                         cudaStream_t st) {
     if (nx <= 0 || ny <= 0) return SSG_OK;
     dim3 grid(ssg_cdiv(ny, TN), ssg_cdiv(nx, TM));
-    sqdist_exact_kernel<<<grid, 256, 0, st>>>(X, nx, Y, ny, d, out, ldo);
+    sqdist_exact_kernel<false><<<grid, 256, 0, st>>>(X, nx, Y, ny, d, out, ldo);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int launch_dot_exact(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
+                     cudaStream_t st) {
+    if (nx <= 0 || ny <= 0) return SSG_OK;
+    dim3 grid(ssg_cdiv(ny, TN), ssg_cdiv(nx, TM));
+    sqdist_exact_kernel<true><<<grid, 256, 0, st>>>(X, nx, Y, ny, d, out, ldo);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -101,7 +101,7 @@ extern "C" int ssg_embed_layer_info(int idx, int* cin, int* cout, int* ksize, in
 
 extern "C" int ssg_embed_plan_destroy(ssg_embed_plan* p) {
     if (!p) return SSG_OK;
-    cudaSetDevice(p->device);
+    SsgDeviceGuard device_guard__(p->device);
     for (void* q : p->w) if (q) cudaFree(q);
     for (int L = 0; L < 4; ++L) { if (p->wf[L]) cudaFree(p->wf[L]); if (p->bf[L]) cudaFree(p->bf[L]); }
     for (float* q : p->b) if (q) cudaFree(q);
@@ -120,7 +120,7 @@ extern "C" int ssg_embed_plan_create(ssg_embed_plan** out, int device, int batch
     if (!out || batch_max <= 0) return ssg_set_error(SSG_ERR_INVALID, "embed_plan_create: bad arguments");
     if (height != 256 || width != 128)
         return ssg_set_error(SSG_ERR_UNSUPPORTED, "embed: only 256x128 inputs are supported (got %dx%d)", height, width);
-    SSG_CUDA_TRY(cudaSetDevice(device));
+    SSG_ON_DEVICE(device);
     ssg_embed_plan* p = new ssg_embed_plan();
     p->device = device; p->batch_max = batch_max; p->bytes = 0;
     p->col = p->stem = p->x = p->y = p->ds = p->t1 = p->t2 = p->planes = p->xs = nullptr;
@@ -175,7 +175,7 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
                                     void* stream) {
     if (!p || idx < 0 || idx >= (int)specs().size() || !d_w || !d_gamma || !d_beta || !d_mean || !d_var)
         return ssg_set_error(SSG_ERR_INVALID, "embed_load_layer: bad arguments");
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     const LayerSpec& s = specs()[idx];
     SSG_TRY(fold_bn(d_w, s.cout, s.cin, s.k, s.k, d_gamma, d_beta, d_mean, d_var, eps, kpad_of(s), p->w[idx],
                     p->b[idx], (cudaStream_t)stream));
@@ -243,9 +243,13 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
                               size_t bank_stride, int row0, void* stream) {
     if (!p || (!d_images && !d_u8) || !d_feat || n <= 0 || n > p->batch_max)
         return ssg_set_error(SSG_ERR_INVALID, "embed_forward: bad arguments (n=%d, batch_max=%d)", n, p ? p->batch_max : -1);
+    // resnet.py:93-108 accepts any num_split up to the map height (8 rows); the pooled tail holds up to 4 stripes
+    // (+ the global bank) in registers, which covers every configuration the drivers use (run.sh: 2; BASELINE: 2, 3)
+    if (num_split < 1 || num_split > 4)
+        return ssg_set_error(SSG_ERR_INVALID, "embed_forward: num_split=%d out of range (1..4)", num_split);
     for (size_t i = 0; i < p->loaded.size(); ++i)
         if (!p->loaded[i]) return ssg_set_error(SSG_ERR_INVALID, "embed_forward: layer %zu (%s) not loaded", i, specs()[i].conv_key);
-    SSG_CUDA_TRY(cudaSetDevice(p->device));
+    SSG_ON_DEVICE(p->device);
     cudaStream_t st = (cudaStream_t)stream;
     const auto& sp = specs();
     const int NB = flip ? 2 * n : n;

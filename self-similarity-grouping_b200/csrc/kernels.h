@@ -9,6 +9,8 @@ namespace ssg {
 // dist.cu
 int launch_sqdist_exact(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
                         cudaStream_t st);
+int launch_dot_exact(const float* X, int nx, const float* Y, int ny, int d, float* out, size_t ldo,
+                     cudaStream_t st);
 int launch_row_minmax(const float* M, size_t ld, int rows, int cols, float* rmin, float* rmax,
                       cudaStream_t st);
 int launch_row_select(const float* M, size_t ld, int rows, int cols, const float* scale, int K, bool largest,

@@ -370,6 +370,7 @@ int launch_query_expand(const int* rank, int n, int k2, const int* v_idx, const 
                         const int* v_cnt, int* q_idx, float* q_val, int* q_cnt, cudaStream_t st) {
     if (k2 < 1 || k2 > 8 || k2 * 252 > QE_CAP)
         return ssg_set_error(SSG_ERR_INVALID, "k2=%d out of range (1..8)", k2);
+    // (the callers check that k2 rows of the k1-dependent V bound fit the SSG_VQ_STRIDE slot: api.cu expanded_row_fits)
     query_expand_kernel<<<n, QE_NT, 0, st>>>(rank, n, k2, v_idx, v_val, v_cnt, q_idx, q_val, q_cnt);
     SSG_CHECK_LAUNCH();
     return SSG_OK;

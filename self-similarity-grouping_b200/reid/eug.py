@@ -8,9 +8,19 @@ reference's ``reid.utils.data``) is outside the pseudo-label hot path (SURVEY.md
 reference's own packages on the path, or a ``loader_factory`` passed by the caller.
 """
 import numpy as np
+import torch
 
 from .evaluators import extract_features
 from .rerank_initial import re_ranking_init
+
+
+def _first_min(dist):
+    """Row minimum and the LOWEST index attaining it (np.argmin's tie rule, eug.py:208,231; torch's CUDA min/argmin
+    do not promise which of several equal entries they return)."""
+    dmin = dist.min(dim=1).values
+    cols = torch.arange(dist.shape[1], device=dist.device).expand_as(dist)
+    big = torch.full_like(cols, dist.shape[1])
+    return dmin, torch.where(dist == dmin[:, None], cols, big).min(dim=1).values
 
 
 class EUG():
@@ -68,7 +78,7 @@ class EUG():
         """eug.py:193-253 — nearest labelled neighbour by L2, or by re-ranked cosine distance (self.rerank)."""
         import torch
         from ssg_b200 import _lib
-        from ssg_b200.rerank import sqdist, re_ranking_init_blocks
+        from ssg_b200.rerank import sqdist, dot, re_ranking_init_blocks
         u_feas = self.get_feature(self.u_data)
         l_feas = self.get_feature(self.l_data)
         print("u_features", u_feas.shape, "l_features", l_feas.shape)
@@ -79,17 +89,12 @@ class EUG():
         confidence = None
         if not self.rerank:
             dist = sqdist(u, l, _lib.DIST_EXACT).sqrt()                     # np.linalg.norm(l_feas - u_fea, axis=1)
-            dmin, index_min = dist.min(dim=1)
+            dmin, index_min = _first_min(dist)
             scores = (-dmin).double().cpu().numpy()
         else:
-            prev = torch.backends.cuda.matmul.allow_tf32
-            torch.backends.cuda.matmul.allow_tf32 = False
-            try:
-                u_l, u_u, l_l = u @ l.t(), u @ u.t(), l @ l.t()            # np.dot blocks, eug.py:223-225
-            finally:
-                torch.backends.cuda.matmul.allow_tf32 = prev
+            u_l, u_u, l_l = dot(u, l), dot(u, u), dot(l, l)                # np.dot blocks, eug.py:223-225 (ssg_dot)
             re_rank_dist = re_ranking_init_blocks(u_l, u_u, l_l)            # CUDA tensor [nu, nl]
-            dmin, index_min = re_rank_dist.min(dim=1)
+            dmin, index_min = _first_min(re_rank_dist)
             scores = (-dmin).double().cpu().numpy()
             colmax = re_rank_dist.max(dim=0).values
             confidence = (1 - dmin / colmax[index_min]).double().cpu().numpy()   # eug.py:236

@@ -15,34 +15,34 @@ def fliplr(img):
 
 
 def pairwise_distance(features, query=None, gallery=None, metric=None):
-    """evaluators.py:63-85.  Returns a CPU float32 tensor like the reference; the GEMM runs on the GPU."""
+    """evaluators.py:63-85.  Returns a CPU float32 tensor like the reference.
+
+    The distances come from the library's own kernel (``ssg_sqdist``, float64 direct difference: the exact
+    ``sum_k (x_k - y_k)^2``) instead of the reference's float32 ``|x|^2 + |y|^2 - 2 x.y`` GEMM, whose cancellation
+    noise (~1e-6 at unit norms) is the only difference -- well inside the 1e-4 distance tolerance.  The all-pairs
+    branch of the reference (evaluators.py:64-72) computes ``2 |x_i|^2 - 2 x_i.x_j``, which equals the squared
+    distance only for equal norms; that expression is reproduced as
+    ``d2(i,j) + |x_i|^2 - |x_j|^2``."""
     from ssg_b200 import _lib
+    from ssg_b200.rerank import sqdist
     dev = _lib.require_cuda()
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        if query is None and gallery is None:
-            n = len(features)
-            x = torch.cat(list(features.values())).view(n, -1)
-            if metric is not None:
-                x = metric.transform(x)
-            x = x.to(dev)
-            dist = torch.pow(x, 2).sum(dim=1, keepdim=True) * 2
-            dist = dist.expand(n, n) - 2 * torch.mm(x, x.t())
-            return dist.cpu()
-        x = torch.cat([features[f].unsqueeze(0) for f, _, _ in query], 0)
-        y = torch.cat([features[f].unsqueeze(0) for f, _, _ in gallery], 0)
-        m, n = x.size(0), y.size(0)
-        x, y = x.view(m, -1), y.view(n, -1)
+    if query is None and gallery is None:
+        n = len(features)
+        x = torch.cat(list(features.values())).view(n, -1)
         if metric is not None:
-            x, y = metric.transform(x), metric.transform(y)
-        x, y = x.to(dev), y.to(dev)
-        dist = torch.pow(x, 2).sum(dim=1, keepdim=True).expand(m, n) + \
-            torch.pow(y, 2).sum(dim=1, keepdim=True).expand(n, m).t()
-        dist = torch.addmm(dist, x, y.t(), beta=1, alpha=-2)
+            x = metric.transform(x)
+        x = x.to(dev, dtype=torch.float32).contiguous()
+        sq = torch.pow(x, 2).sum(dim=1, keepdim=True)
+        dist = sqdist(x, x, _lib.DIST_EXACT) + (sq - sq.t())
         return dist.cpu()
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    x = torch.cat([features[f].unsqueeze(0) for f, _, _ in query], 0)
+    y = torch.cat([features[f].unsqueeze(0) for f, _, _ in gallery], 0)
+    m, n = x.size(0), y.size(0)
+    x, y = x.view(m, -1), y.view(n, -1)
+    if metric is not None:
+        x, y = metric.transform(x), metric.transform(y)
+    x, y = x.to(dev, dtype=torch.float32).contiguous(), y.to(dev, dtype=torch.float32).contiguous()
+    return sqdist(x, y, _lib.DIST_EXACT).cpu()
 
 
 def evaluate_all(distmat, query=None, gallery=None, query_ids=None, gallery_ids=None, query_cams=None,

@@ -26,11 +26,7 @@ def re_ranking_init(query_feature, gallery_feature, k1=20, k2=6, lambda_value=0.
     dev = _lib.require_cuda()
     q = torch.as_tensor(np.ascontiguousarray(query_feature, dtype=np.float32)).to(dev)
     g = torch.as_tensor(np.ascontiguousarray(gallery_feature, dtype=np.float32)).to(dev)
-    # np.dot of the reference (float32 GEMM); any float32 GEMM agrees to rounding
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        q_g, q_q, g_g = q @ g.t(), q @ q.t(), g @ g.t()
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    # np.dot of the reference (rerank.py:174-176) on the library's own kernel (exact products, float64 sum)
+    from ssg_b200.rerank import dot
+    q_g, q_q, g_g = dot(q, g), dot(q, q), dot(g, g)
     return _init(q_g, q_q, g_g, k1=k1, k2=k2, lambda_value=lambda_value).cpu().numpy()

@@ -27,6 +27,7 @@ PROTOTYPES = {
     "ssg_last_error": (ctypes.c_char_p, []),
     "ssg_device_info": (c_int, [c_int, P(c_int), P(c_int)]),
     "ssg_sqdist": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "ssg_dot": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "ssg_rerank_plan_create": (c_int, [P(c_void_p), c_int, c_int, c_int, c_int]),
     "ssg_rerank_plan_destroy": (c_int, [c_void_p]),
     "ssg_rerank_plan_bytes": (c_size_t, [c_void_p]),
@@ -159,6 +160,14 @@ def profile(on=None, reset=False):
     return out
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream OF `device` (default: the current device) as a void*.  A stream belongs to one
+    device: plans pass their own device so that a call made while another device is current still launches on a
+    stream of the plan's device."""
     import torch
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def same_device(t, device):
+    """True when CUDA tensor `t` lives on `device` (type AND index)."""
+    return t.is_cuda and t.device.index == device.index

@@ -27,23 +27,30 @@ class ClusterPlan(object):
                 pass
 
     # ---- device matrices (torch CUDA tensors, float64 or float32, [n,n] contiguous)
+    def _check_device(self, t):
+        if not _lib.same_device(t, self.device):
+            raise ValueError("ssg_b200: the matrix must live on the plan's device (%s), got %s" % (self.device, t.device))
+
     def eps(self, dist, rho):
+        self._check_device(dist)
         dt = _dtype_code(dist)
         eps, top = ctypes.c_double(), ctypes.c_longlong()
         _lib.check(_lib.load().ssg_eps_estimate(self._h, dist.data_ptr(), dt, dist.shape[0], float(rho),
-                                                ctypes.byref(eps), ctypes.byref(top), _lib.stream_ptr()))
+                                                ctypes.byref(eps), ctypes.byref(top), _lib.stream_ptr(self.device)))
         return eps.value, top.value
 
-    def dbscan(self, dist, eps, min_samples=4, sync=True):
+    def dbscan(self, dist, eps, min_samples=4):
+        """-> (labels int64 CUDA tensor, number of clusters).  Synchronises the stream once (the library always reads
+        the neighbour-capacity flag back; OverflowError -> _with_capacity_retry grows the plan)."""
         import torch
+        self._check_device(dist)
         dt = _dtype_code(dist)
         n = dist.shape[0]
         labels = torch.empty((n,), dtype=torch.int64, device=dist.device)
         ncl = ctypes.c_int()
         _lib.check(_lib.load().ssg_dbscan(self._h, dist.data_ptr(), dt, n, float(eps), int(min_samples),
-                                          labels.data_ptr(), ctypes.byref(ncl) if sync else None,
-                                          _lib.stream_ptr()))
-        return labels, (ncl.value if sync else None)
+                                          labels.data_ptr(), ctypes.byref(ncl), _lib.stream_ptr(self.device)))
+        return labels, ncl.value
 
     def core_mask(self, n):
         out = np.empty((n,), dtype=np.uint8)
@@ -56,7 +63,7 @@ class ClusterPlan(object):
         eps, top, ok = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_int()
         _lib.check(_lib.load().ssg_eps_sparse(self._h, int(n), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
                                               float(threshold), float(rho), ctypes.byref(eps), ctypes.byref(top),
-                                              ctypes.byref(ok), _lib.stream_ptr()))
+                                              ctypes.byref(ok), _lib.stream_ptr(self.device)))
         return eps.value, top.value, bool(ok.value)
 
     def dbscan_sparse(self, n, rowptr, col, val, eps, min_samples=4):
@@ -65,7 +72,7 @@ class ClusterPlan(object):
         ncl = ctypes.c_int()
         _lib.check(_lib.load().ssg_dbscan_sparse(self._h, int(n), rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
                                                  float(eps), int(min_samples), labels.data_ptr(), ctypes.byref(ncl),
-                                                 _lib.stream_ptr()))
+                                                 _lib.stream_ptr(self.device)))
         return labels, ncl.value
 
     # ---- row-sharded primitives (one process per GPU; the collectives between them are run by ssg_b200.dist)
@@ -82,37 +89,37 @@ class ClusterPlan(object):
                 for k, p, (shape, ts) in zip(names, ptrs, specs)}
 
     def eps_shard_begin(self):
-        _lib.check(_lib.load().ssg_eps_shard_begin(self._h, _lib.stream_ptr()))
+        _lib.check(_lib.load().ssg_eps_shard_begin(self._h, _lib.stream_ptr(self.device)))
 
     def eps_shard_hist(self, rows, n, world, rank, npass):
         _lib.check(_lib.load().ssg_eps_shard_hist(self._h, _ptr(rows), _rows_dtype(rows, n), n, world, rank,
-                                                  int(npass), _lib.stream_ptr()))
+                                                  int(npass), _lib.stream_ptr(self.device)))
 
     def eps_shard_pick(self, npass, rho):
-        _lib.check(_lib.load().ssg_eps_shard_pick(self._h, int(npass), float(rho), _lib.stream_ptr()))
+        _lib.check(_lib.load().ssg_eps_shard_pick(self._h, int(npass), float(rho), _lib.stream_ptr(self.device)))
 
     def eps_shard_gather(self, rows, n, world, rank, exact):
         cnt = ctypes.c_longlong()
         _lib.check(_lib.load().ssg_eps_shard_gather(self._h, _ptr(rows), _rows_dtype(rows, n), n, world, rank,
                                                     int(bool(exact)), None if exact else ctypes.byref(cnt),
-                                                    _lib.stream_ptr()))
+                                                    _lib.stream_ptr(self.device)))
         return None if exact else cnt.value
 
     def eps_shard_finish(self, n, exact):
         eps, top = ctypes.c_double(), ctypes.c_longlong()
         _lib.check(_lib.load().ssg_eps_shard_finish(self._h, n, int(bool(exact)), ctypes.byref(eps), ctypes.byref(top),
-                                                    _lib.stream_ptr()))
+                                                    _lib.stream_ptr(self.device)))
         return eps.value, top.value
 
     def dbscan_shard_count(self, rows, n, row0, eps):
         _lib.check(_lib.load().ssg_dbscan_shard_count(self._h, _ptr(rows), _rows_dtype(rows, n), n, int(row0),
-                                                      rows.shape[0], float(eps), _lib.stream_ptr()))
+                                                      rows.shape[0], float(eps), _lib.stream_ptr(self.device)))
 
     def dbscan_shard_fill(self, rows, n, row0, eps):
         total = ctypes.c_longlong()
         _lib.check(_lib.load().ssg_dbscan_shard_fill(self._h, _ptr(rows), _rows_dtype(rows, n), n, int(row0),
                                                      rows.shape[0], float(eps), ctypes.byref(total),
-                                                     _lib.stream_ptr()))
+                                                     _lib.stream_ptr(self.device)))
         return total.value
 
     def dbscan_shard_label(self, n, min_samples=4):
@@ -120,7 +127,7 @@ class ClusterPlan(object):
         labels = torch.empty((n,), dtype=torch.int64, device=self.device)
         ncl = ctypes.c_int()
         _lib.check(_lib.load().ssg_dbscan_shard_label(self._h, n, int(min_samples), labels.data_ptr(),
-                                                      ctypes.byref(ncl), _lib.stream_ptr()))
+                                                      ctypes.byref(ncl), _lib.stream_ptr(self.device)))
         return labels, ncl.value
 
     # ---- host matrices (numpy)

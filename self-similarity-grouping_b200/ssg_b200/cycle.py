@@ -143,7 +143,7 @@ def pseudo_label_cycle(source_features, target_features, lambda_value=0.1, rho=1
             if final is None or final.shape[0] != n:
                 final = torch.empty((n, n), dtype=torch.float64, device=dev)
             _lib.check(_lib.load().ssg_rerank_finish(plan._h, t.data_ptr(), n, t.shape[1], int(k1), int(k2),
-                                                     float(lambda_value), final.data_ptr(), _lib.stream_ptr()))
+                                                     float(lambda_value), final.data_ptr(), _lib.stream_ptr(dev)))
         else:
             if final is None or final.shape[0] != n:
                 final = torch.empty((n, n), dtype=torch.float64, device=dev)

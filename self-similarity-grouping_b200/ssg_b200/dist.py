@@ -134,7 +134,7 @@ class CudaBackend(object):
         L = self._lib
         L.check(L.load().ssg_rerank_distance_rows(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), tgt.shape[0],
                                                   tgt.shape[1], int(k1), self.mode, int(row0), int(rows), None,
-                                                  L.stream_ptr()))
+                                                  L.stream_ptr(self.dev)))
 
     def tables(self, plan, n):
         """Zero-copy torch views of the plan's per-row tables: rowmin [n], rowmax [n], rank [n,32], rank_val [n,32]."""
@@ -149,7 +149,7 @@ class CudaBackend(object):
     def finish(self, plan, tgt, k1, k2, lambda_value, final):
         L = self._lib
         L.check(L.load().ssg_rerank_finish(plan._h, tgt.data_ptr(), tgt.shape[0], tgt.shape[1], int(k1), int(k2),
-                                           float(lambda_value), final.data_ptr(), L.stream_ptr()))
+                                           float(lambda_value), final.data_ptr(), L.stream_ptr(self.dev)))
 
     def new_final(self, n):
         import torch
@@ -181,7 +181,7 @@ class CudaBackend(object):
         L = self._lib
         L.check(L.load().ssg_rerank_finish_rows(plan._h, tgt.data_ptr(), tgt.shape[0], tgt.shape[1], int(k1), int(k2),
                                                 float(lambda_value), int(row0), int(rows),
-                                                final_rows.data_ptr() if rows else None, L.stream_ptr()))
+                                                final_rows.data_ptr() if rows else None, L.stream_ptr(self.dev)))
 
     def new_final_rows(self, rows, n):
         import torch

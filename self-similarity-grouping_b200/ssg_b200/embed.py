@@ -33,6 +33,12 @@ def unwrap(model):
     return model
 
 
+def _check_num_split(num_split):
+    """The pooled tail keeps up to 4 stripes + the global bank in registers (csrc/conv.cu pooled_tail_kernel)."""
+    if not 1 <= int(num_split) <= 4:
+        raise ValueError("ssg_b200: num_split=%r out of range (1..4)" % (num_split,))
+
+
 class EmbedPlan(object):
     """Device workspace + folded weights of one ResNet-50 trunk for batches of up to ``batch_max`` images."""
 
@@ -70,8 +76,8 @@ class EmbedPlan(object):
                 raise ValueError("layer %s: weight shape %s, expected %s" % (ck, tuple(w.shape), (cout, cin, k, k)))
             gamma, beta, mean, var = g(bk + ".weight"), g(bk + ".bias"), g(bk + ".running_mean"), g(bk + ".running_var")
             _lib.check(lib.ssg_embed_load_layer(self._h, i, w.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
-                                                mean.data_ptr(), var.data_ptr(), 1e-5, _lib.stream_ptr()))
-        torch.cuda.current_stream().synchronize()     # the staging tensors above die here
+                                                mean.data_ptr(), var.data_ptr(), 1e-5, _lib.stream_ptr(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()     # the staging tensors above die here
 
     def load_model(self, model):
         """Ingest ``model.base`` of a reference-style ResNet (re-ingests only when the parameters changed)."""
@@ -98,6 +104,9 @@ class EmbedPlan(object):
         eval mode  -> out [rows, banks*2048]."""
         import torch
         assert images.is_cuda and images.dim() == 4
+        if not _lib.same_device(images, self.device):
+            raise ValueError("ssg_b200: images must live on the plan's device (%s), got %s" % (self.device, images.device))
+        _check_num_split(num_split)
         images = images.contiguous()
         n = images.shape[0]
         banks = num_split + 1 if num_split > 1 else 1
@@ -111,26 +120,27 @@ class EmbedPlan(object):
             c3 = ctypes.c_float * 3
             _lib.check(_lib.load().ssg_embed_forward_u8(self._h, images.data_ptr(), c3(*mean), c3(*std), n,
                                                         int(num_split), int(bool(for_eval)), int(bool(flip)),
-                                                        out.data_ptr(), bank_stride, int(row0), _lib.stream_ptr()))
+                                                        out.data_ptr(), bank_stride, int(row0), _lib.stream_ptr(self.device)))
             return out
         if images.dtype != torch.float32 or tuple(images.shape[1:]) != (3, 256, 128):
             raise ValueError("images must be float32 [n,3,256,128] or uint8 [n,256,128,3], got %s %s"
                              % (images.dtype, tuple(images.shape)))
         _lib.check(_lib.load().ssg_embed_forward(self._h, images.data_ptr(), n, int(num_split), int(bool(for_eval)),
                                                  int(bool(flip)), out.data_ptr(), bank_stride, int(row0),
-                                                 _lib.stream_ptr()))
+                                                 _lib.stream_ptr(self.device)))
         return out
 
 
     def forward_raw(self, images, num_split=1):
         """One forward without flip and without normalisation: [banks, n, 2048] pooled banks (cnn.py:16)."""
         import torch
+        _check_num_split(num_split)
         images = images.contiguous()
         n = images.shape[0]
         banks = num_split + 1 if num_split > 1 else 1
         out = torch.empty((banks, n, 2048), dtype=torch.float32, device=images.device)
         _lib.check(_lib.load().ssg_embed_forward(self._h, images.data_ptr(), n, int(num_split), 2, 0,
-                                                 out.data_ptr(), out.stride(0), 0, _lib.stream_ptr()))
+                                                 out.data_ptr(), out.stride(0), 0, _lib.stream_ptr(self.device)))
         return out
 
 

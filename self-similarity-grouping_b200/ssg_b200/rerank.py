@@ -36,7 +36,7 @@ class RerankPlan(object):
         """src [ns,d], tgt [n,d]: float32 CUDA tensors.  Returns (euclid or None, final) CUDA tensors
         (float32 [n,n], float64 [n,n]); asynchronous on the current stream."""
         import torch
-        if src.device.type != self.device.type or tgt.device.type != self.device.type:
+        if not (_lib.same_device(src, self.device) and _lib.same_device(tgt, self.device)):
             raise ValueError("ssg_b200: features must live on the plan's device (%s), got %s / %s"
                              % (self.device, src.device, tgt.device))
         assert src.dtype == torch.float32 and tgt.dtype == torch.float32
@@ -47,7 +47,7 @@ class RerankPlan(object):
         euclid = torch.empty((n, n), dtype=torch.float32, device=tgt.device) if want_euclid else None
         _lib.check(_lib.load().ssg_rerank_run(
             self._h, src.data_ptr(), ns, tgt.data_ptr(), n, d, int(k1), int(k2), float(lambda_value),
-            int(dist_mode), final.data_ptr(), euclid.data_ptr() if want_euclid else None, _lib.stream_ptr()))
+            int(dist_mode), final.data_ptr(), euclid.data_ptr() if want_euclid else None, _lib.stream_ptr(self.device)))
         return euclid, final
 
     def run_host(self, src, tgt, k1=20, k2=6, lambda_value=0.2, dist_mode=_lib.DIST_EXACT, no_rerank=False,
@@ -71,7 +71,7 @@ class RerankPlan(object):
         rows = tgt.shape[0] - row0 if rows is None else rows
         _lib.check(_lib.load().ssg_rerank_distance_rows(self._h, src.data_ptr(), src.shape[0], tgt.data_ptr(),
                                                         tgt.shape[0], tgt.shape[1], int(k1), int(dist_mode), int(row0),
-                                                        int(rows), None, _lib.stream_ptr()))
+                                                        int(rows), None, _lib.stream_ptr(self.device)))
 
     def finish_sparse(self, tgt, k1=20, k2=6, lambda_value=0.2):
         """final_dist as a CSR over the touched columns (see include/ssg_b200.h).  Returns (rowptr int32 [n+1],
@@ -82,7 +82,7 @@ class RerankPlan(object):
         n = tgt.shape[0]
         nnz = ctypes.c_longlong()
         _lib.check(_lib.load().ssg_rerank_finish_sparse(self._h, tgt.data_ptr(), n, tgt.shape[1], int(k1), int(k2),
-                                                        float(lambda_value), ctypes.byref(nnz), _lib.stream_ptr()))
+                                                        float(lambda_value), ctypes.byref(nnz), _lib.stream_ptr(self.device)))
         ptrs = [ctypes.c_void_p() for _ in range(3)]
         cnt, thr = ctypes.c_longlong(), ctypes.c_double()
         _lib.check(_lib.load().ssg_rerank_sparse_view(self._h, ctypes.byref(ptrs[0]), ctypes.byref(ptrs[1]),
@@ -140,9 +140,21 @@ def re_ranking(input_feature_source, input_feature, k1=20, k2=6, lambda_value=0.
     """Drop-in for reid/rerank.py:27 re_ranking (same positional order and defaults).
 
     Returns (euclidean_dist, final_dist) as numpy arrays — float32 [N,N] and float64 [N,N]
-    (``final_dist`` is None when ``no_rerank``).  Arithmetic follows the reference with float16
-    replaced by float32 and a stable argsort (the O-f32 oracle); MemorySave/Minibatch
-    only chunk the reference's cdist and have no effect on results, so they are accepted and ignored.
+    (``final_dist`` is None when ``no_rerank``).  MemorySave/Minibatch only chunk the reference's cdist and have no
+    effect on results, so they are accepted and ignored.
+
+    Deviation from the reference, by design: the reference stores its intermediates
+    in float16 (rerank.py:33-70) and ranks with numpy's unstable argsort, so its exact bits depend on the host CPU's
+    float16 ``exp`` and sort kernels and cannot be reproduced anywhere else.  This function computes the same
+    pipeline with float16 replaced by float32 and ties broken by (value, index) -- the "O-f32" oracle -- and
+    ``euclidean_dist`` comes back as float32 instead of float16.  On tie-heavy float16 data eps and labels can
+    therefore differ from a run of the reference itself (as two runs of the reference on different CPUs can).
+
+    dist_mode: one rule for the whole package -- ``SSG_DIST_MODE`` when set, else the exact float64 distances
+    (``DIST_EXACT``) for calls that RETURN the Euclidean matrix (this function: the matrix is then bit-identical to
+    scipy's cdist squared) and the tensor-core distances with exact re-scoring (``DIST_TENSOR``) for calls that
+    only return ``final_dist`` / labels (``compute_dist``, ``pseudo_label_cycle``).  ``final_dist`` is bit-identical
+    in both modes (tests/test_gpu_tensor.py); only the returned Euclidean matrix differs (|err| <= 4.1e-5).
     """
     import os
     if dist_mode is None:
@@ -175,7 +187,7 @@ def re_ranking_plain(input_feature_source, input_feature, k=20, lambda_value=0.1
     print('computing original distance...')
     final = torch.empty((n, n), dtype=torch.float64, device=dev)
     _lib.check(_lib.load().ssg_rerank_plain(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), n, d, int(k),
-                                            float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr()))
+                                            float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr(dev)))
     out = final.cpu().numpy()
     return out, out
 
@@ -197,7 +209,7 @@ def re_ranking_lh(input_feature_source, input_feature, k1=20, k2=6, lambda_value
     print('starting re_ranking...')
     final = torch.empty((n, n), dtype=torch.float64, device=dev)
     _lib.check(_lib.load().ssg_rerank_lh(plan._h, src.data_ptr(), src.shape[0], tgt.data_ptr(), n, d, int(k1), int(k2),
-                                         float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr()))
+                                         float(lambda_value), int(dist_mode), final.data_ptr(), _lib.stream_ptr(dev)))
     euclid = sqdist(tgt, tgt, _lib.DIST_EXACT)
     return euclid.cpu().numpy(), final.cpu().numpy()
 
@@ -218,7 +230,7 @@ def re_ranking_init_blocks(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_val
     plan = get_plan(q + g, 1, 64, dev.index)
     out = torch.empty((q, g), dtype=torch.float32, device=dev)
     _lib.check(_lib.load().ssg_rerank_init(plan._h, qg.data_ptr(), qq.data_ptr(), gg.data_ptr(), q, g, int(k1),
-                                           int(k2), float(lambda_value), out.data_ptr(), _lib.stream_ptr()))
+                                           int(k2), float(lambda_value), out.data_ptr(), _lib.stream_ptr(dev)))
     return out.cpu().numpy() if host else out
 
 
@@ -228,5 +240,16 @@ def sqdist(x, y, mode=_lib.DIST_EXACT):
     x, y = x.contiguous(), y.contiguous()
     out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().ssg_sqdist(x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], x.shape[1], int(mode),
-                                      out.data_ptr(), y.shape[0], _lib.stream_ptr()))
+                                      out.data_ptr(), y.shape[0], _lib.stream_ptr(x.device)))
+    return out
+
+
+def dot(x, y):
+    """Dot-product block x @ y.T of two float32 CUDA tensors on the library's own kernel (ssg_dot: products exact,
+    float64 sequential sum) -- the np.dot blocks of reid/rerank.py:174-176 and reid/eug.py:223-225."""
+    import torch
+    x, y = x.contiguous(), y.contiguous()
+    out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().ssg_dot(x.data_ptr(), x.shape[0], y.data_ptr(), y.shape[0], x.shape[1], out.data_ptr(),
+                                   y.shape[0], _lib.stream_ptr(x.device)))
     return out

@@ -92,9 +92,16 @@ int main(int argc, char** argv) {
     {
         double e = 0; long long top = 0; int ok = 0;
         CK(ssg_eps_sparse(cp, n, d_rp, d_col, d_val, thr, rho, &e, &top, &ok, NULL));
-        const int bad = !ok || top != top0 || !(fabs(e - eps0) <= 1e-13 * fabs(eps0));
+        /* the slice can be certified iff the dense matrix holds at least top_num non-zero upper-triangle entries below
+         * the bound (all of those are in the CSR); otherwise the refusal is the correct answer */
+        long long below = 0;
+        for (int i = 0; i < n; ++i)
+            for (int m = i + 1; m < n; ++m) { const double v = h_f[(size_t)i * n + m]; below += (v != 0.0 && v < thr); }
+        const int expect = top0 <= below;
+        const int bad = ok != expect || (ok && (top != top0 || !(fabs(e - eps0) <= 1e-13 * fabs(eps0))));
         fails += bad;
-        printf("eps sparse %.17g vs dense %.17g (top %lld vs %lld, certified %d): %s\n", e, eps0, top, top0, ok, bad ? "FAIL" : "ok");
+        printf("eps sparse %.17g vs dense %.17g (top %lld vs %lld, %lld entries below the bound, certified %d, expected %d): %s\n",
+               e, eps0, top, top0, below, ok, expect, bad ? "FAIL" : "ok");
         CK(ssg_eps_sparse(cp, n, d_rp, d_col, d_val, thr, 0.5, &e, &top, &ok, NULL));
         fails += ok != 0;
         printf("rho = 0.5 must not be certified: certified %d: %s\n", ok, ok ? "FAIL" : "ok");

@@ -23,7 +23,7 @@ def install():
     import build_emu
     lib_path, _ = build_emu.build()
     from ssg_b200 import _lib, cluster, dist, rerank
-    saved = dict(lib=_lib._lib, require=_lib.require_cuda, stream=_lib.stream_ptr, c_dev=cluster._DevArray,
+    saved = dict(lib=_lib._lib, require=_lib.require_cuda, stream=_lib.stream_ptr, same=_lib.same_device, c_dev=cluster._DevArray,
                  d_dev=dist._DevArray, c_dt=cluster._dtype_code, c_rd=cluster._rows_dtype, plans=dict(rerank._plans),
                  cplans=dict(cluster._plans))
     lib = ctypes.CDLL(lib_path)
@@ -34,7 +34,8 @@ def install():
     _lib._lib = lib
     dev = torch.device("cpu", 0)
     _lib.require_cuda = lambda device=None: dev
-    _lib.stream_ptr = lambda: ctypes.c_void_p(None)
+    _lib.stream_ptr = lambda device=None: ctypes.c_void_p(None)
+    _lib.same_device = lambda t, device: True
     np_types = {"<i4": ctypes.c_int32, "<f4": ctypes.c_float, "<i8": ctypes.c_int64, "<f8": ctypes.c_double}
 
     def host_view(ptr, shape, typestr):
@@ -71,6 +72,7 @@ def install():
         rerank._plans.clear()
         cluster._plans.clear()
         _lib._lib, _lib.require_cuda, _lib.stream_ptr = saved["lib"], saved["require"], saved["stream"]
+        _lib.same_device = saved["same"]
         cluster._DevArray, dist._DevArray = saved["c_dev"], saved["d_dev"]
         cluster._dtype_code, cluster._rows_dtype = saved["c_dt"], saved["c_rd"]
         rerank._plans.update(saved["plans"])

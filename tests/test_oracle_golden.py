@@ -88,3 +88,38 @@ def test_embed_oracle_matches_reference(golden_dir):
             np.testing.assert_allclose(mine, gl[b], rtol=0, atol=2e-5)
         np.testing.assert_allclose(torch.stack([fe[k] for k in names]).numpy(), g["eval_S%d" % S],
                                    rtol=0, atol=2e-5)
+
+
+def test_whole_path_golden_is_pinned_to_the_oracle(golden_dir):
+    """tests/golden/cycle_n512_S2.npz (images -> labels through the unmodified reference): the oracle's ResNet
+    restatement reproduces the stored head of the reference features from the same seeded images, and the stored
+    eps / labels are what the oracle's eps estimator and DBSCAN give on the stored final_dist."""
+    import torch
+    from sklearn.metrics import adjusted_rand_score
+    from oracle import resnet_oracle as R
+    g = np.load(os.path.join(golden_dir, "cycle_n512_S2.npz"))
+    n, S = int(g["n"]), int(g["num_split"])
+    head = g["feat_tgt_head"]
+    k = 8
+    # the generator draws the images in order, so a prefix needs the whole set's generator state: draw the set
+    imgs, ident = R.synth_identity_images(n, int(g["seed_tgt"]), int(g["per_identity"]), float(g["noise"]))
+    assert np.array_equal(ident.numpy(), g["identity"])
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
+    model = R.build_model(S, int(g["weight_seed"]))
+    names = ["i%d" % i for i in range(k)]
+    f, _ = R.extract_features(model, [(imgs[:k], names, [0] * k, [0] * k)], for_eval=False)
+    for b in range(S + 1):
+        got = torch.stack([f[nm][b] for nm in names]).numpy()
+        np.testing.assert_allclose(got, head[b, :k], rtol=0, atol=2e-6)
+    iu = np.triu_indices(n)
+    for b in range(S + 1):
+        tri = g["final_f32_b%d" % b].astype(np.float64)
+        D = np.zeros((n, n))
+        D[iu] = tri
+        D = D + np.triu(D, 1).T
+        for ri, rho in enumerate(g["rhos"]):
+            eps = O.eps_estimate(D, float(rho))
+            want = float(g["eps_f32_r%d_b%d" % (ri, b)])
+            assert abs(eps - want) <= 1e-6 * want              # the stored triangle is float32-rounded
+            lab = O.dbscan_dfs(D, want, 4)
+            assert adjusted_rand_score(g["labels_f32_r%d_b%d" % (ri, b)], lab) >= 0.995
