@@ -121,6 +121,36 @@ def cycle_case(name, n, ns, num_split=2, lam=0.1, rhos=(1.6e-3, 1.6e-2, 5e-2), p
                seed_tgt=1234, seed_src=4321, weight_seed=0, identity=ident["tgt"], versions=versions(),
                feat_tgt_head=np.stack([b[:keep_rows].numpy() for b in feats["tgt"]]),
                feat_src_head=np.stack([b[:keep_rows].numpy() for b in feats["src"]]))
+    # how well-conditioned is the problem?  (1) spread of the features: nearest / 21st-nearest / median squared distance;
+    # (2) the REFERENCE arithmetic (oracle O-f32) fed its own features perturbed by Gaussian noise of relative L2 size
+    # 4e-3 per row -- the size of the bf16 trunk's feature error -- : rank-table and label changes caused by the
+    # perturbation alone.  The CUDA path cannot be closer to the reference than the reference is to itself under that
+    # perturbation; tests/test_gpu_whole_path.py compares against these numbers.
+    from scipy.spatial.distance import cdist
+    rng = np.random.RandomState(2024)
+    cond = {k: [] for k in ("d2_nn", "d2_k21", "d2_median", "noise_rank_entry_mismatch", "noise_rank_set_mismatch_rows")}
+    noisy_final = []
+    for b in range(banks):
+        t, s_ = feats["tgt"][b].numpy(), feats["src"][b].numpy()
+        d2 = np.sort(cdist(t, t) ** 2, axis=1)
+        cond["d2_nn"].append(float(np.median(d2[:, 1])))
+        cond["d2_k21"].append(float(np.median(d2[:, 20])))
+        cond["d2_median"].append(float(np.median(d2[:, n // 2])))
+
+        def perturb(x):
+            e = rng.randn(*x.shape).astype(np.float32)
+            e *= (4e-3 * np.linalg.norm(x, axis=1, keepdims=True) / np.linalg.norm(e, axis=1, keepdims=True))
+            return (x + e).astype(np.float32)
+        st0, st1 = {}, {}
+        O.re_ranking(s_, t, lambda_value=lam, mode="f32", stages=st0)
+        _, f1 = O.re_ranking(perturb(s_), perturb(t), lambda_value=lam, mode="f32", stages=st1)
+        r0, r1 = st0["rank"][:, :21], st1["rank"][:, :21]
+        cond["noise_rank_entry_mismatch"].append(float((r0 != r1).mean()))
+        cond["noise_rank_set_mismatch_rows"].append(float(np.mean([set(a) != set(c) for a, c in zip(r0, r1)])))
+        noisy_final.append(f1)
+    for k, v in cond.items():
+        out[k] = np.array(v)
+    print(name, "conditioning", {k: [round(x, 5) for x in v] for k, v in cond.items()})
     iu = np.triu_indices(n)
     for mode in ("f32", "ref"):
         # the driver's `from reid.rerank import *` bound re_ranking when selftraining.py was imported: patch the `np` of
@@ -144,6 +174,12 @@ def cycle_case(name, n, ns, num_split=2, lam=0.1, rhos=(1.6e-3, 1.6e-2, 5e-2), p
             for b in range(banks):
                 out["labels_%s_r%d_b%d" % (mode, ri, b)] = labels[b].astype(np.int32)
                 out["eps_%s_r%d_b%d" % (mode, ri, b)] = np.float64(clusters[b].eps)
+            if mode == "f32":
+                with contextlib.redirect_stdout(io.StringIO()):
+                    labels_n, _ = drv.generate_selflabel([[]] * banks, noisy_final, 0, args, [])
+                out["noise_ari_r%d" % ri] = np.array([adjusted_rand_score(labels[b], labels_n[b]) for b in range(banks)])
+                print(name, "rho", rho, "ARI(reference, reference on 4e-3-perturbed features)",
+                      [round(float(x), 3) for x in out["noise_ari_r%d" % ri]])
             print(name, mode, "rho", rho, "clusters", [int(l.max()) + 1 for l in labels],
                   "noise", [int((l < 0).sum()) for l in labels],
                   "ARI vs identity", [round(adjusted_rand_score(ident["tgt"], l), 3) for l in labels])

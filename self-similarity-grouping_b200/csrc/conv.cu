@@ -44,11 +44,10 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     static int epi2 = -1;
     if (epi2 < 0) { const char* e = getenv("SSG_CONV_EPI2"); epi2 = e ? atoi(e) : 0; }
     const bool stem_kernel = stem_variant() && A.mode == 3 && cout == 64 && k == tc::BRES_K;
-    if (epi2 && !stem_kernel && !pool_out) {
-        if (!residual && cout % 256 == 0 && k >= 256)
-            return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
-        if (residual && cout % 256 == 0 && k >= 256)
-            return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_RRING, true>(A, m, w, cout, k, epi, st);
+    // (the 128x256 tiles keep the default epilogue: with the doubled bias rows the EPI2 layout is 256 bytes over the
+    // 227 KB limit -- first B200 run of round 2 -- and those launches are L2-bandwidth bound, not epilogue bound)
+    const bool wide = cout % 256 == 0 && k >= 256;
+    if (epi2 && !stem_kernel && !pool_out && !wide) {
         if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
     }
@@ -221,6 +220,10 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
         epi.has_res = 0;
         SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
         SSG_TRY(make_tmap_2d_bf16(&epi.mapR, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+        // weights resident in shared memory (72 KB, loaded once per CTA) unless SSG_KHS_BRES=0
+        static int khs_bres = -1;
+        if (khs_bres < 0) { const char* e = getenv("SSG_KHS_BRES"); khs_bres = e ? atoi(e) : 1; }
+        if (khs_bres) return tc::launch_gemm_op<64, tc::StagedEpi, true, true, tc::VAR_KHSB>(A, m, w, cout, 9 * cin, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, true>(A, m, w, cout, 9 * cin, epi, st);
     }
     return gemm_dispatch(A, m, w, cout, 9 * cin, bias, nullptr, relu, y, st);

@@ -73,7 +73,12 @@ struct StagedEpi {
 //             tile touches are loaded ONCE, as two stride-2 TMA boxes of five rows (even / odd offsets: 2 x 20 KB), and
 //             kernel row kh reads plane kh & 1 starting (kh >> 1) rows in -- 40 KB per tile instead of the 64 KB of eight
 //             per-kernel-row boxes.  Same MMA sequence, hence the same bits.
-constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3;
+//   VAR_KHSB  (KHS with resident weights; C = 64 -> 64 3x3 convolutions of layer 1): all nine 64x64 weight tiles
+//             (72 KB) are loaded ONCE per CTA and the operand stages carry the haloed activation box only (4 stages of
+//             24 KB).  The plain KHS kernel re-fetches the 72 KB of weights for every 128-pixel tile, which is half of
+//             its L2 -> shared-memory traffic (144 KB per tile at ~42 B/clk/SM: the launch is L2-bandwidth bound).
+//             Same MMA sequence, hence the same bits.
+constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3, VAR_KHSB = 4;
 constexpr int STEM_ROW_BYTES = 64 * 64;     // one input row of a stem tile in shared memory: 64 windows x 64 B
 constexpr int BRES_K = 256;
 
@@ -86,10 +91,11 @@ template <int BN, bool STAGED, bool KHS = false, int VAR = VAR_NONE, bool EPI2 =
 struct SmemLayout {
     static constexpr bool PLANES = VAR == VAR_BRESP;
     static constexpr bool BRES = VAR == VAR_BRES || PLANES, RRING = VAR == VAR_RRING;
+    static constexpr bool KRES = VAR == VAR_KHSB;                // KHS + resident weights
     static constexpr int RSLOTS = 3;                             // residual ring slots (RRING)
     static constexpr int A_BYTES = PLANES ? 2 * 5 * STEM_ROW_BYTES : (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int B_BYTES = BRES ? 0 : (KHS ? 3 : 1) * B_TILE;
+    static constexpr int B_BYTES = (BRES || KRES) ? 0 : (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
@@ -98,15 +104,16 @@ struct SmemLayout {
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
     static constexpr int RSTAGE_BYTES = RRING ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
-    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KHS ? 3 :
+    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KRES ? 4 : KHS ? 3 :
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
-    static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : 0;
+    static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : KRES ? 9 * B_TILE : 0;
     static constexpr int C_OFFSET = BRES_OFFSET + BRES_BYTES;    // output staging, then the residual staging buffers
     static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + RSTAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
     static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
+    static_assert(!(KRES && (!KHS || !STAGED || BN != 64)), "VAR_KHSB is the 64-channel kernel-row-sharing kernel");
     static_assert(!(EPI2 && (BRES || !STAGED)), "EPI2 is a variant of the generic staged epilogue");
     static_assert(TOTAL <= 232448, "shared-memory layout exceeds 227 KB");
 };
@@ -196,6 +203,13 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     tma_load_2d(bres + kb * L::B_TILE + L::B_TILE / 2, &mapB, bres_bar, kb * BK + 32, 0);
                 }
             }
+            if constexpr (L::KRES) {
+                // the nine [64, 64] weight tiles (tap t = kh*3 + kw at K offset t*64: one channel block), once
+                unsigned char* bres = smem + L::BRES_OFFSET;
+                mbar_arrive_expect_tx(bres_bar, L::BRES_BYTES);
+#pragma unroll
+                for (int tp = 0; tp < 9; ++tp) tma_load_2d(bres + tp * L::B_TILE, &mapB, bres_bar, tp * BK, 0);
+            }
             for (int t = t_begin; t < t_end; t += t_step) {
                 int m_blk, n_blk;
                 tile_coords(t, m_blk, n_blk);
@@ -214,10 +228,12 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         // stage kb = (kernel column kw, channel block cb): rows h0-1 .. h0+bh of the tile's image
                         const int kw = kb / A.cblks, cb = kb - kw * A.cblks;
                         tma_load_4d(sa, &A.map[0], &full_bar[stage], cb * BK, kw - 1, h0 - 1, b0);
+                        if constexpr (!L::KRES) {
 #pragma unroll
-                        for (int kh = 0; kh < 3; ++kh)
-                            tma_load_2d(sb + kh * L::B_TILE, &mapB, &full_bar[stage], ((kh * 3 + kw) * A.cblks + cb) * BK,
-                                        n_blk * BN);
+                            for (int kh = 0; kh < 3; ++kh)
+                                tma_load_2d(sb + kh * L::B_TILE, &mapB, &full_bar[stage],
+                                            ((kh * 3 + kw) * A.cblks + cb) * BK, n_blk * BN);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -264,7 +280,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        if constexpr (L::BRES) {
+        if constexpr (L::BRES || L::KRES) {
             mbar_wait(bres_bar, 0);                           // resident weights have landed
             tc_fence_after();
         }
@@ -289,7 +305,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
                             const uint64_t da = make_desc_k_sw128(sa + (uint32_t)(kh * A.khs_row_bytes));
-                            const uint64_t db = make_desc_k_sw128(sb + (uint32_t)(kh * L::B_TILE));
+                            // resident weights: tap (kh, kw = kb) sits (kh*3 + kb) tiles into the resident region
+                            const uint64_t db = make_desc_k_sw128(
+                                L::KRES ? smem_u32(smem + L::BRES_OFFSET) + (uint32_t)((kh * 3 + kb) * L::B_TILE)
+                                        : sb + (uint32_t)(kh * L::B_TILE));
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k)
                                 umma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
@@ -675,6 +694,8 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     using L = SmemLayout<BN, STAGED, KHS, VAR, EPI2>;
     if ((VAR == VAR_BRES || VAR == VAR_BRESP) && (A.mode != 3 || n != BN || k != BRES_K))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
+    if (VAR == VAR_KHSB && (n != BN || k != 9 * BK || A.cblks != 1))
+        return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-weight KHS variant needs C = N = 64 (N=%d, K=%d)", n, k);
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;

@@ -1,6 +1,9 @@
-"""GPU, marker `gpu_next` (NOT part of `-m gpu`): opt-in variants written after the round's GPU budget was spent.
-Run `python -m pytest tests -m gpu_next -q` on a B200 before making any of them a default; each must reproduce the
-default path bit for bit."""
+"""GPU: the kernel variants and entry points that were written after round 1's GPU budget was spent (marker `gpu_next`
+then) -- the sparse form of final_dist, the symmetric distance epilogue, rerank_plain / re_ranking_lh (SURVEY.md row
+f4), tiny target sets (n < k1 + 1, n < k2), k2 > k1 + 1, a matrix beyond 2^31 elements, the L2-chunked schedule and the
+one-barrier epilogue.  All of them had their first B200 run in round 2 (profiles/r02b_gpu_next.log: 19 of 20 passed;
+the one-barrier epilogue failed to LAUNCH for 128x256 tiles and is now limited to the narrower tiles) and are part of
+`-m gpu` since.  Each variant must reproduce the default path bit for bit."""
 import os
 import subprocess
 import sys
@@ -28,7 +31,7 @@ def _embed_in_subprocess(tmp_path, name, env, n_img=21, batch=32):
     return np.load(out_file)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("chunk,graph", [(8, 1), (10, 1), (32, 1), (10, 0)])
 def test_l2_chunked_layers_are_bit_identical(tmp_path, chunk, graph):
     """SSG_L2_CHUNK: layers 1-2 over chunks of image-passes that stay in L2 (embed.cu) -- same kernels on the same
@@ -43,7 +46,7 @@ def test_l2_chunked_layers_are_bit_identical(tmp_path, chunk, graph):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,d", [(2000, 64), (3001, 128)])
 def test_c_harness_sparse_final_dist_matches_dense(n, d):
     """tests/c/sparse_check.c: CSR entries byte-equal to the dense matrix, everything outside >= the bound, eps within
@@ -55,7 +58,7 @@ def test_c_harness_sparse_final_dist_matches_dense(n, d):
     assert r.returncode == 0 and "SPARSE_CHECK PASSED" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["exact", "tensor"])
 def test_sparse_cycle_matches_dense_cycle(mode):
     """pseudo_label_cycle(sparse=True) against the dense cycle: labels identical, eps to 1e-13; a rho so large that the
@@ -82,7 +85,7 @@ def test_sparse_cycle_matches_dense_cycle(mode):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("switch", ["SSG_DIST_SYM", "SSG_PAIR_VEC8"])
 def test_distance_stage_variants_give_the_exact_mode_results(tmp_path, switch):
     """SSG_DIST_SYM=1: only the tiles touching the upper triangle of the target x target distance GEMM are computed and
@@ -113,7 +116,7 @@ def test_distance_stage_variants_give_the_exact_mode_results(tmp_path, switch):
     assert int(o["tensor_flagged"][0]) < 30          # the mirrored values certify as well as the direct ones
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_one_barrier_epilogue_is_bit_identical(tmp_path):
     """SSG_CONV_EPI2=1: the generic staged epilogue with one named barrier per sub-tile, pipelined tcgen05.ld and a
     full-ring residual prefetch -- same bias / residual / ReLU arithmetic per element, so the same features."""
@@ -123,7 +126,7 @@ def test_one_barrier_epilogue_is_bit_identical(tmp_path):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("n,ns", [(2, 1), (3, 5), (10, 7), (21, 30), (22, 22)])
 def test_tiny_target_sets_against_oracle(n, ns):
     """Fewer targets than k1 + 1 = 21 rank columns (reid/rerank.py:76 slices whatever is there): an edge the
@@ -142,7 +145,7 @@ def test_tiny_target_sets_against_oracle(n, ns):
     np.testing.assert_allclose(got.cpu().numpy(), want, rtol=0, atol=1e-4)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["exact", "tensor"])
 def test_plain_knn_set_reranker_on_the_device(mode):
     """reid.rerank_plain.re_ranking (row f4) on the GPU against the pinned restatement: the Jaccard part is exact, the
@@ -163,7 +166,7 @@ def test_plain_knn_set_reranker_on_the_device(mode):
         np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_re_ranking_lh_on_the_device():
     """reid.rerank_plain.re_ranking_lh (row f4) on the GPU against the pinned restatement."""
     from ssg_b200.rerank import re_ranking_lh
@@ -175,7 +178,7 @@ def test_re_ranking_lh_on_the_device():
     np.testing.assert_allclose(f, P.re_ranking_lh(src, tgt, 20, 6, 0.2, "f32"), rtol=0, atol=1e-4)
 
 
-@pytest.mark.gpu_next
+@pytest.mark.gpu
 def test_matrix_beyond_2_31_elements():
     """N = 47 000: N^2 = 2.209e9 > 2^31 elements (17.7 GB of float64 final_dist), the first size at which a 32-bit row
     offset anywhere in the distance / Jaccard / eps / DBSCAN kernels would read the wrong rows.  Size-independent
