@@ -120,6 +120,52 @@ int conv_fused_ds(const void* t2, const void* x, int B, int H, int W, int mid, i
     return gemm_dispatch(A, m, w, cout, mid + cin, bias, nullptr, 1, y, st);
 }
 
+// Layer-1 bottleneck tail AND the next block's conv1 in one launch (tc::VAR_CHAIN in gemm_tc.cuh):
+//   y  = relu( conv3(t2) + shortcut ),  shortcut = residual [M, 256]  or  downsample(x_ds) K-concatenated (w = [W3 | Wds])
+//   t1 = relu( conv1_next(y) )          [M, n2], n2 = 64 (next block of layer 1) or 128 (first block of layer 2)
+// t2 [M = B*H*W, mid], x_ds [M, cin_ds] (or NULL), w [256, mid (+ cin_ds)], w_next [n2, 256]; stride 1 only.
+int conv_chain(const void* t2, int B, int H, int W, int mid, const void* x_ds, int cin_ds, const void* w,
+               const float* bias, const void* residual, void* y, const void* w_next, const float* bias_next, int n2,
+               void* t1_next, cudaStream_t st) {
+    const int cout = 256, m = B * H * W;
+    if (mid % 64 || (x_ds && cin_ds % 64) || (x_ds && residual))
+        return ssg_set_error(SSG_ERR_INVALID, "conv_chain: bad arguments");
+    tc::AOperand A;
+    memset(&A, 0, sizeof(A));
+    A.mode = 0;
+    A.cblks = mid / tc::BK;
+    A.taps = 1;
+    A.tiles_per_img = 1;
+    A.hmul = 1;
+    SSG_TRY(make_tmap_2d_bf16(&A.map[0], t2, (uint64_t)m, (uint64_t)mid, (uint64_t)mid, tc::BM));
+    int k = mid;
+    if (x_ds) {
+        A.kb_split = mid / tc::BK;
+        A.mode1 = 0;
+        SSG_TRY(make_tmap_2d_bf16(&A.map[1], x_ds, (uint64_t)m, (uint64_t)cin_ds, (uint64_t)cin_ds, tc::BM));
+        k += cin_ds;
+    }
+    tc::StagedEpi epi;
+    memset(&epi, 0, sizeof(epi));
+    epi.bias = bias;
+    epi.relu = 1;
+    epi.has_res = residual != nullptr;
+    epi.bias2 = bias_next;
+    epi.n2 = n2;
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapR, residual ? residual : y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapW2, w_next, (uint64_t)n2, (uint64_t)cout, (uint64_t)cout, (uint32_t)n2));
+    SSG_TRY(make_tmap_2d_bf16(&epi.mapC2, t1_next, (uint64_t)m, (uint64_t)n2, (uint64_t)n2, tc::BM));
+    return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_CHAIN>(A, m, w, cout, k, epi, st);
+}
+
+// the chained kernel is used for the blocks of layer 1 unless SSG_CONV_CHAIN=0
+bool conv_chain_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SSG_CONV_CHAIN"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 // tile geometry of a 128-pixel M tile on an [H, W] output map (W divides 128, H*W multiple or divisor of 128)
 static int tile_geometry(int H, int W, int* bw, int* bh, int* bb, int* tiles_per_img) {
     if (W <= 0 || 128 % W) return ssg_set_error(SSG_ERR_INVALID, "conv3x3: width %d does not divide 128", W);

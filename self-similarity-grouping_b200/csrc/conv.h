@@ -25,6 +25,10 @@ int fold_bn_stem(const float* w, const float* gamma, const float* beta, const fl
 int conv_stem_windows64(const void* P, int images, const void* w256, const float* bias, void* y, cudaStream_t st,
                         void* pool_out = nullptr);
 bool stem_pool_fused();
+int conv_chain(const void* t2, int B, int H, int W, int mid, const void* x_ds, int cin_ds, const void* w,
+               const float* bias, const void* residual, void* y, const void* w_next, const float* bias_next, int n2,
+               void* t1_next, cudaStream_t st);
+bool conv_chain_enabled();
 int conv_stem_windows(const void* P, int images, const void* w448, const float* bias, void* y, cudaStream_t st);
 int stem_im2col(const float* img, int n, int flip_too, void* out, cudaStream_t st);
 int maxpool3x3s2(const void* x, int B, int H, int W, int C, void* y, cudaStream_t st);

@@ -190,14 +190,22 @@ extern "C" int ssg_embed_load_layer(ssg_embed_plan* p, int idx, const float* d_w
 // One bottleneck block (conv1 1x1 -> conv2 3x3 [stride on it] -> conv3 1x1 + shortcut, ReLU) over NB image-passes.
 // x: input [NB,H,W,C], y: the other ping-pong buffer; on return x holds the output and H, W, C, li are advanced.
 // out (chunked mode, last block of a chunk): the output goes there instead of y, and x / y are left alone.
+// t1_ready (layer 1 with the chained kernel): on entry, true = the previous block's chained launch already wrote this
+// block's conv1 output into p->t1; on return, true = this block did the same for the next one.
 static int run_block(ssg_embed_plan* p, int L, int b, int NB, int fuse_ds, void*& x, void*& y, int& H, int& W, int& C,
-                     int& li, void* out, cudaStream_t st) {
+                     int& li, void* out, cudaStream_t st, bool* t1_ready = nullptr) {
     const int mid = 64 << L, outc = mid * 4;
     const int stride = (b == 0 && L > 0) ? 2 : 1;
     const int OH = H / stride, OW = W / stride;
     const int i1 = li, i2 = li + 1, i3 = li + 2, id = li + 3;
     li += (b == 0) ? 4 : 3;
-    { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
+    const bool have_t1 = t1_ready && *t1_ready;
+    if (t1_ready) *t1_ready = false;
+    if (!have_t1) { SSG_PROF("conv1x1_tc", st); SSG_TRY(conv1x1(x, NB * H * W, C, p->w[i1], p->b[i1], mid, nullptr, 1, p->t1, st)); }
+    // layer 1: conv3 (+ shortcut, ReLU) and the NEXT block's conv1 (index li after the advance above: the next block of
+    // layer 1, or the first block of layer 2) as one launch; its conv2 below reads p->t1 before this block overwrites it
+    const bool chain = L == 0 && t1_ready && !out && conv_chain_enabled() && (b > 0 || fuse_ds) &&
+                       li < (int)specs().size() && specs()[li].k == 1 && specs()[li].cin == outc;
     if (stride == 2 && s2_strided_tma()) {
         { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
     } else if (stride == 2) {
@@ -205,6 +213,18 @@ static int run_block(ssg_embed_plan* p, int L, int b, int NB, int fuse_ds, void*
         { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->planes, NB, OH, OW, mid, 2, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
     } else {
         { SSG_PROF("conv3x3_tc", st); SSG_TRY(conv3x3(p->t1, NB, H, W, mid, 1, p->w[i2], p->b[i2], mid, 1, p->t2, st)); }
+    }
+    if (chain) {
+        const int n2 = specs()[li].cout;
+        SSG_PROF("conv1x1_tc", st);
+        if (b == 0)
+            SSG_TRY(conv_chain(p->t2, NB, OH, OW, mid, x, C, p->wf[L], p->bf[L], nullptr, y, p->w[li], p->b[li], n2, p->t1, st));
+        else
+            SSG_TRY(conv_chain(p->t2, NB, OH, OW, mid, nullptr, 0, p->w[i3], p->b[i3], x, y, p->w[li], p->b[li], n2, p->t1, st));
+        *t1_ready = true;
+        void* t = x; x = y; y = t;
+        H = OH; W = OW; C = outc;
+        return SSG_OK;
     }
     if (b == 0 && fuse_ds) {
         if (out) return ssg_set_error(SSG_ERR_INVALID, "embed: a chunk cannot end on a downsample block");
@@ -389,9 +409,10 @@ static int embed_forward_impl(ssg_embed_plan* p, const float* d_images, const ui
     int H = 64, W = 32, C = 64;
     void *x = p->x, *y = p->y;
     const int blocks[4] = {3, 4, 6, 3};
+    bool t1_ready = false;
     for (int L = 0; L < 4; ++L)
         for (int b = 0; b < blocks[L]; ++b)
-            SSG_TRY(run_block(p, L, b, NB, fuse_ds, x, y, H, W, C, li, nullptr, st));
+            SSG_TRY(run_block(p, L, b, NB, fuse_ds, x, y, H, W, C, li, nullptr, st, &t1_ready));
     (void)sp;
     { SSG_PROF("pooled_tail", st); SSG_TRY(pooled_tail(x, n, num_split, eval_mode, flip, d_feat, bank_stride, row0, st)); }
     return SSG_OK;

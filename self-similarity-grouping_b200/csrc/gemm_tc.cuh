@@ -50,6 +50,11 @@ struct StagedEpi {
     int relu;
     int has_res;
     void* pool_out;        // VAR_BRES only: != NULL fuses the 3x3/2 max-pool behind the stem (the conv map is not stored)
+    // VAR_CHAIN only: the NEXT 1x1 convolution (the following block's conv1) fused behind this one
+    CUtensorMap mapW2;     // its weights [n2, 256] bf16, box 64 cols x n2 rows, 128B swizzle
+    CUtensorMap mapC2;     // its output  [M, n2] bf16, box 64 cols x 128 rows
+    const float* bias2;    // [n2]
+    int n2;                // 64 or 128 output channels
     static constexpr bool kSkippable = false;   // every tile is computed
 };
 
@@ -78,7 +83,19 @@ struct StagedEpi {
 //             24 KB).  The plain KHS kernel re-fetches the 72 KB of weights for every 128-pixel tile, which is half of
 //             its L2 -> shared-memory traffic (144 KB per tile at ~42 B/clk/SM: the launch is L2-bandwidth bound).
 //             Same MMA sequence, hence the same bits.
-constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3, VAR_KHSB = 4;
+//   VAR_CHAIN (BN = 256 = all output channels of a layer-1 block; K = 64 or 128): conv3 (+ residual or K-concatenated
+//             downsample, ReLU) AND the next block's conv1 in one kernel.  The bf16 output sub-tiles that the epilogue
+//             stages for the TMA store are valid 128B-swizzled K-major A operands: after sub-tile j (64 output channels
+//             = K block j of the next 1x1) is staged, the MMA warp issues D2 += ysub_j * W1'_j^T into a second TMEM
+//             region while the TMA store drains the same buffer; when the four sub-tiles are done the epilogue drains
+//             D2 (+bias', ReLU) and stores t1' -- the next block never re-reads y for its conv1 (512 of layer 1's
+//             2048 HBM bytes per pixel and block) and one launch per block disappears.  Both weight matrices
+//             (W3: 32 / 64 KB, W1': 32 / 64 KB) are resident in shared memory, the operand stages carry A only, the
+//             accumulator is single-buffered (the kernel is HBM bound: ~6 K cycles per tile against ~0.5 K of MMAs).
+//             Same MMA order per output element as the two separate launches, hence the same bits.
+constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3, VAR_KHSB = 4, VAR_CHAIN = 5;
+constexpr int CHAIN_WRES_BYTES = 96 * 1024;  // resident W3 + W1' (never both 64 KB)
+constexpr int CHAIN_D2_COL = 256;            // TMEM column of the second accumulator
 constexpr int STEM_ROW_BYTES = 64 * 64;     // one input row of a stem tile in shared memory: 64 windows x 64 B
 constexpr int BRES_K = 256;
 
@@ -92,28 +109,30 @@ struct SmemLayout {
     static constexpr bool PLANES = VAR == VAR_BRESP;
     static constexpr bool BRES = VAR == VAR_BRES || PLANES, RRING = VAR == VAR_RRING;
     static constexpr bool KRES = VAR == VAR_KHSB;                // KHS + resident weights
+    static constexpr bool CHAIN = VAR == VAR_CHAIN;              // conv3 + next conv1
     static constexpr int RSLOTS = 3;                             // residual ring slots (RRING)
     static constexpr int A_BYTES = PLANES ? 2 * 5 * STEM_ROW_BYTES : (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
-    static constexpr int B_BYTES = (BRES || KRES) ? 0 : (KHS ? 3 : 1) * B_TILE;
+    static constexpr int B_BYTES = (BRES || KRES || CHAIN) ? 0 : (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
     static constexpr int NBUF = EPI2 ? 2 : (NSUB > 2 ? 2 : NSUB);   // output sub-buffers
-    static constexpr bool HAS_R = BN <= 128 || RRING;            // residual staging available
+    static constexpr bool HAS_R = BN <= 128 || RRING || CHAIN;   // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
     static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
-    static constexpr int RSTAGE_BYTES = RRING ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
-    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KRES ? 4 : KHS ? 3 :
+    static constexpr int RSTAGE_BYTES = (RRING || CHAIN) ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
+    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KRES ? 4 : CHAIN ? 2 : KHS ? 3 :
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
-    static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : KRES ? 9 * B_TILE : 0;
+    static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : KRES ? 9 * B_TILE : CHAIN ? CHAIN_WRES_BYTES : 0;
     static constexpr int C_OFFSET = BRES_OFFSET + BRES_BYTES;    // output staging, then the residual staging buffers
     static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + RSTAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
     static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
     static_assert(!(KRES && (!KHS || !STAGED || BN != 64)), "VAR_KHSB is the 64-channel kernel-row-sharing kernel");
+    static_assert(!(CHAIN && (KHS || !STAGED || BN != 256 || EPI2)), "VAR_CHAIN is the layer-1 conv3 + conv1 kernel");
     static_assert(!(EPI2 && (BRES || !STAGED)), "EPI2 is a variant of the generic staged epilogue");
     static_assert(TOTAL <= 232448, "shared-memory layout exceeds 227 KB");
 };
@@ -143,8 +162,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     uint64_t* tfull_bar = empty_bar + STAGES;     // [2] accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;         // [2] accumulator drained
     uint64_t* res_bar = tempty_bar + 2;           // [6] residual tile / sub-tile landed (staged epilogue)
-    uint64_t* bres_bar = res_bar + 6;             // [1] resident B operand landed (VAR_BRES)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    uint64_t* bres_bar = res_bar + 6;             // [1] resident B operand landed (VAR_BRES / KHSB / CHAIN)
+    uint64_t* ysub_full = bres_bar + 1;           // [2] VAR_CHAIN: staged output sub-tile ready as an A operand
+    uint64_t* ysub_free = ysub_full + 2;          // [2] VAR_CHAIN: the MMAs reading that buffer have retired
+    uint64_t* d2_full = ysub_free + 2;            // [1] VAR_CHAIN: second accumulator complete
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d2_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
@@ -157,6 +179,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
         for (int s = 0; s < 6; ++s) mbar_init(&res_bar[s], 1);
         mbar_init(bres_bar, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&ysub_full[s], 1); mbar_init(&ysub_free[s], 1); }
+        mbar_init(d2_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -202,6 +226,15 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                     tma_load_2d(bres + kb * L::B_TILE, &mapB, bres_bar, kb * BK, 0);
                     tma_load_2d(bres + kb * L::B_TILE + L::B_TILE / 2, &mapB, bres_bar, kb * BK + 32, 0);
                 }
+            }
+            if constexpr (L::CHAIN) {
+                // W3 [256, K] as K/64 blocks of [256 x 64] (32 KB each), then W1' [n2, 256] as four [n2 x 64] K blocks
+                unsigned char* wres = smem + L::BRES_OFFSET;
+                const int n2 = epi.n2;
+                mbar_arrive_expect_tx(bres_bar, (uint32_t)(num_k_blocks * L::B_TILE + 4 * n2 * 128));
+                for (int kb = 0; kb < num_k_blocks; ++kb) tma_load_2d(wres + kb * L::B_TILE, &mapB, bres_bar, kb * BK, 0);
+                for (int j = 0; j < 4; ++j)
+                    tma_load_2d(wres + num_k_blocks * L::B_TILE + j * n2 * 128, &epi.mapW2, bres_bar, j * BK, 0);
             }
             if constexpr (L::KRES) {
                 // the nine [64, 64] weight tiles (tap t = kh*3 + kw at K offset t*64: one channel block), once
@@ -261,7 +294,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         tma_load_4d(sa, &A.map[A.tap_plane[tap]], &full_bar[stage], cb * BK, A.tap_dw[tap],
                                     h0 * A.hmul + A.tap_dh[tap], b0);
                     }
-                    if constexpr (L::BRES) {
+                    if constexpr (L::BRES || L::CHAIN) {
                         // weights are resident: the stage carries A only
                     } else if (A.mode == 3) {
                         tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
@@ -280,9 +313,58 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        if constexpr (L::BRES || L::KRES) {
+        if constexpr (L::BRES || L::KRES || L::CHAIN) {
             mbar_wait(bres_bar, 0);                           // resident weights have landed
             tc_fence_after();
+        }
+        if constexpr (L::CHAIN) {
+            // per tile: D1 = A * W3^T (single accumulator at column 0), then for each staged output sub-tile j
+            // D2 (+)= ysub_j * W1'_j^T (column CHAIN_D2_COL).  Staging step g = it * steps + j uses buffer g & 1.
+            const uint32_t idesc2 = make_idesc_bf16_f32(BM, epi.n2);
+            const uint32_t wres = smem_u32(smem + L::BRES_OFFSET);
+            const uint32_t w2 = wres + (uint32_t)(num_k_blocks * L::B_TILE);
+            const uint32_t cs = smem_u32(smem + L::C_OFFSET);
+            const uint32_t w2_blk = (uint32_t)(epi.n2 * 128);
+            const int steps = 4 + epi.n2 / 64;
+            uint32_t yph = 0;                                  // phase bit of ysub_full[b] in bit b
+            int it = 0;
+            for (int t = t_begin; t < t_end; t += t_step, ++it) {
+                mbar_wait(&tempty_bar[0], (uint32_t)((it & 1) ^ 1));    // epilogue has drained D1 of the previous tile
+                tc_fence_after();
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t da = make_desc_k_sw128(smem_u32(smem + stage * L::STAGE_BYTES));
+                        const uint64_t db = make_desc_k_sw128(wres + (uint32_t)(kb * L::B_TILE));
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == num_k_blocks - 1) umma_commit(&tfull_bar[0]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                for (int j = 0; j < 4; ++j) {
+                    const int b = (it * steps + j) & 1;
+                    mbar_wait(&ysub_full[b], (yph >> b) & 1u);
+                    yph ^= (1u << b);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t da = make_desc_k_sw128(cs + (uint32_t)(b * L::SUB_BYTES));
+                        const uint64_t db = make_desc_k_sw128(w2 + (uint32_t)j * w2_blk);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_f16(tmem_base + (uint32_t)CHAIN_D2_COL, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc2,
+                                     (j > 0 || k > 0) ? 1u : 0u);
+                        umma_commit(&ysub_free[b]);                       // staging buffer b may be overwritten
+                        if (j == 3) umma_commit(d2_full);                  // second accumulator complete
+                    }
+                    __syncwarp();
+                }
+            }
+            t_begin = t_end;                                              // nothing left for the generic loop below
         }
         for (int t = t_begin; t < t_end; t += t_step) {
             if constexpr (Epi::kSkippable) {
@@ -591,7 +673,114 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 if (leader) tma_store_wait_all();
                 t_begin = t_end;                                          // nothing left for the loop below
             }
-            if constexpr (L::RRING) {
+            if constexpr (L::CHAIN) {
+                // ---- conv3 + next conv1.  Per tile: four output sub-tiles (bias, residual, ReLU -> bf16 staging -> TMA
+                // store AND A operand of the second GEMM), then n2/64 sub-tiles of the second accumulator (bias', ReLU
+                // -> staging -> TMA store through mapC2).  Staging step g = it * steps + j uses buffer g & 1; a buffer
+                // is re-written once the TMA store issued from it two steps ago has been read out AND -- if that step
+                // was an output sub-tile -- the MMAs reading it have retired (ysub_free).
+                const int n2 = epi.n2, steps = 4 + n2 / 64;
+                __shared__ float s_bias2[128];
+                if (epi_tid < BN) s_bias[epi_tid] = epi.bias[epi_tid];
+                if (epi_tid < n2) s_bias2[epi_tid] = epi.bias2[epi_tid];
+                if (leader && has_res) {
+                    for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
+                }
+                uint32_t fph = 0, pend = 0;                               // leader only: phase / pending bits per buffer
+                epi_bar_sync();                                           // bias rows visible
+                int itc = 0;
+                for (int t = t_begin; t < t_end; t += t_step, ++itc) {
+                    int m_blk, n_blk;
+                    tile_coords(t, m_blk, n_blk);
+                    mbar_wait(&tfull_bar[0], (uint32_t)(itc & 1));
+                    tc_fence_after();
+#pragma unroll 1
+                    for (int j = 0; j < steps; ++j) {
+                        const int b = (itc * steps + j) & 1;
+                        if (leader) {
+                            tma_store_wait_read<1>();                     // the store issued from buffer b has been read
+                            if (pend & (1u << b)) {                       // ... and the MMAs that read it have retired
+                                mbar_wait(&ysub_free[b], (fph >> b) & 1u);
+                                fph ^= (1u << b);
+                                pend &= ~(1u << b);
+                            }
+                        }
+                        if (j == 4) {                                     // (first sub-tile of the second accumulator)
+                            mbar_wait(d2_full, (uint32_t)(itc & 1));
+                            tc_fence_after();
+                        }
+                        epi_bar_sync();
+                        unsigned char* csub = c_s + b * L::SUB_BYTES + row_off;
+                        const bool first = j < 4;
+                        const unsigned char* rsub = nullptr;
+                        if (first) {
+                            const int s = itc * 4 + j;
+                            if (leader && has_res) load_residual_sub(s + RS - 1);
+                            if (has_res) {
+                                mbar_wait(&res_bar[s % RS], (uint32_t)((s / RS) & 1));
+                                rsub = r_s + (s % RS) * L::SUB_BYTES + row_off;
+                            }
+                        }
+                        const int c = 2 * (first ? j : j - 4) + grp;      // 32-column chunk of the accumulator
+                        const float* sb = first ? s_bias : s_bias2;
+                        uint32_t v[32];
+                        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((first ? 0 : CHAIN_D2_COL) + c * 32), v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {                  // 8 columns = one 16-byte chunk
+                            const uint32_t chunk = ((uint32_t)(grp * 4 + gq) ^ sw) << 4;
+                            float f[8];
+                            const float4 b0 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * gq);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sb + c * 32 + 8 * gq + 4);
+                            f[0] = __uint_as_float(v[8 * gq + 0]) + b0.x; f[1] = __uint_as_float(v[8 * gq + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[8 * gq + 2]) + b0.z; f[3] = __uint_as_float(v[8 * gq + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[8 * gq + 4]) + b1.x; f[5] = __uint_as_float(v[8 * gq + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[8 * gq + 6]) + b1.z; f[7] = __uint_as_float(v[8 * gq + 7]) + b1.w;
+                            if (rsub != nullptr) {
+                                const uint4 rr = *reinterpret_cast<const uint4*>(rsub + chunk);
+                                const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&rr);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 ff = __bfloat1622float2(rp[e]);
+                                    f[2 * e] += ff.x;
+                                    f[2 * e + 1] += ff.y;
+                                }
+                            }
+                            if (!first || epi.relu) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                            }
+                            uint4 pk;
+                            __nv_bfloat162* pp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) pp[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                            *reinterpret_cast<uint4*>(csub + chunk) = pk;
+                        }
+                        // TMEM reads ordered before what follows the barriers below: j == 3 hands D1 back to the MMA warp,
+                        // the last step of a tile precedes the next tile's first write to D2
+                        tc_fence_before();
+                        if (j == 3) {
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tempty_bar[0]);
+                        }
+                        fence_proxy_async();                              // smem writes -> visible to TMA and the tensor core
+                        epi_bar_sync();
+                        if (leader) {
+                            if (first) {
+                                tma_store_2d(&epi.mapC, c_s + b * L::SUB_BYTES, j * 64, m_blk * BM);
+                                tma_store_commit();
+                                mbar_arrive(&ysub_full[b]);               // K block j of the second GEMM is staged
+                                pend |= (1u << b);
+                            } else {
+                                tma_store_2d(&epi.mapC2, c_s + b * L::SUB_BYTES, (j - 4) * 64, m_blk * BM);
+                                tma_store_commit();
+                            }
+                        }
+                    }
+                }
+                if (leader) tma_store_wait_all();
+                t_begin = t_end;                                          // nothing left for the loop below
+            } else if constexpr (L::RRING) {
                 if (leader && has_res && !EPI2) {
                     for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
                 }
@@ -694,6 +883,12 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     using L = SmemLayout<BN, STAGED, KHS, VAR, EPI2>;
     if ((VAR == VAR_BRES || VAR == VAR_BRESP) && (A.mode != 3 || n != BN || k != BRES_K))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
+    if constexpr (VAR == VAR_CHAIN) {
+        if (n != BN || k % BK || k / BK < 1 || (epi.n2 != 64 && epi.n2 != 128) ||
+            (k / BK) * SmemLayout<BN, STAGED, KHS, VAR, EPI2>::B_TILE + 4 * epi.n2 * 128 > CHAIN_WRES_BYTES)
+            return ssg_set_error(SSG_ERR_INVALID, "gemm: the chained kernel needs N = 256, K = 64 / 128 and resident weights "
+                                 "within %d bytes (N=%d, K=%d, n2=%d)", CHAIN_WRES_BYTES, n, k, epi.n2);
+    }
     if (VAR == VAR_KHSB && (n != BN || k != 9 * BK || A.cblks != 1))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-weight KHS variant needs C = N = 64 (N=%d, K=%d)", n, k);
     // K need not be a multiple of BK: the last K block reads past the end and TMA zero-fills it (both operands)

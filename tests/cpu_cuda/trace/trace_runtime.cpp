@@ -65,6 +65,16 @@ int conv_fused_ds(const void* t2, const void* x, int B, int H, int W, int mid, i
     logf("conv_fused_ds t2=%lld x=%lld B=%d H=%d W=%d mid=%d cin=%d stride=%d w=%lld b=%lld cout=%d y=%lld", off(t2), off(x), B, H, W, mid, cin, stride, off(w), off(bias), cout, off(y));
     return 0;
 }
+// the chained launch is logged as the two launches it replaces, in their original order (the next block then skips its
+// own conv1): the default trace stays comparable with the validated revision line by line
+bool conv_chain_enabled() { const char* e = getenv("SSG_CONV_CHAIN"); return !e || atoi(e) != 0; }
+int conv_chain(const void* t2, int B, int H, int W, int mid, const void* x_ds, int cin_ds, const void* w, const float* bias,
+               const void* residual, void* y, const void* w_next, const float* bias_next, int n2, void* t1_next, cudaStream_t st) {
+    const int m = B * H * W;
+    if (x_ds) conv_fused_ds(t2, x_ds, B, H, W, mid, cin_ds, 1, w, bias, 256, y, st);
+    else conv1x1(t2, m, mid, w, bias, 256, residual, 1, y, st);
+    return conv1x1(y, m, 256, w_next, bias_next, n2, nullptr, 1, t1_next, st);
+}
 int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void* w, const float* bias, int cout, int relu, void* y, cudaStream_t) {
     logf("conv3x3 x=%lld B=%d H=%d W=%d cin=%d stride=%d w=%lld b=%lld cout=%d relu=%d y=%lld", off(x), B, H, W, cin, stride, off(w), off(bias), cout, relu, off(y));
     return 0;

@@ -160,7 +160,9 @@ def test_whole_trunk_against_reference_golden_and_variants_bit_identical(tmp_pat
                 ("epi2_chunk", {"SSG_CONV_EPI2": "1", "SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "0"}),
                 ("chunk_graph", {"SSG_L2_CHUNK": "1", "SSG_L2_GRAPH": "1"}),
                 ("plain_stem", {"SSG_STEM_BRES": "0", "SSG_STEM_POOL": "0", "SSG_CONV_BN256_RES": "0"}),
-                ("khs_streamed_weights", {"SSG_KHS_BRES": "0"}))            # default: VAR_KHSB (weights resident)
+                ("khs_streamed_weights", {"SSG_KHS_BRES": "0"}),            # default: VAR_KHSB (weights resident)
+                ("no_chain", {"SSG_CONV_CHAIN": "0"}),                      # default: layer-1 conv3 + next conv1 chained
+                ("no_chain_reverse", {"SSG_CONV_CHAIN": "0", "SSG_EMU_SCHED": "reverse"}))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # one subprocess each
         first = pool.submit(_embed, tmp_path, "default", {})
         rest = [(name, pool.submit(_embed, tmp_path, name, dict({"SSG_EMU_ASYNC": "late"}, **env))) for name, env in variants]

@@ -315,11 +315,17 @@ def test_conv_variants_are_bit_identical(tmp_path):
         "plan = ssg_b200.EmbedPlan(16); plan.load_model(R.build_model(2, 0))\n"
         "out = plan.forward(R.synth_images(9, 11).cuda(), 2); torch.cuda.synchronize()\n"
         "np.save(sys.argv[1], out.cpu().numpy())\n" % ([os.path.join(root, "self-similarity-grouping_b200"), root],))
-    env = dict(os.environ, SSG_STEM_BRES="0", SSG_STEM_POOL="0", SSG_CONV_BN256_RES="0")
-    out_file = str(tmp_path / "plain.npy")
-    subprocess.run([sys.executable, "-c", script, out_file], check=True, env=env, timeout=300)
     plan = ssg_b200.EmbedPlan(16)
     plan.load_model(R.build_model(2, 0))
     got = plan.forward(R.synth_images(9, 11).cuda(), 2)
     torch.cuda.synchronize()
-    assert np.array_equal(got.cpu().numpy(), np.load(out_file))
+    got = got.cpu().numpy()
+    # round 2: the layer-1 chained kernel (conv3 + next conv1 in one launch, SSG_CONV_CHAIN) and the kernel-row-sharing
+    # 3x3 with resident weights (SSG_KHS_BRES) are defaults; their plain predecessors must give the same bits
+    for name, switches in (("plain", dict(SSG_STEM_BRES="0", SSG_STEM_POOL="0", SSG_CONV_BN256_RES="0")),
+                           ("no_chain", dict(SSG_CONV_CHAIN="0")),
+                           ("khs_streamed", dict(SSG_KHS_BRES="0")),
+                           ("round1_default", dict(SSG_CONV_CHAIN="0", SSG_KHS_BRES="0"))):
+        out_file = str(tmp_path / (name + ".npy"))
+        subprocess.run([sys.executable, "-c", script, out_file], check=True, env=dict(os.environ, **switches), timeout=300)
+        assert np.array_equal(got, np.load(out_file)), name
