@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--sparse-finish", action="store_true",
                     help="never materialise final_dist (CSR over the touched pairs, certified "
                          "eps + DBSCAN on it; DESIGN.md 3.6) instead of the dense N x N float64 matrix")
+    ap.add_argument("--no-reference-api", action="store_true",
+                    help="skip the e2e leg through the reference-shaped API (dict of CPU tensors -> numpy N x N -> labels)")
+    ap.add_argument("--no-u8", action="store_true", help="skip the uint8-pixel e2e leg (ssg_embed_forward_u8)")
     ap.add_argument("--quick", action="store_true",
                     help="profiling runs (ncu): exactly --warmup warm-up steps, no e2e leg, no CPU baseline")
     return ap.parse_args()
@@ -170,55 +173,171 @@ def cpu_embed_sample(n_img, seed=1234, budget_s=10.0):
     return time.perf_counter() - t0, done
 
 
+def fit_stage_time(points):
+    """Least-squares fit t(N) = a*N^2 + c*N through the measured (N, seconds) points of the re-rank + eps + DBSCAN
+    stage (t = a*N^2*d + b*N^2 + c*N; d is fixed at 2048 here, so the two N^2 terms are one
+    coefficient).  Returns (a, c); c is clamped at 0 (a negative linear term would be noise)."""
+    import numpy as np
+    n = np.array([p[0] for p in points], dtype=np.float64)
+    t = np.array([p[1] for p in points], dtype=np.float64)
+    if len(set(n.tolist())) < 2:
+        return float((t / (n * n)).mean()), 0.0
+    A = np.stack([n * n, n], 1)
+    (a, c), *_ = np.linalg.lstsq(A, t, rcond=None)
+    if c < 0 or a <= 0:
+        a, c = float((t * n * n).sum() / (n ** 4).sum()), 0.0
+    return float(a), float(c)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # every step is a bounded sample; the samples are sized so that the whole run stays within ~4 minutes whatever
-    # --steps is: a 512-row probe (also the warm-up) gives the cost of the O(n^2) stage, the sample is the largest
-    # multiple of 64 rows (<= --cpu-sample) whose projected time fits the per-step budget
-    per_step = min(30.0, 240.0 / max(args.steps, 1))
-    embed_budget = min(10.0, per_step / 3.0)
+    # Every step is a bounded sample.  The O(N^2) stage is timed at three sizes n0, 2*n0, 4*n0 (one size per step, in
+    # turn) and extrapolated to the full N with the fit of BASELINE.md 3.3; n0 is sized from a 512-row probe (also the
+    # warm-up) so that the whole run stays within ~4 minutes whatever --steps is (n0 = 1024 -> {1024, 2048, 4096}, the
+    # sizes BASELINE.md names, when the budget allows: e.g. --steps 3).
+    budget = 240.0
+    embed_budget = min(10.0, 0.25 * budget / max(args.steps, 1))
     t_probe, _ = cpu_cycle_sample(512)
-    n_s = int(512.0 * ((per_step - embed_budget) / max(t_probe, 1e-3)) ** 0.5) // 64 * 64
-    n_s = max(512, min(args.cpu_sample, n_s))
-    times, etimes, eimgs_all = [], [], []
+    c_probe = max(t_probe, 1e-3) / 512.0 ** 2
+    cycles = max(args.steps, 1) / 3.0
+    n0 = int(((budget - embed_budget * args.steps) / (21.0 * cycles * c_probe)) ** 0.5) // 64 * 64
+    n0 = max(256, min(1024, n0))
+    sizes = [n0, 2 * n0, 4 * n0]
+    points, etimes, eimgs_all = [(512, t_probe)], [], []
+    step_s = []
     kind = "port"
-    for _ in range(args.steps):
+    for i in range(args.steps):
+        n_s = sizes[i % 3]
         t, kind = cpu_cycle_sample(n_s)
         esec, eimgs = cpu_embed_sample(args.cpu_embed_sample, budget_s=embed_budget)
-        times.append(t)
+        points.append((n_s, t))
         etimes.append(esec)
         eimgs_all.append(eimgs)
-    sec = sum(times) / len(times)
-    stage_val = n_s * n_s / sec / 1e6
+        step_s.append(t + esec)
+    a, c = fit_stage_time(points)
+    t_full = a * args.n ** 2 + c * args.n                      # one bank at the full size, extrapolated
+    stage_val = args.n ** 2 / t_full / 1e6
+    measured = {}
+    for n_s, t in points:
+        measured.setdefault(n_s, []).append(t)
+    measured_rows = ", ".join("N=%d: %.2f s (%.3f Mpairs/s)" % (k, sum(v) / len(v), k * k / (sum(v) / len(v)) / 1e6)
+                              for k, v in sorted(measured.items()))
     img_rate = sum(eimgs_all) / sum(etimes)
-    esec, eimgs = etimes[-1], eimgs_all[-1]
+    eimgs = eimgs_all[-1]
     # the same metric as the GPU arm: whole-cycle Mpairs/s at the full workload, from the two measured stage rates
     val = cycle_mpairs(args.n, args.banks, img_rate, stage_val)
-    sample = ("per step: 1 bank, N=Ns=%d rows of the %d-row workload, d=%d, fp16 reference arithmetic (re-rank + eps + "
-              "DBSCAN: %.3f Mpairs/s) and %d images through the torch CPU ResNet-50 x2 passes (%.1f images/s); value = "
-              "banks*N^2 / (2N / images_per_s + banks*N^2 / stage_pairs_per_s) at N=%d, banks=%d"
-              % (n_s, args.n, D, stage_val, eimgs, img_rate, args.n, args.banks))
+    sample = ("re-rank + eps + DBSCAN of ONE bank (fp16 reference arithmetic, Ns=N, d=%d) measured at %s; fit "
+              "t(N) = %.3e*N^2 + %.3e*N -> EXTRAPOLATED to N=%d: %.0f s per bank = %.3f Mpairs/s; embedding: %d images "
+              "per step through the torch CPU ResNet-50 x2 passes (%.1f images/s); value = banks*N^2 / (2N / "
+              "images_per_s + banks*N^2 / stage_pairs_per_s) at N=%d, banks=%d"
+              % (D, measured_rows, a, c, args.n, t_full, stage_val, eimgs, img_rate, args.n, args.banks))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": (sec + sum(etimes) / len(etimes)) * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": sum(step_s) / len(step_s) * 1e3, "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None, "dtype": "f16/f64 (numpy/scipy/sklearn)", "data": "synthetic",
         "config": {"workload": "configs[1]: N=Ns=%d synthetic, pseudo-label cycle (re-rank k1=20 k2=6 lambda=0.1 -> eps "
                                "rho=1.6e-3 -> DBSCAN min_samples=4); each step is a bounded sample of it: %s"
                                % (args.n, sample),
-                   "value_is": "whole-cycle Mpairs/s on the host cores, extrapolated from the two measured stage rates "
-                               "(see cpu_baseline.sample); stage rates under 'rerank' and 'embed'"},
+                   "value_is": "whole-cycle Mpairs/s on the host cores, EXTRAPOLATED from the measured small-N stage "
+                               "times (three-size fit, BASELINE.md 3.3) and the measured embedding rate; the measured "
+                               "rows are in cpu_baseline.sample; stage rates under 'rerank' and 'embed'"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample,
-                         "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8"},
+                         "fit": {"a_s_per_pair": a, "c_s_per_row": c, "points": [[int(n_), float(t_)] for n_, t_ in points]},
+                         "note": "cdist/numpy loops are single-threaded; sklearn DBSCAN uses n_jobs=8; torch CPU conv uses "
+                                 "all %d host threads" % (os.cpu_count() or 1)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "rerank": {"value": stage_val, "unit": UNIT_STAGE, "ms_per_step": sec * 1e3},
+        "rerank": {"value": stage_val, "unit": UNIT_STAGE, "ms_per_step": t_full * args.banks * 1e3,
+                   "extrapolated": True},
         "embed": {"value": img_rate, "unit": "images/s (two forward passes per image)",
                   "cores": os.cpu_count(), "sample": "%d images, torch CPU fp32, all host threads" % eimgs},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+
+# ------------------------------------------------------------------------------------------- parity gate
+def parity_gate(dev_index):
+    """no number is reported unless the CUDA path reproduces the oracle on a small case.
+    (1) re-rank -> eps -> DBSCAN on 384 synthetic feature rows against the oracle restatement (final_dist <= 1e-4,
+    eps to 1e-12, labels bit-exact); (2) the embedding trunk on the reference's 4 golden images (relative error of
+    every bank <= 8e-3).  The images -> labels comparison against the unmodified reference (512 + 384 images) is
+    tests/test_gpu_whole_path.py; its last measured numbers are copied from profiles/ into `result`."""
+    import numpy as np
+    import torch
+    import ssg_b200
+    from oracle import ssg_oracle as O, resnet_oracle as R
+    n, ns, d, lam, rho = 384, 256, 256, 0.1, 1.6e-2
+    tgt, _ = O.synth_features(n, d, 0)
+    src, _ = O.synth_features(ns, d, 1, noise=0.6)
+    dev = torch.device("cuda", dev_index)
+    _, f = ssg_b200.re_ranking_device(torch.from_numpy(src).to(dev), torch.from_numpy(tgt).to(dev), lambda_value=lam,
+                                      dist_mode=1)
+    plan = ssg_b200.ClusterPlan(n, 0, dev_index)
+    eps, _ = plan.eps(f, rho)
+    labels, _ = plan.dbscan(f, eps, 4)
+    fh = f.cpu().numpy()
+    _, f_ref = O.re_ranking(src, tgt, lambda_value=lam, mode="f32")
+    err = float(np.abs(fh - f_ref).max())
+    eps_ref = O.eps_estimate(fh, rho)
+    labels_ok = bool(np.array_equal(labels.cpu().numpy(), O.dbscan_dfs(fh, eps, 4)))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "embed_4img.npz"))
+    imgs = R.synth_images(int(g["n_img"]), int(g["seed_img"]))
+    model = R.build_model(2, int(g["weight_seed"]))
+    names = ["im%03d" % i for i in range(imgs.shape[0])]
+    feats, _ = ssg_b200.extract_features(model, [(imgs, names, [0] * len(names), [0] * len(names))], for_eval=False)
+    rel = max(float((feats[k][b] - torch.from_numpy(g["list_S2"][b, i])).norm()) for i, k in enumerate(names)
+              for b in range(3))
+    gate = {"final_dist_max_abs_err": err, "final_dist_tol": 1e-4, "eps_rel_err": abs(eps - eps_ref) / eps_ref,
+            "labels_bit_exact": labels_ok, "embed_rel_err": rel, "embed_tol": 8e-3}
+    gate["ok"] = bool(err <= 1e-4 and gate["eps_rel_err"] <= 1e-12 and labels_ok and rel <= 8e-3)
+    return gate
+
+
+def reference_api_cycle(model, host_tgt, host_src, num_split, batch):
+    """One cycle through the REFERENCE-SHAPED API, as the unmodified driver calls it (selftraining.py:189-222):
+    reid.evaluators.extract_features over a loader of host batches -> OrderedDict of per-image CPU tensors -> the
+    driver's bank re-stacking -> reid.rerank.re_ranking (numpy in, N x N float64 numpy out) -> eps
+    (selftraining.py:289-293 through reid.cluster.eps_estimate) -> reid.rerank.DBSCAN.fit_predict(host matrix).
+    Returns (labels per bank, seconds per part)."""
+    import contextlib
+    import io
+    import time
+    import torch
+    import reid.evaluators as E
+    import reid.rerank as RR
+    from reid.cluster import eps_estimate
+    parts = {}
+    banks = num_split + 1 if num_split > 1 else 1
+    feats = {}
+    t0 = time.perf_counter()
+    for tag, host in (("src", host_src), ("tgt", host_tgt)):
+        cnt = host.shape[0]
+        names = ["%s%06d" % (tag, i) for i in range(cnt)]
+        loader = [(host[i:i + batch], names[i:i + batch], [0] * len(names[i:i + batch]), [0] * len(names[i:i + batch]))
+                  for i in range(0, cnt, batch)]
+        f, _ = E.extract_features(model, loader, print_freq=10 ** 9, for_eval=False)
+        feats[tag] = [torch.cat([f[nm][i].unsqueeze(0) for nm in names], 0) for i in range(banks)]   # selftraining.py:197-209
+    parts["extract_features_and_restack_s"] = time.perf_counter() - t0
+    labels = []
+    t_rr = t_cl = 0.0
+    for b in range(banks):
+        t1 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, final = RR.re_ranking(feats["src"][b].numpy(), feats["tgt"][b].numpy(), lambda_value=LAMBDA)
+        t2 = time.perf_counter()
+        eps = eps_estimate(final, RHO)
+        labels.append(RR.DBSCAN(eps=eps, min_samples=MIN_SAMPLES, metric="precomputed", n_jobs=8).fit_predict(final))
+        t3 = time.perf_counter()
+        t_rr += t2 - t1
+        t_cl += t3 - t2
+        del final
+    parts["re_ranking_s"], parts["eps_dbscan_s"] = t_rr, t_cl
+    parts["total_s"] = time.perf_counter() - t0
+    return labels, parts
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -233,6 +352,21 @@ ALGO = {   # per launch: (bound, algorithmic work as a function of (rows, cols, 
     "row_select": ("hbm", lambda r, c, d: 4.0 * r * c),                 # fp32 distance block read once
     "row_minmax": ("hbm", lambda r, c, d: 4.0 * r * c),
 }
+
+
+def load_whole_path_parity():
+    """Last measured images -> labels parity against the unmodified reference (tests/test_gpu_whole_path.py on a B200)."""
+    path = os.path.join(ROOT, "profiles", "r02_whole_path_parity.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        m = json.load(f)
+    keep = ("feature_rel_err_max", "rank_entry_mismatch", "rank_set_mismatch_rows", "final_within_1e-4", "rho", "ari_vs_f32",
+            "exact_label_fraction_vs_f32", "ari_vs_fp16_ref", "ari_f32_vs_fp16_ref", "eps_rel_err",
+            "reference_under_4e-3_feature_noise")
+    out = {kk: m.get(kk) for kk in keep}
+    out["source"] = "profiles/r02_whole_path_parity.json (N=512 + 384 synthetic identity images, see the test's docstring)"
+    return out
 
 
 def load_peaks():
@@ -304,7 +438,11 @@ def main():
         """selftraining.py:196-218: embed source + target sets, then re-rank / eps / DBSCAN per bank."""
         if record:
             ev[0].record()
-        if with_embed:
+        if with_embed and sharded:
+            # embed this rank's shards straight into the gather buffers; the all-gather of the target banks overlaps the
+            # embedding of the source shard (ssg_b200.dist.embed_and_gather)
+            tf, sf = sdist.embed_and_gather(model, tgt_in, src_in, n, n, num_split, backend, comm)
+        elif with_embed:
             tf = ssg_b200.embed_images(model, tgt_in, num_split, False, args.batch, local)
             sf = ssg_b200.embed_images(model, src_in, num_split, False, args.batch, local)
             tfl, sfl = [tf[b] for b in range(banks)], [sf[b] for b in range(banks)]
@@ -314,7 +452,7 @@ def main():
             ev[1].record()
         if sharded:
             out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, RHO, backend=backend,
-                                                   comm=comm, features=(tf, sf),
+                                                   comm=comm, features_full=(tf, sf),
                                                    shard_finish=True if args.shard_finish else None,
                                                    sparse=True if args.sparse_finish else None)
         else:
@@ -354,6 +492,11 @@ def main():
             _lib.profile(on=False)
         return [float(v) for v in t.tolist()], out, prof
 
+    gate = None
+    if not args.quick:
+        gate = parity_gate(local)
+        if not gate["ok"]:
+            raise SystemExit("bench.py: parity gate FAILED, no number is reported: %s" % json.dumps(gate))
     dev_in = (tgt_img, src_img) if with_embed else (tgt_f, src_f)
     n_warm = args.warmup if args.quick else max(args.warmup, 3)
     for _ in range(n_warm):
@@ -379,6 +522,36 @@ def main():
         h2d = 2 * banks * n * D * 4
     cycle(host_in[0], host_in[1], False)
     (ms_e2e, ms_e2e_embed, ms_e2e_rerank), out_e2e, _ = timed(host_in[0], host_in[1], args.steps)
+
+    # e2e through raw uint8 pixels (ToTensor + Normalize on the device, a quarter of the H2D bytes)
+    e2e_u8 = None
+    if with_embed and not args.no_u8 and not sharded:
+        def to_u8(img):
+            return (img.permute(0, 2, 3, 1) * 50.0 + 128.0).clamp_(0, 255).to(torch.uint8).contiguous()
+        u8_host = (to_u8(tgt_img).cpu().pin_memory(), to_u8(src_img).cpu().pin_memory())
+        ku = max(1, min(args.steps, 5))
+        cycle(u8_host[0], u8_host[1], False)
+        (ms_u8, ms_u8_embed, _), out_u8, _ = timed(u8_host[0], u8_host[1], ku)
+        e2e_u8 = {"value": pairs_per_step * world * ku / (ms_u8 / 1e3) / 1e6, "unit": UNIT, "ms_per_step": ms_u8 / ku,
+                  "embed_ms_per_step": ms_u8_embed / ku, "steps": ku,
+                  "h2d_bytes_per_step": 2 * n * 256 * 128 * 3 * world,
+                  "api": "ssg_b200.embed_images(pinned host uint8 HWC pixels; normalised on the device) + "
+                         "pseudo_label_cycle -> host labels", "clusters": [int(l.max()) + 1 for l in out_u8[0]]}
+        del u8_host
+    # e2e through the reference-shaped API (what the unmodified driver pays): N=1 only, one timed pass after one warm-up
+    ref_api = None
+    if with_embed and world == 1 and not args.no_reference_api:
+        reference_api_cycle(model, host_in[0][:2048], host_in[1][:2048], num_split, args.batch)     # warm-up (plans)
+        torch.cuda.synchronize()
+        lab_api, parts = reference_api_cycle(model, host_in[0], host_in[1], num_split, args.batch)
+        ref_api = {"value": pairs_per_step / parts["total_s"] / 1e6, "unit": UNIT, "ms_per_step": parts["total_s"] * 1e3,
+                   "parts_s": {kk: round(v, 3) for kk, v in parts.items()}, "steps": 1,
+                   "h2d_bytes_per_step": h2d + banks * (2 * n * D * 4 + n * n * 8),
+                   "d2h_bytes_per_step": 2 * banks * n * D * 4 + banks * n * n * (8 + 4) + banks * n * 8,
+                   "api": "reid.evaluators.extract_features(loader of host batches) -> OrderedDict of per-image CPU "
+                          "tensors -> re-stack -> reid.rerank.re_ranking (numpy, N x N float64 + float32 to the host) -> "
+                          "eps -> reid.rerank.DBSCAN.fit_predict(host matrix)",
+                   "labels_equal_device_resident_path": bool(all((a == b).all() for a, b in zip(lab_api, out_e2e[0])))}
 
     labels, eps_list, keep = out
     k = args.steps
@@ -483,8 +656,10 @@ def main():
                        "value_is": "whole-cycle Mpairs/s: banks*N^2 pairs / ms_per_step (images in HBM -> labels); the two "
                                    "stages of the BASELINE metric are under 'embed' (images/s) and 'rerank' (Mpairs/s of "
                                    "that stage alone)",
-                       "parallelism": ("one cycle sharded over %d GPUs: image shards, NCCL all-gather of the feature banks, "
-                                       "row-block distance stage, %s finish"
+                       "parallelism": ("one cycle sharded over %d GPUs: image shards embedded straight into the gather buffer, "
+                                       "in-place NCCL all-gather of the feature banks (the target set's overlaps the "
+                                       "source set's embedding; counted in the embed stage), row-block distance stage, "
+                                       "%s finish"
                                        % (world, "row-sharded" if (args.shard_finish or sdist._shard_finish_default())
                                           else "bank-parallel")) if sharded else
                                       "%d independent replicas (one target set per GPU)" % world,
@@ -497,10 +672,13 @@ def main():
                     "embed_ms_per_step": ms_e2e_embed / k, "h2d_bytes_per_step": h2d_job, "d2h_bytes_per_step": banks * n * 8 * world,
                     "h2d_bytes_per_step_rank0": h2d,
                     "api": "ssg_b200.embed_images(pinned host images) + ssg_b200.pseudo_label_cycle -> host labels"},
+            "e2e_u8": e2e_u8, "e2e_reference_api": ref_api,
             "gpu_launches": int(launches),
             "kernels_ms_per_step": {kk: round(v[0] / k, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
+            "parity_gate": gate,
             "result": {"clusters": [int(l.max()) + 1 for l in labels], "eps": [round(e, 6) for e in eps_list],
+                       "whole_path_parity": load_whole_path_parity(),
                        "kept_images": int(keep.sum()),
                        "rows_recomputed_exactly_last_bank": int(ssg_b200.rerank.get_plan(n, n, D, local).stage(
                            _lib.STAGE_FLAGGED, n)[0]) if mode == _lib.DIST_TENSOR else None},

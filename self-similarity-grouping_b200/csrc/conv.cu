@@ -69,6 +69,13 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_BRES>(A, m, w, cout, k, epi, st);
     }
     if (pool_out) return ssg_set_error(SSG_ERR_UNSUPPORTED, "the fused stem max-pool needs the resident-weight stem kernel");
+    // without a residual the residual buffers of the layout become operand stages (SSG_CONV_NORES=0 disables)
+    static int nores = -1;
+    if (nores < 0) { const char* e = getenv("SSG_CONV_NORES"); nores = e ? atoi(e) : 1; }
+    if (nores && !residual) {
+        if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NORES>(A, m, w, cout, k, epi, st);
+        return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NORES>(A, m, w, cout, k, epi, st);
+    }
     if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     return tc::launch_gemm_op<64, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
 }

@@ -93,7 +93,12 @@ struct StagedEpi {
 //             (W3: 32 / 64 KB, W1': 32 / 64 KB) are resident in shared memory, the operand stages carry A only, the
 //             accumulator is single-buffered (the kernel is HBM bound: ~6 K cycles per tile against ~0.5 K of MMAs).
 //             Same MMA order per output element as the two separate launches, hence the same bits.
-constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3, VAR_KHSB = 4, VAR_CHAIN = 5;
+//   VAR_NORES (BN <= 128, no residual): the two whole-tile residual buffers of the generic layout (32 / 64 KB) become
+//             operand stages -- 6 stages of 32 KB (BN = 128) or 8 of 24 KB (BN = 64) instead of 3 / 5.  ncu (round 2,
+//             profiles/r02d_*): in the 128x128 3x3 launches the MMA warp waits for operands 65 % of the time and the
+//             producer for a free stage, with L2 and DRAM far from saturated -- the loads are latency bound, so bytes
+//             in flight are what counts.  Same MMA sequence, hence the same bits.
+constexpr int VAR_NONE = 0, VAR_BRES = 1, VAR_RRING = 2, VAR_BRESP = 3, VAR_KHSB = 4, VAR_CHAIN = 5, VAR_NORES = 6;
 constexpr int CHAIN_WRES_BYTES = 96 * 1024;  // resident W3 + W1' (never both 64 KB)
 constexpr int CHAIN_D2_COL = 256;            // TMEM column of the second accumulator
 constexpr int STEM_ROW_BYTES = 64 * 64;     // one input row of a stem tile in shared memory: 64 windows x 64 B
@@ -110,6 +115,7 @@ struct SmemLayout {
     static constexpr bool BRES = VAR == VAR_BRES || PLANES, RRING = VAR == VAR_RRING;
     static constexpr bool KRES = VAR == VAR_KHSB;                // KHS + resident weights
     static constexpr bool CHAIN = VAR == VAR_CHAIN;              // conv3 + next conv1
+    static constexpr bool NORES = VAR == VAR_NORES || KHS;       // no residual staging (KHS kernels never have one)
     static constexpr int RSLOTS = 3;                             // residual ring slots (RRING)
     static constexpr int A_BYTES = PLANES ? 2 * 5 * STEM_ROW_BYTES : (KHS ? 192 : BM) * BK * 2;
     static constexpr int B_TILE = BN * BK * 2;
@@ -118,21 +124,28 @@ struct SmemLayout {
     static constexpr int SUB_BYTES = BM * 128;                   // one 128-row x 64-col bf16 sub-tile
     static constexpr int NSUB = BN / 64;
     static constexpr int NBUF = EPI2 ? 2 : (NSUB > 2 ? 2 : NSUB);   // output sub-buffers
-    static constexpr bool HAS_R = BN <= 128 || RRING || CHAIN;   // residual staging available
+    static constexpr bool HAS_R = (BN <= 128 && !NORES) || RRING || CHAIN;   // residual staging available
     static constexpr int C_BYTES = STAGED ? NBUF * SUB_BYTES : 0;
-    static constexpr int R_BYTES = (STAGED && BN <= 128) ? NSUB * SUB_BYTES : 0;   // one residual tile
+    static constexpr int R_BYTES = (STAGED && BN <= 128 && !NORES) ? NSUB * SUB_BYTES : 0;   // one residual tile
     static constexpr int RSTAGE_BYTES = (RRING || CHAIN) ? RSLOTS * SUB_BYTES : 2 * R_BYTES;  // residual staging in total
-    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KRES ? 4 : CHAIN ? 2 : KHS ? 3 :
+    static constexpr int STAGES = PLANES ? 3 : BRES ? 8 : RRING ? 3 : KRES ? 5 : CHAIN ? 2 : KHS ? 4 :
+        VAR == VAR_NORES ? (BN <= 64 ? 8 : 6) :
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
     static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : KRES ? 9 * B_TILE : CHAIN ? CHAIN_WRES_BYTES : 0;
-    static constexpr int C_OFFSET = BRES_OFFSET + BRES_BYTES;    // output staging, then the residual staging buffers
-    static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + RSTAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;        // barriers + alignment slack
+    // output staging, then the residual staging buffers.  VAR_CHAIN puts the output staging FIRST and the resident
+    // weights next to the residual ring, so that the part of the weight region a configuration does not need
+    // (W3 + W1' = 64 KB of the 96) extends the ring: 5 slots instead of 3 (the residual prefetch depth is what bounds
+    // the chained kernel: ncu r02d, 2 x 16 KB in flight against ~3 K cycles of HBM latency)
+    static constexpr int C_OFFSET = CHAIN ? BRES_OFFSET : BRES_OFFSET + BRES_BYTES;
+    static constexpr int W_OFFSET = CHAIN ? BRES_OFFSET + C_BYTES : BRES_OFFSET;
+    static constexpr int BAR_OFFSET = BRES_OFFSET + BRES_BYTES + C_BYTES + RSTAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 384 + 1024;        // barriers (up to 2*8 + 16 of them) + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
     static_assert(!(RRING && (KHS || !STAGED || BN != 256)), "VAR_RRING is the 128x256 residual kernel");
     static_assert(!(KRES && (!KHS || !STAGED || BN != 64)), "VAR_KHSB is the 64-channel kernel-row-sharing kernel");
     static_assert(!(CHAIN && (KHS || !STAGED || BN != 256 || EPI2)), "VAR_CHAIN is the layer-1 conv3 + conv1 kernel");
+    static_assert(!(VAR == VAR_NORES && (KHS || !STAGED || BN > 128 || EPI2)), "VAR_NORES: generic staged kernel, BN <= 128");
     static_assert(!(EPI2 && (BRES || !STAGED)), "EPI2 is a variant of the generic staged epilogue");
     static_assert(TOTAL <= 232448, "shared-memory layout exceeds 227 KB");
 };
@@ -229,7 +242,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             }
             if constexpr (L::CHAIN) {
                 // W3 [256, K] as K/64 blocks of [256 x 64] (32 KB each), then W1' [n2, 256] as four [n2 x 64] K blocks
-                unsigned char* wres = smem + L::BRES_OFFSET;
+                unsigned char* wres = smem + L::W_OFFSET;
                 const int n2 = epi.n2;
                 mbar_arrive_expect_tx(bres_bar, (uint32_t)(num_k_blocks * L::B_TILE + 4 * n2 * 128));
                 for (int kb = 0; kb < num_k_blocks; ++kb) tma_load_2d(wres + kb * L::B_TILE, &mapB, bres_bar, kb * BK, 0);
@@ -321,7 +334,7 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
             // per tile: D1 = A * W3^T (single accumulator at column 0), then for each staged output sub-tile j
             // D2 (+)= ysub_j * W1'_j^T (column CHAIN_D2_COL).  Staging step g = it * steps + j uses buffer g & 1.
             const uint32_t idesc2 = make_idesc_bf16_f32(BM, epi.n2);
-            const uint32_t wres = smem_u32(smem + L::BRES_OFFSET);
+            const uint32_t wres = smem_u32(smem + L::W_OFFSET);
             const uint32_t w2 = wres + (uint32_t)(num_k_blocks * L::B_TILE);
             const uint32_t cs = smem_u32(smem + L::C_OFFSET);
             const uint32_t w2_blk = (uint32_t)(epi.n2 * 128);
@@ -683,8 +696,22 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 __shared__ float s_bias2[128];
                 if (epi_tid < BN) s_bias[epi_tid] = epi.bias[epi_tid];
                 if (epi_tid < n2) s_bias2[epi_tid] = epi.bias2[epi_tid];
+                // residual ring: starts right behind the resident weights and takes what they leave of the pool
+                const int wres_bytes = num_k_blocks * L::B_TILE + 4 * n2 * 128;
+                unsigned char* r_ring = smem + L::W_OFFSET + wres_bytes;
+                int rs_n = (CHAIN_WRES_BYTES - wres_bytes) / L::SUB_BYTES + L::RSLOTS;
+                if (rs_n > 6) rs_n = 6;                                   // res_bar has six slots
+                auto load_res = [&](int s) {                              // sub-tile s of this CTA -> ring slot s % rs_n
+                    const int tile = (int)blockIdx.x + (s / 4) * (int)gridDim.x;
+                    if (tile >= num_tiles) return;
+                    int mb, nb;
+                    tile_coords(tile, mb, nb);
+                    const int slot = s % rs_n;
+                    mbar_arrive_expect_tx(&res_bar[slot], L::SUB_BYTES);
+                    tma_load_2d(r_ring + slot * L::SUB_BYTES, &epi.mapR, &res_bar[slot], (s % 4) * 64, mb * BM);
+                };
                 if (leader && has_res) {
-                    for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
+                    for (int s0 = 0; s0 < rs_n - 1; ++s0) load_res(s0);
                 }
                 uint32_t fph = 0, pend = 0;                               // leader only: phase / pending bits per buffer
                 epi_bar_sync();                                           // bias rows visible
@@ -715,10 +742,11 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         const unsigned char* rsub = nullptr;
                         if (first) {
                             const int s = itc * 4 + j;
-                            if (leader && has_res) load_residual_sub(s + RS - 1);
+                            // every thread is past the barrier above, i.e. done with sub-tile s-1: its slot is free
+                            if (leader && has_res) load_res(s + rs_n - 1);
                             if (has_res) {
-                                mbar_wait(&res_bar[s % RS], (uint32_t)((s / RS) & 1));
-                                rsub = r_s + (s % RS) * L::SUB_BYTES + row_off;
+                                mbar_wait(&res_bar[s % rs_n], (uint32_t)((s / rs_n) & 1));
+                                rsub = r_ring + (s % rs_n) * L::SUB_BYTES + row_off;
                             }
                         }
                         const int c = 2 * (first ? j : j - 4) + grp;      // 32-column chunk of the accumulator

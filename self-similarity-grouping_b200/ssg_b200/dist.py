@@ -66,6 +66,48 @@ class Comm(object):
             parts.append(out[r * m: r * m + (hi - lo)])
         return torch.cat(parts, 0).movedim(0, dim).contiguous()
 
+    # ---- feature banks: [banks, rows, d] gathered along the row axis without staging copies.  The gather buffer is
+    # [banks, world * m, d] (m = largest shard): rank r owns rows [r*m, r*m + cnt_r) of every bank, the embedding writes
+    # its features straight there (gather_slot), one in-place all_gather_into_tensor per bank runs asynchronously
+    # (NCCL's own stream: it overlaps whatever the caller launches next, e.g. the embedding of the other image set) and
+    # gather_banks_finish returns the [banks, n_total, d] result -- a zero-copy view when the shards are even, one
+    # compaction pass otherwise.  (all_gather_rows above pads, gathers, concatenates and transposes: four extra passes
+    # over the data; SURVEY.md 2.2 asks for kernels that write straight into the gather buffer.)
+    def gather_buffer(self, banks, n_total, d, dtype, device):
+        import torch
+        m = max_shard(n_total, self.world)
+        return torch.empty((banks, self.world * m, d), dtype=dtype, device=device)
+
+    def gather_slot(self, buf, n_total):
+        """The rows of `buf` this rank must fill: buf[:, rank*m : rank*m + (hi - lo)]."""
+        m = buf.shape[1] // self.world
+        lo, hi = shard_bounds(n_total, self.world, self.rank)
+        return buf[:, self.rank * m: self.rank * m + (hi - lo)]
+
+    def gather_banks_begin(self, buf):
+        """Start the in-place all-gathers of a filled gather buffer; returns the work handles."""
+        if self.world == 1:
+            return []
+        m = buf.shape[1] // self.world
+        works = []
+        for b in range(buf.shape[0]):
+            works.append(self.dist.all_gather_into_tensor(buf[b], buf[b, self.rank * m: (self.rank + 1) * m],
+                                                          group=self.group, async_op=True))
+        return works
+
+    def gather_banks_finish(self, buf, works, n_total):
+        import torch
+        for w in works:
+            w.wait()
+        m = buf.shape[1] // self.world
+        if self.world * m == n_total:
+            return buf                                       # even shards: the buffer IS the result
+        out = torch.empty((buf.shape[0], n_total, buf.shape[2]), dtype=buf.dtype, device=buf.device)
+        for r in range(self.world):
+            lo, hi = shard_bounds(n_total, self.world, r)
+            out[:, lo:hi].copy_(buf[:, r * m: r * m + (hi - lo)])
+        return out
+
     def all_gather_rows_inplace(self, full, n_total):
         """full: [n_total, ...] tensor whose rows [lo_r, hi_r) are valid on rank r -> all rows valid everywhere."""
         if self.world == 1:
@@ -122,9 +164,9 @@ class CudaBackend(object):
         self.mode = _dist_mode(dist_mode)
         self.batch = batch
 
-    def embed(self, model, images, num_split):
+    def embed(self, model, images, num_split, out=None):
         from .embed import embed_images
-        return embed_images(model, images, num_split, False, self.batch, self.dev.index)   # [banks, n_local, 2048]
+        return embed_images(model, images, num_split, False, self.batch, self.dev.index, out=out)   # [banks, n_local, 2048]
 
     def plan(self, n, ns, d):
         from .rerank import get_plan
@@ -254,27 +296,48 @@ def _shard_finish_default():
     return os.environ.get("SSG_SHARD_FINISH", "0") not in ("", "0")
 
 
+def embed_and_gather(model, tgt_shard, src_shard, n_tgt, n_src, num_split=2, backend=None, comm=None):
+    """Steps 1-2 of the sharded cycle with the exchange overlapped: embed this rank's target shard straight into the
+    gather buffer, start its all-gather (asynchronous), embed the source shard while it runs, gather that too.
+    Returns (tgt, src): [banks, n, d] float32 feature banks of ALL images on every rank."""
+    import torch
+    comm = comm or Comm()
+    backend = backend or CudaBackend()
+    banks = num_split + 1 if num_split > 1 else 1
+    dev = getattr(backend, "dev", None) or tgt_shard.device
+    d = getattr(backend, "feature_dim", 2048)
+    bufs, works = [], []
+    for shard, n in ((tgt_shard, n_tgt), (src_shard, n_src)):
+        buf = comm.gather_buffer(banks, n, d, torch.float32, dev)
+        backend.embed(model, shard, num_split, out=comm.gather_slot(buf, n))
+        works.append(comm.gather_banks_begin(buf))
+        bufs.append(buf)
+    return (comm.gather_banks_finish(bufs[0], works[0], n_tgt), comm.gather_banks_finish(bufs[1], works[1], n_src))
+
+
 def sharded_pseudo_label_cycle(model, tgt_shard, src_shard, n_tgt, n_src, num_split=2, lambda_value=0.1, rho=1.6e-3,
                                eps_list=None, min_samples=4, k1=20, k2=6, backend=None, comm=None, features=None,
-                               shard_finish=None, sparse=None):
+                               shard_finish=None, sparse=None, features_full=None):
     """Run one pseudo-label cycle sharded over the ranks of `comm`.
 
     tgt_shard / src_shard: this rank's image rows [shard_bounds(n, world, rank)) (host or device tensors).
-    `features=(tgt_local, src_local)` ([banks, n_local, d] each) skips the embedding (pre-extracted features).
+    `features=(tgt_local, src_local)` ([banks, n_local, d] each) skips the embedding (pre-extracted features);
+    `features_full=(tgt, src)` ([banks, n, d], already gathered by embed_and_gather) skips the exchange as well.
     Returns (labels_list [np.int64 arrays], eps_list, keep_mask) — identical on every rank.
     """
     import torch
     comm = comm or Comm()
     backend = backend or CudaBackend()
     banks = num_split + 1 if num_split > 1 else 1
-    if features is None:
-        tloc = backend.embed(model, tgt_shard, num_split)
-        sloc = backend.embed(model, src_shard, num_split)
+    if features_full is not None:
+        tgt, src = features_full                 # already gathered (embed_and_gather): [banks, n, d] on every rank
+    elif features is None:
+        # the one real exchange step, overlapped with the embedding of the other set
+        tgt, src = embed_and_gather(model, tgt_shard, src_shard, n_tgt, n_src, num_split, backend, comm)
     else:
         tloc, sloc = features
-    # the one real exchange step: feature banks of every image on every rank
-    tgt = comm.all_gather_rows(tloc, n_tgt, dim=1)
-    src = comm.all_gather_rows(sloc, n_src, dim=1)
+        tgt = comm.all_gather_rows(tloc, n_tgt, dim=1)
+        src = comm.all_gather_rows(sloc, n_src, dim=1)
     lo, hi = shard_bounds(n_tgt, comm.world, comm.rank)
     plan = backend.plan(n_tgt, n_src, tgt.shape[2])
     k1d = max(k1, k2 - 1)        # the rank table must hold k2 columns too (rerank.py:97), as in ssg_rerank_run

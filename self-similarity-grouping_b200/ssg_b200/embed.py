@@ -155,10 +155,10 @@ def get_plan(batch_max=256, device=None):
 
 
 def embed_images(model, images, num_split=None, for_eval=False, batch=256, device=None, out_device=True,
-                 mean=IMAGENET_MEAN, std=IMAGENET_STD):
+                 mean=IMAGENET_MEAN, std=IMAGENET_STD, out=None):
     """Embed a whole image tensor (normalised float32 [N,3,256,128] or raw uint8 [N,256,128,3]; host (ideally
     pinned) or device) in batches with copy/compute overlap.  Returns a CUDA tensor: [banks, N, 2048] (list mode)
-    or [N, banks*2048] (eval mode)."""
+    or [N, banks*2048] (eval mode); `out` (optional) receives the features instead of a fresh tensor."""
     import torch
     dev = _lib.require_cuda(device)
     plan = get_plan(batch, dev.index)
@@ -166,7 +166,14 @@ def embed_images(model, images, num_split=None, for_eval=False, batch=256, devic
     num_split = ns if num_split is None else num_split
     banks = num_split + 1 if num_split > 1 else 1
     N = images.shape[0]
-    out = torch.empty((N, banks * 2048) if for_eval else (banks, N, 2048), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((N, banks * 2048) if for_eval else (banks, N, 2048), dtype=torch.float32, device=dev)
+    else:
+        # caller-owned destination, e.g. this rank's slot of a multi-GPU gather buffer (rows may be strided per bank)
+        want = (N, banks * 2048) if for_eval else (banks, N, 2048)
+        if tuple(out.shape) != want or out.dtype != torch.float32 or not _lib.same_device(out, dev) or \
+                out.stride(-1) != 1 or (not for_eval and out.stride(1) != 2048):
+            raise ValueError("ssg_b200: `out` must be a float32 CUDA tensor of shape %s with contiguous rows" % (want,))
     if images.is_cuda:
         for r0 in range(0, N, batch):
             plan.forward(images[r0:r0 + batch], num_split, for_eval, True, out, r0, mean, std)

@@ -38,15 +38,20 @@ class OracleBackend(object):
     def __init__(self, n_banks, d_img, d):
         rng = np.random.RandomState(5)
         self.W = [rng.randn(d_img, d).astype(np.float32) for _ in range(n_banks)]
+        self.feature_dim = d
 
-    def embed(self, model, images, num_split):
+    def embed(self, model, images, num_split, out=None):
         import torch
         x = images.numpy()
         banks = []
         for W in self.W:
             f = x @ W
             banks.append(f / np.linalg.norm(f, axis=1, keepdims=True))
-        return torch.from_numpy(np.stack(banks, 0).astype(np.float32))
+        res = torch.from_numpy(np.stack(banks, 0).astype(np.float32))
+        if out is not None:                    # this rank's slot of the gather buffer (ssg_b200.dist.embed_and_gather)
+            out.copy_(res)
+            return out
+        return res
 
     def plan(self, n, ns, d):
         return FakePlan(n)
