@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "conv.h"
 
 namespace ssg {
@@ -50,6 +51,19 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     if (epi2 && !stem_kernel && !pool_out && !wide) {
         if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
+    }
+    // SSG_CONV_PAIR=1 (opt-in): two-CTA 256 x BN tiles (cta_group::2, gemm_tc2.cuh) for the plain / implicit GEMMs
+    static int pair = -1;
+    if (pair < 0) { const char* e = getenv("SSG_CONV_PAIR"); pair = e ? atoi(e) : 0; }
+    if (pair && !stem_kernel && !pool_out && m >= 2 * tc::BM && A.mode != 2 && A.mode != 3) {
+        if (wide && (pair & 1)) {
+            if (residual) return tc::launch_gemm2_op<256, true>(A, m, w, cout, k, epi, st);
+            return tc::launch_gemm2_op<256, false>(A, m, w, cout, k, epi, st);
+        }
+        if (!wide && cout % 128 == 0 && (pair & 2)) {
+            if (residual) return tc::launch_gemm2_op<128, true>(A, m, w, cout, k, epi, st);
+            return tc::launch_gemm2_op<128, false>(A, m, w, cout, k, epi, st);
+        }
     }
     // 128x256 tiles for the K-heavy convolutions without a residual (SSG_CONV_BN256=0 disables, for A/B runs)
     static int bn256 = -1;
