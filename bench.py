@@ -14,6 +14,7 @@ out, copies inside the timed region).  The two halves of the BASELINE metric are
 (images/s of the embedding stage) and "rerank" (Mpairs/s of the re-rank + eps + DBSCAN stage alone).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -62,6 +63,9 @@ def parse():
     ap.add_argument("--sparse-finish", action="store_true",
                     help="never materialise final_dist (CSR over the touched pairs, certified "
                          "eps + DBSCAN on it; DESIGN.md 3.6) instead of the dense N x N float64 matrix")
+    ap.add_argument("--rho", type=float, default=RHO, help="fraction of the smallest pair distances averaged into eps")
+    ap.add_argument("--finetune-step", action="store_true",
+                    help="after the cycle, time one FinedTrainer2 step on the pseudo-labels (rank 0; BASELINE configs[4])")
     ap.add_argument("--no-reference-api", action="store_true",
                     help="skip the e2e leg through the reference-shaped API (dict of CPU tensors -> numpy N x N -> labels)")
     ap.add_argument("--no-u8", action="store_true", help="skip the uint8-pixel e2e leg (ssg_embed_forward_u8)")
@@ -331,6 +335,7 @@ def reference_api_cycle(model, host_tgt, host_src, num_split, batch):
         t2 = time.perf_counter()
         eps = eps_estimate(final, RHO)
         labels.append(RR.DBSCAN(eps=eps, min_samples=MIN_SAMPLES, metric="precomputed", n_jobs=8).fit_predict(final))
+        parts.setdefault("eps", []).append(float(eps))
         t3 = time.perf_counter()
         t_rr += t2 - t1
         t_cl += t3 - t2
@@ -352,6 +357,57 @@ ALGO = {   # per launch: (bound, algorithmic work as a function of (rows, cols, 
     "row_select": ("hbm", lambda r, c, d: 4.0 * r * c),                 # fp32 distance block read once
     "row_minmax": ("hbm", lambda r, c, d: 4.0 * r * c),
 }
+
+
+def workload_name(n, banks, world):
+    """Which BASELINE.json config a run corresponds to (by shape)."""
+    if n == 126441:
+        return "configs[4] (MSMT17 shape)"
+    if n == 36411:
+        return "configs[3] (DukeMTMC shape)"
+    if n == 16702 and banks == 4:
+        return "configs[2] (num_split=3)"
+    if n == 16702 and banks == 3:
+        return "configs[1]"
+    return "custom"
+
+
+def finetune_step(model, images, labels, keep, dev, P=16, K=4):
+    """One FinedTrainer2 step on pseudo-labels (selftraining.py:149-161, 239-253; trainers.py:204-271): P identities x
+    K images drawn from the kept images, global + per-bank triplet losses (own CUDA kernels, csrc/triplet.cu), model
+    forward / backward through torch autograd (cuDNN convolutions: library code), SGD.  -> dict with the device time."""
+    import numpy as np
+    import torch
+    from reid.loss import TripletLoss
+    from reid.trainers import FinedTrainer2
+    lab0 = np.asarray(labels[0])
+    ids = [c for c in np.unique(lab0[keep]) if c >= 0 and (lab0[keep] == c).sum() >= K][:P]
+    if len(ids) < 2:
+        return {"skipped": "fewer than two pseudo-identities with %d kept images" % K}
+    idx = np.concatenate([np.flatnonzero((lab0 == c) & keep)[:K] for c in ids])
+    imgs = images[torch.from_numpy(idx).to(images.device)].to(dev).float()
+    pids = [torch.from_numpy(np.asarray(l)[idx].astype(np.int64)) for l in labels]
+    model = model.to(dev)
+    crit = [TripletLoss(0.5, K, True).to(dev), TripletLoss(0.5, K, True).to(dev)]
+    trainer = FinedTrainer2(model, crit)
+    opt = torch.optim.SGD(model.parameters(), lr=6e-5, momentum=0.9, weight_decay=5e-4, nesterov=True)
+    model.train()
+    times = []
+    for it in range(3):                                          # 2 warm-up steps, the third is reported
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        inputs, p, _ = trainer._parse_data((imgs, None, pids, [0] * len(idx)))
+        loss, prec = trainer._forward(inputs, p, 0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    model.eval()
+    return {"ms": times[-1], "batch": int(len(idx)), "identities": int(len(ids)), "instances": K, "loss": float(loss.item()),
+            "note": "FinedTrainer2 step: model forward/backward = torch autograd over cuDNN (library code); the global + "
+                    "per-bank triplet losses and their gradients are this repo's kernels (csrc/triplet.cu)"}
 
 
 def load_whole_path_parity():
@@ -406,8 +462,6 @@ def main():
     # (NCCL) -> row-block distance stage + table gather -> bank-parallel finish (ssg_b200.dist).  --replicas: every rank
     # owns an independent set of the same shape (weak scaling, no data-path collective).
     sharded = world > 1 and not args.replicas
-    if sharded and not with_embed:
-        raise SystemExit("--features-only is a single-GPU / --replicas mode")
     if with_embed:
         model = synth.build_model(num_split, 0)
         if sharded:
@@ -427,6 +481,14 @@ def main():
             src_img, _ = synth.synth_images(n, 4321 + 100 * rank, dev)
         plan_e = ssg_b200.embed.get_plan(args.batch, local)
         plan_e.load_model(model)
+    elif sharded:
+        # one global synthetic feature set (same seeds on every rank); this rank keeps its row shard [banks, n_local, d]
+        from ssg_b200 import dist as sdist
+        comm = sdist.Comm()
+        backend = sdist.CudaBackend(local, mode, args.batch)
+        lo, hi = sdist.shard_bounds(n, world, rank)
+        tgt_f = torch.stack([synth_bank(n, D, 10 + b, 0.5, dev)[lo:hi] for b in range(banks)]).contiguous()
+        src_f = torch.stack([synth_bank(n, D, 20 + b, 0.6, dev)[lo:hi] for b in range(banks)]).contiguous()
     else:
         tgt_f = [synth_bank(n, D, 1000 * rank + 10 + b, 0.5, dev) for b in range(banks)]
         src_f = [synth_bank(n, D, 1000 * rank + 20 + b, 0.6, dev) for b in range(banks)]
@@ -448,15 +510,22 @@ def main():
             tfl, sfl = [tf[b] for b in range(banks)], [sf[b] for b in range(banks)]
         else:
             tfl, sfl = tgt_in, src_in
+            if sharded and not tfl.is_cuda:                      # e2e leg: this rank's feature shards from pinned host memory
+                tfl, sfl = tfl.to(dev, non_blocking=True), sfl.to(dev, non_blocking=True)
         if record:
             ev[1].record()
-        if sharded:
-            out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, RHO, backend=backend,
+        if sharded and with_embed:
+            out = sdist.sharded_pseudo_label_cycle(model, None, None, n, n, num_split, LAMBDA, args.rho, backend=backend,
                                                    comm=comm, features_full=(tf, sf),
                                                    shard_finish=True if args.shard_finish else None,
                                                    sparse=True if args.sparse_finish else None)
+        elif sharded:
+            out = sdist.sharded_pseudo_label_cycle(None, None, None, n, n, num_split, LAMBDA, args.rho, backend=backend,
+                                                   comm=comm, features=(tfl, sfl),
+                                                   shard_finish=True if args.shard_finish else None,
+                                                   sparse=True if args.sparse_finish else None)
         else:
-            out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, RHO, dist_mode=mode, device=local,
+            out = ssg_b200.pseudo_label_cycle(sfl, tfl, LAMBDA, args.rho, dist_mode=mode, device=local,
                                               sparse=True if args.sparse_finish else None)
         if record:
             ev[2].record()
@@ -517,6 +586,9 @@ def main():
     if with_embed:
         host_in = (tgt_img.cpu().pin_memory(), src_img.cpu().pin_memory())
         h2d = (tgt_img.shape[0] + src_img.shape[0]) * 3 * 256 * 128 * 4      # per rank
+    elif sharded:
+        host_in = (tgt_f.cpu().pin_memory(), src_f.cpu().pin_memory())
+        h2d = (tgt_f.numel() + src_f.numel()) * 4
     else:
         host_in = ([t.cpu().pin_memory() for t in tgt_f], [t.cpu().pin_memory() for t in src_f])
         h2d = 2 * banks * n * D * 4
@@ -545,7 +617,9 @@ def main():
         torch.cuda.synchronize()
         lab_api, parts = reference_api_cycle(model, host_in[0], host_in[1], num_split, args.batch)
         ref_api = {"value": pairs_per_step / parts["total_s"] / 1e6, "unit": UNIT, "ms_per_step": parts["total_s"] * 1e3,
-                   "parts_s": {kk: round(v, 3) for kk, v in parts.items()}, "steps": 1,
+                   "parts_s": {kk: round(v, 3) for kk, v in parts.items() if kk != "eps"}, "steps": 1,
+                   "eps": parts["eps"], "eps_device_resident_path": [float(e) for e in out_e2e[1]],
+                   "labels_differ_per_bank": [int((a != b).sum()) for a, b in zip(lab_api, out_e2e[0])],
                    "h2d_bytes_per_step": h2d + banks * (2 * n * D * 4 + n * n * 8),
                    "d2h_bytes_per_step": 2 * banks * n * D * 4 + banks * n * n * (8 + 4) + banks * n * 8,
                    "api": "reid.evaluators.extract_features(loader of host batches) -> OrderedDict of per-image CPU "
@@ -556,13 +630,17 @@ def main():
     labels, eps_list, keep = out
     k = args.steps
     # whole job: a sharded cycle copies every image once (the ranks' shards add up to the set), replicas copy one set each
-    h2d_job = (2 * n * 3 * 256 * 128 * 4 if sharded else h2d * world) if with_embed else h2d * world
+    h2d_job = (2 * n * 3 * 256 * 128 * 4 if sharded else h2d * world) if with_embed else \
+        (2 * banks * n * D * 4 if sharded else h2d * world)
     units = 1 if sharded else world          # sharded: all ranks together process ONE data set
     value = pairs_per_step * units * k / (ms_dev / 1e3) / 1e6             # whole cycle (== stage alone with --features-only)
     e2e_value = pairs_per_step * units * k / (ms_e2e / 1e3) / 1e6
     stage_value = pairs_per_step * units * k / (ms_rerank / 1e3) / 1e6
     e2e_stage_value = pairs_per_step * units * k / (ms_e2e_rerank / 1e3) / 1e6
 
+    finetune = None
+    if args.finetune_step and with_embed and rank == 0:
+        finetune = finetune_step(model, tgt_img, labels, keep, dev)
     line = None
     if rank == 0:
         peaks = load_peaks()
@@ -647,7 +725,7 @@ def main():
                      ("f32/f64 re-rank (bf16x3 tensor-core candidates, exact f64 re-score)"
                       if mode == _lib.DIST_TENSOR else "f32/f64 re-rank (exact f64 distances)"),
             "data": "synthetic",
-            "config": {"workload": "configs[1]: N=Ns=%d synthetic 256x128 images, random-init ResNet-50 (num_split=%d -> %d "
+            "config": {"workload": workload_name(n, banks, world) + ": N=Ns=%d synthetic 256x128 images, random-init ResNet-50 (num_split=%d -> %d "
                                    "banks x 2048-d): embed source+target sets (flip TTA) -> per bank re-rank k1=20 k2=6 "
                                    "lambda=0.1 -> eps rho=1.6e-3 -> DBSCAN min_samples=4%s"
                                    % (n, num_split, banks, "" if with_embed else "; EMBED SKIPPED (--features-only)"),
@@ -676,8 +754,12 @@ def main():
             "gpu_launches": int(launches),
             "kernels_ms_per_step": {kk: round(v[0] / k, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
             "roofline": roof, "cpu_baseline": cpu, "clocks": clk,
-            "parity_gate": gate,
+            "parity_gate": gate, "finetune_step": finetune,
             "result": {"clusters": [int(l.max()) + 1 for l in labels], "eps": [round(e, 6) for e in eps_list],
+                       "eps_exact": [float(e).hex() for e in eps_list],
+                       "labels_sha1": hashlib.sha1(b"".join(np.ascontiguousarray(l, dtype=np.int64).tobytes()
+                                                            for l in labels)).hexdigest(),
+                       "rho": args.rho,
                        "whole_path_parity": load_whole_path_parity(),
                        "kept_images": int(keep.sum()),
                        "rows_recomputed_exactly_last_bank": int(ssg_b200.rerank.get_plan(n, n, D, local).stage(

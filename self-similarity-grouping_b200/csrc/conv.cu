@@ -52,15 +52,21 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
         if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
     }
-    // SSG_CONV_PAIR=1 (opt-in): two-CTA 256 x BN tiles (cta_group::2, gemm_tc2.cuh) for the plain / implicit GEMMs
+    // two-CTA 256 x BN tiles (cta_group::2, gemm_tc2.cuh) for the plain / implicit GEMMs; SSG_CONV_PAIR=0 disables
+    // bit 0: the 256-wide tiles; bit 1: the 128-wide 3x3 convolutions; bit 2: the 128-wide 1x1 convolutions.
+    // Default 3 (round 2, B200, profiles/r02f_ab_pair*.json: embedding 601.9 -> 578.8 ms per cycle; the 128-wide 1x1
+    // convolutions are HBM bound and lose 1 % as pairs).  Bit-identical to the single-CTA kernels (tests/c/embed_dump).
     static int pair = -1;
-    if (pair < 0) { const char* e = getenv("SSG_CONV_PAIR"); pair = e ? atoi(e) : 0; }
+    if (pair < 0) { const char* e = getenv("SSG_CONV_PAIR"); pair = e ? atoi(e) : 3; }
+#ifdef SSG_PAIR_KERNEL_UNAVAILABLE      // CPU emulation (tests/cpu_cuda): no thread-block clusters there
+    pair = 0;
+#endif
     if (pair && !stem_kernel && !pool_out && m >= 2 * tc::BM && A.mode != 2 && A.mode != 3) {
         if (wide && (pair & 1)) {
             if (residual) return tc::launch_gemm2_op<256, true>(A, m, w, cout, k, epi, st);
             return tc::launch_gemm2_op<256, false>(A, m, w, cout, k, epi, st);
         }
-        if (!wide && cout % 128 == 0 && (pair & 2)) {
+        if (!wide && cout % 128 == 0 && (pair & (A.taps == 9 ? 2 : 4))) {
             if (residual) return tc::launch_gemm2_op<128, true>(A, m, w, cout, k, epi, st);
             return tc::launch_gemm2_op<128, false>(A, m, w, cout, k, epi, st);
         }

@@ -320,12 +320,16 @@ def test_conv_variants_are_bit_identical(tmp_path):
     got = plan.forward(R.synth_images(9, 11).cuda(), 2)
     torch.cuda.synchronize()
     got = got.cpu().numpy()
-    # round 2: the layer-1 chained kernel (conv3 + next conv1 in one launch, SSG_CONV_CHAIN) and the kernel-row-sharing
-    # 3x3 with resident weights (SSG_KHS_BRES) are defaults; their plain predecessors must give the same bits
+    # round 2: the layer-1 chained kernel (conv3 + next conv1 in one launch, SSG_CONV_CHAIN), the kernel-row-sharing
+    # 3x3 with resident weights (SSG_KHS_BRES), the deeper pipelines (SSG_CONV_NORES) and the two-CTA cta_group::2
+    # tiles (SSG_CONV_PAIR) are defaults; their plain predecessors must give the same bits
     for name, switches in (("plain", dict(SSG_STEM_BRES="0", SSG_STEM_POOL="0", SSG_CONV_BN256_RES="0")),
                            ("no_chain", dict(SSG_CONV_CHAIN="0")),
                            ("khs_streamed", dict(SSG_KHS_BRES="0")),
-                           ("round1_default", dict(SSG_CONV_CHAIN="0", SSG_KHS_BRES="0"))):
+                           ("no_pairs", dict(SSG_CONV_PAIR="0")),            # default: two-CTA tiles where they win
+                           ("all_pairs", dict(SSG_CONV_PAIR="7")),
+                           ("round1_default", dict(SSG_CONV_CHAIN="0", SSG_KHS_BRES="0", SSG_CONV_PAIR="0",
+                                                   SSG_CONV_NORES="0"))):
         out_file = str(tmp_path / (name + ".npy"))
         subprocess.run([sys.executable, "-c", script, out_file], check=True, env=dict(os.environ, **switches), timeout=300)
         assert np.array_equal(got, np.load(out_file)), name
