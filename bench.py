@@ -440,6 +440,7 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import ssg_b200
