@@ -566,7 +566,9 @@ pair_exact_kernel(const float* __restrict__ A, int rows, const float* __restrict
     }
 }
 
-// v4 (default, SSG_PAIR_STAGED=0 disables): one WARP per (row, group of 32 pairs), lane = pair.  The partner rows are
+// v4 (opt-in, SSG_PAIR_STAGED=1; MEASURED SLOWER on the B200: 15.0 vs 9.9 ms per cycle, profiles/r02h_ab_*.json -- one
+// dependent float64 add chain per lane leaves the FP64 pipe latency bound, v3's four chains per thread matter more than
+// its half-used sectors): one WARP per (row, group of 32 pairs), lane = pair.  The partner rows are
 // staged through shared memory in 64-float chunks with coalesced loads (half a warp reads the 256 contiguous bytes of
 // one partner row), then every lane walks its own pair's chunk out of shared memory.  In v3 a lane read its partner row
 // straight from global memory, 16 bytes at a time: 32 lanes x 32 different rows = 32 half-used sectors per instruction,
@@ -634,7 +636,7 @@ int launch_pair_exact(const float* A, int rows, const float* B, int d, const int
                       const int* cnt, int fixed_cnt, float* out, int out_stride, cudaStream_t st) {
     if (rows <= 0) return SSG_OK;
     static int staged = -1;
-    if (staged < 0) { const char* e = getenv("SSG_PAIR_STAGED"); staged = e ? atoi(e) : 1; }
+    if (staged < 0) { const char* e = getenv("SSG_PAIR_STAGED"); staged = e ? atoi(e) : 0; }
     if (staged && (reinterpret_cast<uintptr_t>(B) & 15) == 0) {
         // pair groups per row: the widest row decides (cnt[] holds at most idx_stride entries per row)
         const int maxc = cnt ? idx_stride : fixed_cnt;
