@@ -48,6 +48,7 @@ class EmbedPlan(object):
         self.batch_max = int(batch_max)
         self._h = ctypes.c_void_p()
         self._weights_token = None
+        self._staging = {}           # host-image staging buffers / events of embed_images, per (image shape, dtype, batch)
         _lib.check(_lib.load().ssg_embed_plan_create(ctypes.byref(self._h), dev.index, self.batch_max, height, width))
 
     def __del__(self):
@@ -178,23 +179,36 @@ def embed_images(model, images, num_split=None, for_eval=False, batch=256, devic
         for r0 in range(0, N, batch):
             plan.forward(images[r0:r0 + batch], num_split, for_eval, True, out, r0, mean, std)
         return out
-    copy_stream = torch.cuda.Stream(device=dev)
+    # host images: double-buffered staging on a copy stream.  The staging buffers, their events and the stream live on
+    # the plan and persist across calls: a slot is re-filled only after the forward that last read it has finished
+    # (`freed`), INCLUDING a forward issued by the previous call.  (Round 1 allocated fresh buffers and a fresh stream
+    # per call; the caching allocator handed the second call the first call's buffers while its last forwards were still
+    # reading them, and the new copy stream overwrote them -- the last batches of the first set were embedded from
+    # partly overwritten images.  Found in round 2 by comparing the host-image path with the device-image path.)
     compute = torch.cuda.current_stream(dev)
-    bufs = [torch.empty((batch,) + tuple(images.shape[1:]), dtype=images.dtype, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    key = (tuple(images.shape[1:]), images.dtype, int(batch))
+    st = plan._staging.get(key)
+    if st is None:
+        st = {"stream": torch.cuda.Stream(device=dev),
+              "bufs": [torch.empty((batch,) + tuple(images.shape[1:]), dtype=images.dtype, device=dev) for _ in range(2)],
+              "ready": [torch.cuda.Event(), torch.cuda.Event()], "freed": [torch.cuda.Event(), torch.cuda.Event()],
+              "used": [False, False]}
+        st["stream"].wait_stream(compute)            # the allocations above are ordered on the compute stream
+        plan._staging[key] = st
+    copy_stream, bufs, ready, freed, used = st["stream"], st["bufs"], st["ready"], st["freed"], st["used"]
     starts = list(range(0, N, batch))
     for it, r0 in enumerate(starts):
         slot = it & 1
         n = min(batch, N - r0)
         with torch.cuda.stream(copy_stream):
-            if it >= 2:
-                copy_stream.wait_event(freed[slot])
+            if used[slot]:
+                copy_stream.wait_event(freed[slot])  # the forward that last read this slot (this call or an earlier one)
             bufs[slot][:n].copy_(images[r0:r0 + n], non_blocking=True)
             ready[slot].record(copy_stream)
         compute.wait_event(ready[slot])
         plan.forward(bufs[slot][:n], num_split, for_eval, True, out, r0, mean, std)
         freed[slot].record(compute)
+        used[slot] = True
     return out
 
 
