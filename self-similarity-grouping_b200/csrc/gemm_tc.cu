@@ -129,6 +129,12 @@ int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, ui
     return SSG_OK;
 }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SSG_PDL"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 int tc_num_sms(int* out) {
     static int cached[64] = {0};
     int dev = 0;

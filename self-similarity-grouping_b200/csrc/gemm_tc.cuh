@@ -15,6 +15,7 @@ int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images);
 int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images, uint32_t box_rows = 4);
 int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int tc_num_sms(int* out);
+bool pdl_enabled();            // SSG_PDL (default 1): launch the GEMM kernels with programmatic stream serialization
 
 namespace tc {
 
@@ -201,6 +202,12 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped
+    // the tail of the previous kernel of the stream; nothing below may touch global memory before that kernel is done.
+    // EVERY kernel of the chain waits, also one that does not read its predecessor's output: completion is transitive
+    // only that way (a residual comes from two or three launches back).
+    pdl_wait();
+    pdl_launch_dependents();
 
     // tile index -> (m_blk, n_blk), grouped along M so that concurrently resident CTAs share B tiles in L2
     auto tile_coords = [&](int t, int& m_blk, int& n_blk) {
@@ -939,7 +946,23 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     // KHS: one K block per (kernel column, channel block), i.e. a third of the plain K blocks
     // VAR_BRESP: the whole K range of a tile rides in one stage
-    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, L::PLANES ? 1 : KHS ? (k / BK) / 3 : (k + BK - 1) / BK, epi);
+    const int nkb = L::PLANES ? 1 : KHS ? (k / BK) / 3 : (k + BK - 1) / BK;
+#ifdef SSG_NO_LAUNCH_EX                 // CPU emulation (tests/cpu_cuda/stub_tc): plain launch
+    kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(A, mapB, m, n, nkb, epi);
+#else
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SSG_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, A, mapB, m, n, nkb, epi));
+#endif
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -126,6 +126,8 @@ gemm2_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtenso
     cluster_sync_all();                            // barriers initialised and TMEM allocated in BOTH CTAs
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();                                    // see gemm_tc.cuh: the prologue overlapped the previous kernel's tail
+    pdl_launch_dependents();
 
     auto tile_coords = [&](int t, int& mp, int& n_blk) {
         const int per_group = GROUP_M * n_blocks;
@@ -326,13 +328,15 @@ int launch_gemm2_op(const AOperand& A, int m, const void* b, int n, int k, const
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = L::TOTAL;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const int nkb = (k + BK - 1) / BK;
     SSG_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, A, mapB, m, n, nkb, epi));
     SSG_CHECK_LAUNCH();

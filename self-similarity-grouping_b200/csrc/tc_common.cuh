@@ -53,6 +53,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------
+// griddepcontrol.wait: block until every grid this one depends on has completed and flushed its memory (a no-op when
+// the kernel was launched without the programmatic-serialization attribute); launch_dependents: the next kernel of
+// the stream may start its CTAs (they run their prologue and then sit in their own griddepcontrol.wait).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMA -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

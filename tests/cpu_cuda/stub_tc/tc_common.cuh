@@ -55,6 +55,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ---- TMA
+#define SSG_NO_LAUNCH_EX 1          // gemm_tc.cuh: plain <<<>>> launches (rewritten to emu::launch) instead of cudaLaunchKernelEx
+__device__ __forceinline__ void pdl_wait() {}                      // launches run one after another under emulation
+__device__ __forceinline__ void pdl_launch_dependents() {}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap*) {}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
     const int c[5] = {c0, c1, 0, 0, 0};

@@ -218,7 +218,9 @@ from ssg_b200 import _lib as L
 from test_cpu_emulated_tensor_kernels import to_bf16, from_bf16, conv_ref
 lib = ctypes.CDLL(build_emu.build_tc(fault=sys.argv[1] if sys.argv[1] != "none" else None))
 lib.ssg_op_conv.restype, lib.ssg_op_conv.argtypes = L.PROTOTYPES["ssg_op_conv"]
-B, H, W, cin, cout = 3, 8, 16, 512, 256                 # 128x256 tiles, 8 K blocks (> stages) and 4 sub-tiles per tile
+B, H, W, cin, cout = 9, 8, 16, 512, 128                 # 128x128 tiles, 8 K blocks (> stages), 2 sub-tiles per tile and
+                                                        # 3 tiles per CTA (3 emulated SMs): staging buffers are re-used
+                                                        # (the one-barrier epilogue is limited to the <= 128-wide tiles)
 rng = np.random.RandomState(7)
 x = from_bf16(to_bf16(rng.randn(B, H, W, cin))); w = from_bf16(to_bf16(rng.randn(cout, 1, 1, cin) / 22))
 bias = (rng.randn(cout) * 0.1).astype(np.float32)

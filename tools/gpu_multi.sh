@@ -13,7 +13,7 @@ run() { # name, timeout, args...
 import json,sys
 f='gpurun_out/r02_multi_%s_%sgpu.json'%(sys.argv[1],sys.argv[2])
 try:
-    d=json.load(open(f)); r=d['result']
+    d=[json.loads(l) for l in open(f) if l.startswith('{')][-1]; r=d['result']
     print(sys.argv[1], 'value %.1f ms %.1f e2e_ms %.1f embed %s rerank %.1f clusters %s sha1 %s'%(d['value'],d['ms_per_step'],d['e2e']['ms_per_step'],(d['embed'] or {}).get('ms_per_step'),d['rerank']['ms_per_step'],r['clusters'],r['labels_sha1']))
     if d.get('finetune_step'): print('finetune', d['finetune_step'])
 except Exception as e: print(sys.argv[1],'ERR',e)
