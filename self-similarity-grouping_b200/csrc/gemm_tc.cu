@@ -131,7 +131,9 @@ int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, ui
 
 bool pdl_enabled() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("SSG_PDL"); v = e ? atoi(e) : 1; }
+    // default off: bit-identical and measured at no gain on the B200 (627.0 vs 627.1 ms per cycle, profiles/r02j_ab_*.json:
+    // a CTA holds > 200 KB of shared memory, so a dependent CTA can only start where a CTA of the previous kernel has left)
+    if (v < 0) { const char* e = getenv("SSG_PDL"); v = e ? atoi(e) : 0; }
     return v != 0;
 }
 

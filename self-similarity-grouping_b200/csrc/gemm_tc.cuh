@@ -15,7 +15,7 @@ int make_tmap_stem_windows(CUtensorMap* map, const void* base, uint64_t images);
 int make_tmap_stem_windows64(CUtensorMap* map, const void* base, uint64_t images, uint32_t box_rows = 4);
 int make_tmap_2d_bf16_sw64(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 int tc_num_sms(int* out);
-bool pdl_enabled();            // SSG_PDL (default 1): launch the GEMM kernels with programmatic stream serialization
+bool pdl_enabled();            // SSG_PDL (default 0: measured no gain): launch the GEMM kernels with programmatic stream serialization
 
 namespace tc {
 
@@ -134,12 +134,8 @@ struct SmemLayout {
         (STAGED ? (BN <= 64 ? 5 : (BN <= 128 ? 3 : 4)) : ((BN <= 64) ? 8 : (BN <= 128 ? 6 : 4)));
     static constexpr int BRES_OFFSET = STAGES * STAGE_BYTES;     // resident B operand (VAR_BRES)
     static constexpr int BRES_BYTES = BRES ? BN * BRES_K * 2 : KRES ? 9 * B_TILE : CHAIN ? CHAIN_WRES_BYTES : 0;
-    // output staging, then the residual staging buffers.  VAR_CHAIN puts the output staging FIRST and the resident
-    // weights next to the residual ring, so that the part of the weight region a configuration does not need
-    // (W3 + W1' = 64 KB of the 96) extends the ring: 5 slots instead of 3 (the residual prefetch depth is what bounds
-    // the chained kernel: ncu r02d, 2 x 16 KB in flight against ~3 K cycles of HBM latency)
-    static constexpr int C_OFFSET = CHAIN ? BRES_OFFSET : BRES_OFFSET + BRES_BYTES;
-    static constexpr int W_OFFSET = CHAIN ? BRES_OFFSET + C_BYTES : BRES_OFFSET;
+    static constexpr int C_OFFSET = BRES_OFFSET + BRES_BYTES;    // output staging, then the residual staging buffers
+    static constexpr int W_OFFSET = BRES_OFFSET;                 // resident weights (VAR_CHAIN)
     static constexpr int BAR_OFFSET = BRES_OFFSET + BRES_BYTES + C_BYTES + RSTAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 384 + 1024;        // barriers (up to 2*8 + 16 of them) + alignment slack
     static_assert(!(BRES && (KHS || !STAGED || BN != 64)), "VAR_BRES is the stem kernel");
@@ -703,22 +699,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                 __shared__ float s_bias2[128];
                 if (epi_tid < BN) s_bias[epi_tid] = epi.bias[epi_tid];
                 if (epi_tid < n2) s_bias2[epi_tid] = epi.bias2[epi_tid];
-                // residual ring: starts right behind the resident weights and takes what they leave of the pool
-                const int wres_bytes = num_k_blocks * L::B_TILE + 4 * n2 * 128;
-                unsigned char* r_ring = smem + L::W_OFFSET + wres_bytes;
-                int rs_n = (CHAIN_WRES_BYTES - wres_bytes) / L::SUB_BYTES + L::RSLOTS;
-                if (rs_n > 6) rs_n = 6;                                   // res_bar has six slots
-                auto load_res = [&](int s) {                              // sub-tile s of this CTA -> ring slot s % rs_n
-                    const int tile = (int)blockIdx.x + (s / 4) * (int)gridDim.x;
-                    if (tile >= num_tiles) return;
-                    int mb, nb;
-                    tile_coords(tile, mb, nb);
-                    const int slot = s % rs_n;
-                    mbar_arrive_expect_tx(&res_bar[slot], L::SUB_BYTES);
-                    tma_load_2d(r_ring + slot * L::SUB_BYTES, &epi.mapR, &res_bar[slot], (s % 4) * 64, mb * BM);
-                };
+                // (a deeper residual ring -- 5 slots where the weights leave room -- was measured in round 2: no change,
+                // profiles/r02k_ab_ring*.json; the ring stays at the three slots of VAR_RRING)
                 if (leader && has_res) {
-                    for (int s0 = 0; s0 < rs_n - 1; ++s0) load_res(s0);
+                    for (int s0 = 0; s0 < RS - 1; ++s0) load_residual_sub(s0);
                 }
                 uint32_t fph = 0, pend = 0;                               // leader only: phase / pending bits per buffer
                 epi_bar_sync();                                           // bias rows visible
@@ -750,10 +734,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         if (first) {
                             const int s = itc * 4 + j;
                             // every thread is past the barrier above, i.e. done with sub-tile s-1: its slot is free
-                            if (leader && has_res) load_res(s + rs_n - 1);
+                            if (leader && has_res) load_residual_sub(s + RS - 1);
                             if (has_res) {
-                                mbar_wait(&res_bar[s % rs_n], (uint32_t)((s / rs_n) & 1));
-                                rsub = r_ring + (s % rs_n) * L::SUB_BYTES + row_off;
+                                mbar_wait(&res_bar[s % RS], (uint32_t)((s / RS) & 1));
+                                rsub = r_s + (s % RS) * L::SUB_BYTES + row_off;
                             }
                         }
                         const int c = 2 * (first ? j : j - 4) + grp;      // 32-column chunk of the accumulator

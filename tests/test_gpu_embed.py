@@ -328,7 +328,7 @@ def test_conv_variants_are_bit_identical(tmp_path):
                            ("khs_streamed", dict(SSG_KHS_BRES="0")),
                            ("no_pairs", dict(SSG_CONV_PAIR="0")),            # default: two-CTA tiles where they win
                            ("all_pairs", dict(SSG_CONV_PAIR="7")),
-                           ("no_pdl", dict(SSG_PDL="0")),                    # default: programmatic dependent launch
+                           ("pdl", dict(SSG_PDL="1")),                       # programmatic dependent launch (opt-in)
                            ("round1_default", dict(SSG_CONV_CHAIN="0", SSG_KHS_BRES="0", SSG_CONV_PAIR="0",
                                                    SSG_CONV_NORES="0"))):
         out_file = str(tmp_path / (name + ".npy"))
