@@ -12,6 +12,15 @@ banks*N^2 ordered pairs taken from images to labels per second (value * ms_per_s
 images resident in HBM; `e2e` is the same metric through the host-buffer API (pinned host images in, host labels
 out, copies inside the timed region).  The two halves of the BASELINE metric are reported beside it: "embed"
 (images/s of the embedding stage) and "rerank" (Mpairs/s of the re-rank + eps + DBSCAN stage alone).
+
+Further keys (round 2): `parity_gate` (a small oracle comparison that must pass before anything is printed;
+BASELINE.md 3.6) and `result.whole_path_parity` (images -> labels against the unmodified reference, last B200
+measurement); `e2e_u8` (the e2e leg with raw uint8 pixels, normalised on the device: a quarter of the H2D bytes);
+`e2e_reference_api` (one cycle through the reference-SHAPED API as the unmodified driver calls it: dict of per-image
+CPU tensors -> re-stack -> numpy N x N matrices -> labels; N=1 only); `result.labels_sha1` (labels of the last timed
+step, for byte-comparison across GPU counts); `finetune_step` with --finetune-step.  --impl reference times the
+reference's CPU path at three sizes and extrapolates with the fit of BASELINE.md 3.3.  Other BASELINE configs:
+--banks 4 (configs[2]), --n 36411 --features-only --rho R (configs[3]), --n 126441 --shard-finish (configs[4]).
 """
 import argparse
 import hashlib
@@ -47,7 +56,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16702)
+    ap.add_argument("--n", "--num-images", dest="n", type=int, default=16702,
+                    help="target (= source) set size; use --num-images under torchrun (its parser rejects --n as ambiguous)")
     ap.add_argument("--banks", type=int, default=3)
     ap.add_argument("--dist-mode", default="tensor", choices=["tensor", "exact"])
     ap.add_argument("--cpu-sample", type=int, default=2560, help="rows of the bounded CPU-baseline sample")
@@ -658,13 +668,14 @@ def main():
             # DRAM traffic of the same launches, from the committed ncu capture of one embedding batch (not re-measured
             # here: a number printed under a profiler is never a bench value, but the byte counts are clock independent)
             traffic = None
-            tpath = os.path.join(ROOT, "profiles", "r01_final_conv_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r02_final_conv_traffic.json")
             if os.path.isfile(tpath):
                 with open(tpath) as f:
                     tj = json.load(f)
                 batches = 2.0 * n * (1.0 / world if sharded else 1.0) / tj["batch_images"]
-                traffic = {"bytes_per_step": tj["dram_bytes_per_batch"] * batches, "source": "profiles/r01_final_conv_traffic.json",
-                           "algorithmic_note": "see DESIGN.md 3.1: the convolution path is HBM bound in its 1x1 layers"}
+                traffic = {"bytes_per_step": tj["dram_bytes_per_batch"] * batches, "source": "profiles/r02_final_conv_traffic.json",
+                           "algorithmic_note": "see DESIGN.md 3.1b: what bounds the convolution tiles (shared-memory operand bandwidth "
+                                               "of the UMMA, load latency; HBM in the layer-1/2 1x1 convolutions)"}
             conv_launches = sum(prof[c][1] for c in conv_names if c in prof)
             roof = {"kernel": "gemm_kernel<StagedEpi> (conv1x1_tc+conv3x3_tc+conv_stem_tc, %d launches)" % conv_launches,
                     "bound": "tensor", "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
