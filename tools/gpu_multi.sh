@@ -28,7 +28,6 @@ case "$N" in
   for rho in 0.0008 0.0016 0.0032; do run config3_rho$rho 600 --num-images 36411 --features-only --rho $rho --steps 2 --warmup 3; done ;;
 8)
   run config1 600 --steps 3 --warmup 3
-  run config1_sparse_owner 600 --steps 3 --warmup 3 --sparse-finish
   run config1_shard_finish 600 --steps 3 --warmup 3 --shard-finish
   run config4 1200 --num-images 126441 --shard-finish --steps 1 --warmup 3 --finetune-step ;;
 esac
