@@ -47,7 +47,10 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     const bool stem_kernel = stem_variant() && A.mode == 3 && cout == 64 && k == tc::BRES_K;
     // (the 128x256 tiles keep the default epilogue: with the doubled bias rows the EPI2 layout is 256 bytes over the
     // 227 KB limit -- first B200 run of round 2 -- and those launches are L2-bandwidth bound, not epilogue bound)
-    const bool wide = cout % 256 == 0 && k >= 256;
+    // (SSG_WIDE_K: smallest K that takes the 256-wide tiles; 256 by default, A/B knob for the K = 128 conv3 of layer 2)
+    static int wide_k = -1;
+    if (wide_k < 0) { const char* e = getenv("SSG_WIDE_K"); wide_k = e ? atoi(e) : 256; }
+    const bool wide = cout % 256 == 0 && k >= wide_k;
     if (epi2 && !stem_kernel && !pool_out && !wide) {
         if (cout % 128 == 0) return tc::launch_gemm_op<128, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
         return tc::launch_gemm_op<64, tc::StagedEpi, true, false, tc::VAR_NONE, true>(A, m, w, cout, k, epi, st);
@@ -74,13 +77,13 @@ static int gemm_dispatch(const tc::AOperand& A, int m, const void* w, int cout, 
     // 128x256 tiles for the K-heavy convolutions without a residual (SSG_CONV_BN256=0 disables, for A/B runs)
     static int bn256 = -1;
     if (bn256 < 0) { const char* e = getenv("SSG_CONV_BN256"); bn256 = e ? atoi(e) : 1; }
-    if (bn256 && !residual && cout % 256 == 0 && k >= 256)
+    if (bn256 && !residual && wide)
         return tc::launch_gemm_op<256, tc::StagedEpi, true>(A, m, w, cout, k, epi, st);
     // ... and WITH a residual (the conv3 of layers 3 and 4): 128x256 tiles with a residual sub-tile ring
     // (SSG_CONV_BN256_RES=0 falls back to 128x128 tiles with a whole-tile residual double buffer)
     static int bn256_res = -1;
     if (bn256_res < 0) { const char* e = getenv("SSG_CONV_BN256_RES"); bn256_res = e ? atoi(e) : 1; }
-    if (bn256_res && residual && cout % 256 == 0 && k >= 256)
+    if (bn256_res && residual && wide)
         return tc::launch_gemm_op<256, tc::StagedEpi, true, false, tc::VAR_RRING>(A, m, w, cout, k, epi, st);
     // the stem (mode 3: N = 64, K = 256) keeps its weights resident in shared memory (SSG_STEM_BRES=0 disables)
     if (stem_variant() && A.mode == 3 && cout == 64 && k == tc::BRES_K) {
@@ -293,6 +296,14 @@ int conv3x3(const void* x, int B, int H, int W, int cin, int stride, const void*
         epi.has_res = 0;
         SSG_TRY(make_tmap_2d_bf16(&epi.mapC, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
         SSG_TRY(make_tmap_2d_bf16(&epi.mapR, y, (uint64_t)m, (uint64_t)cout, (uint64_t)cout, tc::BM));
+        // SSG_KHS_PAIR=1 (opt-in until measured): the two-CTA form (gemm_tc2.cuh): per MMA and CTA 4 KB of A + 1 KB of B
+        // instead of 4 + 2 (the single-CTA kernel is bound by the UMMA's shared-memory operand bandwidth)
+        static int khs_pair = -1;
+        if (khs_pair < 0) { const char* e = getenv("SSG_KHS_PAIR"); khs_pair = e ? atoi(e) : 0; }
+#ifdef SSG_PAIR_KERNEL_UNAVAILABLE
+        khs_pair = 0;
+#endif
+        if (khs_pair && m >= 2 * tc::BM) return tc::launch_gemm2_op<64, false, true>(A, m, w, cout, 9 * cin, epi, st);
         // weights resident in shared memory (72 KB, loaded once per CTA) unless SSG_KHS_BRES=0
         static int khs_bres = -1;
         if (khs_bres < 0) { const char* e = getenv("SSG_KHS_BRES"); khs_bres = e ? atoi(e) : 1; }

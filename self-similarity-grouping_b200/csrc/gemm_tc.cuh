@@ -417,8 +417,10 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         // kh & 1 -- 128 contiguous 64-byte rows; weights of kernel row kh sit kh * 4 KB into the
                         // resident B operand.  Same (kh, k-step) order as the per-kernel-row stages.
                         const uint32_t bres = smem_u32(smem + L::BRES_OFFSET);
+                        // (kernel row 7 of the K = 8 x 32 layout carries zero weights only: its two MMAs are skipped --
+                        // adding exact zeros cannot change the accumulator, and the MMA issue rate bounds this kernel)
 #pragma unroll
-                        for (int kh = 0; kh < 8; ++kh) {
+                        for (int kh = 0; kh < 7; ++kh) {
                             const uint64_t da = make_desc_k_sw64(sa + (uint32_t)((kh & 1) * (L::A_BYTES / 2) +
                                                                               (kh >> 1) * STEM_ROW_BYTES));
                             const uint64_t db = make_desc_k_sw64(bres + (uint32_t)(kh * (L::B_TILE / 2)));

@@ -72,10 +72,13 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
                  : "memory");
 }
 
-template <int BN, bool RES>
+// KHS (kernel-row sharing, the C = 64 3x3 convolutions of layer 1; see gemm_tc.cuh): a stage holds this CTA's haloed
+// activation box for one kernel COLUMN (192 pixel rows) and its halves of the three weight tiles of that column.
+template <int BN, bool RES, bool KHS = false>
 struct Smem2 {
-    static constexpr int A_BYTES = BM * BK * 2;                  // this CTA's 128 rows
-    static constexpr int B_BYTES = (BN / 2) * BK * 2;            // this CTA's half of the weight tile
+    static constexpr int A_BYTES = (KHS ? 192 : BM) * BK * 2;    // this CTA's 128 rows (KHS: + halo)
+    static constexpr int B_TILE = (BN / 2) * BK * 2;             // this CTA's half of one weight tile
+    static constexpr int B_BYTES = (KHS ? 3 : 1) * B_TILE;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SUB_BYTES = BM * 128;
     static constexpr int NSUB = BN / 64;
@@ -88,13 +91,14 @@ struct Smem2 {
     static constexpr int BAR_OFFSET = C_OFFSET + C_BYTES + R_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 384 + 1024;
     static_assert(STAGES >= 3, "pair kernel: too few operand stages");
+    static_assert(!(KHS && (RES || BN != 64)), "pair kernel: KHS is the 64 -> 64 channel 3x3 convolution");
 };
 
-template <int BN, bool RES>
+template <int BN, bool RES, bool KHS = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensorMap mapB, int M, int N, int num_k_blocks,
              const __grid_constant__ StagedEpi epi) {
-    using L = Smem2<BN, RES>;
+    using L = Smem2<BN, RES, KHS>;
     constexpr int STAGES = L::STAGES, NSUB = L::NSUB, RS = L::RSLOTS;
     constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
     extern __shared__ unsigned char smem_raw[];
@@ -159,6 +163,16 @@ gemm2_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtenso
                     unsigned char* sb = sa + L::A_BYTES;
                     const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);   // both CTAs' bytes
+                    if constexpr (KHS) {
+                        // stage kb = kernel column kw (one channel block): rows h0-1 .. h0+bh of this CTA's tile, and this
+                        // CTA's half (32 output channels) of the weight tiles of taps (kh, kw), kh = 0..2
+                        tma2_load_4d(sa, &A.map[0], full_leader, 0, kb - 1, h0 - 1, b0);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh)
+                            tma2_load_2d(sb + kh * L::B_TILE, &mapB, full_leader, (kh * 3 + kb) * BK, (int)rank * (BN / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     if (A.kb_split > 0 && kb >= A.kb_split) {
                         const int kb2 = kb - A.kb_split;
                         if (A.mode1 == 0) tma2_load_2d(sa, &A.map[1], full_leader, kb2 * BK, m_blk * BM);
@@ -190,10 +204,23 @@ gemm2_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtenso
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                        if constexpr (KHS) {
+                            // three kernel rows out of one haloed buffer: A starts kh*bw pixel rows in (both CTAs alike)
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint64_t da = make_desc_k_sw128(sa + (uint32_t)(kh * A.khs_row_bytes));
+                                const uint64_t db = make_desc_k_sw128(sa + L::A_BYTES + (uint32_t)(kh * L::B_TILE));
+#pragma unroll
+                                for (int k = 0; k < BK / UMMA_K; ++k)
+                                    umma2_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                              (kb > 0 || kh > 0 || k > 0) ? 1u : 0u);
+                            }
+                        } else {
                         const uint64_t da = make_desc_k_sw128(sa), db = make_desc_k_sw128(sa + L::A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k)
                             umma2_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        }
                         umma2_commit_both(&empty_bar[stage]);
                         if (kb == num_k_blocks - 1) umma2_commit_both(&tfull_bar[acc]);
                     }
@@ -308,9 +335,11 @@ gemm2_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtenso
 }
 
 // Launch: clusters of two CTAs, one cluster per pair of SMs.
-template <int BN, bool RES>
+template <int BN, bool RES, bool KHS = false>
 int launch_gemm2_op(const AOperand& A, int m, const void* b, int n, int k, const StagedEpi& epi, cudaStream_t st) {
-    using L = Smem2<BN, RES>;
+    using L = Smem2<BN, RES, KHS>;
+    if (KHS && (n != BN || k != 9 * BK || A.cblks != 1))
+        return ssg_set_error(SSG_ERR_INVALID, "gemm2: the KHS pair kernel needs C = N = 64 (N=%d, K=%d)", n, k);
     if (k % 8 || n % BN) return ssg_set_error(SSG_ERR_INVALID, "gemm2: N=%d must be a multiple of %d, K=%d of 8", n, BN, k);
     CUtensorMap mapB;
     SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN / 2));
@@ -320,7 +349,7 @@ int launch_gemm2_op(const AOperand& A, int m, const void* b, int n, int k, const
     const int tiles = ((m_blocks + 1) / 2) * (n / BN);
     int pairs = tiles < sms / 2 ? tiles : sms / 2;
     if (pairs < 1) pairs = 1;
-    auto kern = gemm2_kernel<BN, RES>;
+    auto kern = gemm2_kernel<BN, RES, KHS>;
     SSG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -337,7 +366,7 @@ int launch_gemm2_op(const AOperand& A, int m, const void* b, int n, int k, const
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    const int nkb = (k + BK - 1) / BK;
+    const int nkb = KHS ? 3 : (k + BK - 1) / BK;         // KHS: one K block per kernel column
     SSG_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, A, mapB, m, n, nkb, epi));
     SSG_CHECK_LAUNCH();
     return SSG_OK;

@@ -245,7 +245,7 @@ def build_tc(verbose=False, force=False, fault=None):
     # replaced by a stand-in that reports SSG_ERR_UNSUPPORTED (the variant is opt-in on the GPU as well)
     with open(os.path.join(src_dir, "gemm_tc2.cuh"), "w") as f:
         f.write('#pragma once\n#define SSG_PAIR_KERNEL_UNAVAILABLE 1\n#include "gemm_tc.cuh"\nnamespace ssg { namespace tc {\n'
-                'template <int BN, bool RES>\n'
+                'template <int BN, bool RES, bool KHS = false>\n'
                 'int launch_gemm2_op(const AOperand&, int, const void*, int, int, const StagedEpi&, cudaStream_t) {\n'
                 '    return ssg_set_error(SSG_ERR_UNSUPPORTED, "the two-CTA kernel is not available under emulation");\n}\n'
                 '} }\n')

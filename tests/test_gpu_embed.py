@@ -329,6 +329,8 @@ def test_conv_variants_are_bit_identical(tmp_path):
                            ("no_pairs", dict(SSG_CONV_PAIR="0")),            # default: two-CTA tiles where they win
                            ("all_pairs", dict(SSG_CONV_PAIR="7")),
                            ("pdl", dict(SSG_PDL="1")),                       # programmatic dependent launch (opt-in)
+                           ("khs_pair", dict(SSG_KHS_PAIR="1")),             # two-CTA form of the layer-1 3x3 kernel
+                           ("wide_k128", dict(SSG_WIDE_K="128")),            # 256-wide tiles also for K = 128
                            ("round1_default", dict(SSG_CONV_CHAIN="0", SSG_KHS_BRES="0", SSG_CONV_PAIR="0",
                                                    SSG_CONV_NORES="0"))):
         out_file = str(tmp_path / (name + ".npy"))
