@@ -45,7 +45,19 @@ def synth_images(n, seed, device, per_identity=20, noise=0.5, h=256, w=128, chun
     pat = torch.randn(ids, 3, h, w, generator=g, device=device)
     lab = torch.randint(0, ids, (n,), generator=g, device=device)
     out = torch.empty(n, 3, h, w, device=device)
+    # torch's vectorised gather kernel asserts on sources beyond 2^31 bytes (seen at n = 126 441: 6 322 patterns = 2.5 GB):
+    # gather from slices of at most `part` identities then (same values, same random stream)
+    part = max(1, (1 << 30) // (3 * h * w * 4))
     for r0 in range(0, n, chunk):
         r1 = min(n, r0 + chunk)
-        out[r0:r1] = pat[lab[r0:r1]] + noise * torch.randn(r1 - r0, 3, h, w, generator=g, device=device)
+        idx = lab[r0:r1]
+        if ids <= part:
+            base = pat[idx]
+        else:
+            base = torch.empty(r1 - r0, 3, h, w, device=device)
+            for p0 in range(0, ids, part):
+                sel = (idx >= p0) & (idx < p0 + part)
+                if bool(sel.any()):
+                    base[sel] = pat[p0:p0 + part][idx[sel] - p0]
+        out[r0:r1] = base + noise * torch.randn(r1 - r0, 3, h, w, generator=g, device=device)
     return out, lab

@@ -6,7 +6,7 @@ The kernels compute in bf16 with fp32 accumulation; tolerances, written per test
   * single convolution, inputs/weights already rounded to bf16: |err| <= 1e-2 * max|out| (one bf16 output
     rounding, 2^-9 relative, + accumulation order);
   * whole trunk (53 convolutions, activations re-rounded to bf16 after each): relative L2 error of a
-    2048-d bank <= 3e-2 and cosine similarity >= 0.9995 against the fp32 reference.
+    2048-d bank <= 8e-3 (measured 4.2e-3 on the B200; the round-1 bound was 3e-2) and cosine similarity >= 0.9995 against the fp32 reference.
 """
 import ctypes
 import os
@@ -172,14 +172,14 @@ def test_trunk_end_to_end_against_fp32_oracle_and_reference_golden(S, golden_dir
             assert isinstance(fl[k], list) and len(fl[k]) == S + 1 and not fl[k][0].is_cuda
             for b in range(S + 1):
                 want = torch.from_numpy(gl[b, i])
-                assert _rel_err(fl[k][b], want) <= 3e-2
+                assert _rel_err(fl[k][b], want) <= 8e-3
                 assert float(torch.dot(fl[k][b], want)) >= 0.9995
                 assert abs(float(fl[k][b].norm()) - 1.0) < 1e-5
         else:
-            assert _rel_err(fl[k], torch.from_numpy(gl[0, i])) <= 3e-2
+            assert _rel_err(fl[k], torch.from_numpy(gl[0, i])) <= 8e-3
         want = torch.from_numpy(ge[i])
         assert fe[k].shape == want.shape
-        assert _rel_err(fe[k], want) <= 3e-2 and float(torch.dot(fe[k], want)) >= 0.9995
+        assert _rel_err(fe[k], want) <= 8e-3 and float(torch.dot(fe[k], want)) >= 0.9995
 
 
 def test_trunk_batch_invariance_and_reset_params_regime():
