@@ -382,7 +382,7 @@ def workload_name(n, banks, world):
     return "custom"
 
 
-def finetune_step(model, images, labels, keep, dev, P=16, K=4):
+def finetune_step(model, images, labels, keep, dev, P=16, K=4, row0=0):
     """One FinedTrainer2 step on pseudo-labels (selftraining.py:149-161, 239-253; trainers.py:204-271): P identities x
     K images drawn from the kept images, global + per-bank triplet losses (own CUDA kernels, csrc/triplet.cu), model
     forward / backward through torch autograd (cuDNN convolutions: library code), SGD.  -> dict with the device time."""
@@ -390,12 +390,17 @@ def finetune_step(model, images, labels, keep, dev, P=16, K=4):
     import torch
     from reid.loss import TripletLoss
     from reid.trainers import FinedTrainer2
+    # `images` holds the rows [row0, row0 + len(images)) of the set (this rank's shard in a sharded run): the batch is
+    # drawn from those rows only
     lab0 = np.asarray(labels[0])
-    ids = [c for c in np.unique(lab0[keep]) if c >= 0 and (lab0[keep] == c).sum() >= K][:P]
+    mine = np.zeros(lab0.shape[0], dtype=bool)
+    mine[row0:row0 + images.shape[0]] = True
+    ok = keep & mine
+    ids = [c for c in np.unique(lab0[ok]) if c >= 0 and (lab0[ok] == c).sum() >= K][:P]
     if len(ids) < 2:
-        return {"skipped": "fewer than two pseudo-identities with %d kept images" % K}
-    idx = np.concatenate([np.flatnonzero((lab0 == c) & keep)[:K] for c in ids])
-    imgs = images[torch.from_numpy(idx).to(images.device)].to(dev).float()
+        return {"skipped": "fewer than two pseudo-identities with %d kept images on this rank" % K}
+    idx = np.concatenate([np.flatnonzero((lab0 == c) & ok)[:K] for c in ids])
+    imgs = images[torch.from_numpy(idx - row0).to(images.device)].to(dev).float()
     pids = [torch.from_numpy(np.asarray(l)[idx].astype(np.int64)) for l in labels]
     model = model.to(dev)
     crit = [TripletLoss(0.5, K, True).to(dev), TripletLoss(0.5, K, True).to(dev)]
@@ -651,7 +656,7 @@ def main():
 
     finetune = None
     if args.finetune_step and with_embed and rank == 0:
-        finetune = finetune_step(model, tgt_img, labels, keep, dev)
+        finetune = finetune_step(model, tgt_img, labels, keep, dev, row0=lo if sharded else 0)
     line = None
     if rank == 0:
         peaks = load_peaks()
