@@ -316,6 +316,24 @@ int ssg_triplet_backward(const float* d_x, int n, int d, const float* d_coef, co
                          float* d_grad_x, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Retrieval metrics of the evaluation step: reid/evaluation_metrics/ranking.py:18-79 cmc(...)
+ * and 82-115 mean_ap(...), as called by reid/evaluators.py:88-133 evaluate_all, from the q x g distance matrix
+ * WITHOUT sorting it: per query i and per match s (gallery entries with the query's id that are not filtered out --
+ * same id AND same camera; with separate_camera_set also same camera -- in ascending gallery index)
+ *   d_slots[i*SSG_RANK_MAX_MATCHES + s] = number of valid non-matching entries ranked before the match under the order
+ *                                         (distance, gallery index) = the reference's  k - j  (ranking.py:67-75),
+ *   d_nmatch[i] = number of matches (0: the reference skips the query; -1: more than SSG_RANK_MAX_MATCHES, and
+ *                 d_flags[0] = 1),
+ *   d_ap[i]     = sklearn.metrics.average_precision_score(matches, -dist) over the valid entries (ranking.py:105-111:
+ *                 tied distances form one threshold).
+ * dtype: SSG_F32 or SSG_F64 matrix elements; ids and cameras int64.  The host sums d_ap and histograms d_slots.
+ * ------------------------------------------------------------------------------------------------ */
+#define SSG_RANK_MAX_MATCHES 1024
+int ssg_rank_metrics(const void* d_dist, int dtype, int m, int n, const long long* d_query_ids,
+                     const long long* d_gallery_ids, const long long* d_query_cams, const long long* d_gallery_cams,
+                     int separate_camera_set, double* d_ap, int* d_nmatch, int* d_slots, int* d_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-kernel CUDA-event timers (the reference only has wall-clock AverageMeters, reid/utils/meters.py:4-23,
  * printed from reid/evaluators.py:48-57).  Disabled by default; when enabled every kernel group launched by
  * this library is bracketed by events on its own stream.  collect() synchronises the device, accumulates

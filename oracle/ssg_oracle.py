@@ -278,8 +278,9 @@ def synth_features(n, d=2048, seed=0, per_cluster=20, noise=0.5):
 
 
 # ----------------------------------------------------------------------------- evaluation metrics (row f2)
-def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, first_match_break=False):
-    """reid/evaluation_metrics/ranking.py:18-79 (separate_camera_set=False, single_gallery_shot=False)."""
+def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, first_match_break=False,
+        separate_camera_set=False):
+    """reid/evaluation_metrics/ranking.py:18-79 (single_gallery_shot=False); ties ranked by gallery index."""
     distmat = np.asarray(distmat)
     m, n = distmat.shape
     query_ids, gallery_ids = np.asarray(query_ids), np.asarray(gallery_ids)
@@ -290,6 +291,8 @@ def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, fir
     num_valid_queries = 0
     for i in range(m):
         valid = ((gallery_ids[indices[i]] != query_ids[i]) | (gallery_cams[indices[i]] != query_cams[i]))
+        if separate_camera_set:
+            valid &= (gallery_cams[indices[i]] != query_cams[i])
         if not np.any(matches[i, valid]):
             continue
         index = np.nonzero(matches[i, valid])[0]
@@ -302,6 +305,8 @@ def cmc(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk=100, fir
                 break
             ret[k - j] += delta
         num_valid_queries += 1
+    if num_valid_queries == 0:
+        raise RuntimeError("No valid query")
     return ret.cumsum() / num_valid_queries
 
 
@@ -322,4 +327,6 @@ def mean_ap(distmat, query_ids, gallery_ids, query_cams, gallery_cams):
         if not np.any(y_true):
             continue
         aps.append(average_precision_score(y_true, y_score))
+    if len(aps) == 0:
+        raise RuntimeError("No valid query")
     return np.mean(aps)

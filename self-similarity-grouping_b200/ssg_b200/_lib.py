@@ -92,6 +92,8 @@ PROTOTYPES = {
     "ssg_triplet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "ssg_triplet_backward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ssg_rank_metrics": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssg_profile_enable": (c_int, [c_int]),
     "ssg_profile_reset": (c_int, []),
     "ssg_profile_collect": (c_int, []),

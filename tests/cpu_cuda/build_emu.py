@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "self-similarity-grouping_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu", "triplet.cu"]
+UNITS = ["api.cu", "rerank.cu", "cluster.cu", "dist.cu", "prof.cu", "triplet.cu", "metrics.cu"]
 
 STUBS = r'''// Stand-ins for the tensor-core distance GEMM (gemm_tc.cu: tcgen05 / TMA, not emulated).  The operand split, the
 // centring and everything downstream of the GEMM (candidate selection, exact re-scoring, certification, fallback) are the

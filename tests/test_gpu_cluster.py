@@ -140,6 +140,33 @@ def test_cmc_and_mean_ap_match_reference_restatement(m, n, nid, quant):
         for fmb in (True, False):
             got = cmc(dist, qid, gid, qcam, gcam, topk=50, first_match_break=fmb)
             np.testing.assert_allclose(got, O.cmc(d, qid, gid, qcam, gcam, topk=50, first_match_break=fmb), atol=1e-12)
+    # the library's own kernel (ssg_rank_metrics) orders ties by gallery index = the stable argsort of the restatement
+    for sep in (False, True):
+        for fmb in (True, False):
+            got = cmc(dist.cuda().double(), qid, gid, qcam, gcam, topk=50, first_match_break=fmb, separate_camera_set=sep)
+            want = O.cmc(d, qid, gid, qcam, gcam, topk=50, first_match_break=fmb, separate_camera_set=sep)
+            np.testing.assert_allclose(got, want, atol=1e-12)
+
+
+def test_rank_metrics_kernel_at_evaluation_size():
+    """Market-1501-shaped evaluation (3 368 queries x 15 913 gallery entries, 6 cameras, ~750 ids): the kernel against
+    the restatement on a sample of the queries (the restatement is a per-query Python loop)."""
+    import torch
+    from reid.evaluation_metrics import ranking
+    rng = np.random.RandomState(7)
+    m, n, nid = 3368, 15913, 750
+    qid, gid = rng.randint(0, nid, m), rng.randint(0, nid + 50, n)
+    qcam, gcam = rng.randint(0, 6, m), rng.randint(0, 6, n)
+    d = torch.rand(m, n, generator=torch.Generator().manual_seed(1)) + 0.3 * torch.from_numpy(qid[:, None] != gid[None, :])
+    ap, nm, slots = ranking.rank_metrics(d.cuda(), qid, gid, qcam, gcam)
+    sel = rng.choice(m, 40, replace=False)
+    dn = d.numpy()
+    for i in sel:
+        one = O.mean_ap(dn[i:i + 1], qid[i:i + 1], gid, qcam[i:i + 1], gcam)
+        assert abs(ap[i] - one) < 1e-12
+        c = O.cmc(dn[i:i + 1], qid[i:i + 1], gid, qcam[i:i + 1], gcam, topk=n, first_match_break=True)
+        assert int(np.argmax(c > 0)) == int(slots[i, :nm[i]].min())
+    assert abs(ranking.mean_ap(d.cuda(), qid, gid, qcam, gcam) - float(np.mean(ap[nm > 0]))) < 1e-15
 
 
 def test_dbscan_and_eps_property_based(ssg):

@@ -118,3 +118,20 @@ def test_rerank_lh_restatement_bit_exact(mode, n, ns, d, seed):
     want = want[-1] if isinstance(want, tuple) else want
     got = P.re_ranking_lh(src, tgt, 20, 6, 0.2, mode)
     assert got.dtype == want.dtype and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("sep", [False, True])
+def test_cmc_and_mean_ap_oracle_against_the_reference_ranking_module(sep):
+    """oracle cmc / mean_ap vs reid/evaluation_metrics/ranking.py:18-115 as the reference's evaluators module imports
+    them (distinct distances: the reference's argsort is unstable under ties)."""
+    ref = refshim.load_reference()
+    rng = np.random.RandomState(5)
+    m, n, nid = 70, 400, 30
+    qid, gid = rng.randint(0, nid, m), rng.randint(0, nid, n)
+    qcam, gcam = rng.randint(0, 3, m), rng.randint(0, 3, n)
+    d = rng.rand(m, n) + 0.5 * (qid[:, None] != gid[None, :])
+    assert abs(ref.evaluators.mean_ap(d, qid, gid, qcam, gcam) - O.mean_ap(d, qid, gid, qcam, gcam)) < 1e-15
+    for fmb in (False, True):
+        want = ref.evaluators.cmc(d, qid, gid, qcam, gcam, topk=40, separate_camera_set=sep, first_match_break=fmb)
+        got = O.cmc(d, qid, gid, qcam, gcam, topk=40, separate_camera_set=sep, first_match_break=fmb)
+        assert np.array_equal(want, got)
