@@ -419,10 +419,33 @@ def finetune_step(model, images, labels, keep, dev, P=16, K=4, row0=0):
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
+    out = {"ms": times[-1], "batch": int(len(idx)), "identities": int(len(ids)), "instances": K, "loss": float(loss.item()),
+           "note": "FinedTrainer2 step: model forward/backward = torch autograd over cuDNN (library code); the global + "
+                   "per-bank triplet losses and their gradients are this repo's kernels (csrc/triplet.cu)"}
+    # the same step with every convolution (forward, data gradient, weight gradient) on this repo's tcgen05 kernels
+    # (ssg_b200.train.own_convs -> csrc/train.cu); BatchNorm / ReLU / pooling / SGD stay with torch
+    try:
+        from ssg_b200 import train as own
+        times = []
+        with own.own_convs(model) as swapped:
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                inputs, p, _ = trainer._parse_data((imgs, None, pids, [0] * len(idx)))
+                loss, prec = trainer._forward(inputs, p, 0)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        out["own_convs"] = {"ms": times[-1], "convolutions": int(swapped), "loss": float(loss.item()),
+                            "note": "forward + dgrad + wgrad of all convolutions on the repo's tcgen05 GEMM kernels behind "
+                                    "torch.autograd.Function (NCHW fp32 <-> NHWC bf16 conversions per layer included)"}
+    except Exception as exc:                                       # reported, never hidden
+        out["own_convs"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     model.eval()
-    return {"ms": times[-1], "batch": int(len(idx)), "identities": int(len(ids)), "instances": K, "loss": float(loss.item()),
-            "note": "FinedTrainer2 step: model forward/backward = torch autograd over cuDNN (library code); the global + "
-                    "per-bank triplet losses and their gradients are this repo's kernels (csrc/triplet.cu)"}
+    return out
 
 
 def load_whole_path_parity():

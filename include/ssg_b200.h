@@ -296,6 +296,27 @@ int ssg_op_stem(const float* d_images, int n, int flip, const void* d_w, const f
 int ssg_op_pooled_tail(const void* d_x, int n, int num_split, int eval_mode, int flip, float* d_feat,
                        size_t bank_stride, int row0, void* stream);
 
+/* Training-side convolution operators: what loss.backward() of reid/trainers.py:204-271
+ * (FinedTrainer2.train -> _forward) asks of the ResNet-50 convolutions of reid/models/resnet.py:52-70, on the same
+ * tcgen05 GEMM kernels as the forward path.  NHWC bf16 activations and gradients; fp32 master weights and weight
+ * gradients [cout,cin,k,k] as torch holds them; k in {1,3}, padding k/2, stride in {1,2}; H, W = INPUT map size.
+ *   ssg_op_conv_pack_weight: fp32 weights -> bf16 GEMM operand; transposed == 0: [cout][k][k][cin], the forward operand
+ *                            of ssg_op_conv (with a zero bias: training-mode BatchNorm cannot be folded); transposed != 0:
+ *                            [cin][k][k][cout] with mirrored taps, the operand of the data gradient.
+ *   ssg_op_conv_dgrad      : d_dx bf16 [B,H,W,cin] from d_dy bf16 [B,H/stride,W/stride,cout] (cin, cout multiples of 64;
+ *                            the map sizes ssg_op_conv accepts for the INPUT map).
+ *   ssg_op_conv_wgrad      : d_dw fp32 [cout,cin,k,k] from d_x bf16 [B,H,W,cin] and d_dy: split-K GEMM over the B*Ho*Wo
+ *                            output pixels; the partial products are summed in a fixed order (deterministic).
+ *   ssg_op_stem_im2col     : the stem's im2col (7x7/2 windows, K padded 147 -> 192, (kh,kw,ci) order) on its own, so that
+ *                            the stem convolution and its weight gradient are 1x1 operators on d_col [n*8192,192].
+ * Scratch memory comes from the stream-ordered allocator (cudaMallocAsync). */
+int ssg_op_conv_pack_weight(const float* d_w, int cout, int cin, int ksize, int transposed, void* d_out, void* stream);
+int ssg_op_conv_dgrad(const void* d_dy, int B, int H, int W, int cout, int ksize, int stride, const float* d_w, int cin,
+                      void* d_dx, void* stream);
+int ssg_op_conv_wgrad(const void* d_x, int B, int H, int W, int cin, const void* d_dy, int cout, int ksize, int stride,
+                      float* d_dw, void* stream);
+int ssg_op_stem_im2col(const float* d_images, int n, int flip, void* d_col, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Fine-tune loss: reid/loss/triplet.py:11-77 TripletLoss(margin, num_instances, use_semi)
  * .forward(inputs, targets, epoch) with w = None, as called per feature bank by reid/trainers.py:257-271

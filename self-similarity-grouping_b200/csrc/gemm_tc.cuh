@@ -40,6 +40,8 @@ struct AOperand {
     int kb_split;          // > 0: K blocks >= kb_split come from a second source, map[1] (K-concatenated GEMM)
     int mode1;             // second source: 0 = plain [M,K1] matrix, 1 = single-tap implicit view (uses bh/bb/hmul)
     int khs_row_bytes;     // KHS kernels: bytes of one image row of the tile in the haloed A buffer (bw * 128)
+    int ksplit_mblks;      // > 0 (plain mode, split-K batches stacked along M: weight-gradient GEMM): m-block mb belongs to
+                           // split mb / ksplit_mblks and reads B's K blocks from (mb / ksplit_mblks) * num_k_blocks on
     signed char tap_plane[9], tap_dh[9], tap_dw[9];
 };
 
@@ -316,7 +318,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
                         tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
                         tma_load_2d(sb + L::B_TILE / 2, &mapB, &full_bar[stage], kb * BK + 32, n_blk * BN);
                     } else {
-                        tma_load_2d(sb, &mapB, &full_bar[stage], kb * BK, n_blk * BN);
+                        const int kb_b = A.ksplit_mblks > 0 ? (m_blk / A.ksplit_mblks) * num_k_blocks + kb : kb;
+                        tma_load_2d(sb, &mapB, &full_bar[stage], kb_b * BK, n_blk * BN);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -900,7 +903,8 @@ gemm_kernel(const __grid_constant__ AOperand A, const __grid_constant__ CUtensor
 
 // Launch with a fully prepared A operand.
 template <int BN, class Epi, bool STAGED = false, bool KHS = false, int VAR = VAR_NONE, bool EPI2 = false>
-int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st) {
+int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const Epi& epi, cudaStream_t st,
+                   int b_cols = 0 /* > 0: B is [n, b_cols] with b_cols > k (split-K: A.ksplit_mblks) */) {
     using L = SmemLayout<BN, STAGED, KHS, VAR, EPI2>;
     if ((VAR == VAR_BRES || VAR == VAR_BRESP) && (A.mode != 3 || n != BN || k != BRES_K))
         return ssg_set_error(SSG_ERR_INVALID, "gemm: the resident-B variant is the stem kernel (N=%d, K=%d)", n, k);
@@ -916,7 +920,7 @@ int launch_gemm_op(const AOperand& A, int m, const void* b, int n, int k, const 
     if (k % 8) return ssg_set_error(SSG_ERR_INVALID, "gemm: K=%d must be a multiple of 8 (16-byte row pitch)", k);
     CUtensorMap mapB;
     if (A.mode == 3) SSG_TRY(make_tmap_2d_bf16_sw64(&mapB, b, (uint64_t)n, (uint64_t)k, BN));
-    else SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)k, (uint64_t)k, BN));
+    else SSG_TRY(make_tmap_2d_bf16(&mapB, b, (uint64_t)n, (uint64_t)(b_cols > 0 ? b_cols : k), (uint64_t)(b_cols > 0 ? b_cols : k), BN));
     int sms = 0;
     SSG_TRY(tc_num_sms(&sms));
     const int tiles = ((m + BM - 1) / BM) * ((n + BN - 1) / BN);

@@ -92,6 +92,10 @@ PROTOTYPES = {
     "ssg_triplet_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
     "ssg_triplet_backward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ssg_op_conv_pack_weight": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ssg_op_conv_dgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "ssg_op_conv_wgrad": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ssg_op_stem_im2col": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ssg_rank_metrics": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "ssg_profile_enable": (c_int, [c_int]),

@@ -1,0 +1,183 @@
+"""Training-side convolutions of the fine-tune step.
+
+The reference fine-tunes the ResNet-50 on the pseudo-labels with ``loss.backward()`` through torch autograd
+(reid/trainers.py:204-271 FinedTrainer2.train / _forward; the convolutions of reid/models/resnet.py:52-70 run on cuDNN).
+Here every 1x1 / 3x3 convolution of the trunk -- forward, data gradient and weight gradient -- and the 7x7 stem
+(forward and weight gradient) run on the library's tcgen05 GEMM kernels (csrc/train.cu, include/ssg_b200.h
+``ssg_op_conv*``) behind ``torch.autograd.Function``s; BatchNorm (batch statistics), ReLU, pooling and the optimiser
+stay with torch.
+
+Numerics: activations and gradients cross the kernels as bf16 (fp32 accumulation), weights are rounded to bf16 per
+call from the fp32 master copy, the weight gradient is fp32.  Against fp32 autograd the relative error of a gradient
+is a few 1e-3 per convolution (tests/test_gpu_train_ops.py).
+
+``own_convs(model)`` swaps the forward of the eligible ``nn.Conv2d`` modules (a context manager / undo handle); the
+model, its parameters and the optimiser are untouched, so the reference's trainer code runs as it is.
+"""
+import contextlib
+
+from . import _lib
+
+
+def _f():
+    import torch
+    return torch
+
+
+class _ConvNHWC(object):
+    """Namespace for the autograd function (defined lazily: importing ssg_b200 must not import torch.autograd eagerly)."""
+    fn = None
+
+
+def _conv_fn():
+    if _ConvNHWC.fn is not None:
+        return _ConvNHWC.fn
+    torch = _f()
+
+    class ConvNHWC(torch.autograd.Function):
+        """y [B,H/s,W/s,cout] bf16 = conv_kxk(x [B,H,W,cin] bf16, weight fp32 [cout,cin,k,k]), padding k//2."""
+
+        @staticmethod
+        def forward(ctx, x, weight, stride):
+            lib = _lib.load()
+            x = x.contiguous()
+            weight = weight.contiguous()
+            B, H, W, cin = x.shape
+            cout, _, k, _ = weight.shape
+            dev = x.device
+            st = _lib.stream_ptr(dev)
+            wp = torch.empty(cout * k * k * cin, dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.ssg_op_conv_pack_weight(weight.data_ptr(), cout, cin, k, 0, wp.data_ptr(), st))
+            y = torch.empty((B, H // stride, W // stride, cout), dtype=torch.bfloat16, device=dev)
+            zero = torch.zeros(cout, dtype=torch.float32, device=dev)
+            scratch = torch.empty(x.numel() + 64, dtype=torch.bfloat16, device=dev) if stride == 2 else None
+            _lib.check(lib.ssg_op_conv(x.data_ptr(), B, H, W, cin, k, stride, wp.data_ptr(), zero.data_ptr(), cout, None, 0,
+                                       y.data_ptr(), scratch.data_ptr() if scratch is not None else None, st))
+            ctx.save_for_backward(x, weight)
+            ctx.stride = stride
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            lib = _lib.load()
+            x, weight = ctx.saved_tensors
+            B, H, W, cin = x.shape
+            cout, _, k, _ = weight.shape
+            dy = dy.contiguous()
+            st = _lib.stream_ptr(x.device)
+            dx = dw = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty_like(x)
+                _lib.check(lib.ssg_op_conv_dgrad(dy.data_ptr(), B, H, W, cout, k, ctx.stride, weight.data_ptr(), cin,
+                                                 dx.data_ptr(), st))
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(weight)
+                _lib.check(lib.ssg_op_conv_wgrad(x.data_ptr(), B, H, W, cin, dy.data_ptr(), cout, k, ctx.stride,
+                                                 dw.data_ptr(), st))
+            return dx, dw, None
+
+    class StemNHWC(torch.autograd.Function):
+        """y [n,128,64,64] bf16 = conv_7x7/2(images fp32 [n,3,256,128], weight fp32 [64,3,7,7]), padding 3: the im2col
+        (ssg_op_stem_im2col, K padded 147 -> 192) followed by a 1x1 operator; no gradient reaches the images."""
+
+        @staticmethod
+        def forward(ctx, images, weight):
+            lib = _lib.load()
+            images = images.contiguous().float()
+            n = images.shape[0]
+            dev = images.device
+            st = _lib.stream_ptr(dev)
+            col = torch.empty((n * 8192, 192), dtype=torch.bfloat16, device=dev)
+            _lib.check(lib.ssg_op_stem_im2col(images.data_ptr(), n, 0, col.data_ptr(), st))
+            w192 = torch.zeros((64, 192), dtype=torch.float32, device=dev)
+            w192[:, :147] = weight.permute(0, 2, 3, 1).reshape(64, 147)          # (kh, kw, ci) order
+            wp = w192.to(torch.bfloat16).contiguous()
+            y = torch.empty((n, 128, 64, 64), dtype=torch.bfloat16, device=dev)
+            zero = torch.zeros(64, dtype=torch.float32, device=dev)
+            _lib.check(lib.ssg_op_conv(col.data_ptr(), n, 128, 64, 192, 1, 1, wp.data_ptr(), zero.data_ptr(), 64, None, 0,
+                                       y.data_ptr(), None, st))
+            ctx.save_for_backward(col)
+            return y
+
+        @staticmethod
+        def backward(ctx, dy):
+            lib = _lib.load()
+            (col,) = ctx.saved_tensors
+            n = col.shape[0] // 8192
+            dy = dy.contiguous()
+            dw = None
+            if ctx.needs_input_grad[1]:
+                dw192 = torch.empty((64, 192, 1, 1), dtype=torch.float32, device=col.device)
+                _lib.check(lib.ssg_op_conv_wgrad(col.data_ptr(), n, 128, 64, 192, dy.data_ptr(), 64, 1, 1, dw192.data_ptr(),
+                                                 _lib.stream_ptr(col.device)))
+                dw = dw192.reshape(64, 192)[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+            return None, dw
+
+    _ConvNHWC.fn = (ConvNHWC, StemNHWC)
+    return _ConvNHWC.fn
+
+
+def conv2d_nhwc(x, weight, stride=1):
+    """NHWC bf16 in / out (see ``ConvNHWC``); differentiable in ``x`` and ``weight``."""
+    _lib.require_cuda()
+    return _conv_fn()[0].apply(x, weight, int(stride))
+
+
+def conv2d(x, weight, stride=1):
+    """torch-layout adapter: x fp32/bf16 NCHW -> fp32 NCHW (channels-last memory), through ``conv2d_nhwc``."""
+    torch = _f()
+    y = conv2d_nhwc(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16), weight, stride)
+    return y.permute(0, 3, 1, 2).float()
+
+
+def stem_conv2d(images, weight):
+    """The 7x7/2 stem on fp32 NCHW images of 256 x 128 pixels -> fp32 NCHW [n,64,128,64]."""
+    _lib.require_cuda()
+    if tuple(images.shape[1:]) != (3, 256, 128) or tuple(weight.shape) != (64, 3, 7, 7):
+        raise ValueError("stem_conv2d: images [n,3,256,128] and weight [64,3,7,7] expected, got %s / %s"
+                         % (tuple(images.shape), tuple(weight.shape)))
+    return _conv_fn()[1].apply(images, weight).permute(0, 3, 1, 2).float()
+
+
+def _eligible(conv, stem_too):
+    k = conv.kernel_size
+    if conv.groups != 1 or conv.bias is not None or conv.dilation != (1, 1) or k[0] != k[1]:
+        return None
+    if k[0] in (1, 3) and conv.padding == (k[0] // 2, k[0] // 2) and conv.stride in ((1, 1), (2, 2)) \
+            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0:
+        return "conv"
+    if stem_too and k[0] == 7 and conv.padding == (3, 3) and conv.stride == (2, 2) and conv.in_channels == 3 \
+            and conv.out_channels == 64:
+        return "stem"
+    return None
+
+
+@contextlib.contextmanager
+def own_convs(model, stem=True):
+    """Inside the block every eligible ``nn.Conv2d`` of ``model`` (1x1 / 3x3, stride 1 / 2, channels multiples of 64, no
+    bias; and the 7x7/2 stem on 256 x 128 images) computes forward AND backward on the library's kernels.  Yields the
+    number of swapped modules."""
+    import types
+    torch = _f()
+    swapped = []
+    for mod in model.modules():
+        if not isinstance(mod, torch.nn.Conv2d):
+            continue
+        kind = _eligible(mod, stem)
+        if kind is None:
+            continue
+        if kind == "conv":
+            def fwd(self, x):
+                return conv2d(x, self.weight, self.stride[0])
+        else:
+            def fwd(self, x):
+                if tuple(x.shape[1:]) != (3, 256, 128):
+                    return torch.nn.Conv2d.forward(self, x)
+                return stem_conv2d(x, self.weight)
+        mod.forward = types.MethodType(fwd, mod)
+        swapped.append(mod)
+    try:
+        yield len(swapped)
+    finally:
+        for mod in swapped:
+            del mod.forward

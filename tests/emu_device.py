@@ -16,12 +16,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def install():
-    """Returns an ``undo`` callable."""
+def install(tc=False):
+    """Returns an ``undo`` callable.  tc=True: the library built against the functional tcgen05 / TMA emulation
+    (build_emu.build_tc: every entry point, tensor distance mode and convolutions included)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "tests", "cpu_cuda"))
     import build_emu
-    lib_path, _ = build_emu.build()
+    lib_path = build_emu.build_tc() if tc else build_emu.build()[0]
     from ssg_b200 import _lib, cluster, dist, rerank
     saved = dict(lib=_lib._lib, require=_lib.require_cuda, stream=_lib.stream_ptr, same=_lib.same_device, c_dev=cluster._DevArray,
                  d_dev=dist._DevArray, c_dt=cluster._dtype_code, c_rd=cluster._rows_dtype, plans=dict(rerank._plans),
