@@ -197,3 +197,41 @@ def test_stem_forward_and_weight_gradient_through_the_im2col_operator():
         assert float((got[1][0] - ref[1][0]).norm() / ref[1][0].norm()) < 1e-3
     finally:
         undo()
+
+
+@pytest.mark.parametrize("cin,mid,stride", [(64, 64, 2), (256, 64, 1)])
+def test_bottleneck_block_through_own_convolutions(cin, mid, stride):
+    """A torchvision Bottleneck in train mode (conv1x1 - BN - ReLU - conv3x3[/2] - BN - ReLU - conv1x1 - BN (+ 1x1[/2]
+    downsample - BN) - add - ReLU): the block structure of reid/models/resnet.py:52-70, every convolution on the
+    library's operators (emulated), against torch autograd with bf16 rounding at the same points: every gradient to 5e-3
+    relative (two valid bf16 evaluations of such a block differ by ~1e-3: ReLU masks flip under single-ulp changes)."""
+    import torch
+    from torchvision.models.resnet import Bottleneck
+    sys.path.insert(0, os.path.join(ROOT, "self-similarity-grouping_b200"))
+    import emu_device
+    import train_ref
+    undo = emu_device.install(tc=True)
+    try:
+        from ssg_b200 import train
+        torch.manual_seed(cin + stride)
+        ds = None
+        if stride != 1 or cin != 4 * mid:
+            ds = torch.nn.Sequential(torch.nn.Conv2d(cin, 4 * mid, 1, stride=stride, bias=False), torch.nn.BatchNorm2d(4 * mid))
+        net = Bottleneck(cin, mid, stride, ds).train()
+        x = torch.randn(2, cin, 8, 16, requires_grad=True)
+        with torch.no_grad():
+            tgt = torch.randn(net(x).shape)
+
+        def run():
+            x.grad = None
+            loss, grads = train_ref.grads_of(net, x, lambda y: (y * tgt).sum() / float(tgt.numel()) ** 0.5)
+            return loss, [x.grad.clone()] + grads
+        with train_ref.bf16_rounding_convs(net) as n_ref:
+            ref = run()
+        with train.own_convs(net) as swapped:
+            got = run()
+        assert swapped == n_ref == (4 if ds is not None else 3)
+        worst = max(float((g - r).norm() / r.norm()) for g, r in zip(got[1], ref[1]))
+        assert worst < 5e-3, worst
+    finally:
+        undo()
