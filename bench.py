@@ -442,6 +442,25 @@ def finetune_step(model, images, labels, keep, dev, P=16, K=4, row0=0):
         out["own_convs"] = {"ms": times[-1], "convolutions": int(swapped), "loss": float(loss.item()),
                             "note": "forward + dgrad + wgrad of all convolutions on the repo's tcgen05 GEMM kernels behind "
                                     "torch.autograd.Function (NCHW fp32 <-> NHWC bf16 conversions per layer included)"}
+        # ... and with the activations between the convolutions kept in bf16 channels-last (no conversions; BatchNorm /
+        # ReLU / adds on bf16 as under autocast; parameters, BatchNorm statistics and weight gradients fp32)
+        times = []
+        with own.own_convs(model, activations="bf16", cast_back=model.base.layer4) as swapped:
+            for it in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                inputs, p, _ = trainer._parse_data((imgs, None, pids, [0] * len(idx)))
+                loss, prec = trainer._forward(inputs, p, 0)
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        out["own_convs_bf16_activations"] = {
+            "ms": times[-1], "convolutions": int(swapped), "loss": float(loss.item()),
+            "note": "as own_convs, the tensors between the convolutions stay bf16 channels-last (zero-copy in and out of "
+                    "the kernels); trunk output cast back to fp32 in front of the heads"}
     except Exception as exc:                                       # reported, never hidden
         out["own_convs"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     model.eval()

@@ -235,3 +235,42 @@ def test_bottleneck_block_through_own_convolutions(cin, mid, stride):
         assert worst < 5e-3, worst
     finally:
         undo()
+
+
+def test_bf16_activation_mode_keeps_the_tensors_between_the_convolutions_in_bf16():
+    """own_convs(activations="bf16"): the swapped convolutions hand their bf16 channels-last output on as a view, BatchNorm /
+    ReLU / the residual add run on bf16 tensors, the next convolution consumes them without a copy and ``cast_back``
+    returns fp32 to the caller.  Against the fp32-activation mode the gradients agree to the rounding of the
+    activations (a few 1e-2); parameters' gradients stay fp32."""
+    import torch
+    from torchvision.models.resnet import Bottleneck
+    sys.path.insert(0, os.path.join(ROOT, "self-similarity-grouping_b200"))
+    import emu_device
+    import train_ref
+    undo = emu_device.install(tc=True)
+    try:
+        from ssg_b200 import train
+        torch.manual_seed(3)
+        ds = torch.nn.Sequential(torch.nn.Conv2d(64, 256, 1, stride=2, bias=False), torch.nn.BatchNorm2d(256))
+        net = Bottleneck(64, 64, 2, ds).train()
+        x = torch.randn(2, 64, 8, 16)
+        with torch.no_grad():
+            tgt = torch.randn(net(x).shape)
+        loss_fn = lambda y: (y.float() * tgt).sum() / float(tgt.numel()) ** 0.5      # noqa: E731
+        with train.own_convs(net) as swapped:
+            want = train_ref.grads_of(net, x, loss_fn)
+        seen = []
+        probe = net.bn2.register_forward_hook(lambda m, i, o: seen.append((i[0].dtype, o.dtype, i[0].is_contiguous(
+            memory_format=torch.channels_last))))
+        with train.own_convs(net, activations="bf16", cast_back=net) as swapped2:
+            out = net(x)
+            got = train_ref.grads_of(net, x, loss_fn)
+        probe.remove()
+        assert swapped == swapped2 == 4 and out.dtype == torch.float32
+        assert seen and all(s == (torch.bfloat16, torch.bfloat16, True) for s in seen)
+        assert abs(got[0] - want[0]) < 3e-2 * max(1.0, abs(want[0]))
+        for g, w in zip(got[1], want[1]):
+            assert g.dtype == torch.float32 and float((g - w).norm() / w.norm()) < 6e-2
+        assert not net._forward_hooks                                     # the cast-back hook is gone
+    finally:
+        undo()

@@ -155,3 +155,13 @@ def test_fine_tune_step_runs_through_own_convolutions():
     print("fine-tune step: loss own %.4f / fp32 autograd %.4f; conv weight-gradient norm ratios own/fp32: median %.2f, "
           "range %.2f .. %.2f" % (got[0], fp32[0], np.median(ratios), min(ratios), max(ratios)))
     assert len(ratios) == 53 and 0.5 < np.median(ratios) < 2.0
+    # the same step with the activations between the convolutions kept in bf16 channels-last
+    seen = []
+    probe = model.base.layer3[0].bn2.register_forward_hook(lambda m, i, o: seen.append(i[0].dtype))
+    with train.own_convs(model, activations="bf16", cast_back=model.base.layer4) as swapped:
+        amp = run()
+    probe.remove()
+    assert swapped == 53 and seen == [torch.bfloat16]
+    assert np.isfinite(amp[0]) and abs(amp[0] - fp32[0]) < 0.15 * abs(fp32[0]), (amp[0], fp32[0])
+    assert all(bool(torch.isfinite(g).all()) and g.dtype == torch.float32 for g in amp[1].values())
+    print("fine-tune step, bf16 activations: loss %.4f" % amp[0])
