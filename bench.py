@@ -461,6 +461,40 @@ def finetune_step(model, images, labels, keep, dev, P=16, K=4, row0=0):
             "ms": times[-1], "convolutions": int(swapped), "loss": float(loss.item()),
             "note": "as own_convs, the tensors between the convolutions stay bf16 channels-last (zero-copy in and out of "
                     "the kernels); trunk output cast back to fp32 in front of the heads"}
+        # ... and the whole step (forward, losses, backward, SGD) captured once in a CUDA graph and replayed: with the own
+        # convolutions + bf16 activations, and -- for reference -- with the cuDNN convolutions
+        def graphed(tag, ctx):
+            try:
+                for c in crit:
+                    c.check = False                                # the host-side no-negative check would break the capture
+                pids_dev = [q.to(dev) for q in pids]
+
+                def step_fn(im, *pp):
+                    return trainer._forward([im], list(pp), 0)[0]
+                with ctx:
+                    gs = own.GraphedStep(step_fn, opt, [imgs] + pids_dev)
+                ts = []
+                for it in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    lg = gs(imgs, *pids_dev)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                out[tag] = {"ms": ts[-1], "loss": float(lg.item())}
+            except Exception as exc:
+                out[tag] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+            finally:
+                for c in crit:
+                    c.check = True
+        import contextlib
+        import gc
+        # the autograd graphs of the eager legs must be gone: their AccumulateGrad nodes are bound to the default stream,
+        # and a capture that reaches one of them is invalidated (torch re-creates the nodes on the warm-up stream)
+        loss = prec = inputs = p = None
+        gc.collect()
+        graphed("own_convs_bf16_cuda_graph", own.own_convs(model, activations="bf16", cast_back=model.base.layer4))
+        graphed("cudnn_cuda_graph", contextlib.nullcontext())
     except Exception as exc:                                       # reported, never hidden
         out["own_convs"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     model.eval()

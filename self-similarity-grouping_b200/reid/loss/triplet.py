@@ -15,13 +15,16 @@ class TripletLoss(nn.Module):
         self.margin = margin
         self.use_semi = use_semi
         self.K = num_instances
+        # True: raise like the reference (triplet.py:55) when an anchor has no other-label row -- one host read of a
+        # device flag per call; False: no host synchronisation (the loss is NaN in that case), e.g. under CUDA-graph capture
+        self.check = True
 
     def forward(self, inputs, targets, epoch=0, w=None):
         if w is not None:
             # triplet.py:68-71: every negative distance against every positive one (an O(T^2) variant no driver
             # reaches: FinedTrainer2 drops `w`, trainers.py:250-258)
             raise NotImplementedError("TripletLoss(w=...) is not on the self-training path")
-        return triplet_loss(inputs, targets, self.K, self.margin, self.use_semi)
+        return triplet_loss(inputs, targets, self.K, self.margin, self.use_semi, check=getattr(self, "check", True))
 
 
 class FocalLoss(nn.Module):

@@ -14,8 +14,9 @@ is a few 1e-3 per convolution (tests/test_gpu_train_ops.py).
 ``own_convs(model)`` swaps the forward of the eligible ``nn.Conv2d`` modules (a context manager / undo handle); the
 model, its parameters and the optimiser are untouched, so the reference's trainer code runs as it is.
 ``own_convs(model, activations="bf16", cast_back=...)`` additionally keeps the tensors between the convolutions in bf16
-channels-last (zero-copy in and out of the kernels).  Measured on a B200 at batch 64: 19.3-19.8 ms per
-FinedTrainer2 step on cuDNN autograd, 24.8-26.7 ms / 25.0 ms here -- the step is launch-bound at that size.
+channels-last (zero-copy in and out of the kernels), and ``GraphedStep`` captures the whole optimisation step in one
+CUDA graph.  Measured on B200s at batch 64: 19.3-19.8 ms per FinedTrainer2 step on eager cuDNN autograd
+(the reference's path); here 23-34 ms eager (launch / host bound, box dependent) and 18.1 ms as a graph.
 """
 import contextlib
 
@@ -219,3 +220,45 @@ def own_convs(model, stem=True, activations=None, cast_back=None):
             hook.remove()
         for mod in swapped:
             del mod.forward
+
+
+class GraphedStep(object):
+    """One optimisation step -- forward, loss, backward, ``optimizer.step()`` -- captured ONCE in a CUDA graph and replayed.
+
+    At the fine-tune batch size (64 images) the step is bound by launch count and host overhead, not by the GPU (DESIGN.md
+    §3.5b): the graph removes both.  ``step_fn(*inputs) -> loss`` (a 0-dim tensor) must be free of host synchronisation
+    (``TripletLoss.check = False``: the no-negative check of reid/loss/triplet.py:55 reads a flag on the host) and is traced
+    with whatever convolution implementation is active at construction time (``with own_convs(model): GraphedStep(...)``);
+    replays do not need the context manager.  ``__call__(*inputs)`` copies the inputs into the captured buffers, replays
+    and returns the captured loss tensor (valid until the next call).  SGD / momentum are capture-safe as they are; the
+    library's own launches go to torch's current stream, which is the capturing stream, and its scratch memory comes
+    from the stream-ordered allocator, which CUDA graphs record as allocation nodes.  Drop every reference to losses /
+    outputs of earlier EAGER steps of the same model first: their autograd graphs keep AccumulateGrad nodes bound to the
+    default stream alive, and a capture that reaches one is invalidated (cudaErrorStreamCaptureInvalidated)."""
+
+    def __init__(self, step_fn, optimizer, example_inputs, warmup=3):
+        torch = _f()
+        _lib.require_cuda()
+        self.static_inputs = [t.clone() for t in example_inputs]
+        self.optimizer = optimizer
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):                      # lazy state (momentum buffers, kernel attributes)
+                optimizer.zero_grad(set_to_none=True)
+                step_fn(*self.static_inputs).backward()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = step_fn(*self.static_inputs)
+            self.loss.backward()
+            optimizer.step()
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.static_inputs, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -165,3 +165,41 @@ def test_fine_tune_step_runs_through_own_convolutions():
     assert np.isfinite(amp[0]) and abs(amp[0] - fp32[0]) < 0.15 * abs(fp32[0]), (amp[0], fp32[0])
     assert all(bool(torch.isfinite(g).all()) and g.dtype == torch.float32 for g in amp[1].values())
     print("fine-tune step, bf16 activations: loss %.4f" % amp[0])
+
+
+def test_graphed_step_replays_the_eager_step():
+    """ssg_b200.train.GraphedStep: forward + backward + SGD of a train-mode Bottleneck on the library's convolutions (bf16
+    activations) captured once in a CUDA graph; three steps through the graph (one warm-up step + two replays) leave the
+    same loss sequence and parameters as three eager steps on a copy of the block (the kernels are deterministic)."""
+    import copy
+    import torch
+    from torchvision.models.resnet import Bottleneck
+    from ssg_b200 import train
+    torch.manual_seed(5)
+    ds = torch.nn.Sequential(torch.nn.Conv2d(256, 512, 1, stride=2, bias=False), torch.nn.BatchNorm2d(512))
+    net_a = Bottleneck(256, 128, 2, ds).cuda().train()
+    net_b = copy.deepcopy(net_a)
+    x = torch.randn(8, 256, 32, 16, device="cuda")
+    tgt = torch.randn(8, 512, 16, 8, device="cuda")
+
+    def make(net):
+        opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, nesterov=True, weight_decay=5e-4)
+        return opt, (lambda xx, tt: ((net(xx).float() - tt) ** 2).mean())
+    opt_a, step_a = make(net_a)
+    eager = []
+    with train.own_convs(net_a, activations="bf16", cast_back=net_a):
+        for _ in range(3):
+            opt_a.zero_grad(set_to_none=True)
+            loss = step_a(x, tgt)
+            loss.backward()
+            opt_a.step()
+            eager.append(float(loss.detach()))
+    opt_b, step_b = make(net_b)
+    with train.own_convs(net_b, activations="bf16", cast_back=net_b):
+        gs = train.GraphedStep(step_b, opt_b, [x, tgt], warmup=1)
+    graphed = [float(gs(x, tgt)) for _ in range(2)]
+    torch.cuda.synchronize()
+    assert eager[0] > eager[2]                                        # it trains
+    np.testing.assert_allclose(graphed, eager[1:], rtol=1e-5)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert float((pa - pb).abs().max()) <= 1e-5 * float(pa.abs().max()) + 1e-7
