@@ -385,7 +385,10 @@ def workload_name(n, banks, world):
 def finetune_step(model, images, labels, keep, dev, P=16, K=4, row0=0):
     """One FinedTrainer2 step on pseudo-labels (selftraining.py:149-161, 239-253; trainers.py:204-271): P identities x
     K images drawn from the kept images, global + per-bank triplet losses (own CUDA kernels, csrc/triplet.cu), model
-    forward / backward through torch autograd (cuDNN convolutions: library code), SGD.  -> dict with the device time."""
+    forward / backward through torch autograd (cuDNN convolutions: library code), SGD.  -> dict with the device time of
+    that step ("ms": the reference's stock path) and of the same step with every convolution on this repo's tcgen05 kernels
+    (ssg_b200.train: "own_convs", "own_convs_bf16_activations", and "own_convs_bf16_cuda_graph" = the whole step replayed
+    as one CUDA graph; "cudnn_cuda_graph" for comparison)."""
     import numpy as np
     import torch
     from reid.loss import TripletLoss

@@ -9,6 +9,7 @@ from .cluster import ClusterPlan, DBSCAN, eps_estimate, dbscan_labels  # noqa: F
 
 from .embed import EmbedPlan, embed_images, extract_features  # noqa: F401
 from .triplet import triplet_loss  # noqa: F401
+from . import train  # noqa: F401  (own_convs, GraphedStep: the fine-tune step on the library's convolutions)
 from .cycle import pseudo_label_cycle, compute_dist, generate_selflabel, generate_keep_mask  # noqa: F401
 
 __version__ = "0.1.0"
